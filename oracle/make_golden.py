@@ -1,0 +1,289 @@
+"""TEST INFRASTRUCTURE — generate `tests/golden/*.npz` by running the UNMODIFIED reference
+(imported from /root/reference through `oracle/ref_shim.py`).  Run in the build container:
+
+    python oracle/make_golden.py
+
+The GPU box has no copy of the reference, so the committed fixtures are what pins the oracle
+(`tests/test_oracle_golden.py`) and the CUDA path (`tests/test_gpu_*.py`) to the reference.
+Cycle-spin shifts are not monkey-patched: the reference draws them from its seeded
+`torch.Generator` (utils/torch.py:108-119); we peek at a clone of the generator state before
+each prior call to record what it is about to draw.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import ref_shim  # noqa: E402
+
+ref_shim.install()
+
+from jolideco.core import MAPDeconvolver  # noqa: E402
+from jolideco.data import disk_source_gauss_psf, gauss_and_point_sources_gauss_psf  # noqa: E402
+from jolideco.loss import PoissonLoss, TotalLoss  # noqa: E402
+from jolideco.models import FluxComponents, NPredModels, SpatialFluxComponent  # noqa: E402
+from jolideco.priors import GMMPatchPrior, UniformPrior  # noqa: E402
+from jolideco.priors.patches.gmm import GaussianMixtureModel, GaussianMixtureModelMeta  # noqa: E402
+from jolideco.utils.torch import convolve_fft_torch, view_as_overlapping_patches_torch  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def synthetic_gmm_arrays(K, D=64, seed=0, mean_scale=0.01):
+    rng = np.random.default_rng(seed)
+    A = rng.normal(0, 0.05, size=(K, D, D))
+    cov = A @ A.transpose(0, 2, 1) + 0.01 * np.eye(D)
+    means = rng.normal(0, mean_scale, size=(K, D))
+    w = rng.uniform(0.5, 1.5, size=K)
+    return means, cov, w / w.sum()
+
+
+def make_gmm(K, seed=0, meta_stride=4):
+    means, cov, w = synthetic_gmm_arrays(K, seed=seed)
+    gmm = GaussianMixtureModel.from_numpy(means, cov, w, meta=GaussianMixtureModelMeta(stride=meta_stride))
+    return gmm, (means, cov, w)
+
+
+def peek_shifts(generator):
+    g = torch.Generator()
+    g.set_state(generator.get_state())
+    sy = int(torch.randint(-2, 3, (1,), generator=g))
+    sx = int(torch.randint(-2, 3, (1,), generator=g))
+    return sy, sx
+
+
+def synthetic_dataset(rng, H, W, kh, kw, f=1, bkg=0.5, level=20.0):
+    y, x = np.mgrid[:H, :W]
+    flux = 0.2 + level * np.exp(-0.5 * ((y - H / 2) ** 2 + (x - W / 3) ** 2) / (H / 8) ** 2)
+    flux[H // 4, W // 2] += 50
+    ky, kx = np.mgrid[:kh, :kw]
+    psf = np.exp(-0.5 * (((ky - (kh - 1) / 2) / (kh / 5)) ** 2 + ((kx - (kw - 1) / 2) / (kw / 5)) ** 2))
+    psf /= psf.sum()
+    exposure = 1 + 0.5 * np.linspace(-1, 1, H).reshape(-1, 1) * np.ones((1, W))
+    background = bkg * np.ones((H, W))
+    from scipy.signal import fftconvolve
+
+    npred = background + fftconvolve(flux * exposure, psf, mode="same")
+    counts = rng.poisson(np.clip(npred, 0, None))
+    return {
+        "counts": counts.astype(np.float32),
+        "psf": psf.astype(np.float32),
+        "exposure": exposure.astype(np.float32),
+        "background": background.astype(np.float32),
+    }
+
+
+def pack_datasets(datasets, prefix, out):
+    for i, (name, d) in enumerate(datasets.items()):
+        for key in ["counts", "psf", "exposure", "background"]:
+            out[f"{prefix}{i}_{key}"] = d[key]
+    out[f"{prefix}n"] = len(datasets)
+
+
+# ----------------------------------------------------------------------------------------
+def golden_kat():
+    out = {}
+    rng = np.random.default_rng(1)
+    # patch order (utils/tests/test_torch.py:8-21) + a ragged image with dropped trailing rows
+    img = rng.normal(size=(21, 19)).astype(np.float32)
+    out["patches_img"] = img
+    out["patches_8_4"] = view_as_overlapping_patches_torch(torch.from_numpy(img[None, None]), (8, 8), 4).numpy()
+    out["patches_8_2"] = view_as_overlapping_patches_torch(torch.from_numpy(img[None, None]), (8, 8), 2).numpy()
+    # convolution: odd x even kernel, float64
+    im = rng.normal(size=(20, 23))
+    ke = rng.uniform(size=(5, 4))
+    out["conv_img"], out["conv_ker"] = im, ke
+    out["conv_out"] = convolve_fft_torch(torch.from_numpy(im[None, None]), torch.from_numpy(ke[None, None])).numpy()[0, 0]
+    # NPred setup + forward with upsampling 2 and an even PSF (6x6 -> 12x12)
+    ds = synthetic_dataset(rng, 24, 20, 6, 6)
+    comps = FluxComponents()
+    flux0 = rng.gamma(5.0, size=(24, 20))
+    comps["flux"] = SpatialFluxComponent.from_numpy(flux=flux0, upsampling_factor=2, prior=UniformPrior())
+    npm = NPredModels.from_dataset_numpy(ds, comps)
+    for k in ds:
+        out[f"npred_ds_{k}"] = ds[k]
+    out["npred_flux_init"] = flux0
+    out["npred_flux_up"] = comps["flux"].flux_upsampled.detach().numpy()[0, 0]
+    out["npred_exposure_up"] = npm["flux"].exposure.numpy()[0, 0]
+    out["npred_psf_up"] = npm["flux"].psf.numpy()[0, 0]
+    fluxes = comps.to_flux_tuple()
+    npred = npm.evaluate(fluxes=fluxes)
+    out["npred_out"] = npred.detach().numpy()[0, 0]
+    pl = PoissonLoss([torch.from_numpy(ds["counts"][None, None])], [npm], ["0"])
+    loss = pl.loss_function(npred, pl.counts_all[0])
+    loss.backward()
+    out["npred_loss"] = loss.item()
+    out["npred_theta_grad"] = comps["flux"]._flux_upsampled.grad.numpy()[0, 0]
+    # Poisson loss with exact zeros in npred and counts in {0,1,2,...}
+    n = rng.gamma(1.0, size=(16, 16)).astype(np.float32)
+    n[0, :4] = 0
+    c = rng.poisson(1.0, size=(16, 16)).astype(np.float32)
+    nt = torch.from_numpy(n[None, None]).requires_grad_()
+    l2 = pl.loss_function(nt, torch.from_numpy(c[None, None]))
+    l2.backward()
+    out["poisson_npred"], out["poisson_counts"] = n, c
+    out["poisson_loss"] = l2.item()
+    out["poisson_grad"] = nt.grad.numpy()[0, 0]
+    # GMM constants + log-prob (float32, the reference's working precision)
+    gmm, (means, cov, w) = make_gmm(5, seed=3)
+    x = rng.normal(0, 0.3, size=(37, 64)).astype(np.float32)
+    x -= x.mean(axis=1, keepdims=True)
+    out["gmm_means"], out["gmm_cov"], out["gmm_w"] = means, cov, w
+    out["gmm_x"] = x
+    out["gmm_logp"] = gmm.estimate_log_prob(torch.from_numpy(x)).numpy()
+    out["gmm_prec_chol"] = gmm.precisions_cholesky.numpy()
+    out["gmm_mu_prec"] = gmm.means_precisions_cholesky.numpy()
+    out["gmm_log_det"] = gmm.log_det_cholesky.numpy()
+    out["gmm_pixel_weights"] = gmm.pixel_weights.numpy()
+    np.savez_compressed(os.path.join(OUT, "kat.npz"), **out)
+    print("kat.npz", len(out))
+
+
+# ----------------------------------------------------------------------------------------
+def golden_prior_step():
+    """Value and autograd gradient of GMMPatchPrior + one dataset's Poisson loss, fp32 and fp64."""
+    out = {}
+    rng = np.random.default_rng(2)
+    K = 6
+    _, (means, cov, w) = make_gmm(K, seed=5)
+    out["gmm_means"], out["gmm_cov"], out["gmm_w"] = means, cov, w
+    H, W = 38, 46  # (38-8)%4 != 0: trailing rows dropped
+    flux = rng.gamma(2.0, size=(H, W)).astype(np.float32)
+    out["flux"] = flux
+    case = 0
+    for marginalize in [False, True]:
+        for seed in [0, 1, 2, 7]:
+            for dtype in [torch.float32, torch.float64]:
+                gmm = GaussianMixtureModel.from_numpy(means, cov, w, meta=GaussianMixtureModelMeta(stride=4))
+                gen = torch.Generator().manual_seed(seed)
+                prior = GMMPatchPrior(gmm=gmm, stride=4, generator=gen, marginalize=marginalize)
+                if dtype == torch.float64:
+                    prior = prior.double()
+                sy, sx = peek_shifts(gen)
+                f = torch.from_numpy(flux[None, None]).to(dtype).requires_grad_()
+                val = prior(flux=f)
+                val.backward()
+                tag = f"c{case}_{'f32' if dtype == torch.float32 else 'f64'}"
+                out[f"{tag}_value"] = val.item()
+                out[f"{tag}_grad"] = f.grad.numpy()[0, 0]
+            out[f"c{case}_shift"] = np.array([sy, sx])
+            out[f"c{case}_marginalize"] = marginalize
+            case += 1
+    out["n_cases"] = case
+    np.savez_compressed(os.path.join(OUT, "prior_step.npz"), **out)
+    print("prior_step.npz", case, "cases")
+
+
+# ----------------------------------------------------------------------------------------
+def run_reference(datasets, flux_init, f, n_epochs, gmm_arrays=None, marginalize=False, seed=0, beta=1.0):
+    if gmm_arrays is not None:
+        gmm = GaussianMixtureModel.from_numpy(*gmm_arrays, meta=GaussianMixtureModelMeta(stride=4))
+        gen = torch.Generator().manual_seed(seed)
+        prior = GMMPatchPrior(gmm=gmm, stride=4, generator=gen, marginalize=marginalize)
+        # record the draws: D per epoch for training + 1 for the trace (loss.py:224)
+        g = torch.Generator()
+        g.set_state(gen.get_state())
+        D = len(datasets)
+        shifts, trace_shifts = [], []
+        for _ in range(n_epochs):
+            for _ in range(D):
+                shifts.append(peek_and_advance(g))
+            trace_shifts.append(peek_and_advance(g))
+    else:
+        prior, shifts, trace_shifts = UniformPrior(), [], []
+    comps = FluxComponents()
+    comps["flux-1"] = SpatialFluxComponent.from_numpy(flux=flux_init, upsampling_factor=f, prior=prior)
+    flux_init_up = comps["flux-1"].flux_upsampled.detach().numpy()[0, 0].copy()
+    deco = MAPDeconvolver(n_epochs=n_epochs, learning_rate=0.1, beta=beta, display_progress=False)
+    res = deco.run(datasets=datasets, components=comps)
+    tr = res.trace_loss
+    D = len(datasets)
+    return dict(
+        flux_init_up=flux_init_up,
+        flux_up=res.flux_upsampled_total,
+        flux=res.flux_total,
+        trace_total=np.asarray(tr["total"]),
+        trace_datasets=np.stack([np.asarray(tr[f"dataset-{n}"]) for n in datasets], axis=1),
+        trace_prior=np.asarray(tr["priors-total"]),
+        shifts=np.array(shifts).reshape(-1, 2),
+        trace_shifts=np.array(trace_shifts).reshape(-1, 2),
+    )
+
+
+def peek_and_advance(g):
+    sy = int(torch.randint(-2, 3, (1,), generator=g))
+    sx = int(torch.randint(-2, 3, (1,), generator=g))
+    return sy, sx
+
+
+def golden_runs():
+    # (1) the reference's own e2e golden (tests/test_core.py:71-79): 3 toy datasets, uniform prior
+    out = {}
+    rs = np.random.RandomState(642020)
+    datasets = {str(i): gauss_and_point_sources_gauss_psf(random_state=rs) for i in range(3)}
+    rs = np.random.RandomState(642020)
+    flux_init = rs.gamma(20, size=(32, 32))
+    pack_datasets(datasets, "ds", out)
+    out["flux_init"] = flux_init
+    for k, v in run_reference(datasets, flux_init, 1, 100).items():
+        out[k] = v
+    np.savez_compressed(os.path.join(OUT, "run_uniform.npz"), **out)
+    print("run_uniform.npz flux[12,12]=%.6f (ref test: 1.542659) total=%.6f (5.842237)" % (
+        out["flux"][12, 12], out["trace_total"][-1]))
+
+    # (2) upsampling 2 (tests/test_core.py:99-124): disk datasets
+    out = {}
+    rs = np.random.RandomState(642020)
+    datasets = {str(i): disk_source_gauss_psf(random_state=rs) for i in range(3)}
+    rs = np.random.RandomState(642020)
+    flux_init = rs.gamma(20, size=(32, 32))
+    pack_datasets(datasets, "ds", out)
+    out["flux_init"] = flux_init
+    for k, v in run_reference(datasets, flux_init, 2, 100).items():
+        out[k] = v
+    np.savez_compressed(os.path.join(OUT, "run_upsampling2.npz"), **out)
+    print("run_upsampling2.npz flux[12,12]=%.6f (ref test: 3.565998) total=%.6f (5.844786)" % (
+        out["flux"][12, 12], out["trace_total"][-1]))
+
+    # (3) GMM patch prior runs (no stored golden exists in the reference for a synthetic GMM:
+    # pinned by this live run of the imported reference), both max and logsumexp modes
+    rng = np.random.default_rng(11)
+    datasets = {str(i): synthetic_dataset(rng, 40, 36, 7, 7) for i in range(2)}
+    flux_init = rng.gamma(20, size=(40, 36)) / 10
+    gmm_arrays = synthetic_gmm_arrays(8, seed=9)
+    for marginalize in [False, True]:
+        out = {}
+        pack_datasets(datasets, "ds", out)
+        out["flux_init"] = flux_init
+        out["gmm_means"], out["gmm_cov"], out["gmm_w"] = gmm_arrays
+        out["marginalize"] = marginalize
+        for k, v in run_reference(datasets, flux_init, 1, 8, gmm_arrays, marginalize, seed=4).items():
+            out[k] = v
+        name = "run_gmm_lse.npz" if marginalize else "run_gmm_max.npz"
+        np.savez_compressed(os.path.join(OUT, name), **out)
+        print(name, "total", out["trace_total"][-1], "shifts", out["shifts"][:3].tolist())
+
+    # (4) GMM prior + upsampling 2 + even PSF
+    rng = np.random.default_rng(12)
+    datasets = {str(i): synthetic_dataset(rng, 24, 24, 6, 6) for i in range(2)}
+    flux_init = rng.gamma(20, size=(24, 24)) / 10
+    out = {}
+    pack_datasets(datasets, "ds", out)
+    out["flux_init"] = flux_init
+    out["gmm_means"], out["gmm_cov"], out["gmm_w"] = gmm_arrays
+    out["marginalize"] = False
+    for k, v in run_reference(datasets, flux_init, 2, 6, gmm_arrays, False, seed=5).items():
+        out[k] = v
+    np.savez_compressed(os.path.join(OUT, "run_gmm_up2.npz"), **out)
+    print("run_gmm_up2.npz total", out["trace_total"][-1])
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    golden_kat()
+    golden_prior_step()
+    golden_runs()
