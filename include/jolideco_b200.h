@@ -1,0 +1,134 @@
+/*
+ * jolideco_b200 — C ABI of the B200-native MAP-deconvolution hot path.
+ *
+ * The reference (jolideco/jolideco) is pure Python on PyTorch and has no FFI: the functions
+ * below are what a binding for its hot path (jolideco/core.py:214-230) would call instead of the
+ * ATen op stream.  Each entry cites the reference code it replaces (paths relative to the
+ * reference root).  See INTEGRATION.md for the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (fp32 unless stated) borrowed for the call; images are
+ *     dense row-major 2-D arrays (the reference's (1,1,H,W) tensors);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing syncs;
+ *   - return 0 on success, a negative jd_status otherwise; jd_last_error() gives the message of
+ *     the last failure on the calling thread;
+ *   - no hidden global state, no allocation: workspaces are caller-provided;
+ *   - sm_100a only.  There is no CPU path: without a Blackwell device every call fails.
+ *
+ * Geometry: flux grid fH x fW (upsampled by f), counts grid H x W = fH/f x fW/f, PSF kh x kw
+ * (already upsampled), patches size 8x8 (D = 64), stride s, ny = (fH-8)/s+1, nx = (fW-8)/s+1,
+ * patch p = iy*nx + ix, patch element d = 8*u + v.
+ */
+#ifndef JOLIDECO_B200_H
+#define JOLIDECO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JD_ABI_VERSION 1
+
+typedef enum {
+  JD_OK = 0,
+  JD_ERR_INVALID = -1,   /* bad argument (shape, null pointer, unsupported size) */
+  JD_ERR_CUDA = -2,      /* CUDA runtime error (message has cudaGetErrorString) */
+  JD_ERR_NO_DEVICE = -3, /* no sm_100 device */
+  JD_ERR_UNSUPPORTED = -4
+} jd_status;
+
+typedef void* jd_stream_t;
+
+int jd_abi_version(void);
+const char* jd_last_error(void);
+/* 1 if `device` is a compute-capability 10.x GPU, 0 if not, <0 on error. */
+int jd_device_supported(int device);
+
+/* ---- a1: flux parameterisation (models/core.py:583-594) --------------------------------
+ * flux = exp(theta) if use_log_flux else theta;  flux *= mask if mask != NULL (uint8 0/1). */
+int jd_flux_forward(const float* theta, const uint8_t* mask, float* flux, int64_t n, int use_log_flux,
+                    jd_stream_t stream);
+
+/* ---- a3: PSF convolution of flux*exposure (models/npred.py:175-178, utils/torch.py:337-370)
+ * conv[i,j] = sum_{a,b} psf[a,b] * g[i+sy-a, j+sx-b],  g = flux*exposure (exposure may be NULL),
+ * s = (k-1)/2, zero outside: identical to rfft2*rfft2 -> irfft2 -> centred crop.
+ * Direct shared-memory-tiled form, any PSF size. */
+int jd_conv_forward_direct(const float* flux, const float* exposure, const float* psf, float* conv, int fH,
+                           int fW, int kh, int kw, jd_stream_t stream);
+
+/* Adjoint of the above w.r.t. flux, fused with the sum-pool adjoint (replicate f x f) and the
+ * exposure product:  dflux[m,n] (+)= E[m,n] * sum_{a,b} psf[a,b] * dc[m-sy+a, n-sx+b],
+ * dc[y,x] = dpool[y/f, x/f] (0 outside H x W).  accumulate != 0 adds into dflux. */
+int jd_conv_backward_direct(const float* dpool, const float* exposure, const float* psf, float* dflux,
+                            int accumulate, int fH, int fW, int kh, int kw, int f, int H, int W,
+                            jd_stream_t stream);
+
+/* ---- a3/a4/a6: sum-pool + clip + background + Poisson cash statistic and its gradient ------
+ * (models/npred.py:181-191, 234-261; loss.py:35-37 = nn.PoissonNLLLoss(log_input=False,
+ * reduction="mean", eps=1e-25, full=True))
+ *   pool  = sum over f x f blocks of conv;  npred = max(pool,0) + B * exp(*bkg_log_norm)
+ *   loss_sum[0] += sum_pix [ npred - c log(npred+eps) + 1{c>1}(c log c - c + .5 log(2 pi c)) ]
+ *   dpool = grad_scale * (1 - c/(npred+eps)) * 1{pool >= 0}        (grad_scale = 1/(H W) for the mean)
+ *   dlogb[0] += sum_pix grad_scale * (1 - c/(npred+eps)) * B * exp(*bkg_log_norm)
+ * npred, dpool, dlogb, bkg_log_norm may be NULL.  loss_sum / dlogb are double accumulators. */
+int jd_poisson_forward_backward(const float* conv, const float* background, const float* bkg_log_norm,
+                                const float* counts, float* npred, float* dpool, double* loss_sum,
+                                double* dlogb, int H, int W, int f, int fW, float eps, float grad_scale,
+                                jd_stream_t stream);
+
+/* ---- a9: GMM log-probabilities of explicit feature vectors (priors/patches/gmm.py:262-281) --
+ * logp[p,k] = -0.5 * sum_j (x_p . Lw[k][:,j] - mw[k][j])^2 + ck[k]
+ * with the packed constants  Lw[k] = L_k diag(sqrt(w)),  mw[k] = (mu_k L_k) sqrt(w),
+ * ck[k] = -D/2 log 2pi + sum_j log L_k[j,j] + log pi_k.  Any D <= 1024. */
+int jd_gmm_log_prob(const float* x, int64_t P, int D, int K, const float* Lw, const float* mw,
+                    const float* ck, float* logp, jd_stream_t stream);
+
+/* ---- a8: cycle-spin roll + overlapping 8x8 patches (utils/torch.py:91-119, 226-275) ----------
+ * X[p', 8u+v] = flux[(s*iy+u-sy) mod fH, (s*ix+v-sx) mod fW] for patch rows iy in [row_begin,row_end).
+ * Integer-exact; shares its index function with every other patch kernel. */
+int jd_extract_patches(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
+                       int row_end, float* X, jd_stream_t stream);
+
+/* ---- a8+a9+a10: GMM patch prior on the flux image (priors/patches/core.py:189-246) ---------
+ * Gathers 8x8 patches of the rolled image r[y,x] = flux[(y-sy) mod fH, (x-sx) mod fW] for patch
+ * rows iy in [row_begin,row_end), subtracts the patch mean, evaluates all K components and
+ * reduces v_p = max_k (marginalize=0) or logsumexp_k (marginalize=1).  shift_yx: 2 int32 on the
+ * device (sy, sx).  Outputs (local patch index p' = (iy-row_begin)*nx + ix):
+ *   value[p'] (v_p), argmax[p'] (int32), sum[0] += sum_p v_p (double), logp (optional, P' x K,
+ *   needed by the marginalize=1 backward).  Patches containing NaN or values <= -1e5 are skipped
+ *   (value 0, argmax -1), as the reference filters them (core.py:215-216).
+ * backend: 0 = FP32 CUDA cores (reference-grade check path), 1 = tcgen05 split-TF32. */
+int jd_gmm_prior_forward(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride,
+                         int row_begin, int row_end, const float* Lw, const float* mw, const float* ck,
+                         int K, int marginalize, float* value, int32_t* argmax, float* logp, double* sum,
+                         int backend, jd_stream_t stream);
+
+/* Per-patch gradient  G[p',:] = scale * sum_k R[p',k] (xc_p Lam_k - bk_k),  minus its row mean,
+ * R = one-hot(argmax) or softmax_k(logp) (marginalize=1; needs logp and value from the forward);
+ * Lam_k = Lw_k Lw_k^T, bk_k = mw_k Lw_k^T.  (Autograd mirror of gmm.py:270-272 + norms.py:97-103.)
+ * For d prior/d flux pass scale = -stride^2/64/(fH fW). */
+int jd_gmm_prior_backward(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride,
+                          int row_begin, int row_end, const float* Lam, const float* bk, int K,
+                          int marginalize, const int32_t* argmax, const float* logp, const float* value,
+                          float scale, float* G, jd_stream_t stream);
+
+/* col2im of the per-patch gradients, gather form (deterministic, no atomics): for every pixel
+ * sum the <= (8/s)^2 patch entries covering it at the rolled coordinates
+ * (unfold_backward x2 + roll backward).  dflux (+)= fold(G) if accumulate else = fold(G). */
+int jd_patch_fold(const float* G, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
+                  int row_end, float* dflux, int accumulate, jd_stream_t stream);
+
+/* ---- a12: fused gradient sum + chain rule + Adam (torch.optim.Adam defaults, core.py:39-42,229)
+ * g = (dflux_a + scale_b * dflux_b) * dflux/dtheta,  dflux/dtheta = flux (log param) or mask;
+ * m,v,theta updated in place with bias correction for step number `step` (1-based).
+ * dflux_b may be NULL. */
+int jd_adam_step(float* theta, float* m, float* v, const float* flux, const uint8_t* mask,
+                 const float* dflux_a, const float* dflux_b, float scale_b, int use_log_flux, int64_t n,
+                 int step, float lr, float beta1, float beta2, float eps, jd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JOLIDECO_B200_H */

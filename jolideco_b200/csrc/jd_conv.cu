@@ -1,0 +1,179 @@
+// Direct (shared-memory tiled) PSF convolution of the NPred forward model and its adjoint.
+//
+// Both directions are one "offset correlation"
+//     out[i,j] = sum_{a<kh, b<kw} Kc[a,b] * in[i+oy+a, j+ox+b]        (in = 0 outside the image)
+//   forward : Kc = flip(psf), (oy,ox) = (sy-(kh-1), sx-(kw-1)), in = flux*exposure      s = (k-1)/2
+//   adjoint : Kc = psf,       (oy,ox) = (-sy, -sx),             in[y,x] = dpool[y/f, x/f], out *= E
+// which reproduces rfft2*rfft2 -> irfft2 -> centred crop of utils/torch.py:337-370 exactly, including
+// the asymmetric crop of even-sized PSFs.
+//
+// Tiling: a CTA of TY x TX threads owns a (4 TY) x (4 TX) output tile; each thread a 4x4 register
+// block.  The PSF is processed in chunks of KC rows: per chunk the input tile
+// (4 TY + KC - 1) x (4 TX + kw_pad - 1) and the chunk rows are staged in shared memory.  For every
+// staged input row t the thread loads a sliding 4+4 window once and feeds the 4 output rows r with
+// kernel row a = t - r (zero rows pad the chunk so no predicate is needed): 64 FMA per
+// 1 window LDS.128 + 4 broadcast LDS.128.
+#include "jd_common.cuh"
+
+namespace jd {
+
+constexpr int R = 4;   // output rows per thread
+constexpr int C = 4;   // output cols per thread
+constexpr int KC = 16; // PSF rows per chunk
+
+enum { CONV_FWD = 0, CONV_BWD = 1 };
+
+template <int MODE, int TY, int TX>
+__global__ void __launch_bounds__(TY * TX)
+conv_kernel(const float* __restrict__ in, const float* __restrict__ scale, const float* __restrict__ psf,
+            float* __restrict__ out, int fH, int fW, int kh, int kw, int oy, int ox, int f, int H, int W,
+            int accumulate) {
+  constexpr int TH = R * TY, TW = C * TX;
+  extern __shared__ __align__(16) float smem[];
+  const int kwp = (kw + 3) & ~3;            // kernel row padded to a multiple of 4
+  const int iw = TW + kwp;                  // staged input row length (multiple of 4)
+  const int ih = TH + KC - 1;
+  float* s_in = smem;                       // ih x iw
+  float* s_k = smem + ih * iw;              // (KC + 2(R-1)) x kwp, rows [R-1, R-1+KC) hold the chunk
+
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const int tile_y = blockIdx.y * TH, tile_x = blockIdx.x * TW;
+  const int nthreads = TY * TX;
+
+  float acc[R][C];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[r][c] = 0.f;
+
+  // zero the kernel staging buffer once: pad rows/cols stay zero for every chunk
+  for (int i = threadIdx.x; i < (KC + 2 * (R - 1)) * kwp; i += nthreads) s_k[i] = 0.f;
+
+  for (int a0 = 0; a0 < kh; a0 += KC) {
+    const int kc = min(KC, kh - a0);
+    __syncthreads();
+    // stage kernel chunk (MODE fwd: flipped psf)
+    for (int i = threadIdx.x; i < KC * kwp; i += nthreads) {
+      int a = i / kwp, b = i - a * kwp;
+      float val = 0.f;
+      if (a < kc && b < kw) {
+        int aa = a0 + a;
+        val = MODE == CONV_FWD ? psf[(kh - 1 - aa) * kw + (kw - 1 - b)] : psf[aa * kw + b];
+      }
+      s_k[(a + R - 1) * kwp + b] = val;
+    }
+    // stage input tile rows [tile_y + oy + a0, +TH+kc-1), cols [tile_x + ox, +iw)
+    const int rows = TH + kc - 1;
+    for (int i = threadIdx.x; i < rows * iw; i += nthreads) {
+      int ry = i / iw, rx = i - ry * iw;
+      int y = tile_y + oy + a0 + ry, x = tile_x + ox + rx;
+      float val = 0.f;
+      if (y >= 0 && y < fH && x >= 0 && x < fW) {
+        if (MODE == CONV_FWD) {
+          val = in[(int64_t)y * fW + x];
+          if (scale) val *= scale[(int64_t)y * fW + x];
+        } else {
+          int py = y / f, px = x / f;
+          if (py < H && px < W) val = in[(int64_t)py * W + px];
+        }
+      }
+      s_in[i] = val;
+    }
+    __syncthreads();
+
+    // t = staged input row relative to the thread's first output row
+    for (int t = 0; t < R - 1 + kc; ++t) {
+      const float* in_row = s_in + (ty * R + t) * iw + tx * C;
+      const float* k_rows = s_k + (t + R - 1) * kwp;   // row for r = 0; row for r is k_rows - r*kwp
+      float4 lo = *reinterpret_cast<const float4*>(in_row);
+      for (int b0 = 0; b0 < kwp; b0 += 4) {
+        float4 hi = *reinterpret_cast<const float4*>(in_row + b0 + 4);
+        float win[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          float4 kv = *reinterpret_cast<const float4*>(k_rows - r * kwp + b0);
+          float kk[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb)
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[r][c] = fmaf(kk[bb], win[bb + c], acc[r][c]);
+        }
+        lo = hi;
+      }
+    }
+  }
+
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    int y = tile_y + ty * R + r;
+    if (y >= fH) continue;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      int x = tile_x + tx * C + c;
+      if (x >= fW) continue;
+      int64_t o = (int64_t)y * fW + x;
+      float val = acc[r][c];
+      if (MODE == CONV_BWD) {
+        if (scale) val *= scale[o];
+        if (accumulate) val += out[o];
+      }
+      out[o] = val;
+    }
+  }
+}
+
+template <int MODE>
+static int launch_conv(const float* in, const float* scale, const float* psf, float* out, int fH, int fW, int kh,
+                       int kw, int oy, int ox, int f, int H, int W, int accumulate, cudaStream_t st,
+                       const char* name) {
+  // 8x8 threads -> 32x32 tiles for small images (fills 148 SMs sooner), 16x16 -> 64x64 otherwise
+  const bool small = (int64_t)fH * fW <= 1024 * 1024;
+  const int kwp = (kw + 3) & ~3;
+  if (small) {
+    constexpr int TY = 8, TX = 8;
+    size_t sm = ((size_t)(R * TY + KC - 1) * (C * TX + kwp) + (size_t)(KC + 2 * (R - 1)) * kwp) * sizeof(float);
+    JD_CHECK_ARG(sm <= 200 * 1024, "%s: PSF too wide for the direct kernel (kw=%d)", name, kw);
+    auto kern = conv_kernel<MODE, TY, TX>;
+    if (sm > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    dim3 grid((fW + C * TX - 1) / (C * TX), (fH + R * TY - 1) / (R * TY));
+    kern<<<grid, TY * TX, sm, st>>>(in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate);
+  } else {
+    constexpr int TY = 16, TX = 16;
+    size_t sm = ((size_t)(R * TY + KC - 1) * (C * TX + kwp) + (size_t)(KC + 2 * (R - 1)) * kwp) * sizeof(float);
+    JD_CHECK_ARG(sm <= 200 * 1024, "%s: PSF too wide for the direct kernel (kw=%d)", name, kw);
+    auto kern = conv_kernel<MODE, TY, TX>;
+    if (sm > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    dim3 grid((fW + C * TX - 1) / (C * TX), (fH + R * TY - 1) / (R * TY));
+    kern<<<grid, TY * TX, sm, st>>>(in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate);
+  }
+  JD_CHECK_LAUNCH(name);
+  return JD_OK;
+}
+
+}  // namespace jd
+
+using namespace jd;
+
+extern "C" {
+
+int jd_conv_forward_direct(const float* flux, const float* exposure, const float* psf, float* conv, int fH,
+                           int fW, int kh, int kw, jd_stream_t stream) {
+  JD_CHECK_ARG(flux && psf && conv, "jd_conv_forward_direct: null pointer");
+  JD_CHECK_ARG(fH > 0 && fW > 0 && kh > 0 && kw > 0, "jd_conv_forward_direct: bad shape");
+  int sy = (kh - 1) / 2, sx = (kw - 1) / 2;
+  return launch_conv<CONV_FWD>(flux, exposure, psf, conv, fH, fW, kh, kw, sy - (kh - 1), sx - (kw - 1), 1, fH, fW,
+                               0, to_stream(stream), "jd_conv_forward_direct");
+}
+
+int jd_conv_backward_direct(const float* dpool, const float* exposure, const float* psf, float* dflux,
+                            int accumulate, int fH, int fW, int kh, int kw, int f, int H, int W,
+                            jd_stream_t stream) {
+  JD_CHECK_ARG(dpool && psf && dflux, "jd_conv_backward_direct: null pointer");
+  JD_CHECK_ARG(fH > 0 && fW > 0 && kh > 0 && kw > 0 && f >= 1 && H * f <= fH && W * f <= fW,
+               "jd_conv_backward_direct: bad shape");
+  int sy = (kh - 1) / 2, sx = (kw - 1) / 2;
+  return launch_conv<CONV_BWD>(dpool, exposure, psf, dflux, fH, fW, kh, kw, -sy, -sx, f, H, W, accumulate,
+                               to_stream(stream), "jd_conv_backward_direct");
+}
+
+}  // extern "C"

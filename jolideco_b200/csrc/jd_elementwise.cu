@@ -1,0 +1,217 @@
+// HBM-bound pieces of the MAP step: flux parameterisation, pooled Poisson cash statistic with its
+// gradient, patch-gradient fold (col2im, gather form) and the fused gradient-sum + Adam update.
+#include <math_constants.h>
+#include <stdarg.h>
+
+#include "jd_common.cuh"
+
+namespace jd {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// a1: flux = exp(theta) * mask                                   (models/core.py:583-594)
+// ------------------------------------------------------------------------------------------
+__global__ void flux_kernel(const float* __restrict__ theta, const uint8_t* __restrict__ mask,
+                            float* __restrict__ flux, int64_t n, int use_log) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float t = theta[i];
+    float f = use_log ? expf(t) : t;
+    if (mask) f *= (float)mask[i];
+    flux[i] = f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// a3/a4/a6: sum-pool, clip, background, Poisson NLL (full Stirling term) and gradient.
+// One thread per counts pixel; warp-shuffle + shared block reduction, one double atomic per block.
+// ------------------------------------------------------------------------------------------
+__global__ void poisson_kernel(const float* __restrict__ conv, const float* __restrict__ background,
+                               const float* __restrict__ bkg_log_norm, const float* __restrict__ counts,
+                               float* __restrict__ npred_out, float* __restrict__ dpool_out,
+                               double* __restrict__ loss_sum, double* __restrict__ dlogb, int H, int W, int f,
+                               int fW, float eps, float grad_scale) {
+  __shared__ double red[32];
+  const float bnorm = bkg_log_norm ? expf(bkg_log_norm[0]) : 1.0f;
+  const int64_t n = (int64_t)H * W;
+  double acc = 0.0, accb = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int y = (int)(i / W), x = (int)(i - (int64_t)y * W);
+    float pool = 0.f;
+    const float* src = conv + (int64_t)y * f * fW + (int64_t)x * f;
+    for (int u = 0; u < f; ++u)
+      for (int v = 0; v < f; ++v) pool += src[(int64_t)u * fW + v];
+    float bkg = background[i] * bnorm;
+    float np_ = fmaxf(pool, 0.f) + bkg;
+    float c = counts[i];
+    float ne = np_ + eps;
+    float loss = np_ - c * logf(ne);
+    if (c > 1.f) loss += c * logf(c) - c + 0.5f * logf(6.283185307179586f * c);
+    acc += (double)loss;
+    float d = (1.f - c / ne) * grad_scale;
+    accb += (double)(d * bkg);
+    if (npred_out) npred_out[i] = np_;
+    if (dpool_out) dpool_out[i] = pool >= 0.f ? d : 0.f;
+  }
+  double s = block_sum(acc, red);
+  if (threadIdx.x == 0 && loss_sum) atomicAdd(loss_sum, s);
+  if (dlogb) {
+    double sb = block_sum(accb, red);
+    if (threadIdx.x == 0) atomicAdd(dlogb, sb);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// col2im, gather form: every flux pixel sums the patch-gradient entries that cover it.
+// Rolled coordinate ry = (y + sy) mod fH; covering patch rows iy with 0 <= ry - s*iy < 8.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fold_gather(const float* __restrict__ G, int y, int x, int fH, int fW, int sy,
+                                             int sx, int stride, int ny, int nx, int row_begin, int row_end) {
+  int ry = wrap(y + sy, fH), rx = wrap(x + sx, fW);
+  int iy_hi = min(ry / stride, min(ny, row_end) - 1);
+  int ix_hi = min(rx / stride, nx - 1);
+  float acc = 0.f;
+  for (int iy = iy_hi; iy >= row_begin && ry - iy * stride < PATCH; --iy) {
+    int u = ry - iy * stride;
+    for (int ix = ix_hi; ix >= 0 && rx - ix * stride < PATCH; --ix) {
+      int v = rx - ix * stride;
+      int64_t p = (int64_t)(iy - row_begin) * nx + ix;
+      acc += G[p * PD + u * PATCH + v];
+    }
+  }
+  return acc;
+}
+
+__global__ void fold_kernel(const float* __restrict__ G, int fH, int fW, const int32_t* __restrict__ shift_yx,
+                            int stride, int row_begin, int row_end, float* __restrict__ dflux, int accumulate) {
+  const int sy = shift_yx ? shift_yx[0] : 0, sx = shift_yx ? shift_yx[1] : 0;
+  const int ny = (fH - PATCH) / stride + 1, nx = (fW - PATCH) / stride + 1;
+  const int64_t n = (int64_t)fH * fW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int y = (int)(i / fW), x = (int)(i - (int64_t)y * fW);
+    float g = fold_gather(G, y, x, fH, fW, sy, sx, stride, ny, nx, row_begin, row_end);
+    dflux[i] = accumulate ? dflux[i] + g : g;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// a12: gradient sum + chain rule + Adam, same operation order as torch.optim.Adam (single tensor):
+//   m.lerp_(g, 1-b1); v.mul_(b2).addcmul_(g, g, 1-b2); denom = sqrt(v)/sqrt(bc2) + eps;
+//   theta.addcdiv_(m, denom, -lr/bc1)
+// ------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v,
+                            const float* __restrict__ flux, const uint8_t* __restrict__ mask,
+                            const float* __restrict__ da, const float* __restrict__ db, float scale_b, int use_log,
+                            int64_t n, float lr_over_bc1, float sqrt_bc2, float b1, float b2, float eps) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float g = da[i];
+    if (db) g += scale_b * db[i];
+    g *= use_log ? flux[i] : (mask ? (float)mask[i] : 1.f);
+    float mi = m[i], vi = v[i];
+    mi = mi + (g - mi) * (1.f - b1);
+    vi = vi * b2 + (1.f - b2) * g * g;
+    float denom = sqrtf(vi) / sqrt_bc2 + eps;
+    theta[i] = theta[i] - lr_over_bc1 * (mi / denom);
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+
+static inline int grid_for(int64_t n, int block) {
+  int64_t g = (n + block - 1) / block;
+  int64_t cap = (int64_t)num_sms() * 8;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace jd
+
+using namespace jd;
+
+extern "C" {
+
+int jd_abi_version(void) { return JD_ABI_VERSION; }
+
+const char* jd_last_error(void) { return jd::g_err; }
+
+int jd_device_supported(int device) {
+  int major = 0;
+  cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  if (e != cudaSuccess) {
+    set_error("jd_device_supported: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return JD_ERR_NO_DEVICE;
+  }
+  return major == 10 ? 1 : 0;
+}
+
+int jd_flux_forward(const float* theta, const uint8_t* mask, float* flux, int64_t n, int use_log_flux,
+                    jd_stream_t stream) {
+  JD_CHECK_ARG(theta && flux && n > 0, "jd_flux_forward: null pointer or n <= 0");
+  flux_kernel<<<grid_for(n, 256), 256, 0, to_stream(stream)>>>(theta, mask, flux, n, use_log_flux);
+  JD_CHECK_LAUNCH("jd_flux_forward");
+  return JD_OK;
+}
+
+int jd_poisson_forward_backward(const float* conv, const float* background, const float* bkg_log_norm,
+                                const float* counts, float* npred, float* dpool, double* loss_sum,
+                                double* dlogb, int H, int W, int f, int fW, float eps, float grad_scale,
+                                jd_stream_t stream) {
+  JD_CHECK_ARG(conv && background && counts, "jd_poisson_forward_backward: null input");
+  JD_CHECK_ARG(H > 0 && W > 0 && f >= 1 && fW >= W * f, "jd_poisson_forward_backward: bad shape H=%d W=%d f=%d fW=%d",
+               H, W, f, fW);
+  int64_t n = (int64_t)H * W;
+  poisson_kernel<<<grid_for(n, 256), 256, 0, to_stream(stream)>>>(conv, background, bkg_log_norm, counts, npred,
+                                                                   dpool, loss_sum, dlogb, H, W, f, fW, eps,
+                                                                   grad_scale);
+  JD_CHECK_LAUNCH("jd_poisson_forward_backward");
+  return JD_OK;
+}
+
+int jd_patch_fold(const float* G, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
+                  int row_end, float* dflux, int accumulate, jd_stream_t stream) {
+  JD_CHECK_ARG(G && dflux, "jd_patch_fold: null pointer");
+  JD_CHECK_ARG(fH >= PATCH && fW >= PATCH && stride >= 1 && stride <= PATCH, "jd_patch_fold: bad geometry");
+  int ny = (fH - PATCH) / stride + 1;
+  JD_CHECK_ARG(row_begin >= 0 && row_end <= ny && row_begin <= row_end, "jd_patch_fold: bad row block [%d,%d) of %d",
+               row_begin, row_end, ny);
+  int64_t n = (int64_t)fH * fW;
+  fold_kernel<<<grid_for(n, 256), 256, 0, to_stream(stream)>>>(G, fH, fW, shift_yx, stride, row_begin, row_end,
+                                                                dflux, accumulate);
+  JD_CHECK_LAUNCH("jd_patch_fold");
+  return JD_OK;
+}
+
+int jd_adam_step(float* theta, float* m, float* v, const float* flux, const uint8_t* mask,
+                 const float* dflux_a, const float* dflux_b, float scale_b, int use_log_flux, int64_t n,
+                 int step, float lr, float beta1, float beta2, float eps, jd_stream_t stream) {
+  JD_CHECK_ARG(theta && m && v && dflux_a && n > 0 && step >= 1, "jd_adam_step: bad arguments");
+  JD_CHECK_ARG(!use_log_flux || flux, "jd_adam_step: flux required for the log parameterisation");
+  double bc1 = 1.0 - pow((double)beta1, (double)step);
+  double bc2 = 1.0 - pow((double)beta2, (double)step);
+  adam_kernel<<<grid_for(n, 256), 256, 0, to_stream(stream)>>>(theta, m, v, flux, mask, dflux_a, dflux_b, scale_b,
+                                                                use_log_flux, n, (float)((double)lr / bc1),
+                                                                (float)sqrt(bc2), beta1, beta2, eps);
+  JD_CHECK_LAUNCH("jd_adam_step");
+  return JD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,431 @@
+// GMM patch prior on FP32 CUDA cores: the check path for the tcgen05 kernel (jd_gmm_tc.cu), the
+// logsumexp backward, the max-mode gather-GEMV backward and the generic-D log-prob.
+//
+// Forward tile kernel: a CTA owns 128 patches.  The mean-subtracted patches are gathered straight
+// from the flux image at rolled coordinates (no roll / unfold / reshape copies) into shared memory
+// (feature-major), then for every mixture component the 64x64 matrix Lw_k is streamed through a
+// double-buffered cp.async stage and a 128x64x64 register-tiled product (8x4 per thread) is formed.
+// The epilogue never writes Y: it subtracts mw_k, squares, reduces over the 64 whitened features
+// with half-warp shuffles and folds the component into a running max/argmax or online logsumexp.
+#include <cuda_pipeline.h>
+#include <math_constants.h>
+
+#include "jd_common.cuh"
+
+namespace jd {
+
+constexpr int TM = 128;        // patches per CTA
+constexpr int NT = 256;        // threads per CTA
+constexpr int AS = TM + 4;     // padded row length of the feature-major A tile
+
+struct PatchGeom {
+  int fH, fW, sy, sx, stride, nx, row_begin, P;  // P = local patch count
+};
+
+// Source offset of element (u,v) of patch (iy,ix): the rolled image r[y,x] = flux[(y-sy) mod fH, (x-sx) mod fW]
+// (torch.roll, utils/torch.py:118-119) sampled at r[s*iy+u, s*ix+v] (unfold, utils/torch.py:226-275).
+// Every kernel that touches patches goes through this one function.
+__device__ __forceinline__ int patch_src_row(const PatchGeom& g, int iy, int u) {
+  return wrap(iy * g.stride + u - g.sy, g.fH);
+}
+__device__ __forceinline__ int patch_src_col(const PatchGeom& g, int ix, int v) {
+  return wrap(ix * g.stride + v - g.sx, g.fW);
+}
+
+// Gather + mean-subtract 128 patches into As[d][row]; returns validity per row in s_valid.
+__device__ __forceinline__ void gather_patches(const float* __restrict__ flux, const PatchGeom& g, int64_t p0,
+                                               float* __restrict__ As, int* __restrict__ s_valid) {
+  // two threads per patch: each loads 4 patch rows (32 values)
+  const int row = threadIdx.x >> 1, half = threadIdx.x & 1;
+  const int64_t p = p0 + row;
+  float vals[32];
+  float sum = 0.f;
+  bool ok = true;
+  if (p < g.P) {
+    int iy = (int)(p / g.nx) + g.row_begin, ix = (int)(p % g.nx);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float* src = flux + (int64_t)patch_src_row(g, iy, half * 4 + u) * g.fW;
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        float val = __ldg(src + patch_src_col(g, ix, v));
+        vals[u * 8 + v] = val;
+        sum += val;
+        ok = ok && (val > -1e5f);  // false for NaN too
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) vals[i] = 0.f;
+    ok = false;
+  }
+  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+  const int ok_other = __shfl_xor_sync(0xffffffffu, (int)ok, 1);  // unconditional: no short-circuit around a shuffle
+  ok = ok && ok_other;
+  const float mean = sum * (1.f / 64.f);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) As[(half * 32 + i) * AS + row] = ok ? vals[i] - mean : 0.f;
+  if (half == 0) s_valid[row] = ok ? 1 : 0;
+}
+
+__device__ __forceinline__ void stage_B(const float* __restrict__ B, float* __restrict__ dst) {
+  // 64x64 floats = 1024 float4, 4 per thread
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int idx = threadIdx.x + i * NT;
+    __pipeline_memcpy_async(dst + idx * 4, B + idx * 4, 16);
+  }
+}
+
+// acc[i][j] = sum_d As[d][ty*8+i] * Bs[d][tx*4+j]
+__device__ __forceinline__ void tile_mma(const float* __restrict__ As, const float* __restrict__ Bs, int ty, int tx,
+                                         float (&acc)[8][4]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 8
+  for (int d = 0; d < PD; ++d) {
+    float4 a0 = *reinterpret_cast<const float4*>(As + d * AS + ty * 8);
+    float4 a1 = *reinterpret_cast<const float4*>(As + d * AS + ty * 8 + 4);
+    float4 b = *reinterpret_cast<const float4*>(Bs + d * PD + tx * 4);
+    float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+  }
+}
+
+// MODE 0: forward (max / logsumexp);  MODE 1: logsumexp backward (B = Lam, bias = bk)
+template <int MODE>
+__global__ void __launch_bounds__(NT)
+gmm_tile_kernel(const float* __restrict__ flux, PatchGeom g, const int32_t* __restrict__ shift_yx,
+                const float* __restrict__ Bmat, const float* __restrict__ bias, const float* __restrict__ ck, int K,
+                int marginalize, float* __restrict__ value, int32_t* __restrict__ argmax, float* __restrict__ logp,
+                double* __restrict__ sum, float scale, float* __restrict__ G) {
+  extern __shared__ __align__(16) float smem[];
+  float* As = smem;                   // 64 x AS
+  float* Bs = As + PD * AS;           // 2 x 64 x 64
+  float* s_bias = Bs + 2 * PD * PD;   // 2 x 64
+  int* s_valid = reinterpret_cast<int*>(s_bias + 2 * PD);  // 128
+  __shared__ double red[32];
+
+  if (shift_yx) {
+    g.sy = shift_yx[0];
+    g.sx = shift_yx[1];
+  }
+  const int64_t p0 = (int64_t)blockIdx.x * TM;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+
+  stage_B(Bmat, Bs);
+  if (threadIdx.x < 16) __pipeline_memcpy_async(s_bias + threadIdx.x * 4, bias + threadIdx.x * 4, 16);
+  __pipeline_commit();
+  gather_patches(flux, g, p0, As, s_valid);
+
+  // running state for the 8 rows of this thread (replicated over the 16 tx lanes)
+  float run_m[8], run_s[8];
+  int run_k[8];
+  float gacc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    run_m[i] = -CUDART_INF_F;
+    run_s[i] = 0.f;
+    run_k[i] = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) gacc[i][j] = 0.f;
+  }
+  float lse[8];
+  if (MODE == 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int64_t p = p0 + ty * 8 + i;
+      lse[i] = p < g.P ? value[p] : 0.f;
+    }
+  }
+
+  for (int k = 0; k < K; ++k) {
+    const int buf = k & 1;
+    if (k + 1 < K) {
+      stage_B(Bmat + (int64_t)(k + 1) * PD * PD, Bs + (buf ^ 1) * PD * PD);
+      if (threadIdx.x < 16)
+        __pipeline_memcpy_async(s_bias + (buf ^ 1) * PD + threadIdx.x * 4, bias + (int64_t)(k + 1) * PD + threadIdx.x * 4,
+                                16);
+      __pipeline_commit();
+      __pipeline_wait_prior(1);
+    } else {
+      __pipeline_wait_prior(0);
+    }
+    __syncthreads();
+
+    float acc[8][4];
+    tile_mma(As, Bs + buf * PD * PD, ty, tx, acc);
+    const float4 bv = *reinterpret_cast<const float4*>(s_bias + buf * PD + tx * 4);
+    const float bvv[4] = {bv.x, bv.y, bv.z, bv.w};
+
+    if (MODE == 0) {
+      const float c_k = ck[k];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float y = acc[i][j] - bvv[j];
+          q = fmaf(y, y, q);
+        }
+        q += __shfl_xor_sync(0xffffffffu, q, 8);
+        q += __shfl_xor_sync(0xffffffffu, q, 4);
+        q += __shfl_xor_sync(0xffffffffu, q, 2);
+        q += __shfl_xor_sync(0xffffffffu, q, 1);
+        float lp = fmaf(-0.5f, q, c_k);
+        if (logp && tx == 0) {
+          int64_t p = p0 + ty * 8 + i;
+          if (p < g.P) logp[p * K + k] = lp;
+        }
+        if (marginalize) {
+          if (lp > run_m[i]) {
+            run_s[i] = run_s[i] * expf(run_m[i] - lp) + 1.f;
+            run_m[i] = lp;
+            run_k[i] = k;
+          } else {
+            run_s[i] += expf(lp - run_m[i]);
+          }
+        } else if (lp > run_m[i]) {  // strict: first index wins ties, as torch.max
+          run_m[i] = lp;
+          run_k[i] = k;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int64_t p = p0 + ty * 8 + i;
+        float r = p < g.P ? expf(logp[p * K + k] - lse[i]) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gacc[i][j] = fmaf(r, acc[i][j] - bvv[j], gacc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+
+  if (MODE == 0) {
+    double part = 0.0;
+    if (tx == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int row = ty * 8 + i;
+        int64_t p = p0 + row;
+        if (p < g.P) {
+          bool ok = s_valid[row] != 0;
+          float v = marginalize ? run_m[i] + logf(run_s[i]) : run_m[i];
+          v = ok ? v : 0.f;
+          if (value) value[p] = v;
+          if (argmax) argmax[p] = ok ? run_k[i] : -1;
+          part += (double)v;
+        }
+      }
+    }
+    double s = block_sum(part, red);
+    if (threadIdx.x == 0 && sum) atomicAdd(sum, s);
+  } else {
+    // G = scale * gacc, minus the row mean; invalid patches get 0
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int row = ty * 8 + i;
+      int64_t p = p0 + row;
+      float rs = gacc[i][0] + gacc[i][1] + gacc[i][2] + gacc[i][3];
+      rs += __shfl_xor_sync(0xffffffffu, rs, 8);
+      rs += __shfl_xor_sync(0xffffffffu, rs, 4);
+      rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+      rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+      float mean = rs * (1.f / 64.f);
+      if (p < g.P) {
+        bool ok = s_valid[row] != 0;
+        float4 o;
+        o.x = ok ? scale * (gacc[i][0] - mean) : 0.f;
+        o.y = ok ? scale * (gacc[i][1] - mean) : 0.f;
+        o.z = ok ? scale * (gacc[i][2] - mean) : 0.f;
+        o.w = ok ? scale * (gacc[i][3] - mean) : 0.f;
+        *reinterpret_cast<float4*>(G + p * PD + tx * 4) = o;
+      }
+    }
+  }
+}
+
+// Max-mode backward: one warp per patch, G_p = scale * (xc_p Lam_k* - bk_k*) minus row mean.
+__global__ void __launch_bounds__(256)
+gmm_bwd_max_kernel(const float* __restrict__ flux, PatchGeom g, const int32_t* __restrict__ shift_yx,
+                   const float* __restrict__ Lam, const float* __restrict__ bk, const int32_t* __restrict__ argmax,
+                   float scale, float* __restrict__ G) {
+  if (shift_yx) {
+    g.sy = shift_yx[0];
+    g.sx = shift_yx[1];
+  }
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p = warp; p < g.P; p += nwarps) {
+    const int k = argmax[p];
+    float* out = G + p * PD;
+    if (k < 0) {
+      out[lane] = 0.f;
+      out[lane + 32] = 0.f;
+      continue;
+    }
+    int iy = (int)(p / g.nx) + g.row_begin, ix = (int)(p % g.nx);
+    // lane holds elements d = lane (u = lane/8, v = lane%8) and d = lane + 32 (u + 4)
+    int u = lane >> 3, v = lane & 7;
+    int x = patch_src_col(g, ix, v);
+    float x0 = __ldg(flux + (int64_t)patch_src_row(g, iy, u) * g.fW + x);
+    float x1 = __ldg(flux + (int64_t)patch_src_row(g, iy, u + 4) * g.fW + x);
+    float mean = warp_sum(x0 + x1) * (1.f / 64.f);
+    x0 -= mean;
+    x1 -= mean;
+    const float* L = Lam + (int64_t)k * PD * PD;
+    float g0 = -bk[(int64_t)k * PD + lane], g1 = -bk[(int64_t)k * PD + lane + 32];
+#pragma unroll 8
+    for (int d = 0; d < 32; ++d) {
+      float xa = __shfl_sync(0xffffffffu, x0, d);
+      float xb = __shfl_sync(0xffffffffu, x1, d);
+      g0 = fmaf(xa, __ldg(L + d * PD + lane), g0);
+      g1 = fmaf(xa, __ldg(L + d * PD + lane + 32), g1);
+      g0 = fmaf(xb, __ldg(L + (d + 32) * PD + lane), g0);
+      g1 = fmaf(xb, __ldg(L + (d + 32) * PD + lane + 32), g1);
+    }
+    float gm = warp_sum(g0 + g1) * (1.f / 64.f);
+    out[lane] = scale * (g0 - gm);
+    out[lane + 32] = scale * (g1 - gm);
+  }
+}
+
+// Raw patch extraction (cycle_spin roll + view_as_overlapping_patches_torch): X[p', 8u+v].
+__global__ void extract_patches_kernel(const float* __restrict__ flux, PatchGeom g,
+                                       const int32_t* __restrict__ shift_yx, float* __restrict__ X) {
+  if (shift_yx) {
+    g.sy = shift_yx[0];
+    g.sx = shift_yx[1];
+  }
+  const int64_t n = (int64_t)g.P * PD;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = i >> 6;
+    int d = (int)(i & 63);
+    int iy = (int)(p / g.nx) + g.row_begin, ix = (int)(p % g.nx);
+    X[i] = flux[(int64_t)patch_src_row(g, iy, d >> 3) * g.fW + patch_src_col(g, ix, d & 7)];
+  }
+}
+
+// Generic-D log-prob: one warp per (sample, component).
+__global__ void gmm_log_prob_kernel(const float* __restrict__ x, int64_t P, int D, int K, const float* __restrict__ Lw,
+                                    const float* __restrict__ mw, const float* __restrict__ ck,
+                                    float* __restrict__ logp) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = warp; w < P * K; w += nwarps) {
+    int64_t p = w / K;
+    int k = (int)(w - p * K);
+    const float* xp = x + p * D;
+    const float* L = Lw + (int64_t)k * D * D;
+    float q = 0.f;
+    for (int j = lane; j < D; j += 32) {
+      float y = -mw[(int64_t)k * D + j];
+      for (int d = 0; d < D; ++d) y = fmaf(xp[d], L[(int64_t)d * D + j], y);
+      q = fmaf(y, y, q);
+    }
+    q = warp_sum(q);
+    if (lane == 0) logp[w] = fmaf(-0.5f, q, ck[k]);
+  }
+}
+
+static int make_geom(const char* name, int fH, int fW, int stride, int row_begin, int row_end, PatchGeom* g) {
+  JD_CHECK_ARG(fH >= PATCH && fW >= PATCH, "%s: image %dx%d smaller than a patch", name, fH, fW);
+  JD_CHECK_ARG(stride >= 1 && stride <= PATCH, "%s: stride %d outside [1,8]", name, stride);
+  int ny = (fH - PATCH) / stride + 1, nx = (fW - PATCH) / stride + 1;
+  JD_CHECK_ARG(row_begin >= 0 && row_end <= ny && row_begin < row_end, "%s: bad patch-row block [%d,%d) of %d", name,
+               row_begin, row_end, ny);
+  g->fH = fH;
+  g->fW = fW;
+  g->sy = 0;
+  g->sx = 0;
+  g->stride = stride;
+  g->nx = nx;
+  g->row_begin = row_begin;
+  g->P = (row_end - row_begin) * nx;
+  return JD_OK;
+}
+
+constexpr size_t TILE_SMEM = (size_t)(PD * AS + 2 * PD * PD + 2 * PD) * sizeof(float) + TM * sizeof(int);
+
+int gmm_prior_forward_simt(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
+                           int row_end, const float* Lw, const float* mw, const float* ck, int K, int marginalize,
+                           float* value, int32_t* argmax, float* logp, double* sum, cudaStream_t st) {
+  PatchGeom g;
+  int rc = make_geom("jd_gmm_prior_forward", fH, fW, stride, row_begin, row_end, &g);
+  if (rc) return rc;
+  auto kern = gmm_tile_kernel<0>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM);
+  int grid = (g.P + TM - 1) / TM;
+  kern<<<grid, NT, TILE_SMEM, st>>>(flux, g, shift_yx, Lw, mw, ck, K, marginalize, value, argmax, logp, sum, 0.f,
+                                    nullptr);
+  JD_CHECK_LAUNCH("jd_gmm_prior_forward(simt)");
+  return JD_OK;
+}
+
+}  // namespace jd
+
+using namespace jd;
+
+extern "C" {
+
+int jd_gmm_log_prob(const float* x, int64_t P, int D, int K, const float* Lw, const float* mw, const float* ck,
+                    float* logp, jd_stream_t stream) {
+  JD_CHECK_ARG(x && Lw && mw && ck && logp, "jd_gmm_log_prob: null pointer");
+  JD_CHECK_ARG(P > 0 && K > 0 && D > 0 && D <= 1024, "jd_gmm_log_prob: bad shape P=%lld D=%d K=%d", (long long)P, D, K);
+  int64_t warps = P * K;
+  int64_t blocks = (warps + 7) / 8;
+  int64_t cap = (int64_t)num_sms() * 16;
+  gmm_log_prob_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, to_stream(stream)>>>(x, P, D, K, Lw, mw, ck, logp);
+  JD_CHECK_LAUNCH("jd_gmm_log_prob");
+  return JD_OK;
+}
+
+int jd_extract_patches(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
+                       int row_end, float* X, jd_stream_t stream) {
+  JD_CHECK_ARG(flux && X, "jd_extract_patches: null pointer");
+  PatchGeom g;
+  int rc = make_geom("jd_extract_patches", fH, fW, stride, row_begin, row_end, &g);
+  if (rc) return rc;
+  int64_t n = (int64_t)g.P * PD;
+  int64_t blocks = (n + 255) / 256, cap = (int64_t)num_sms() * 16;
+  extract_patches_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, to_stream(stream)>>>(flux, g, shift_yx, X);
+  JD_CHECK_LAUNCH("jd_extract_patches");
+  return JD_OK;
+}
+
+int jd_gmm_prior_backward(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
+                          int row_end, const float* Lam, const float* bk, int K, int marginalize,
+                          const int32_t* argmax, const float* logp, const float* value, float scale, float* G,
+                          jd_stream_t stream) {
+  JD_CHECK_ARG(flux && Lam && bk && G && K > 0, "jd_gmm_prior_backward: null pointer");
+  PatchGeom g;
+  int rc = make_geom("jd_gmm_prior_backward", fH, fW, stride, row_begin, row_end, &g);
+  if (rc) return rc;
+  cudaStream_t st = to_stream(stream);
+  if (marginalize) {
+    JD_CHECK_ARG(logp && value, "jd_gmm_prior_backward: marginalize=1 needs logp and value from the forward");
+    auto kern = gmm_tile_kernel<1>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM);
+    int grid = (g.P + TM - 1) / TM;
+    kern<<<grid, NT, TILE_SMEM, st>>>(flux, g, shift_yx, Lam, bk, nullptr, K, 1, const_cast<float*>(value), nullptr,
+                                      const_cast<float*>(logp), nullptr, scale, G);
+  } else {
+    JD_CHECK_ARG(argmax, "jd_gmm_prior_backward: marginalize=0 needs argmax from the forward");
+    int64_t blocks = ((int64_t)g.P + 7) / 8;
+    int64_t cap = (int64_t)num_sms() * 16;
+    gmm_bwd_max_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, st>>>(flux, g, shift_yx, Lam, bk, argmax, scale, G);
+  }
+  JD_CHECK_LAUNCH("jd_gmm_prior_backward");
+  return JD_OK;
+}
+
+}  // extern "C"

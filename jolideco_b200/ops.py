@@ -1,0 +1,231 @@
+"""Tensor-level wrappers over the C ABI: validate, allocate outputs with torch, pass raw device
+pointers and the current CUDA stream.  No arithmetic happens in Python/PyTorch here."""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+PATCH = 8
+PD = 64
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check(t, name, dtype=torch.float32):
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.JolidecoB200Error(f"{name}: expected a CUDA tensor (jolideco_b200 has no CPU path), got "
+                                     f"{type(t).__name__} on {getattr(t, 'device', '?')}")
+    if t.dtype != dtype:
+        raise _lib.JolidecoB200Error(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.JolidecoB200Error(f"{name}: tensor must be contiguous")
+    return t
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _hw(t):
+    return int(t.shape[-2]), int(t.shape[-1])
+
+
+def require_device(device=None):
+    """Raise unless `device` (default: current) is a Blackwell (sm_100) GPU."""
+    if not torch.cuda.is_available():
+        raise _lib.JolidecoB200Error("no CUDA device: jolideco_b200 runs on B200 (sm_100a) only, there is no CPU fallback")
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+    ok = _lib.load().jd_device_supported(idx)
+    if ok != 1:
+        raise _lib.JolidecoB200Error(f"cuda:{idx} is not an sm_100 device ({torch.cuda.get_device_name(idx)})")
+
+
+# ------------------------------------------------------------------------------------------------
+def flux_forward(theta, mask=None, use_log_flux=True, out=None):
+    _check(theta, "theta")
+    _check(mask, "mask", torch.uint8)
+    out = torch.empty_like(theta) if out is None else _check(out, "out")
+    _lib.call("jd_flux_forward", _ptr(theta), _ptr(mask), _ptr(out), theta.numel(), int(use_log_flux), _stream())
+    return out
+
+
+def conv_forward(flux, exposure, psf, out=None):
+    _check(flux, "flux"), _check(exposure, "exposure"), _check(psf, "psf")
+    fH, fW = _hw(flux)
+    kh, kw = _hw(psf)
+    out = torch.empty_like(flux) if out is None else _check(out, "out")
+    _lib.call("jd_conv_forward_direct", _ptr(flux), _ptr(exposure), _ptr(psf), _ptr(out), fH, fW, kh, kw, _stream())
+    return out
+
+
+def conv_backward(dpool, exposure, psf, f, out=None, accumulate=False):
+    _check(dpool, "dpool"), _check(exposure, "exposure"), _check(psf, "psf")
+    H, W = _hw(dpool)
+    fH, fW = _hw(exposure)
+    kh, kw = _hw(psf)
+    if out is None:
+        out = torch.empty_like(exposure)
+        accumulate = False
+    _check(out, "out")
+    _lib.call("jd_conv_backward_direct", _ptr(dpool), _ptr(exposure), _ptr(psf), _ptr(out), int(accumulate), fH, fW,
+              kh, kw, int(f), H, W, _stream())
+    return out
+
+
+def poisson_forward_backward(conv, background, counts, f=1, bkg_log_norm=None, loss_sum=None, dlogb=None,
+                             want_npred=False, want_grad=True, grad_scale=None, eps=1e-25):
+    """Returns dict(loss_sum=double[1] tensor (sum over pixels), npred, dpool, dlogb)."""
+    _check(conv, "conv"), _check(background, "background"), _check(counts, "counts")
+    _check(bkg_log_norm, "bkg_log_norm")
+    H, W = _hw(counts)
+    fW = int(conv.shape[-1])
+    if loss_sum is None:
+        loss_sum = torch.zeros(1, dtype=torch.float64, device=conv.device)
+    if dlogb is None and bkg_log_norm is not None and want_grad:
+        dlogb = torch.zeros(1, dtype=torch.float64, device=conv.device)
+    npred = torch.empty_like(counts) if want_npred else None
+    dpool = torch.empty_like(counts) if want_grad else None
+    if grad_scale is None:
+        grad_scale = 1.0 / (H * W)
+    _lib.call("jd_poisson_forward_backward", _ptr(conv), _ptr(background), _ptr(bkg_log_norm), _ptr(counts),
+              _ptr(npred), _ptr(dpool), _ptr(loss_sum), _ptr(dlogb), H, W, int(f), fW, float(eps), float(grad_scale),
+              _stream())
+    return dict(loss_sum=loss_sum, npred=npred, dpool=dpool, dlogb=dlogb)
+
+
+# ------------------------------------------------------------------------------------------------
+class GMMPacked:
+    """Device constants of a Gaussian mixture in the layout the kernels consume.
+
+    Built once at setup (float64 on the host, then rounded to float32) from the buffers the
+    reference keeps (priors/patches/gmm.py:83-86, 217-240, 283-299):
+        Lw[k]  = L_k diag(sqrt(w))            (K, D, D)   L_k = precisions_cholesky[k]
+        mw[k]  = (mu_k L_k) sqrt(w)           (K, D)
+        ck[k]  = -D/2 log 2pi + sum log diag L_k + log pi_k
+        Lam[k] = Lw_k Lw_k^T,  bk[k] = mw_k Lw_k^T        (backward: xc Lam - bk = (xc Lw - mw) Lw^T)
+    """
+
+    def __init__(self, means, precisions_cholesky, weights, pixel_weights, device):
+        L = np.asarray(precisions_cholesky, dtype=np.float32).astype(np.float64)
+        mu = np.asarray(means, dtype=np.float32).astype(np.float64)
+        pi = np.asarray(weights, dtype=np.float32).astype(np.float64)
+        w = np.asarray(pixel_weights, dtype=np.float32).astype(np.float64).reshape(-1)
+        K, D, _ = L.shape
+        self.K, self.D = K, D
+        sw = np.sqrt(w)
+        Lw = L * sw[None, None, :]
+        # mu L evaluated in float32 like the reference's lazily cached means_precisions_cholesky
+        muL = np.einsum("ki,kij->kj", mu.astype(np.float32), L.astype(np.float32)).astype(np.float64)
+        mw = muL * sw[None, :]
+        log_det = np.log(np.diagonal(L, axis1=1, axis2=2)).sum(axis=1)
+        ck = -0.5 * D * math.log(2 * math.pi) + log_det + np.log(pi)
+        Lam = Lw @ Lw.transpose(0, 2, 1)
+        bk = np.einsum("kj,kij->ki", mw, Lw)
+
+        def dev(a):
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device)
+
+        self.Lw, self.mw, self.ck, self.Lam, self.bk = dev(Lw), dev(mw), dev(ck), dev(Lam), dev(bk)
+        self.device = torch.device(device)
+
+
+def gmm_log_prob(x, packed):
+    _check(x, "x")
+    P, D = x.shape
+    if D != packed.D:
+        raise _lib.JolidecoB200Error(f"gmm_log_prob: x has {D} features, GMM has {packed.D}")
+    out = torch.empty((P, packed.K), dtype=torch.float32, device=x.device)
+    _lib.call("jd_gmm_log_prob", _ptr(x), P, D, packed.K, _ptr(packed.Lw), _ptr(packed.mw), _ptr(packed.ck),
+              _ptr(out), _stream())
+    return out
+
+
+def patch_grid(fH, fW, stride):
+    return (fH - PATCH) // stride + 1, (fW - PATCH) // stride + 1
+
+
+def as_shift_tensor(shift_yx, device):
+    if isinstance(shift_yx, torch.Tensor):
+        return _check(shift_yx, "shift_yx", torch.int32)
+    return torch.tensor([int(shift_yx[0]), int(shift_yx[1])], dtype=torch.int32, device=device)
+
+
+def extract_patches(flux, shift_yx=(0, 0), stride=4, rows=None):
+    _check(flux, "flux")
+    fH, fW = _hw(flux)
+    ny, nx = patch_grid(fH, fW, stride)
+    r0, r1 = (0, ny) if rows is None else rows
+    shift = as_shift_tensor(shift_yx, flux.device)
+    X = torch.empty(((r1 - r0) * nx, PD), dtype=torch.float32, device=flux.device)
+    _lib.call("jd_extract_patches", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(X), _stream())
+    return X
+
+
+def gmm_prior_forward(flux, shift_yx, packed, stride=4, marginalize=False, rows=None, want_logp=None, sum_out=None,
+                      backend=0):
+    """Returns (value[P'], argmax[P'], logp[P',K] or None, sum double[1])."""
+    _check(flux, "flux")
+    if packed.D != PD:
+        raise _lib.JolidecoB200Error("gmm_prior_forward: only 8x8 patches (D=64) are supported")
+    fH, fW = _hw(flux)
+    ny, nx = patch_grid(fH, fW, stride)
+    r0, r1 = (0, ny) if rows is None else rows
+    P = (r1 - r0) * nx
+    shift = as_shift_tensor(shift_yx, flux.device)
+    value = torch.empty(P, dtype=torch.float32, device=flux.device)
+    argmax = torch.empty(P, dtype=torch.int32, device=flux.device)
+    if want_logp is None:
+        want_logp = bool(marginalize)
+    logp = torch.empty((P, packed.K), dtype=torch.float32, device=flux.device) if want_logp else None
+    if sum_out is None:
+        sum_out = torch.zeros(1, dtype=torch.float64, device=flux.device)
+    _lib.call("jd_gmm_prior_forward", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(packed.Lw),
+              _ptr(packed.mw), _ptr(packed.ck), packed.K, int(bool(marginalize)), _ptr(value), _ptr(argmax),
+              _ptr(logp), _ptr(sum_out), int(backend), _stream())
+    return value, argmax, logp, sum_out
+
+
+def gmm_prior_backward(flux, shift_yx, packed, scale, stride=4, marginalize=False, rows=None, argmax=None, logp=None,
+                       value=None, out=None):
+    _check(flux, "flux")
+    fH, fW = _hw(flux)
+    ny, nx = patch_grid(fH, fW, stride)
+    r0, r1 = (0, ny) if rows is None else rows
+    P = (r1 - r0) * nx
+    shift = as_shift_tensor(shift_yx, flux.device)
+    G = torch.empty((P, PD), dtype=torch.float32, device=flux.device) if out is None else _check(out, "out")
+    _lib.call("jd_gmm_prior_backward", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(packed.Lam),
+              _ptr(packed.bk), packed.K, int(bool(marginalize)), _ptr(_check(argmax, "argmax", torch.int32)),
+              _ptr(_check(logp, "logp")), _ptr(_check(value, "value")), float(scale), _ptr(G), _stream())
+    return G
+
+
+def patch_fold(G, fH, fW, shift_yx, stride=4, rows=None, out=None, accumulate=False):
+    _check(G, "G")
+    ny, nx = patch_grid(fH, fW, stride)
+    r0, r1 = (0, ny) if rows is None else rows
+    shift = as_shift_tensor(shift_yx, G.device)
+    if out is None:
+        out = torch.empty((fH, fW), dtype=torch.float32, device=G.device)
+        accumulate = False
+    _check(out, "out")
+    _lib.call("jd_patch_fold", _ptr(G), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(out), int(accumulate),
+              _stream())
+    return out
+
+
+def adam_step(theta, m, v, flux, dflux_a, dflux_b=None, scale_b=0.0, mask=None, use_log_flux=True, step=1, lr=0.1,
+              beta1=0.9, beta2=0.999, eps=1e-8):
+    for t, n in [(theta, "theta"), (m, "m"), (v, "v"), (flux, "flux"), (dflux_a, "dflux_a"), (dflux_b, "dflux_b")]:
+        _check(t, n)
+    _check(mask, "mask", torch.uint8)
+    _lib.call("jd_adam_step", _ptr(theta), _ptr(m), _ptr(v), _ptr(flux), _ptr(mask), _ptr(dflux_a), _ptr(dflux_b),
+              float(scale_b), int(use_log_flux), theta.numel(), int(step), float(lr), float(beta1), float(beta2),
+              float(eps), _stream())
+    return theta

@@ -1,0 +1,254 @@
+"""Parity of every C-ABI kernel against the oracle on seeded inputs (B200 only)."""
+import numpy as np
+import pytest
+import torch
+from numpy.testing import assert_allclose
+
+from conftest import load_golden
+from oracle import jolideco_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from jolideco_b200 import ops
+
+DEV = "cuda"
+
+
+def t(a, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dtype).to(DEV)
+
+
+def rel_max(a, ref):
+    return np.abs(a - ref).max() / np.abs(ref).max()
+
+
+def synthetic_gmm(K, seed=0, mean_scale=0.01):
+    rng = np.random.default_rng(seed)
+    A = rng.normal(0, 0.05, size=(K, 64, 64))
+    cov = A @ A.transpose(0, 2, 1) + 0.01 * np.eye(64)
+    means = rng.normal(0, mean_scale, size=(K, 64))
+    w = rng.uniform(0.5, 1.5, size=K)
+    return means, cov, w / w.sum()
+
+
+def pack(gmm):
+    return ops.GMMPacked(gmm.means, gmm.precisions_cholesky, gmm.weights, gmm.pixel_weights, DEV)
+
+
+def test_device_is_blackwell():
+    ops.require_device()
+
+
+def test_flux_forward():
+    rng = np.random.default_rng(0)
+    theta = rng.normal(size=(33, 47)).astype(np.float32)
+    mask = (rng.uniform(size=theta.shape) > 0.3).astype(np.uint8)
+    out = ops.flux_forward(t(theta), t(mask, torch.uint8)).cpu().numpy()
+    assert_allclose(out, O.flux_from_theta(theta, mask), rtol=5e-7)  # expf: <= 2 ulp
+    out = ops.flux_forward(t(theta), None, use_log_flux=False).cpu().numpy()
+    assert np.array_equal(out, theta)
+
+
+@pytest.mark.parametrize("shape,kshape", [((37, 45), (5, 4)), ((64, 64), (17, 17)), ((130, 70), (34, 34)),
+                                          ((96, 96), (64, 64)), ((20, 23), (1, 1)), ((50, 40), (41, 67))])
+def test_conv_forward_and_adjoint(shape, kshape):
+    rng = np.random.default_rng(1)
+    flux = rng.gamma(2.0, size=shape)
+    E = rng.uniform(0.5, 1.5, size=shape)
+    psf = rng.uniform(size=kshape)
+    psf /= psf.sum()
+    ref = O.convolve_fft(flux * E, psf)
+    out = ops.conv_forward(t(flux), t(E), t(psf)).cpu().numpy()
+    assert rel_max(out, ref) < 5e-6
+    d = rng.normal(size=shape)
+    ref_b = O.correlate_adjoint(d, psf) * E
+    out_b = ops.conv_backward(t(d), t(E), t(psf), 1).cpu().numpy()
+    assert rel_max(out_b, ref_b) < 5e-6
+
+
+def test_conv_golden_even_kernel():
+    g = load_golden("kat.npz")
+    out = ops.conv_forward(t(g["conv_img"]), t(np.ones_like(g["conv_img"])), t(g["conv_ker"])).cpu().numpy()
+    assert rel_max(out, g["conv_out"]) < 5e-6
+
+
+@pytest.mark.parametrize("f", [1, 2, 3])
+def test_conv_backward_upsampled(f):
+    rng = np.random.default_rng(2)
+    H, W = 21, 17
+    fH, fW = H * f, W * f
+    psf = rng.uniform(size=(6, 6))
+    E = rng.uniform(0.5, 1.5, size=(fH, fW))
+    dn = rng.normal(size=(H, W))
+    pool = np.ones((H, W))
+    ref = O.npred_backward(dn, pool, np.ones((fH, fW)), E, psf, f)
+    out = ops.conv_backward(t(dn), t(E), t(psf), f).cpu().numpy()
+    assert rel_max(out, ref) < 5e-6
+    acc = t(np.ones((fH, fW)))
+    ops.conv_backward(t(dn), t(E), t(psf), f, out=acc, accumulate=True)
+    assert rel_max(acc.cpu().numpy(), ref + 1) < 5e-6
+
+
+@pytest.mark.parametrize("f", [1, 2])
+def test_poisson_forward_backward(f):
+    rng = np.random.default_rng(3)
+    H, W = 40, 28
+    conv = rng.gamma(1.0, size=(H * f, W * f)).astype(np.float32)
+    conv[0:f, 0 : 4 * f] = 0.0
+    conv[3 * f : 4 * f, :f] = -0.3  # negative pool -> clipped, zero gradient
+    bkg = np.full((H, W), 0.2, dtype=np.float32)
+    bkg[0, :2] = 0.0  # npred exactly 0 -> log(eps)
+    counts = rng.poisson(1.5, size=(H, W)).astype(np.float32)
+    pool = O.sum_pool(conv.astype(np.float64), f)
+    npred = np.clip(pool, 0, np.inf) + bkg
+    loss_ref = O.poisson_nll(npred, counts.astype(np.float64))
+    with np.errstate(over="ignore", divide="ignore"):
+        grad_ref = (O.poisson_nll_grad(npred.astype(np.float32), counts) * (pool >= 0)).astype(np.float32)
+    res = ops.poisson_forward_backward(t(conv), t(bkg), t(counts), f=f, want_npred=True)
+    loss = res["loss_sum"].item() / (H * W)
+    assert_allclose(loss, loss_ref, rtol=1e-6)
+    assert_allclose(res["npred"].cpu().numpy(), npred, rtol=1e-6)
+    # 1 - c/n cancels where c ~ n: absolute tolerance 1e-6 x grad_scale
+    assert_allclose(res["dpool"].cpu().numpy(), grad_ref, rtol=2e-6, atol=1e-9)
+    # background-norm gradient
+    logb = np.float32(0.3)
+    res = ops.poisson_forward_backward(t(conv), t(bkg), t(counts), f=f, bkg_log_norm=t(np.array([logb])))
+    npred_b = np.clip(pool, 0, np.inf) + bkg.astype(np.float64) * np.exp(np.float64(logb))
+    assert_allclose(res["loss_sum"].item() / (H * W), O.poisson_nll(npred_b, counts.astype(np.float64)), rtol=1e-6)
+    m = npred_b > 0
+    dlogb_ref = ((1 - counts[m] / npred_b[m]) / (H * W) * (npred_b[m] - np.clip(pool, 0, np.inf)[m])).sum()
+    assert_allclose(res["dlogb"].item(), dlogb_ref, rtol=1e-5)
+
+
+def test_gmm_log_prob_generic_d_sklearn_kat():
+    # reference priors/patches/tests/test_gmm.py:10-35 (D=9, identity covariance, no pixel weights)
+    means = np.linspace(-1, 1, 9).reshape((1, 9))
+    gmm = O.GMM(means, np.array([np.eye(9)]), np.array([1.0]), meta_stride=None)
+    packed = ops.GMMPacked(gmm.means, gmm.precisions_cholesky, gmm.weights, gmm.pixel_weights, DEV)
+    x = np.ones((2, 9), dtype=np.float32)
+    out = ops.gmm_log_prob(t(x), packed).cpu().numpy()
+    assert_allclose(out, gmm.estimate_log_prob(x), rtol=1e-6)
+
+
+def test_gmm_log_prob_golden():
+    g = load_golden("kat.npz")
+    gmm = O.GMM(g["gmm_means"], g["gmm_cov"], g["gmm_w"])
+    out = ops.gmm_log_prob(t(g["gmm_x"]), pack(gmm)).cpu().numpy()
+    assert_allclose(out, g["gmm_logp"], rtol=2e-5, atol=2e-4)
+
+
+@pytest.mark.parametrize("shape", [(21, 19), (64, 64), (38, 46)])
+def test_patch_extraction_bit_exact(shape):
+    img = np.arange(shape[0] * shape[1], dtype=np.float32).reshape(shape)
+    ny = (shape[0] - 8) // 4 + 1
+    for sy in range(-2, 3):
+        for sx in range(-2, 3):
+            ref = O.view_as_overlapping_patches(O.cycle_spin_roll(img, sy, sx), 8, 4)
+            out = ops.extract_patches(t(img), (sy, sx)).cpu().numpy()
+            assert np.array_equal(out, ref)
+            # row-block shards (multi-GPU prior): concatenation of shards == whole
+            cut = max(1, ny // 3)
+            parts = [ops.extract_patches(t(img), (sy, sx), rows=r).cpu().numpy() for r in [(0, cut), (cut, ny)]]
+            assert np.array_equal(np.concatenate(parts), ref)
+
+
+def test_patch_extraction_golden_stride2():
+    g = load_golden("kat.npz")
+    out = ops.extract_patches(t(g["patches_img"]), (0, 0), stride=2).cpu().numpy()
+    assert np.array_equal(out, g["patches_8_2"])
+    out = ops.extract_patches(t(g["patches_img"]), (0, 0), stride=4).cpu().numpy()
+    assert np.array_equal(out, g["patches_8_4"])
+
+
+def prior_cuda(flux, gmm_packed, sy, sx, marginalize, rows=None, backend=0):
+    fH, fW = flux.shape
+    c = 16.0 / 64.0 / (fH * fW)
+    fl = t(flux)
+    value, argmax, logp, s = ops.gmm_prior_forward(fl, (sy, sx), gmm_packed, 4, marginalize, rows, backend=backend)
+    G = ops.gmm_prior_backward(fl, (sy, sx), gmm_packed, -c, 4, marginalize, rows, argmax, logp, value)
+    dflux = ops.patch_fold(G, fH, fW, (sy, sx), 4, rows)
+    return s.item() * c, dflux.cpu().numpy(), argmax.cpu().numpy()
+
+
+@pytest.mark.parametrize("marginalize", [False, True])
+@pytest.mark.parametrize("shape,shift", [((38, 46), (0, 0)), ((38, 46), (-2, 1)), ((64, 80), (2, -2)), ((24, 24), (1, 2))])
+def test_gmm_prior_value_and_grad(marginalize, shape, shift):
+    rng = np.random.default_rng(5)
+    flux = rng.gamma(2.0, size=shape).astype(np.float32)
+    gmm64 = O.GMM(*synthetic_gmm(11, seed=2), dtype=np.float64)
+    ref_v, ref_g, ref_k = O.gmm_patch_prior(flux.astype(np.float64), gmm64, shift[0], shift[1], 4, marginalize, True)
+    v, gr, k = prior_cuda(flux, pack(O.GMM(*synthetic_gmm(11, seed=2))), shift[0], shift[1], marginalize)
+    assert_allclose(v, ref_v, rtol=1e-5)
+    flipped = (k != ref_k).sum()
+    assert flipped <= 0.01 * len(k)
+    tol = 1e-5 if flipped == 0 else 1e-3
+    assert np.linalg.norm(gr - ref_g) / np.linalg.norm(ref_g) < tol
+    if flipped == 0:
+        assert rel_max(gr, ref_g) < 2e-5
+
+
+@pytest.mark.parametrize("case", range(8))
+def test_gmm_prior_golden(case):
+    g = load_golden("prior_step.npz")
+    sy, sx = (int(v) for v in g[f"c{case}_shift"])
+    marg = bool(g[f"c{case}_marginalize"])
+    gmm = O.GMM(g["gmm_means"], g["gmm_cov"], g["gmm_w"])
+    v, gr, _ = prior_cuda(g["flux"], pack(gmm), sy, sx, marg)
+    assert_allclose(v, g[f"c{case}_f64_value"], rtol=1e-5)
+    ref = g[f"c{case}_f64_grad"]
+    assert rel_max(gr, ref) < 2e-5
+
+
+def test_gmm_prior_row_blocks_sum_to_whole():
+    rng = np.random.default_rng(6)
+    flux = rng.gamma(2.0, size=(72, 40)).astype(np.float32)
+    packed = pack(O.GMM(*synthetic_gmm(7, seed=3)))
+    v, gr, _ = prior_cuda(flux, packed, -1, 2, False)
+    ny = (72 - 8) // 4 + 1
+    parts = [prior_cuda(flux, packed, -1, 2, False, rows=r) for r in [(0, 5), (5, 6), (6, ny)]]
+    assert_allclose(sum(p[0] for p in parts), v, rtol=1e-6)
+    assert rel_max(sum(p[1] for p in parts), gr) < 1e-6
+
+
+def test_gmm_prior_nan_patch_is_skipped():
+    rng = np.random.default_rng(7)
+    flux = rng.gamma(2.0, size=(32, 32)).astype(np.float32)
+    flux[5, 5] = np.nan
+    gmm = O.GMM(*synthetic_gmm(5, seed=4))
+    ref = O.gmm_patch_prior(flux, gmm, 0, 0)
+    v, _, k = prior_cuda(flux, pack(gmm), 0, 0, False)
+    assert_allclose(v, ref, rtol=1e-5)
+    assert (k == -1).sum() == 4
+
+
+def test_adam_matches_torch_and_oracle():
+    rng = np.random.default_rng(8)
+    n = (37, 29)
+    theta0 = rng.normal(size=n).astype(np.float32)
+    ga = rng.normal(size=(6,) + n).astype(np.float32)
+    gb = rng.normal(size=(6,) + n).astype(np.float32)
+    th = t(theta0.copy())
+    m, v = torch.zeros_like(th), torch.zeros_like(th)
+    p = torch.nn.Parameter(torch.from_numpy(theta0.copy()))
+    opt = torch.optim.Adam([p], lr=0.1)
+    adam = O.Adam(n, lr=0.1)
+    th_o = theta0.copy()
+    for s in range(6):
+        flux = ops.flux_forward(th)
+        ops.adam_step(th, m, v, flux, t(ga[s]), t(gb[s]), scale_b=-0.5, step=s + 1, lr=0.1)
+        gtheta = (ga[s] - np.float32(0.5) * gb[s]) * np.exp(p.detach().numpy())
+        p.grad = torch.from_numpy(gtheta)
+        opt.step()
+        th_o = adam.step(th_o, (ga[s] - np.float32(0.5) * gb[s]) * np.exp(th_o))
+    assert_allclose(th.cpu().numpy(), p.detach().numpy(), rtol=1e-5, atol=1e-6)
+    assert_allclose(th.cpu().numpy(), th_o, rtol=1e-5, atol=1e-6)
+
+
+def test_bad_arguments_raise():
+    from jolideco_b200._lib import JolidecoB200Error
+
+    with pytest.raises(JolidecoB200Error):
+        ops.extract_patches(t(np.zeros((4, 4))))  # smaller than a patch
+    with pytest.raises(JolidecoB200Error):
+        ops.flux_forward(torch.zeros(3, 3, device=DEV, dtype=torch.float64))
