@@ -65,6 +65,11 @@ int jd_conv_backward_direct(const float* dpool, const float* exposure, const flo
                             int accumulate, int fH, int fW, int kh, int kw, int f, int H, int W,
                             jd_stream_t stream);
 
+/* Pre-clip sum-pool alone (F.avg_pool2d(kernel_size=f, divisor_override=1), models/npred.py:181-184):
+ * pool[I,J] = sum_{u,v<f} conv[f I+u, f J+v]; conv has row stride fW.  Used by the autograd binding of
+ * NPredModel.forward; the fused step uses jd_poisson_forward_backward instead. */
+int jd_pool_sum(const float* conv, float* pool, int H, int W, int f, int fW, jd_stream_t stream);
+
 /* ---- a3/a4/a6: sum-pool + clip + background + Poisson cash statistic and its gradient ------
  * (models/npred.py:181-191, 234-261; loss.py:35-37 = nn.PoissonNLLLoss(log_input=False,
  * reduction="mean", eps=1e-25, full=True))
@@ -127,6 +132,22 @@ int jd_patch_fold(const float* G, int fH, int fW, const int32_t* shift_yx, int s
 int jd_adam_step(float* theta, float* m, float* v, const float* flux, const uint8_t* mask,
                  const float* dflux_a, const float* dflux_b, float scale_b, int use_log_flux, int64_t n,
                  int step, float lr, float beta1, float beta2, float eps, jd_stream_t stream);
+
+/* Same update with the bias-correction scalars read from device memory (adam_scalars[0] = lr/(1-b1^t),
+ * adam_scalars[1] = sqrt(1-b2^t), written by jd_step_begin) so that the step can live in a CUDA graph. */
+int jd_adam_step_dev(float* theta, float* m, float* v, const float* flux, const uint8_t* mask,
+                     const float* dflux_a, const float* dflux_b, float scale_b, int use_log_flux, int64_t n,
+                     const float* adam_scalars, float beta1, float beta2, float eps, jd_stream_t stream);
+
+/* ---- device-side step bookkeeping (replaces the host-side state of core.py:214-229: the two
+ * torch.randint draws of utils/torch.py:108-116 and torch.optim.Adam's step counter) --------------
+ * counters[0] = cycle-spin draws consumed, counters[1] = Adam step t (both int32 on the device).
+ * If shift_table != NULL: shift_out[0..1] = shift_table[counters[0]] (clamped to n_shifts-1), counters[0]++.
+ * If advance_adam: counters[1]++ and adam_scalars = {lr/(1-b1^t), sqrt(1-b2^t)}.
+ * zero_acc[0..n_acc) (double loss accumulators) are cleared. */
+int jd_step_begin(int32_t* counters, const int32_t* shift_table, int n_shifts, int32_t* shift_out,
+                  int advance_adam, float lr, float beta1, float beta2, float* adam_scalars, double* zero_acc,
+                  int n_acc, jd_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,11 @@ PROTOTYPES = {
     "jd_conv_forward_direct": [c_f32p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_stream],
     "jd_conv_backward_direct": [c_f32p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_stream],
+    "jd_pool_sum": [c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_stream],
+    "jd_adam_step_dev": [c_f32p, c_f32p, c_f32p, c_f32p, c_u8p, c_f32p, c_f32p, c_float, c_int, c_i64, c_f32p,
+                         c_float, c_float, c_float, c_stream],
+    "jd_step_begin": [c_i32p, c_i32p, c_int, c_i32p, c_int, c_float, c_float, c_float, c_f32p, c_f64p, c_int,
+                      c_stream],
     "jd_poisson_forward_backward": [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f64p, c_f64p, c_int, c_int,
                                     c_int, c_int, c_float, c_float, c_stream],
     "jd_gmm_log_prob": [c_f32p, c_i64, c_int, c_int, c_f32p, c_f32p, c_f32p, c_f32p, c_stream],

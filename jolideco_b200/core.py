@@ -1,0 +1,237 @@
+"""MAP deconvolver behind the reference's public API (jolideco/core.py).
+
+`MAPDeconvolver(...).run(datasets, datasets_validation, components, calibrations)` keeps the
+reference's signature, error behaviour and result object.  The inner loop (core.py:209-230) runs on
+the fused CUDA engine (`engine.MapEngine`) whenever the configuration is the hot path the engine
+covers (one spatial flux component, uniform or GMM patch prior, Adam); anything else still runs on
+the same kernels through the autograd bindings with `torch.optim`, mirroring the reference loop.
+There is no CPU fallback: a non-CUDA device raises.
+"""
+import copy
+import logging
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import JolidecoB200Error
+from .engine import DatasetBuffers, MapEngine
+from .loss import TotalLoss
+from .models import FluxComponents, SpatialFluxComponent
+from .priors import GMMPatchPrior, UniformPrior, default_backend
+
+log = logging.getLogger(__name__)
+
+__all__ = ["MAPDeconvolver", "MAPDeconvolverResult"]
+
+OPTIMIZER = {"adam": torch.optim.Adam, "sgd": torch.optim.SGD}
+
+
+class MAPDeconvolver:
+    """Maximum A-Posteriori deconvolver (core.py:46-282); same constructor arguments."""
+
+    _default_flux_component = "flux"
+    _default_checkpoint_filename = "checkpoint-epoch-{epoch}.npz"
+
+    def __init__(self, n_epochs=1_000, beta=1, learning_rate=0.1, compute_error=False, stop_early=False,
+                 stop_early_n_average=10, device="cuda", display_progress=True, optimizer_type="adam",
+                 optimizer_kwargs=None, checkpoint_path=None, use_cuda_graph=True, fused=True):
+        self.n_epochs = n_epochs
+        self.beta = beta
+        self.learning_rate = learning_rate
+        self.compute_error = compute_error
+        self.stop_early = stop_early
+        self.stop_early_n_average = stop_early_n_average
+        self.display_progress = display_progress
+        if "cuda" not in str(device):
+            raise JolidecoB200Error(f"device {device!r}: jolideco_b200 runs on CUDA (sm_100a) only; no CPU fallback")
+        self.device = torch.device(device)
+        if optimizer_type not in OPTIMIZER:
+            raise ValueError(f"Unknown optimizer: {optimizer_type}, must be one of {OPTIMIZER}")
+        self.optimizer_type = optimizer_type
+        self.optimizer_kwargs = {} if optimizer_kwargs is None else optimizer_kwargs
+        self.optimizer_kwargs.setdefault("lr", self.learning_rate)
+        if checkpoint_path is not None:
+            checkpoint_path = Path(checkpoint_path)
+            checkpoint_path.mkdir(exist_ok=True, parents=True)
+        self.checkpoint_path = checkpoint_path
+        self.use_cuda_graph = use_cuda_graph
+        self.fused = fused
+
+    def to_dict(self):
+        data = {}
+        data.update(self.__dict__)
+        data["device"] = str(self.device)
+        data["checkpoint_path"] = str(self.checkpoint_path)
+        data.pop("optimizer", None)
+        data.pop("optimizer_kwargs", None)
+        return data
+
+    def __str__(self):
+        return f"{self.__class__.__name__}\n" + "\n".join(f"  {k:24s}: {v}" for k, v in self.to_dict().items())
+
+    # ------------------------------------------------------------------------------------------
+    def _engine_supported(self, components, calibrations):
+        if not self.fused or self.optimizer_type != "adam" or calibrations:
+            return False
+        if set(self.optimizer_kwargs) - {"lr", "betas", "eps"}:
+            return False
+        comps = list(components.values())
+        if len(comps) != 1 or not isinstance(comps[0], SpatialFluxComponent) or comps[0].frozen:
+            return False
+        prior = comps[0].prior
+        if isinstance(prior, UniformPrior):
+            return True
+        return isinstance(prior, GMMPatchPrior) and prior.norm is None and prior.gmm.n_features == ops.PD
+
+    def _build_engine(self, total_loss, components, n_draws):
+        (name, comp), = components.items()
+        theta = comp._flux_upsampled.data[0, 0]
+        mask = comp.mask[0, 0].contiguous() if comp.mask is not None else None
+
+        def buffers(poisson_loss):
+            out = []
+            for ds_name, counts, models in zip(poisson_loss.names_all, poisson_loss.counts_all,
+                                               poisson_loss.npred_models_all):
+                model = models[name]
+                out.append(DatasetBuffers(counts[0, 0].contiguous(), model.exposure[0, 0], model.psf[0, 0],
+                                          models.background[0, 0].contiguous(), model.upsampling_factor, name=ds_name))
+            return out
+
+        prior_cfg, table = None, None
+        prior = comp.prior
+        if isinstance(prior, GMMPatchPrior):
+            backend = default_backend() if prior.backend is None else prior.backend
+            prior_cfg = dict(packed=prior.gmm.packed(self.device), stride=prior.stride, marginalize=prior.marginalize,
+                             backend=backend)
+            table = np.array([prior.draw_shifts() for _ in range(n_draws)], dtype=np.int32).reshape(-1, 2)
+        validation = buffers(total_loss.poisson_loss_validation) if total_loss.poisson_loss_validation else []
+        return MapEngine(theta, buffers(total_loss.poisson_loss), prior=prior_cfg, mask=mask,
+                         use_log_flux=comp.use_log_flux, beta=self.beta, lr=self.optimizer_kwargs["lr"],
+                         betas=self.optimizer_kwargs.get("betas", (0.9, 0.999)),
+                         eps=self.optimizer_kwargs.get("eps", 1e-8), shift_table=table,
+                         datasets_validation=validation, use_graph=self.use_cuda_graph)
+
+    def _early_stop(self, trace):
+        if self.stop_early and len(trace) > self.stop_early_n_average:
+            values = trace["datasets-validation-total"]
+            return trace[-1]["datasets-validation-total"] > np.mean(values[-self.stop_early_n_average:])
+        return False
+
+    def _checkpoint(self, epoch, total_loss, components):
+        if not self.checkpoint_path:
+            return ""
+        filename = self._default_checkpoint_filename.format(epoch=epoch)
+        np.savez(self.checkpoint_path / filename, **{f"flux_upsampled_{k}": v for k, v in components.to_numpy().items()})
+        return filename
+
+    # ------------------------------------------------------------------------------------------
+    def run(self, datasets, datasets_validation=None, components=None, calibrations=None):
+        """Run the MAP deconvolver (core.py:149-282); returns a `MAPDeconvolverResult`."""
+        if self.stop_early and datasets_validation is None:
+            raise ValueError("Early stopping requires providing test datasets")
+        if self.compute_error:
+            raise NotImplementedError("compute_error (Hessian-vector errors, loss.py:263-300) is not accelerated yet")
+        ops.require_device(self.device)
+        if isinstance(components, SpatialFluxComponent):
+            components = {self._default_flux_component: components}
+        components = FluxComponents(components)
+        components_init = copy.deepcopy(components)
+        calibrations_init = copy.deepcopy(calibrations)
+        components = components.to(self.device)
+        if calibrations:
+            calibrations = calibrations.to(self.device)
+
+        with torch.cuda.device(self.device):
+            total_loss = TotalLoss.from_datasets_and_components(
+                datasets=datasets, datasets_validation=datasets_validation, components=components,
+                calibrations=calibrations, beta=self.beta, device=self.device)
+            if self._engine_supported(components, calibrations):
+                self._run_fused(total_loss, components, len(datasets))
+            else:
+                self._run_autograd(total_loss, components, calibrations)
+
+        return MAPDeconvolverResult(config=self.to_dict(), components=components, components_init=components_init,
+                                    trace_loss=total_loss.trace, calibrations=calibrations,
+                                    calibrations_init=calibrations_init, wcs=None)
+
+    def _run_fused(self, total_loss, components, n_datasets):
+        engine = self._build_engine(total_loss, components, self.n_epochs * (n_datasets + 1))
+        self.engine = engine
+        engine.warmup()
+        prior_names = list(total_loss.prior_loss.priors)
+        for epoch in range(self.n_epochs):
+            for i in range(n_datasets):
+                engine.step(i)
+            filename = self._checkpoint(epoch, total_loss, components)
+            ld, lp, lv = engine.trace_losses()
+            total_loss.append_trace_values(ld, [lp] * len(prior_names), filename, lv if lv else None)
+            if self._early_stop(total_loss.trace):
+                break
+        torch.cuda.synchronize(self.device)
+
+    def _run_autograd(self, total_loss, components, calibrations):
+        """The reference loop verbatim (core.py:197-267) on the autograd bindings of the kernels."""
+        parameters = list(components.parameters())
+        if calibrations:
+            parameters.extend(calibrations.parameters())
+        self.optimizer = OPTIMIZER[self.optimizer_type](params=parameters, **self.optimizer_kwargs)
+        for epoch in range(self.n_epochs):
+            components.train()
+            for counts, npred_model in total_loss.poisson_loss.iter_by_dataset:
+                self.optimizer.zero_grad()
+                fluxes = components.to_flux_tuple()
+                npred = npred_model.evaluate(fluxes=fluxes)
+                loss = total_loss.poisson_loss.loss_function(npred, counts)
+                loss_prior = total_loss.prior_loss(fluxes=fluxes)
+                loss_total = loss - self.beta * loss_prior / total_loss.prior_weight
+                loss_total.backward()
+                self.optimizer.step()
+            components.eval()
+            filename = self._checkpoint(epoch, total_loss, components)
+            total_loss.append_trace(fluxes=fluxes, filename=filename)
+            if self._early_stop(total_loss.trace):
+                break
+
+
+class MAPDeconvolverResult:
+    """MAP deconvolver result (core.py:285-471)."""
+
+    def __init__(self, config, components, trace_loss, components_init=None, calibrations=None,
+                 calibrations_init=None, wcs=None):
+        self._components = components
+        self._components_init = components_init
+        self.trace_loss = trace_loss
+        self._calibrations = calibrations
+        self._calibrations_init = calibrations_init
+        self._config = config
+        self._wcs = wcs
+
+    @property
+    def components(self):
+        return self._components
+
+    @property
+    def components_init(self):
+        return self._components_init
+
+    @property
+    def calibrations(self):
+        return self._calibrations
+
+    @property
+    def calibrations_init(self):
+        return self._calibrations_init
+
+    @property
+    def flux_total(self):
+        return self.components.flux_total_numpy
+
+    @property
+    def flux_upsampled_total(self):
+        return self.components.flux_upsampled_total_numpy
+
+    @property
+    def config(self):
+        return self._config

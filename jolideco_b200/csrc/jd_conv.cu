@@ -134,7 +134,11 @@ static int launch_conv(const float* in, const float* scale, const float* psf, fl
     size_t sm = ((size_t)(R * TY + KC - 1) * (C * TX + kwp) + (size_t)(KC + 2 * (R - 1)) * kwp) * sizeof(float);
     JD_CHECK_ARG(sm <= 200 * 1024, "%s: PSF too wide for the direct kernel (kw=%d)", name, kw);
     auto kern = conv_kernel<MODE, TY, TX>;
-    if (sm > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    static bool attr_set = false;  // once per process and instantiation: opt in to the 200 KB limit checked above
+    if (!attr_set) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_set = true;
+    }
     dim3 grid((fW + C * TX - 1) / (C * TX), (fH + R * TY - 1) / (R * TY));
     kern<<<grid, TY * TX, sm, st>>>(in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate);
   } else {
@@ -142,7 +146,11 @@ static int launch_conv(const float* in, const float* scale, const float* psf, fl
     size_t sm = ((size_t)(R * TY + KC - 1) * (C * TX + kwp) + (size_t)(KC + 2 * (R - 1)) * kwp) * sizeof(float);
     JD_CHECK_ARG(sm <= 200 * 1024, "%s: PSF too wide for the direct kernel (kw=%d)", name, kw);
     auto kern = conv_kernel<MODE, TY, TX>;
-    if (sm > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_set = true;
+    }
     dim3 grid((fW + C * TX - 1) / (C * TX), (fH + R * TY - 1) / (R * TY));
     kern<<<grid, TY * TX, sm, st>>>(in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate);
   }

@@ -136,6 +136,64 @@ __global__ void adam_kernel(float* __restrict__ theta, float* __restrict__ m, fl
   }
 }
 
+// sum-pool f x f (F.avg_pool2d(divisor_override=1), models/npred.py:181-184); pre-clip values
+__global__ void pool_kernel(const float* __restrict__ conv, float* __restrict__ pool, int H, int W, int f, int fW) {
+  const int64_t n = (int64_t)H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int y = (int)(i / W), x = (int)(i - (int64_t)y * W);
+    const float* src = conv + (int64_t)y * f * fW + (int64_t)x * f;
+    float acc = 0.f;
+    for (int u = 0; u < f; ++u)
+      for (int v = 0; v < f; ++v) acc += src[(int64_t)u * fW + v];
+    pool[i] = acc;
+  }
+}
+
+// Device-side bookkeeping of one MAP step so the whole step replays from a CUDA graph:
+// counters[0] = number of cycle-spin draws consumed, counters[1] = Adam step count t.
+__global__ void step_begin_kernel(int32_t* __restrict__ counters, const int32_t* __restrict__ shift_table,
+                                  int n_shifts, int32_t* __restrict__ shift_out, int advance_adam, float lr, float b1,
+                                  float b2, float* __restrict__ adam_scalars, double* __restrict__ zero_acc,
+                                  int n_acc) {
+  if (threadIdx.x == 0) {
+    if (shift_table && shift_out) {
+      int d = counters[0];
+      int idx = d < n_shifts ? d : n_shifts - 1;
+      shift_out[0] = shift_table[2 * idx];
+      shift_out[1] = shift_table[2 * idx + 1];
+      counters[0] = d + 1;
+    }
+    if (advance_adam) {
+      int t = counters[1] + 1;
+      counters[1] = t;
+      double bc1 = 1.0 - pow((double)b1, (double)t);
+      double bc2 = 1.0 - pow((double)b2, (double)t);
+      adam_scalars[0] = (float)((double)lr / bc1);
+      adam_scalars[1] = (float)sqrt(bc2);
+    }
+  }
+  for (int i = threadIdx.x; i < n_acc; i += blockDim.x) zero_acc[i] = 0.0;
+}
+
+__global__ void adam_dev_kernel(float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v,
+                                const float* __restrict__ flux, const uint8_t* __restrict__ mask,
+                                const float* __restrict__ da, const float* __restrict__ db, float scale_b, int use_log,
+                                int64_t n, const float* __restrict__ scalars, float b1, float b2, float eps) {
+  const float lr_over_bc1 = scalars[0], sqrt_bc2 = scalars[1];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float g = da[i];
+    if (db) g += scale_b * db[i];
+    g *= use_log ? flux[i] : (mask ? (float)mask[i] : 1.f);
+    float mi = m[i], vi = v[i];
+    mi = mi + (g - mi) * (1.f - b1);
+    vi = vi * b2 + (1.f - b2) * g * g;
+    float denom = sqrtf(vi) / sqrt_bc2 + eps;
+    theta[i] = theta[i] - lr_over_bc1 * (mi / denom);
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+
 static inline int grid_for(int64_t n, int block) {
   int64_t g = (n + block - 1) / block;
   int64_t cap = (int64_t)num_sms() * 8;
@@ -183,6 +241,37 @@ int jd_poisson_forward_backward(const float* conv, const float* background, cons
                                                                    dpool, loss_sum, dlogb, H, W, f, fW, eps,
                                                                    grad_scale);
   JD_CHECK_LAUNCH("jd_poisson_forward_backward");
+  return JD_OK;
+}
+
+int jd_pool_sum(const float* conv, float* pool, int H, int W, int f, int fW, jd_stream_t stream) {
+  JD_CHECK_ARG(conv && pool && H > 0 && W > 0 && f >= 1 && fW >= W * f, "jd_pool_sum: bad arguments");
+  pool_kernel<<<grid_for((int64_t)H * W, 256), 256, 0, to_stream(stream)>>>(conv, pool, H, W, f, fW);
+  JD_CHECK_LAUNCH("jd_pool_sum");
+  return JD_OK;
+}
+
+int jd_step_begin(int32_t* counters, const int32_t* shift_table, int n_shifts, int32_t* shift_out, int advance_adam,
+                  float lr, float beta1, float beta2, float* adam_scalars, double* zero_acc, int n_acc,
+                  jd_stream_t stream) {
+  JD_CHECK_ARG(counters, "jd_step_begin: null counters");
+  JD_CHECK_ARG(!advance_adam || adam_scalars, "jd_step_begin: adam_scalars required");
+  JD_CHECK_ARG(!shift_table || n_shifts > 0, "jd_step_begin: empty shift table");
+  JD_CHECK_ARG(n_acc == 0 || zero_acc, "jd_step_begin: null accumulator block");
+  step_begin_kernel<<<1, 32, 0, to_stream(stream)>>>(counters, shift_table, n_shifts, shift_out, advance_adam, lr,
+                                                     beta1, beta2, adam_scalars, zero_acc, n_acc);
+  JD_CHECK_LAUNCH("jd_step_begin");
+  return JD_OK;
+}
+
+int jd_adam_step_dev(float* theta, float* m, float* v, const float* flux, const uint8_t* mask, const float* dflux_a,
+                     const float* dflux_b, float scale_b, int use_log_flux, int64_t n, const float* adam_scalars,
+                     float beta1, float beta2, float eps, jd_stream_t stream) {
+  JD_CHECK_ARG(theta && m && v && dflux_a && adam_scalars && n > 0, "jd_adam_step_dev: bad arguments");
+  JD_CHECK_ARG(!use_log_flux || flux, "jd_adam_step_dev: flux required for the log parameterisation");
+  adam_dev_kernel<<<grid_for(n, 256), 256, 0, to_stream(stream)>>>(theta, m, v, flux, mask, dflux_a, dflux_b, scale_b,
+                                                                    use_log_flux, n, adam_scalars, beta1, beta2, eps);
+  JD_CHECK_LAUNCH("jd_adam_step_dev");
   return JD_OK;
 }
 

@@ -1,0 +1,255 @@
+"""Fused MAP engine: the body of the reference's inner loop (jolideco/core.py:214-229) as a fixed
+sequence of C-ABI kernel launches on one CUDA stream, replayed from a CUDA graph.
+
+No autograd, no host synchronisation inside a step: the two `torch.randint` draws of the cycle spin
+(utils/torch.py:108-116) are pre-drawn on the host into a device table, the Adam step counter and
+bias corrections live on the device (`jd_step_begin`), and losses accumulate into device doubles
+that are only read for the per-epoch trace (loss.py:212-250).
+
+Two step semantics (SURVEY.md §7 "semantics of iteration"):
+  * `step(d)`      — the reference's: one dataset's likelihood + the full prior scaled 1/D + Adam;
+  * `joint_step()` — one pass over all (local) datasets + one prior + one Adam on
+                     sum_d L_d - beta * prior (`TotalLoss.__call__`, loss.py:257-261); with
+                     `torch.distributed` the datasets are sharded over ranks, the prior is
+                     row-block sharded and the flux gradient is all-reduced (NCCL / NVLink).
+"""
+import numpy as np
+import torch
+
+from . import _lib, ops
+
+_call = _lib.call
+_p = ops._ptr
+
+
+class DatasetBuffers:
+    """Device-resident arrays of one dataset (loss.py:104-118, npred.py:281-295)."""
+
+    def __init__(self, counts, exposure, psf, background, f, bkg_log_norm=None, name=""):
+        self.counts, self.exposure, self.psf, self.background = counts, exposure, psf, background
+        self.f = int(f) if f else 1
+        self.bkg_log_norm = bkg_log_norm
+        self.name = name
+        self.H, self.W = int(counts.shape[-2]), int(counts.shape[-1])
+        self.fH, self.fW = int(exposure.shape[-2]), int(exposure.shape[-1])
+        self.kh, self.kw = int(psf.shape[-2]), int(psf.shape[-1])
+        for t in (counts, exposure, psf, background):
+            ops._check(t, "dataset buffer")
+
+
+class MapEngine:
+    def __init__(self, theta, datasets, prior=None, mask=None, use_log_flux=True, beta=1.0, lr=0.1, betas=(0.9, 0.999),
+                 eps=1e-8, shift_table=None, datasets_validation=(), use_graph=True, process_group=None,
+                 prior_weight=None):
+        """theta: 2-D CUDA fp32 tensor updated in place (the component's parameter storage).
+        prior: None (uniform) or dict(packed=GMMPacked, stride, marginalize, backend).
+        shift_table: (N, 2) int array of pre-drawn (row, col) cycle-spin shifts in consumption order."""
+        ops.require_device(theta.device)
+        self.theta = ops._check(theta, "theta")
+        assert theta.ndim == 2
+        self.dev = theta.device
+        self.fH, self.fW = (int(s) for s in theta.shape)
+        self.n = self.fH * self.fW
+        self.mask = ops._check(mask, "mask", torch.uint8)
+        self.use_log_flux = bool(use_log_flux)
+        self.datasets = list(datasets)
+        self.datasets_validation = list(datasets_validation)
+        self.D = len(self.datasets)
+        self.prior_weight = self.D if prior_weight is None else prior_weight
+        self.beta, self.lr, self.b1, self.b2, self.eps = float(beta), float(lr), float(betas[0]), float(betas[1]), float(eps)
+        self.prior = prior
+        self.pg = process_group
+        self.world = 1 if process_group is None else torch.distributed.get_world_size(process_group)
+        self.rank = 0 if process_group is None else torch.distributed.get_rank(process_group)
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.m = torch.zeros_like(theta)
+        self.v = torch.zeros_like(theta)
+        self.flux = torch.empty_like(theta)
+        self.conv = torch.empty_like(theta)
+        self.dflux_l = torch.zeros_like(theta)
+        Hmax = max([d.H for d in self.datasets + self.datasets_validation] + [1])
+        Wmax = max([d.W for d in self.datasets + self.datasets_validation] + [1])
+        self.dpool = torch.empty((Hmax, Wmax), **f32)
+        self.counters = torch.zeros(2, dtype=torch.int32, device=self.dev)
+        self.cur_shift = torch.zeros(2, dtype=torch.int32, device=self.dev)
+        self.adam_scalars = torch.zeros(2, **f32)
+        # acc[0] = Poisson loss sum of the last step, acc[1] = sum_p v_p of the last prior evaluation
+        self.acc = torch.zeros(2, dtype=torch.float64, device=self.dev)
+        self.n_trace = self.D + 1 + len(self.datasets_validation)
+        self.acc_trace = torch.zeros(self.n_trace, dtype=torch.float64, device=self.dev)
+        self.shift_table = None
+        self.n_shifts = 0
+        if prior is not None:
+            self.stride = int(prior["stride"])
+            self.marginalize = bool(prior["marginalize"])
+            self.backend = int(prior.get("backend", 0))
+            self.packed = prior["packed"]
+            self.ny, self.nx = ops.patch_grid(self.fH, self.fW, self.stride)
+            self.c = self.stride**2 / ops.PD / self.n
+            # row-block shard of the prior (whole grid on one GPU)
+            self.rows = self._row_block(self.rank, self.world)
+            P = (self.rows[1] - self.rows[0]) * self.nx
+            self.P = P
+            self.value = torch.empty(max(P, 1), **f32)
+            self.argmax = torch.empty(max(P, 1), dtype=torch.int32, device=self.dev)
+            self.logp = torch.empty((max(P, 1), self.packed.K), **f32) if self.marginalize else None
+            self.G = torch.empty((max(P, 1), ops.PD), **f32)
+            self.dflux_p = torch.zeros_like(theta)
+            if shift_table is None:
+                shift_table = np.zeros((1, 2), dtype=np.int32)
+            tab = np.ascontiguousarray(np.asarray(shift_table, dtype=np.int32).reshape(-1, 2))
+            self.shift_table = torch.from_numpy(tab).to(self.dev)
+            self.n_shifts = int(tab.shape[0])
+        self.use_graph = bool(use_graph) and process_group is None
+        self._graphs = {}
+        self.launches_per_step = 0
+
+    # ------------------------------------------------------------------------------------------
+    def _row_block(self, rank, world):
+        lo = (self.ny * rank) // world
+        hi = (self.ny * (rank + 1)) // world
+        return lo, hi
+
+    def _s(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def _begin(self, advance_adam, zero_acc, with_shift):
+        tab = self.shift_table if (with_shift and self.prior is not None) else None
+        _call("jd_step_begin", _p(self.counters), _p(tab), self.n_shifts, _p(self.cur_shift), int(advance_adam),
+              self.lr, self.b1, self.b2, _p(self.adam_scalars), _p(zero_acc), int(zero_acc.numel()), self._s())
+
+    def _flux(self):
+        _call("jd_flux_forward", _p(self.theta), _p(self.mask), _p(self.flux), self.n, int(self.use_log_flux), self._s())
+
+    def _likelihood(self, d, loss_acc, want_grad, accumulate=False):
+        s = self._s()
+        _call("jd_conv_forward_direct", _p(self.flux), _p(d.exposure), _p(d.psf), _p(self.conv), d.fH, d.fW, d.kh, d.kw, s)
+        _call("jd_poisson_forward_backward", _p(self.conv), _p(d.background), _p(d.bkg_log_norm), _p(d.counts), None,
+              _p(self.dpool) if want_grad else None, loss_acc, None, d.H, d.W, d.f, d.fW, 1e-25, 1.0 / (d.H * d.W), s)
+        if want_grad:
+            _call("jd_conv_backward_direct", _p(self.dpool), _p(d.exposure), _p(d.psf), _p(self.dflux_l),
+                  int(accumulate), d.fH, d.fW, d.kh, d.kw, d.f, d.H, d.W, s)
+
+    def _prior_forward(self, sum_acc):
+        if self.P <= 0:
+            return
+        _call("jd_gmm_prior_forward", _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride, self.rows[0],
+              self.rows[1], _p(self.packed.Lw), _p(self.packed.mw), _p(self.packed.ck), self.packed.K,
+              int(self.marginalize), _p(self.value), _p(self.argmax), _p(self.logp), sum_acc, self.backend, self._s())
+
+    def _prior_backward(self, scale, out, accumulate):
+        if self.P <= 0:
+            if not accumulate:
+                out.zero_()
+            return
+        s = self._s()
+        _call("jd_gmm_prior_backward", _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride, self.rows[0],
+              self.rows[1], _p(self.packed.Lam), _p(self.packed.bk), self.packed.K, int(self.marginalize),
+              _p(self.argmax), _p(self.logp), _p(self.value), float(scale), _p(self.G), s)
+        _call("jd_patch_fold", _p(self.G), self.fH, self.fW, _p(self.cur_shift), self.stride, self.rows[0], self.rows[1],
+              _p(out), int(accumulate), s)
+
+    def _adam(self, dflux_b, scale_b):
+        _call("jd_adam_step_dev", _p(self.theta), _p(self.m), _p(self.v), _p(self.flux), _p(self.mask), _p(self.dflux_l),
+              _p(dflux_b), float(scale_b), int(self.use_log_flux), self.n, _p(self.adam_scalars), self.b1, self.b2,
+              self.eps, self._s())
+
+    # ------------------------------------------------------------------------------------------
+    def _step_body(self, i):
+        """Reference step for dataset i: total = L_i - beta * prior / D  (core.py:214-229)."""
+        d = self.datasets[i]
+        self._begin(advance_adam=1, zero_acc=self.acc, with_shift=True)
+        self._flux()
+        self._likelihood(d, self.acc.data_ptr(), want_grad=True)
+        if self.prior is not None:
+            self._prior_forward(self.acc.data_ptr() + 8)
+            self._prior_backward(-self.c, self.dflux_p, accumulate=False)
+            self._adam(self.dflux_p, -self.beta / self.prior_weight)
+        else:
+            self._adam(None, 0.0)
+
+    def _joint_body(self):
+        """Joint step on sum_d L_d - beta * prior (loss.py:257-261); prior gradient folded into dflux_l."""
+        self._begin(advance_adam=1, zero_acc=self.acc, with_shift=True)
+        self._flux()
+        if not self.datasets:
+            self.dflux_l.zero_()
+        for j, d in enumerate(self.datasets):
+            self._likelihood(d, self.acc.data_ptr(), want_grad=True, accumulate=j > 0)
+        if self.prior is not None:
+            self._prior_forward(self.acc.data_ptr() + 8)
+            self._prior_backward(self.c * self.beta, self.dflux_l, accumulate=True)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.dflux_l, group=self.pg)
+        self._adam(None, 0.0)
+
+    def _run(self, key, body):
+        if not self.use_graph:
+            body()
+            return
+        g = self._graphs.get(key)
+        if g is None:
+            # one eager pass would advance the state; capture directly instead (kernels are not
+            # executed during capture) after making sure lazy one-time setup has happened
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            self._graphs[key] = g
+        g.replay()
+
+    def warmup(self):
+        """Run every kernel once outside graph capture (function attributes, module load), then
+        restore the optimiser state so that training starts from step 0."""
+        state = [t.clone() for t in (self.theta, self.m, self.v, self.counters, self.acc)]
+        graph = self.use_graph
+        self.use_graph = False
+        for i in range(min(self.D, 1)):
+            self._step_body(i)
+        self.use_graph = graph
+        torch.cuda.synchronize(self.dev)
+        for t, s in zip((self.theta, self.m, self.v, self.counters, self.acc), state):
+            t.copy_(s)
+
+    def step(self, i):
+        self._run(("step", i), lambda: self._step_body(i))
+
+    def joint_step(self):
+        self._run(("joint",), self._joint_body)
+
+    # ------------------------------------------------------------------------------------------
+    def trace_losses(self, refresh_flux=False):
+        """Per-epoch trace (loss.py:212-250): every dataset's Poisson loss and one more prior draw,
+        evaluated at the flux of the LAST step's start (the reference hands the stale `fluxes` tuple
+        to append_trace, core.py:217/245).  One host sync.  Returns (datasets, prior, validation)."""
+
+        def body():
+            self._begin(advance_adam=0, zero_acc=self.acc_trace, with_shift=True)
+            if refresh_flux:
+                self._flux()
+            base = self.acc_trace.data_ptr()
+            for j, d in enumerate(self.datasets):
+                self._likelihood(d, base + 8 * j, want_grad=False)
+            if self.prior is not None:
+                self._prior_forward(base + 8 * self.D)
+            for j, d in enumerate(self.datasets_validation):
+                self._likelihood(d, base + 8 * (self.D + 1 + j), want_grad=False)
+
+        self._run(("trace", bool(refresh_flux)), body)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.acc_trace, group=self.pg)
+        vals = self.acc_trace.cpu().numpy()
+        ld = [vals[j] / (d.H * d.W) for j, d in enumerate(self.datasets)]
+        lp = float(vals[self.D] * self.c) if self.prior is not None else 0.0
+        lv = [vals[self.D + 1 + j] / (d.H * d.W) for j, d in enumerate(self.datasets_validation)]
+        return [float(x) for x in ld], lp, [float(x) for x in lv]
+
+    def last_step_losses(self):
+        """(Poisson mean loss, prior value) of the most recent step; syncs."""
+        vals = self.acc.cpu().numpy()
+        d = self.datasets[0]
+        return float(vals[0] / (d.H * d.W)), float(vals[1] * self.c) if self.prior is not None else 0.0
+
+    def flux_numpy(self):
+        self._flux()
+        return self.flux.cpu().numpy()

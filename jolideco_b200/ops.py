@@ -78,6 +78,14 @@ def conv_backward(dpool, exposure, psf, f, out=None, accumulate=False):
     return out
 
 
+def pool_clip(conv, H, W, f):
+    """Pre-clip sum-pool of the convolution (the caller clamps)."""
+    _check(conv, "conv")
+    out = torch.empty((H, W), dtype=torch.float32, device=conv.device)
+    _lib.call("jd_pool_sum", _ptr(conv), _ptr(out), H, W, int(f), int(conv.shape[-1]), _stream())
+    return out
+
+
 def poisson_forward_backward(conv, background, counts, f=1, bkg_log_norm=None, loss_sum=None, dlogb=None,
                              want_npred=False, want_grad=True, grad_scale=None, eps=1e-25):
     """Returns dict(loss_sum=double[1] tensor (sum over pixels), npred, dpool, dlogb)."""

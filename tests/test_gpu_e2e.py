@@ -1,0 +1,136 @@
+"""End-to-end parity of the drop-in API (MAPDeconvolver.run, loss classes, priors) on B200 against
+the reference's golden values and the runs of the imported reference stored in tests/golden/."""
+import numpy as np
+import pytest
+import torch
+from numpy.testing import assert_allclose
+
+from conftest import load_golden, unpack_datasets
+from oracle import jolideco_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import jolideco_b200 as J
+
+DEV = "cuda"
+
+
+def as_datasets(g):
+    return {str(i): d for i, d in enumerate(unpack_datasets(g))}
+
+
+def make_prior(g, seed):
+    gmm = J.GaussianMixtureModel.from_numpy(g["gmm_means"], g["gmm_cov"], g["gmm_w"],
+                                            meta=J.GaussianMixtureModelMeta(stride=4))
+    gen = torch.Generator().manual_seed(seed)
+    return J.GMMPatchPrior(gmm=gmm, stride=4, generator=gen, marginalize=bool(g["marginalize"]))
+
+
+def run(g, f, n_epochs, prior, fused=True, graph=True):
+    comps = J.FluxComponents()
+    comps["flux-1"] = J.SpatialFluxComponent.from_numpy(flux=g["flux_init"], upsampling_factor=f, prior=prior)
+    deco = J.MAPDeconvolver(n_epochs=n_epochs, learning_rate=0.1, display_progress=False, device=DEV, fused=fused,
+                            use_cuda_graph=graph)
+    return deco.run(datasets=as_datasets(g), components=comps)
+
+
+def check(res, g, n_epochs, rtol_flux=1e-3):
+    flux_up = res.flux_upsampled_total
+    rel = np.linalg.norm(flux_up - g["flux_up"]) / np.linalg.norm(g["flux_up"])
+    assert rel < rtol_flux, rel
+    tr = res.trace_loss
+    assert len(tr) == n_epochs
+    assert_allclose(tr["total"], g["trace_total"], rtol=2e-5)
+    for i in range(g["trace_datasets"].shape[1]):
+        assert_allclose(tr[f"dataset-{i}"], g["trace_datasets"][:, i], rtol=2e-5)
+    assert_allclose(tr["priors-total"], g["trace_prior"], rtol=1e-4, atol=1e-9)
+
+
+@pytest.mark.parametrize("fused,graph", [(True, True), (True, False), (False, False)])
+def test_reference_e2e_golden_uniform(fused, graph):
+    g = load_golden("run_uniform.npz")
+    res = run(g, 1, 100, J.UniformPrior(), fused, graph)
+    check(res, g, 100)
+    # the reference's own golden numbers (jolideco/tests/test_core.py:71-79)
+    assert_allclose(res.flux_total[12, 12], 1.542659, rtol=1e-3)
+    assert_allclose(res.flux_total[0, 0], 3.927929, rtol=1e-3)
+    t = res.trace_loss[-1]
+    assert_allclose(t["total"], 5.842237, rtol=1e-3)
+    assert_allclose([t["dataset-0"], t["dataset-1"], t["dataset-2"]], [1.956523, 1.945902, 1.939812], rtol=1e-3)
+
+
+def test_reference_e2e_golden_upsampling2():
+    g = load_golden("run_upsampling2.npz")
+    res = run(g, 2, 100, J.UniformPrior())
+    check(res, g, 100)
+    # jolideco/tests/test_core.py:99-124
+    assert res.flux_upsampled_total.shape == (64, 64)
+    assert res.components["flux-1"].upsampling_factor == 2
+    assert_allclose(res.flux_total[12, 12], 3.565998, rtol=1e-3)
+    assert_allclose(res.flux_total[0, 0], 1.605782, rtol=1e-3)
+    assert_allclose(res.trace_loss[-1]["total"], 5.844786, rtol=1e-3)
+
+
+@pytest.mark.parametrize("name,f,n,seed", [("run_gmm_max.npz", 1, 8, 4), ("run_gmm_lse.npz", 1, 8, 4),
+                                           ("run_gmm_up2.npz", 2, 6, 5)])
+@pytest.mark.parametrize("fused", [True, False])
+def test_gmm_prior_run_matches_imported_reference(name, f, n, seed, fused):
+    g = load_golden(name)
+    prior = make_prior(g, seed)
+    res = run(g, f, n, prior, fused=fused, graph=fused)
+    check(res, g, n)
+
+
+def test_seeded_generator_reproduces_reference_shifts():
+    g = load_golden("run_gmm_max.npz")
+    prior = make_prior(g, 4)
+    draws = [prior.draw_shifts() for _ in range(6)]
+    # consumption order: D training draws then 1 trace draw per epoch (D = 2)
+    expect = [tuple(g["shifts"][0]), tuple(g["shifts"][1]), tuple(g["trace_shifts"][0]),
+              tuple(g["shifts"][2]), tuple(g["shifts"][3]), tuple(g["trace_shifts"][1])]
+    assert [tuple(int(v) for v in d) for d in draws] == [tuple(int(v) for v in e) for e in expect]
+
+
+def test_per_iteration_loss_and_gradient_vs_oracle_autograd_api():
+    """One reference iteration through the class API: loss and theta.grad within 1e-5 of the oracle."""
+    g = load_golden("run_gmm_max.npz")
+    prior = make_prior(g, 4)
+    comps = J.FluxComponents()
+    comps["flux-1"] = J.SpatialFluxComponent.from_numpy(flux=g["flux_init"], upsampling_factor=1, prior=prior)
+    comps = comps.to(DEV)
+    datasets = as_datasets(g)
+    total = J.TotalLoss.from_datasets_and_components(datasets=datasets, components=comps, beta=1.0, device=DEV)
+    counts, npred_model = next(iter(total.poisson_loss.iter_by_dataset))
+    fluxes = comps.to_flux_tuple()
+    npred = npred_model.evaluate(fluxes=fluxes)
+    loss = total.poisson_loss.loss_function(npred, counts)
+    sh = tuple(int(v) for v in g["shifts"][0])
+    loss_prior = prior(flux=fluxes[0], shift_yx=sh)
+    loss_total = loss - 1.0 * loss_prior / total.prior_weight
+    loss_total.backward()
+    grad = comps["flux-1"]._flux_upsampled.grad.cpu().numpy()[0, 0]
+    # oracle in float64
+    ds = O.prepare_dataset(unpack_datasets(g)[0], f=1, dtype=np.float64)
+    theta = np.log(g["flux_init_up"].astype(np.float64))
+    l_ref, dth_ref, _ = O.dataset_loss_and_grad(theta, ds)
+    gmm = O.GMM(g["gmm_means"], g["gmm_cov"], g["gmm_w"], dtype=np.float64)
+    p_ref, dfl_ref, _ = O.gmm_patch_prior(np.exp(theta), gmm, sh[0], sh[1], return_grad=True)
+    g_ref = dth_ref - 0.5 * dfl_ref * np.exp(theta)
+    assert_allclose(loss.item(), l_ref, rtol=1e-5)
+    assert_allclose(loss_prior.item(), p_ref, rtol=1e-5)
+    assert np.abs(grad - g_ref).max() <= 1e-5 * np.abs(g_ref).max()
+
+
+def test_cpu_device_is_refused():
+    with pytest.raises(J.JolidecoB200Error):
+        J.MAPDeconvolver(device="cpu")
+
+
+def test_bad_arguments_match_reference_errors():
+    with pytest.raises(ValueError):
+        J.MAPDeconvolver(optimizer_type="lbfgs", device=DEV)
+    with pytest.raises(ValueError):
+        J.MAPDeconvolver(stop_early=True, device=DEV).run(datasets={}, components=None)
+    with pytest.raises(ValueError):
+        J.SpatialFluxComponent(flux_upsampled=torch.ones(4, 4))
