@@ -18,8 +18,23 @@ import torch
 
 from . import _lib, ops
 
-_call = _lib.call
 _p = ops._ptr
+
+# launch accounting / per-kernel timing hooks (bench.py): every C-ABI call below is exactly one
+# kernel launch on the current stream
+_STATS = {"launches": 0, "timed": None, "events": []}
+
+
+def _call(name, *args):
+    _STATS["launches"] += 1
+    if _STATS["timed"] == name:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.call(name, *args)
+        e1.record()
+        _STATS["events"].append((e0, e1))
+        return
+    _lib.call(name, *args)
 
 
 class DatasetBuffers:
@@ -102,7 +117,7 @@ class MapEngine:
             self.n_shifts = int(tab.shape[0])
         self.use_graph = bool(use_graph) and process_group is None
         self._graphs = {}
-        self.launches_per_step = 0
+        self._graph_nodes = {}
 
     # ------------------------------------------------------------------------------------------
     def _row_block(self, rank, world):
@@ -188,13 +203,17 @@ class MapEngine:
             body()
             return
         g = self._graphs.get(key)
+        if g is not None:
+            _STATS["launches"] += self._graph_nodes[key]
         if g is None:
             # one eager pass would advance the state; capture directly instead (kernels are not
             # executed during capture) after making sure lazy one-time setup has happened
             torch.cuda.synchronize(self.dev)
             g = torch.cuda.CUDAGraph()
+            before = _STATS["launches"]
             with torch.cuda.graph(g):
                 body()
+            self._graph_nodes[key] = _STATS["launches"] - before
             self._graphs[key] = g
         g.replay()
 

@@ -191,3 +191,26 @@ def test_run_upsampling2_reference_e2e_golden():
 def test_run_gmm_prior_matches_imported_reference(name, f, n):
     g, flux_up, trace = _run(name, f, n, 1e-3, gmm=True)
     assert_allclose([t["priors-total"] for t in trace], g["trace_prior"], rtol=1e-4)
+
+
+@pytest.mark.parametrize("name,f,n", [("run_gmm_max.npz", 1, 8), ("run_gmm_up2.npz", 2, 6), ("run_uniform.npz", 1, 20)])
+def test_torch_port_matches_imported_reference(name, f, n):
+    """The torch-CPU port timed by bench.py as the CPU baseline reproduces the reference's runs."""
+    from oracle import torch_port as T
+
+    g = load_golden(name)
+    datasets = [T.Dataset(d, f) for d in unpack_datasets(g)]
+    gmm = None
+    if "gmm_means" in g:
+        og = O.GMM(g["gmm_means"], g["gmm_cov"], g["gmm_w"])
+        gmm = T.GMM(g["gmm_means"], g["gmm_cov"], g["gmm_w"], og.pixel_weights)
+    loop = T.MapLoop(g["flux_init_up"], datasets, gmm, marginalize=bool(g.get("marginalize", False)))
+    step = 0
+    for epoch in range(n):
+        for i in range(len(datasets)):
+            loop.step(i, g["shifts"][step] if gmm is not None else None)
+            step += 1
+        tr = loop.trace(g["trace_shifts"][epoch] if gmm is not None else None)
+        assert_allclose(tr["total"], g["trace_total"][epoch], rtol=1e-5)
+    if n == len(g["trace_total"]):
+        assert_allclose(loop.flux_numpy(), g["flux_up"], rtol=1e-4)
