@@ -104,11 +104,22 @@ int jd_extract_patches(const float* flux, int fH, int fW, const int32_t* shift_y
  *   value[p'] (v_p), argmax[p'] (int32), sum[0] += sum_p v_p (double), logp (optional, P' x K,
  *   needed by the marginalize=1 backward).  Patches containing NaN or values <= -1e5 are skipped
  *   (value 0, argmax -1), as the reference filters them (core.py:215-216).
- * backend: 0 = FP32 CUDA cores (reference-grade check path), 1 = tcgen05 split-TF32. */
+ * backend: 0 = FP32 CUDA cores (check path; the tensor-core path is jd_gmm_prior_forward_tc). */
 int jd_gmm_prior_forward(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride,
                          int row_begin, int row_end, const float* Lw, const float* mw, const float* ck,
                          int K, int marginalize, float* value, int32_t* argmax, float* logp, double* sum,
                          int backend, jd_stream_t stream);
+
+/* tcgen05 (5th-gen tensor core) forward, split-TF32 with FP32 accumulation in TMEM.  Same contract
+ * and outputs as jd_gmm_prior_forward; the component matrices are passed as the pre-packed operand
+ * image Bt built once by jd_gmm_tc_pack from Lw (K x 64 x 64): per component 32 KB holding Lw_k^T
+ * split into TF32 hi/lo halves in the 128B-swizzled K-major shared-memory layout the MMA reads. */
+size_t jd_gmm_tc_packed_bytes(int K);
+int jd_gmm_tc_pack(const float* Lw, int K, void* Bt, jd_stream_t stream);
+int jd_gmm_prior_forward_tc(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride,
+                            int row_begin, int row_end, const void* Bt, const float* mw, const float* ck,
+                            int K, int marginalize, float* value, int32_t* argmax, float* logp,
+                            double* sum, jd_stream_t stream);
 
 /* Per-patch gradient  G[p',:] = scale * sum_k R[p',k] (xc_p Lam_k - bk_k),  minus its row mean,
  * R = one-hot(argmax) or softmax_k(logp) (marginalize=1; needs logp and value from the forward);

@@ -99,6 +99,8 @@ class MapEngine:
             self.marginalize = bool(prior["marginalize"])
             self.backend = int(prior.get("backend", 0))
             self.packed = prior["packed"]
+            if self.backend == 1:
+                self.packed.Bt  # pack the tensor-core operand before any graph capture
             self.ny, self.nx = ops.patch_grid(self.fH, self.fW, self.stride)
             self.c = self.stride**2 / ops.PD / self.n
             # row-block shard of the prior (whole grid on one GPU)
@@ -147,6 +149,11 @@ class MapEngine:
 
     def _prior_forward(self, sum_acc):
         if self.P <= 0:
+            return
+        if self.backend == 1:
+            _call("jd_gmm_prior_forward_tc", _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride,
+                  self.rows[0], self.rows[1], _p(self.packed.Bt), _p(self.packed.mw), _p(self.packed.ck), self.packed.K,
+                  int(self.marginalize), _p(self.value), _p(self.argmax), _p(self.logp), sum_acc, self._s())
             return
         _call("jd_gmm_prior_forward", _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride, self.rows[0],
               self.rows[1], _p(self.packed.Lw), _p(self.packed.mw), _p(self.packed.ck), self.packed.K,

@@ -141,6 +141,20 @@ class GMMPacked:
 
         self.Lw, self.mw, self.ck, self.Lam, self.bk = dev(Lw), dev(mw), dev(ck), dev(Lam), dev(bk)
         self.device = torch.device(device)
+        self._Bt = None
+
+    @property
+    def Bt(self):
+        """Tensor-core operand image of Lw (split-TF32, swizzled K-major), packed once on the device."""
+        if self._Bt is None:
+            if self.D != PD:
+                raise _lib.JolidecoB200Error("the tcgen05 prior kernel supports 8x8 patches (D=64) only")
+            nbytes = _lib.load().jd_gmm_tc_packed_bytes(self.K)
+            with torch.cuda.device(self.device):
+                bt = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+                _lib.call("jd_gmm_tc_pack", _ptr(self.Lw), self.K, _ptr(bt), _stream())
+            self._Bt = bt
+        return self._Bt
 
 
 def gmm_log_prob(x, packed):
@@ -193,9 +207,14 @@ def gmm_prior_forward(flux, shift_yx, packed, stride=4, marginalize=False, rows=
     logp = torch.empty((P, packed.K), dtype=torch.float32, device=flux.device) if want_logp else None
     if sum_out is None:
         sum_out = torch.zeros(1, dtype=torch.float64, device=flux.device)
-    _lib.call("jd_gmm_prior_forward", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(packed.Lw),
-              _ptr(packed.mw), _ptr(packed.ck), packed.K, int(bool(marginalize)), _ptr(value), _ptr(argmax),
-              _ptr(logp), _ptr(sum_out), int(backend), _stream())
+    if int(backend) == 1:
+        _lib.call("jd_gmm_prior_forward_tc", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(packed.Bt),
+                  _ptr(packed.mw), _ptr(packed.ck), packed.K, int(bool(marginalize)), _ptr(value), _ptr(argmax),
+                  _ptr(logp), _ptr(sum_out), _stream())
+    else:
+        _lib.call("jd_gmm_prior_forward", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(packed.Lw),
+                  _ptr(packed.mw), _ptr(packed.ck), packed.K, int(bool(marginalize)), _ptr(value), _ptr(argmax),
+                  _ptr(logp), _ptr(sum_out), int(backend), _stream())
     return value, argmax, logp, sum_out
 
 

@@ -259,7 +259,7 @@ class GMMPatchPrior(Prior):
                                       backend)
 
 
-_DEFAULT_BACKEND = 0
+_DEFAULT_BACKEND = 1  # tcgen05 split-TF32 forward; 0 = FP32 CUDA-core check path
 
 
 def default_backend():

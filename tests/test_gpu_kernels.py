@@ -171,14 +171,16 @@ def prior_cuda(flux, gmm_packed, sy, sx, marginalize, rows=None, backend=0):
     return s.item() * c, dflux.cpu().numpy(), argmax.cpu().numpy()
 
 
+@pytest.mark.parametrize("backend", [0, 1])
 @pytest.mark.parametrize("marginalize", [False, True])
 @pytest.mark.parametrize("shape,shift", [((38, 46), (0, 0)), ((38, 46), (-2, 1)), ((64, 80), (2, -2)), ((24, 24), (1, 2))])
-def test_gmm_prior_value_and_grad(marginalize, shape, shift):
+def test_gmm_prior_value_and_grad(marginalize, shape, shift, backend):
     rng = np.random.default_rng(5)
     flux = rng.gamma(2.0, size=shape).astype(np.float32)
     gmm64 = O.GMM(*synthetic_gmm(11, seed=2), dtype=np.float64)
     ref_v, ref_g, ref_k = O.gmm_patch_prior(flux.astype(np.float64), gmm64, shift[0], shift[1], 4, marginalize, True)
-    v, gr, k = prior_cuda(flux, pack(O.GMM(*synthetic_gmm(11, seed=2))), shift[0], shift[1], marginalize)
+    v, gr, k = prior_cuda(flux, pack(O.GMM(*synthetic_gmm(11, seed=2))), shift[0], shift[1], marginalize,
+                          backend=backend)
     assert_allclose(v, ref_v, rtol=1e-5)
     flipped = (k != ref_k).sum()
     assert flipped <= 0.01 * len(k)
@@ -188,13 +190,14 @@ def test_gmm_prior_value_and_grad(marginalize, shape, shift):
         assert rel_max(gr, ref_g) < 2e-5
 
 
+@pytest.mark.parametrize("backend", [0, 1])
 @pytest.mark.parametrize("case", range(8))
-def test_gmm_prior_golden(case):
+def test_gmm_prior_golden(case, backend):
     g = load_golden("prior_step.npz")
     sy, sx = (int(v) for v in g[f"c{case}_shift"])
     marg = bool(g[f"c{case}_marginalize"])
     gmm = O.GMM(g["gmm_means"], g["gmm_cov"], g["gmm_w"])
-    v, gr, _ = prior_cuda(g["flux"], pack(gmm), sy, sx, marg)
+    v, gr, _ = prior_cuda(g["flux"], pack(gmm), sy, sx, marg, backend=backend)
     assert_allclose(v, g[f"c{case}_f64_value"], rtol=1e-5)
     ref = g[f"c{case}_f64_grad"]
     assert rel_max(gr, ref) < 2e-5
@@ -209,6 +212,24 @@ def test_gmm_prior_row_blocks_sum_to_whole():
     parts = [prior_cuda(flux, packed, -1, 2, False, rows=r) for r in [(0, 5), (5, 6), (6, ny)]]
     assert_allclose(sum(p[0] for p in parts), v, rtol=1e-6)
     assert rel_max(sum(p[1] for p in parts), gr) < 1e-6
+
+
+@pytest.mark.parametrize("marginalize", [False, True])
+def test_gmm_prior_tensor_core_vs_cuda_core_full_size(marginalize):
+    """tcgen05 split-TF32 forward against the FP32 CUDA-core forward at the BASELINE config-2 size
+    (512x512 flux, 16129 patches), K=32 with non-zero means: per-patch values to FP32 accuracy,
+    identical argmax except near-ties."""
+    rng = np.random.default_rng(9)
+    flux = t(rng.gamma(2.0, size=(512, 512)) * np.exp(rng.normal(0, 1.0, size=(512, 512))))
+    packed = pack(O.GMM(*synthetic_gmm(32, seed=5, mean_scale=0.05)))
+    v0, k0, lp0, s0 = ops.gmm_prior_forward(flux, (1, -2), packed, 4, marginalize, want_logp=True, backend=0)
+    v1, k1, lp1, s1 = ops.gmm_prior_forward(flux, (1, -2), packed, 4, marginalize, want_logp=True, backend=1)
+    lp0, lp1 = lp0.cpu().numpy().astype(np.float64), lp1.cpu().numpy().astype(np.float64)
+    scale = np.abs(lp0).max(axis=1, keepdims=True)
+    assert (np.abs(lp1 - lp0) / scale).max() < 2e-6
+    assert_allclose(s1.item(), s0.item(), rtol=1e-6)
+    assert_allclose(v1.cpu().numpy(), v0.cpu().numpy(), rtol=1e-5, atol=1e-3)
+    assert (k0 != k1).sum().item() <= 3
 
 
 def test_gmm_prior_nan_patch_is_skipped():
