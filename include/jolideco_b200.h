@@ -113,13 +113,15 @@ int jd_gmm_prior_forward(const float* flux, int fH, int fW, const int32_t* shift
 /* tcgen05 (5th-gen tensor core) forward, split-TF32 with FP32 accumulation in TMEM.  Same contract
  * and outputs as jd_gmm_prior_forward; the component matrices are passed as the pre-packed operand
  * image Bt built once by jd_gmm_tc_pack from Lw (K x 64 x 64): per component 32 KB holding Lw_k^T
- * split into TF32 hi/lo halves in the 128B-swizzled K-major shared-memory layout the MMA reads. */
+ * split into TF32 hi/lo halves in the 128B-swizzled K-major shared-memory layout the MMA reads.
+ * upper_tri != 0 asserts that every Lw_k is upper triangular (true for precision Cholesky factors,
+ * utils/numpy.py:16-34): the kernel then skips the structurally-zero part of the product. */
 size_t jd_gmm_tc_packed_bytes(int K);
 int jd_gmm_tc_pack(const float* Lw, int K, void* Bt, jd_stream_t stream);
 int jd_gmm_prior_forward_tc(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride,
                             int row_begin, int row_end, const void* Bt, const float* mw, const float* ck,
-                            int K, int marginalize, float* value, int32_t* argmax, float* logp,
-                            double* sum, jd_stream_t stream);
+                            int K, int upper_tri, int marginalize, float* value, int32_t* argmax,
+                            float* logp, double* sum, jd_stream_t stream);
 
 /* Per-patch gradient  G[p',:] = scale * sum_k R[p',k] (xc_p Lam_k - bk_k),  minus its row mean,
  * R = one-hot(argmax) or softmax_k(logp) (marginalize=1; needs logp and value from the forward);

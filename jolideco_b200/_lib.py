@@ -41,7 +41,7 @@ PROTOTYPES = {
     "jd_gmm_tc_packed_bytes": [c_int],
     "jd_gmm_tc_pack": [c_f32p, c_int, ctypes.c_void_p, c_stream],
     "jd_gmm_prior_forward_tc": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, ctypes.c_void_p, c_f32p, c_f32p,
-                                c_int, c_int, c_f32p, c_i32p, c_f32p, c_f64p, c_stream],
+                                c_int, c_int, c_int, c_f32p, c_i32p, c_f32p, c_f64p, c_stream],
     "jd_gmm_prior_backward": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, c_f32p, c_f32p, c_int, c_int,
                               c_i32p, c_f32p, c_f32p, c_float, c_f32p, c_stream],
     "jd_patch_fold": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, c_f32p, c_int, c_stream],

@@ -8,11 +8,15 @@
 // CTA = 128 patches (UMMA M = 128), 6 warps:
 //   warp 0      bulk-TMA producer: streams the pre-packed B image of component k
 //               (Lw_k^T split hi/lo, 128B-swizzled K-major, 32 KB) into a 4-stage smem ring;
-//   warp 1      TMEM allocator + MMA issuer: 24 tcgen05.mma (M128 N64 K8, kind::tf32) per component
-//               into one of 8 accumulator slots (64 TMEM columns each);
+//   warp 1      TMEM allocator + MMA issuer: 24 tcgen05.mma (M128 N<=64 K8, kind::tf32, A from TMEM,
+//               B from smem) per component into one of 6 accumulator slots (64 TMEM columns each).
+//               Lw_k is upper triangular (a Cholesky factor), so k-step kk only feeds whitened
+//               features j >= 8 kk: the MMA N extent shrinks 64,64,48,48,32,32,16,16 (62.5 % of
+//               the dense tensor work);
 //   warps 2..5  gather the 128 patches from the flux image at rolled coordinates, subtract the
-//               patch mean, split hi/lo and write the A operand (swizzled K-major) to smem once;
-//               then act as the epilogue: tcgen05.ld the 128x64 accumulator of each component
+//               patch mean, split hi/lo and store the A operand straight into TMEM (tcgen05.st,
+//               thread = patch row = TMEM lane; 128 columns) so the MMA never re-reads A from shared
+//               memory; then act as the epilogue: tcgen05.ld the 128x64 accumulator of each component
 //               (thread = patch row), subtract mw_k, square, reduce over the 64 whitened features,
 //               add ck_k and fold into a running max/argmax or online logsumexp.  Y never leaves
 //               the SM; only value/argmax (and optionally logp) are written.
@@ -30,15 +34,16 @@ int gmm_prior_forward_simt(const float* flux, int fH, int fW, const int32_t* shi
 namespace tc {
 
 constexpr int TM = 128;                 // patches per CTA
-constexpr int NSTAGE = 4;               // B ring depth
-constexpr int NSLOT = 8;                // TMEM accumulator slots
+constexpr int NSTAGE = 5;               // B ring depth
+constexpr int NSLOT = 6;                // TMEM accumulator slots
 constexpr int SLOT_COLS = 64;
-constexpr int KBLOCK_BYTES_A = TM * 128;      // 128 rows x 128 B (32 tf32) = 16 KB
+constexpr int A_COLS = 128;             // TMEM columns [0,64) = A hi, [64,128) = A lo
+constexpr int TMEM_COLS = 512;          // A_COLS + NSLOT * SLOT_COLS
 constexpr int KBLOCK_BYTES_B = 64 * 128;      // 64 rows x 128 B = 8 KB
-constexpr int A_BYTES = 4 * KBLOCK_BYTES_A;   // hi(kb0,kb1) lo(kb0,kb1) = 64 KB
 constexpr int B_BYTES = 4 * KBLOCK_BYTES_B;   // hi(kb0,kb1) lo(kb0,kb1) = 32 KB per component
 constexpr int NTHREADS = 192;
-constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + A_BYTES + NSTAGE * B_BYTES + 1024 /*barriers etc.*/;
+constexpr int MW_BYTES = 64 * 4;        // mw_k staged per accumulator slot
+constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + NSTAGE * B_BYTES + NSLOT * MW_BYTES + 1024 /*barriers etc.*/;
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -85,16 +90,31 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] . B[smem]   (A: lane = row, column = K element)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// 32 lanes x 32 columns of 32-bit: thread i of the warp receives row (lane base + i)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+      "%30,%31,%32};" ::"r"(taddr),
+      "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+      "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]),
+      "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]),
+      "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 32 lanes x 32 columns of 32-bit: thread i of the warp receives row (lane base + i); no wait
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   asm volatile(
@@ -106,9 +126,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// One elected lane of a converged warp (cute::elect_one_sync): keeps the enclosing code warp-uniform so
+// that descriptor / TMEM-address operands stay in uniform registers (no per-lane R2UR loops).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ float tf32_rna(float x) {
@@ -130,8 +161,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return d;
 }
 
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128, N = 64
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+// high word of make_desc (SBO, version, layout) and low word for a 16-byte-aligned shared address
+constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc_from_lo(uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; }
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128, N = n
+__device__ __host__ constexpr uint32_t idesc_n(uint32_t n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
 
 // byte offset of element (row, d) inside a [rows x 64 tf32] operand stored as two 128B-swizzled k-blocks
 __device__ __host__ __forceinline__ uint32_t sw128_offset(int row, int d, int kblock_bytes) {
@@ -162,6 +200,7 @@ __global__ void pack_b_kernel(const float* __restrict__ Lw, int K, uint8_t* __re
 }
 
 // ---------------------------------------------------------------- the forward kernel
+template <bool TRI>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restrict__ shift_yx,
                   const uint8_t* __restrict__ Bt, const float* __restrict__ mw, const float* __restrict__ ck, int K,
@@ -169,11 +208,11 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
                   double* __restrict__ sum) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;                          // 64 KB
-  uint8_t* sB = smem + A_BYTES;                // NSTAGE x 32 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + NSTAGE * B_BYTES);
-  // barrier indices: full[NSTAGE], empty[NSTAGE], tfull[NSLOT], tempty[NSLOT]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 2 * NSLOT);
+  uint8_t* sB = smem;                          // NSTAGE x 32 KB
+  float* sMW = reinterpret_cast<float*>(sB + NSTAGE * B_BYTES);  // NSLOT x 64 floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + NSTAGE * B_BYTES + NSLOT * MW_BYTES);
+  // barrier indices: full[NSTAGE], empty[NSTAGE], tfull[NSLOT], tempty[NSLOT], mwfull[NSLOT]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 3 * NSLOT);
   int* s_valid = reinterpret_cast<int*>(s_tmem + 4);       // 128 ints
   double* s_red = reinterpret_cast<double*>(s_valid + TM);  // 4 doubles
 
@@ -183,6 +222,12 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
   auto empty_bar = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
   auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + s); };
   auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + NSLOT + s); };
+  auto mwfull_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 * NSLOT + s); };
+  // Every CTA walks the components in a different cyclic order (start k0): at any instant the
+  // CTAs stream different B images / mw rows, which spreads the L2 reads over the slices instead
+  // of 148 SMs hammering the same lines in lockstep.  max / logsumexp do not depend on the order
+  // (ties in max resolve to the lowest component index, as torch.max does).
+  const int k0 = (int)(((long long)blockIdx.x * K) / gridDim.x);
 
   if (shift_yx) {
     g.sy = shift_yx[0];
@@ -198,15 +243,39 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+      mbar_init(mwfull_bar(s), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(s_tmem), NSLOT * SLOT_COLS);
+  if (warp == 1) tmem_alloc(smem_u32(s_tmem), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
 
-  if (warp >= 2) {
-    // ---- gather: thread = patch row; 64 loads, mean, hi/lo split, swizzled stores
-    const int row = threadIdx.x - 64;
-    const int64_t p = p0 + row;
+  // TMEM lane quarter of an epilogue/gather warp, and the patch row (= TMEM lane) of its threads
+  const int q = warp & 3;
+  const int row = q * 32 + lane;
+  const int64_t p = p0 + row;
+
+  if (warp == 0) {
+    // ===================== bulk-TMA producer (whole warp waits, one elected lane issues) ==========
+    for (int k = 0; k < K; ++k) {
+      const int s = k % NSTAGE, t = k % NSLOT;
+      const int kc = (k + k0) % K;  // component handled at position k
+      mbar_wait(empty_bar(s), ((k / NSTAGE) & 1) ^ 1);
+      // mw_k rides with accumulator slot t: free once the epilogue of component k - NSLOT is done
+      mbar_wait(tempty_bar(t), ((k / NSLOT) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(full_bar(s), B_BYTES);
+        bulk_g2s(smem_u32(sB + s * B_BYTES), Bt + (size_t)kc * B_BYTES, B_BYTES, full_bar(s));
+        mbar_arrive_expect_tx(mwfull_bar(t), MW_BYTES);
+        bulk_g2s(smem_u32(sMW + t * 64), mw + (size_t)kc * 64, MW_BYTES, mwfull_bar(t));
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 2) {
+    // ---- gather: thread = patch row; 64 loads, mean, hi/lo split, tcgen05.st into TMEM lane `row`
     float vals[64];
     float s = 0.f;
     bool ok = p < g.P;
@@ -231,110 +300,109 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
       for (int i = 0; i < 64; ++i) vals[i] = 0.f;
     }
     const float mean = s * (1.f / 64.f);
+    const uint32_t a_lane = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      float4 hi, lo;
-      float x0 = ok ? vals[4 * c + 0] - mean : 0.f, x1 = ok ? vals[4 * c + 1] - mean : 0.f;
-      float x2 = ok ? vals[4 * c + 2] - mean : 0.f, x3 = ok ? vals[4 * c + 3] - mean : 0.f;
-      hi.x = tf32_rna(x0), hi.y = tf32_rna(x1), hi.z = tf32_rna(x2), hi.w = tf32_rna(x3);
-      lo.x = tf32_rna(x0 - hi.x), lo.y = tf32_rna(x1 - hi.y), lo.z = tf32_rna(x2 - hi.z), lo.w = tf32_rna(x3 - hi.w);
-      uint32_t off = sw128_offset(row, 4 * c, KBLOCK_BYTES_A);
-      *reinterpret_cast<float4*>(sA + off) = hi;
-      *reinterpret_cast<float4*>(sA + 2 * KBLOCK_BYTES_A + off) = lo;
-    }
-    s_valid[row] = ok ? 1 : 0;
-    // make the generic-proxy writes of A visible to the async proxy (UMMA operand reads)
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *s_tmem;
-
-  if (warp == 0) {
-    // ===================== bulk-TMA producer =====================
-    if (lane == 0) {
-      for (int k = 0; k < K; ++k) {
-        const int s = k % NSTAGE;
-        const uint32_t ph = (k / NSTAGE) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
-        mbar_arrive_expect_tx(full_bar(s), B_BYTES);
-        bulk_g2s(smem_u32(sB + s * B_BYTES), Bt + (size_t)k * B_BYTES, B_BYTES, full_bar(s));
+    for (int h = 0; h < 2; ++h) {
+      float hi[32], lo[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float x = ok ? vals[h * 32 + i] - mean : 0.f;
+        hi[i] = tf32_rna(x);
+        lo[i] = tf32_rna(x - hi[i]);
       }
+      tmem_st32(a_lane + h * 32, hi);
+      tmem_st32(a_lane + 64 + h * 32, lo);
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + 2 * KBLOCK_BYTES_A;
-      for (int k = 0; k < K; ++k) {
-        const int s = k % NSTAGE, t = k % NSLOT;
-        mbar_wait(tempty_bar(t), ((k / NSLOT) & 1) ^ 1);
-        mbar_wait(full_bar(s), (k / NSTAGE) & 1);
-        tc_fence_after();
-        const uint32_t b_hi = smem_u32(sB + s * B_BYTES), b_lo = b_hi + 2 * KBLOCK_BYTES_B;
-        const uint32_t d = tmem_base + t * SLOT_COLS;
+    tmem_st_wait();
+    s_valid[row] = ok ? 1 : 0;
+    tc_fence_before();
+    // the 4 gather warps -> MMA warp: named barrier 1 (128 gather threads + 32 MMA-warp threads)
+    asm volatile("bar.arrive 1, 160;" ::: "memory");
+  }
+
+  if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =========
+    asm volatile("bar.sync 1, 160;" ::: "memory");  // A operand is in TMEM
+    tc_fence_after();
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t sB_lo0 = desc_lo(smem_u32(sB));
+    for (int k = 0; k < K; ++k) {
+      const int s = k % NSTAGE, t = k % NSLOT;
+      mbar_wait(tempty_bar(t), ((k / NSLOT) & 1) ^ 1);
+      mbar_wait(full_bar(s), (k / NSTAGE) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t b_hi = sB_lo0 + s * (B_BYTES >> 4), b_lo = b_hi + ((2 * KBLOCK_BYTES_B) >> 4);
+        const uint32_t d = tmem_u + A_COLS + t * SLOT_COLS;
         uint32_t acc = 0;
         // small terms first: lo.hi, hi.lo, then hi.hi
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t a_base = pass == 0 ? a_lo : a_hi;
+          const uint32_t a_col = pass == 0 ? 64u : 0u;
           const uint32_t b_base = pass == 1 ? b_lo : b_hi;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
-            const uint32_t a_addr = a_base + (kk >> 2) * KBLOCK_BYTES_A + (kk & 3) * 32;
-            const uint32_t b_addr = b_base + (kk >> 2) * KBLOCK_BYTES_B + (kk & 3) * 32;
-            umma_tf32(d, make_desc(a_addr), make_desc(b_addr), IDESC, acc);
+            // upper-triangular Lw: input features [8kk, 8kk+8) only reach whitened features >= 8kk
+            const uint32_t n0 = TRI ? 16u * (kk >> 1) : 0u;
+            const uint32_t off16 = ((kk >> 2) * KBLOCK_BYTES_B + (kk & 3) * 32 + n0 * 128) >> 4;
+            umma_tf32_ts(d + n0, tmem_u + a_col + kk * 8, desc_from_lo(b_base + off16), idesc_n(64 - n0), acc);
             acc = 1;
           }
         }
         umma_commit(empty_bar(s));  // smem stage reusable once these MMAs have read it
         umma_commit(tfull_bar(t));  // accumulator slot complete
       }
+      __syncwarp();
     }
-  } else {
+  } else if (warp >= 2) {
     // ===================== epilogue =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
-    const int64_t p = p0 + row;
     float run_m = -CUDART_INF_F, run_s = 0.f;
     int run_k = 0;
     for (int k = 0; k < K; ++k) {
       const int t = k % NSLOT;
+      const int kc = (k + k0) % K;
+      const float4* mwk = reinterpret_cast<const float4*>(sMW + t * 64);
+      const float c_k = __ldg(ck + kc);
+      mbar_wait(mwfull_bar(t), (k / NSLOT) & 1);
       mbar_wait(tfull_bar(t), (k / NSLOT) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + t * SLOT_COLS;
-      const float4* mwk = reinterpret_cast<const float4*>(mw + (size_t)k * 64);
-      float qv = 0.f;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + A_COLS + t * SLOT_COLS;
+      float y0[32], y1[32];
+      tmem_ld32(taddr, y0);
+      tmem_ld32(taddr + 32, y1);
+      tmem_ld_wait();
+      float qa = 0.f, qb = 0.f;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float y[32];
-        tmem_ld32(taddr + h * 32, y);
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          float4 b = __ldg(mwk + h * 8 + c4);
-          float d0 = y[4 * c4] - b.x, d1 = y[4 * c4 + 1] - b.y, d2 = y[4 * c4 + 2] - b.z, d3 = y[4 * c4 + 3] - b.w;
-          qv = fmaf(d0, d0, qv);
-          qv = fmaf(d1, d1, qv);
-          qv = fmaf(d2, d2, qv);
-          qv = fmaf(d3, d3, qv);
-        }
+      for (int c4 = 0; c4 < 8; ++c4) {
+        float4 b0 = mwk[c4], b1 = mwk[8 + c4];
+        float d0 = y0[4 * c4] - b0.x, d1 = y0[4 * c4 + 1] - b0.y, d2 = y0[4 * c4 + 2] - b0.z, d3 = y0[4 * c4 + 3] - b0.w;
+        float e0 = y1[4 * c4] - b1.x, e1 = y1[4 * c4 + 1] - b1.y, e2 = y1[4 * c4 + 2] - b1.z, e3 = y1[4 * c4 + 3] - b1.w;
+        qa = fmaf(d0, d0, qa);
+        qb = fmaf(e0, e0, qb);
+        qa = fmaf(d1, d1, qa);
+        qb = fmaf(e1, e1, qb);
+        qa = fmaf(d2, d2, qa);
+        qb = fmaf(e2, e2, qb);
+        qa = fmaf(d3, d3, qa);
+        qb = fmaf(e3, e3, qb);
       }
+      // accumulator slot and mw row are free once both are consumed
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(t));
-      const float lp = fmaf(-0.5f, qv, __ldg(ck + k));
-      if (logp && p < g.P) logp[p * K + k] = lp;
+      const float lp = fmaf(-0.5f, qa + qb, c_k);
+      if (logp && p < g.P) logp[p * K + kc] = lp;
       if (marginalize) {
         if (lp > run_m) {
           run_s = run_s * expf(run_m - lp) + 1.f;
           run_m = lp;
-          run_k = k;
+          run_k = kc;
         } else {
           run_s += expf(lp - run_m);
         }
-      } else if (lp > run_m) {
+      } else if (lp > run_m || (lp == run_m && kc < run_k)) {
         run_m = lp;
-        run_k = k;
+        run_k = kc;
       }
     }
     double part = 0.0;
@@ -355,7 +423,7 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
   if (threadIdx.x == 0 && sum) atomicAdd(sum, s_red[0] + s_red[1] + s_red[2] + s_red[3]);
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, NSLOT * SLOT_COLS);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -377,19 +445,24 @@ int jd_gmm_tc_pack(const float* Lw, int K, void* Bt, jd_stream_t stream) {
 }
 
 int jd_gmm_prior_forward_tc(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
-                            int row_end, const void* Bt, const float* mw, const float* ck, int K, int marginalize,
-                            float* value, int32_t* argmax, float* logp, double* sum, jd_stream_t stream) {
+                            int row_end, const void* Bt, const float* mw, const float* ck, int K, int upper_tri,
+                            int marginalize, float* value, int32_t* argmax, float* logp, double* sum,
+                            jd_stream_t stream) {
   JD_CHECK_ARG(flux && Bt && mw && ck && K > 0, "jd_gmm_prior_forward_tc: null pointer");
   JD_CHECK_ARG(fH >= PATCH && fW >= PATCH && stride >= 1 && stride <= PATCH, "jd_gmm_prior_forward_tc: bad geometry");
   int ny = (fH - PATCH) / stride + 1, nx = (fW - PATCH) / stride + 1;
   JD_CHECK_ARG(row_begin >= 0 && row_end <= ny && row_begin < row_end,
                "jd_gmm_prior_forward_tc: bad patch-row block [%d,%d) of %d", row_begin, row_end, ny);
-  JD_CHECK_ARG((reinterpret_cast<uintptr_t>(Bt) & 15) == 0, "jd_gmm_prior_forward_tc: Bt must be 16-byte aligned");
+  JD_CHECK_ARG((reinterpret_cast<uintptr_t>(Bt) & 15) == 0 && (reinterpret_cast<uintptr_t>(mw) & 15) == 0,
+               "jd_gmm_prior_forward_tc: Bt and mw must be 16-byte aligned");
   tc::Geom g{fH, fW, 0, 0, stride, nx, row_begin, (row_end - row_begin) * nx};
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc::gmm_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(tc::gmm_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)tc::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc::gmm_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)tc::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("jd_gmm_prior_forward_tc: cannot reserve %zu B of shared memory: %s", tc::SMEM_BYTES,
                 cudaGetErrorString(e));
@@ -398,7 +471,8 @@ int jd_gmm_prior_forward_tc(const float* flux, int fH, int fW, const int32_t* sh
     attr_set = true;
   }
   int grid = (g.P + tc::TM - 1) / tc::TM;
-  tc::gmm_fwd_tc_kernel<<<grid, tc::NTHREADS, tc::SMEM_BYTES, to_stream(stream)>>>(
+  auto kern = upper_tri ? tc::gmm_fwd_tc_kernel<true> : tc::gmm_fwd_tc_kernel<false>;
+  kern<<<grid, tc::NTHREADS, tc::SMEM_BYTES, to_stream(stream)>>>(
       flux, g, shift_yx, reinterpret_cast<const uint8_t*>(Bt), mw, ck, K, marginalize, value, argmax, logp, sum);
   JD_CHECK_LAUNCH("jd_gmm_prior_forward_tc");
   return JD_OK;

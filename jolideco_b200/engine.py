@@ -153,7 +153,8 @@ class MapEngine:
         if self.backend == 1:
             _call("jd_gmm_prior_forward_tc", _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride,
                   self.rows[0], self.rows[1], _p(self.packed.Bt), _p(self.packed.mw), _p(self.packed.ck), self.packed.K,
-                  int(self.marginalize), _p(self.value), _p(self.argmax), _p(self.logp), sum_acc, self._s())
+                  int(self.packed.upper_tri), int(self.marginalize), _p(self.value), _p(self.argmax), _p(self.logp),
+                  sum_acc, self._s())
             return
         _call("jd_gmm_prior_forward", _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride, self.rows[0],
               self.rows[1], _p(self.packed.Lw), _p(self.packed.mw), _p(self.packed.ck), self.packed.K,

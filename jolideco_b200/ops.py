@@ -142,6 +142,7 @@ class GMMPacked:
         self.Lw, self.mw, self.ck, self.Lam, self.bk = dev(Lw), dev(mw), dev(ck), dev(Lam), dev(bk)
         self.device = torch.device(device)
         self._Bt = None
+        self.upper_tri = bool(np.all(np.tril(L, -1) == 0))
 
     @property
     def Bt(self):
@@ -209,8 +210,8 @@ def gmm_prior_forward(flux, shift_yx, packed, stride=4, marginalize=False, rows=
         sum_out = torch.zeros(1, dtype=torch.float64, device=flux.device)
     if int(backend) == 1:
         _lib.call("jd_gmm_prior_forward_tc", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(packed.Bt),
-                  _ptr(packed.mw), _ptr(packed.ck), packed.K, int(bool(marginalize)), _ptr(value), _ptr(argmax),
-                  _ptr(logp), _ptr(sum_out), _stream())
+                  _ptr(packed.mw), _ptr(packed.ck), packed.K, int(packed.upper_tri), int(bool(marginalize)), _ptr(value),
+                  _ptr(argmax), _ptr(logp), _ptr(sum_out), _stream())
     else:
         _lib.call("jd_gmm_prior_forward", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(packed.Lw),
                   _ptr(packed.mw), _ptr(packed.ck), packed.K, int(bool(marginalize)), _ptr(value), _ptr(argmax),

@@ -232,6 +232,22 @@ def test_gmm_prior_tensor_core_vs_cuda_core_full_size(marginalize):
     assert (k0 != k1).sum().item() <= 3
 
 
+def test_gmm_prior_tensor_core_dense_precision_factors():
+    """Non-triangular component matrices take the untrimmed MMA schedule (upper_tri = 0)."""
+    rng = np.random.default_rng(10)
+    K = 9
+    L = rng.normal(0, 1.0, size=(K, 64, 64)).astype(np.float32)
+    L[:, np.arange(64), np.arange(64)] = np.abs(L[:, np.arange(64), np.arange(64)]) + 1
+    packed = ops.GMMPacked(rng.normal(0, 0.05, size=(K, 64)), L, np.full(K, 1.0 / K), O.get_pixel_weights(8, 4), DEV)
+    assert not packed.upper_tri
+    flux = t(rng.gamma(2.0, size=(100, 84)))
+    v0, k0, lp0, s0 = ops.gmm_prior_forward(flux, (0, 1), packed, 4, False, want_logp=True, backend=0)
+    v1, k1, lp1, s1 = ops.gmm_prior_forward(flux, (0, 1), packed, 4, False, want_logp=True, backend=1)
+    lp0, lp1 = lp0.cpu().numpy().astype(np.float64), lp1.cpu().numpy().astype(np.float64)
+    assert (np.abs(lp1 - lp0) / np.abs(lp0).max(axis=1, keepdims=True)).max() < 2e-6
+    assert (k0 != k1).sum().item() == 0
+
+
 def test_gmm_prior_nan_patch_is_skipped():
     rng = np.random.default_rng(7)
     flux = rng.gamma(2.0, size=(32, 32)).astype(np.float32)
