@@ -65,6 +65,20 @@ int jd_conv_backward_direct(const float* dpool, const float* exposure, const flo
                             int accumulate, int fH, int fW, int kh, int kw, int f, int H, int W,
                             jd_stream_t stream);
 
+/* ---- a3, large PSFs: shared-memory FFT convolution (same arithmetic contract as the direct entries) ----
+ * jd_fftconv_sizes: element counts (floats) of the cached PSF spectrum and of the scratch workspace for an
+ * fH x fW image and a kh x kw PSF (both axes padded to the next power of two >= n + k - 1).
+ * jd_fftconv_prepare_psf: PSF spectrum, computed once per dataset (the reference recomputes rfft2(psf) on every
+ * call, utils/torch.py:368).  jd_conv_forward_fft / jd_conv_backward_fft: drop-in for the *_direct entries. */
+int jd_fftconv_sizes(int fH, int fW, int kh, int kw, int64_t* psf_hat_elems, int64_t* workspace_elems);
+int jd_fftconv_prepare_psf(const float* psf, int kh, int kw, int fH, int fW, float* psf_hat, float* workspace,
+                           jd_stream_t stream);
+int jd_conv_forward_fft(const float* flux, const float* exposure, const float* psf_hat, float* workspace,
+                        float* conv, int fH, int fW, int kh, int kw, jd_stream_t stream);
+int jd_conv_backward_fft(const float* dpool, const float* exposure, const float* psf_hat, float* workspace,
+                         float* dflux, int accumulate, int fH, int fW, int kh, int kw, int f, int H, int W,
+                         jd_stream_t stream);
+
 /* Pre-clip sum-pool alone (F.avg_pool2d(kernel_size=f, divisor_override=1), models/npred.py:181-184):
  * pool[I,J] = sum_{u,v<f} conv[f I+u, f J+v]; conv has row stride fW.  Used by the autograd binding of
  * NPredModel.forward; the fused step uses jd_poisson_forward_backward instead. */
@@ -115,13 +129,15 @@ int jd_gmm_prior_forward(const float* flux, int fH, int fW, const int32_t* shift
  * image Bt built once by jd_gmm_tc_pack from Lw (K x 64 x 64): per component 32 KB holding Lw_k^T
  * split into TF32 hi/lo halves in the 128B-swizzled K-major shared-memory layout the MMA reads.
  * upper_tri != 0 asserts that every Lw_k is upper triangular (true for precision Cholesky factors,
- * utils/numpy.py:16-34): the kernel then skips the structurally-zero part of the product. */
+ * utils/numpy.py:16-34): the kernel then skips the structurally-zero part of the product.
+ * zero_mean != 0 asserts mw == 0 (zero-mean mixtures such as zoran-weiss): the epilogue skips the
+ * mean subtraction. */
 size_t jd_gmm_tc_packed_bytes(int K);
 int jd_gmm_tc_pack(const float* Lw, int K, void* Bt, jd_stream_t stream);
 int jd_gmm_prior_forward_tc(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride,
                             int row_begin, int row_end, const void* Bt, const float* mw, const float* ck,
-                            int K, int upper_tri, int marginalize, float* value, int32_t* argmax,
-                            float* logp, double* sum, jd_stream_t stream);
+                            int K, int upper_tri, int zero_mean, int marginalize, float* value,
+                            int32_t* argmax, float* logp, double* sum, jd_stream_t stream);
 
 /* Per-patch gradient  G[p',:] = scale * sum_k R[p',k] (xc_p Lam_k - bk_k),  minus its row mean,
  * R = one-hot(argmax) or softmax_k(logp) (marginalize=1; needs logp and value from the forward);

@@ -27,6 +27,11 @@ PROTOTYPES = {
     "jd_conv_forward_direct": [c_f32p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_stream],
     "jd_conv_backward_direct": [c_f32p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_stream],
+    "jd_fftconv_sizes": [c_int, c_int, c_int, c_int, ctypes.c_void_p, ctypes.c_void_p],
+    "jd_fftconv_prepare_psf": [c_f32p, c_int, c_int, c_int, c_int, c_f32p, c_f32p, c_stream],
+    "jd_conv_forward_fft": [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_stream],
+    "jd_conv_backward_fft": [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                             c_int, c_stream],
     "jd_pool_sum": [c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_stream],
     "jd_adam_step_dev": [c_f32p, c_f32p, c_f32p, c_f32p, c_u8p, c_f32p, c_f32p, c_float, c_int, c_i64, c_f32p,
                          c_float, c_float, c_float, c_stream],
@@ -41,7 +46,7 @@ PROTOTYPES = {
     "jd_gmm_tc_packed_bytes": [c_int],
     "jd_gmm_tc_pack": [c_f32p, c_int, ctypes.c_void_p, c_stream],
     "jd_gmm_prior_forward_tc": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, ctypes.c_void_p, c_f32p, c_f32p,
-                                c_int, c_int, c_int, c_f32p, c_i32p, c_f32p, c_f64p, c_stream],
+                                c_int, c_int, c_int, c_int, c_f32p, c_i32p, c_f32p, c_f64p, c_stream],
     "jd_gmm_prior_backward": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, c_f32p, c_f32p, c_int, c_int,
                               c_i32p, c_f32p, c_f32p, c_float, c_f32p, c_stream],
     "jd_patch_fold": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, c_f32p, c_int, c_stream],

@@ -1,0 +1,318 @@
+// Shared-memory FFT convolution of the NPred forward model and its adjoint (large PSFs).
+//
+// Same result as utils/torch.py:347-370 (rfft2 * rfft2 -> irfft2 -> centred crop) and, for the adjoint, as its
+// autograd mirror, with three differences in how the work is organised:
+//   * the PSF spectrum is computed ONCE per dataset (jd_fftconv_prepare_psf); the reference recomputes it on
+//     every call;
+//   * any FFT size >= the linear-convolution support gives the same answer, so both axes are padded to the
+//     next power of two and a radix-2 Stockham autosort FFT runs entirely in shared memory;
+//   * three kernels instead of rfft2 / multiply / irfft2 / slice:
+//       rows   : [input transform] 2 real rows per complex FFT (even/odd split), half spectrum written
+//                transposed  specT[kx][row]
+//       cols   : per kx: column FFT . PSF^ (or conj PSF^ for the adjoint) . inverse column FFT fused, only the
+//                cropped rows are written back (in place)
+//       rows^-1: Hermitian rebuild, inverse FFT of 2 rows at a time, column crop and the output transform
+//                (x exposure, accumulate) fused.
+//   Crop / adjoint geometry: output index i reads circular index (i + off) mod S with off = +(k-1)/2 for the
+//   forward model and off = -(k-1)/2 with conj(PSF^) for the adjoint (correlation), which reproduces the
+//   asymmetric crop of even-sized PSFs exactly.
+#include "jd_common.cuh"
+
+namespace jd {
+namespace fft {
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
+// tw[j] = exp(-2 pi i j / N), j < N/2
+__device__ __forceinline__ void make_twiddles(float2* tw, int N) {
+  for (int j = threadIdx.x; j < N / 2; j += blockDim.x) {
+    float s, c;
+    sincospif(2.0f * (float)j / (float)N, &s, &c);
+    tw[j] = make_float2(c, -s);
+  }
+}
+
+// Radix-2 Stockham autosort FFT of length N = 2^logN in shared memory (ping-pong x <-> y).
+// INV conjugates the twiddles (no scaling).  Returns the buffer holding the result (natural order).
+// All threads of the block must call it; x must be fully written and synchronised by the caller.
+template <bool INV>
+__device__ __forceinline__ float2* fft_pow2(float2* x, float2* y, const float2* tw, int N, int logN) {
+  int n = N, ls = 0;  // s = 1 << ls
+  for (int stage = 0; stage < logN; ++stage) {
+    const int m = n >> 1, s = 1 << ls;
+    for (int t = threadIdx.x; t < N / 2; t += blockDim.x) {
+      const int q = t & (s - 1), p = t >> ls;
+      float2 w = tw[p << stage];  // exp(-2 pi i p / n), n = N >> stage
+      if (INV) w.y = -w.y;
+      const float2 a = x[q + s * p], b = x[q + s * (p + m)];
+      y[q + s * (2 * p)] = make_float2(a.x + b.x, a.y + b.y);
+      y[q + s * (2 * p + 1)] = cmul(make_float2(a.x - b.x, a.y - b.y), w);
+    }
+    __syncthreads();
+    float2* tmp = x;
+    x = y;
+    y = tmp;
+    n = m;
+    ++ls;
+  }
+  return x;
+}
+
+struct Plan {
+  int fH, fW, Sy, Sx, logSy, logSx, ld;  // ld = row stride (in complex) of specT: fH rounded up to 8
+};
+
+enum { IN_FLUX = 0, IN_DPOOL = 1, IN_PSF = 2 };
+
+// ---- pass 1: row FFTs.  CTA handles row pair (2 rows) per iteration, `pairs` pairs per CTA.
+template <int MODE>
+__global__ void rows_fwd_kernel(const float* __restrict__ in, const float* __restrict__ scale, Plan pl, int nrows,
+                                int ncols, int f, int H, int W, float2* __restrict__ specT, int pairs) {
+  extern __shared__ __align__(16) float2 sm[];
+  float2* bx = sm;
+  float2* by = sm + pl.Sx;
+  float2* tw = sm + 2 * pl.Sx;
+  make_twiddles(tw, pl.Sx);
+  for (int it = 0; it < pairs; ++it) {
+    const int ra = (blockIdx.x * pairs + it) * 2, rb = ra + 1;
+    if (ra >= nrows) break;
+    __syncthreads();
+    for (int j = threadIdx.x; j < pl.Sx; j += blockDim.x) {
+      float va = 0.f, vb = 0.f;
+      if (j < ncols) {
+        if (MODE == IN_FLUX) {
+          va = in[(int64_t)ra * ncols + j] * (scale ? scale[(int64_t)ra * ncols + j] : 1.f);
+          if (rb < nrows) vb = in[(int64_t)rb * ncols + j] * (scale ? scale[(int64_t)rb * ncols + j] : 1.f);
+        } else if (MODE == IN_DPOOL) {
+          int px = j / f;
+          if (px < W) {
+            if (ra / f < H) va = in[(int64_t)(ra / f) * W + px];
+            if (rb < nrows && rb / f < H) vb = in[(int64_t)(rb / f) * W + px];
+          }
+        } else {
+          va = in[(int64_t)ra * ncols + j];
+          if (rb < nrows) vb = in[(int64_t)rb * ncols + j];
+        }
+      }
+      bx[j] = make_float2(va, vb);
+    }
+    __syncthreads();
+    float2* z = fft_pow2<false>(bx, by, tw, pl.Sx, pl.logSx);
+    // split: A[k] = (Z[k] + conj Z[N-k]) / 2,  B[k] = (Z[k] - conj Z[N-k]) / (2i)
+    for (int k = threadIdx.x; k <= pl.Sx / 2; k += blockDim.x) {
+      const float2 zk = z[k], zn = z[(pl.Sx - k) & (pl.Sx - 1)];
+      const float2 A = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+      const float2 B = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
+      float2* dst = specT + (int64_t)k * pl.ld + ra;
+      dst[0] = A;
+      if (rb < nrows) dst[1] = B;
+    }
+  }
+}
+
+// ---- pass 2: per kx column FFT, spectrum product, inverse column FFT, cropped write-back (in place).
+// PSF_MODE: 0 = multiply by psf_hat, 1 = multiply by conj(psf_hat), 2 = no product (PSF spectrum setup: forward only)
+template <int PSF_MODE>
+__global__ void cols_kernel(float2* __restrict__ specT, const float2* __restrict__ psf_hat, Plan pl, int nrows_in,
+                            int nrows_out, int off, float norm, float2* __restrict__ psf_out) {
+  extern __shared__ __align__(16) float2 sm[];
+  float2* bx = sm;
+  float2* by = sm + pl.Sy;
+  float2* tw = sm + 2 * pl.Sy;
+  make_twiddles(tw, pl.Sy);
+  const int k = blockIdx.x;
+  float2* col = specT + (int64_t)k * pl.ld;
+  for (int r = threadIdx.x; r < pl.Sy; r += blockDim.x) bx[r] = r < nrows_in ? col[r] : make_float2(0.f, 0.f);
+  __syncthreads();
+  float2* z = fft_pow2<false>(bx, by, tw, pl.Sy, pl.logSy);
+  if (PSF_MODE == 2) {
+    float2* dst = psf_out + (int64_t)k * pl.Sy;
+    for (int r = threadIdx.x; r < pl.Sy; r += blockDim.x) dst[r] = z[r];
+    return;
+  }
+  const float2* ph = psf_hat + (int64_t)k * pl.Sy;
+  for (int r = threadIdx.x; r < pl.Sy; r += blockDim.x) {
+    float2 p = ph[r];
+    if (PSF_MODE == 1) p.y = -p.y;
+    const float2 v = cmul(z[r], p);
+    z[r] = make_float2(v.x * norm, v.y * norm);
+  }
+  __syncthreads();
+  float2* other = z == bx ? by : bx;
+  float2* w = fft_pow2<true>(z, other, tw, pl.Sy, pl.logSy);
+  for (int i = threadIdx.x; i < nrows_out; i += blockDim.x) col[i] = w[(i + off) & (pl.Sy - 1)];
+}
+
+// ---- pass 3: inverse row FFTs of row pairs, column crop, output transform.
+// OUT_MODE 0: out = value;  1: out (+)= value * scale
+template <int OUT_MODE>
+__global__ void rows_inv_kernel(const float2* __restrict__ specT, Plan pl, int nrows, int ncols, int off,
+                                const float* __restrict__ scale, float* __restrict__ out, int accumulate, int pairs) {
+  extern __shared__ __align__(16) float2 sm[];
+  float2* bx = sm;
+  float2* by = sm + pl.Sx;
+  float2* tw = sm + 2 * pl.Sx;
+  make_twiddles(tw, pl.Sx);
+  for (int it = 0; it < pairs; ++it) {
+    const int ra = (blockIdx.x * pairs + it) * 2, rb = ra + 1;
+    if (ra >= nrows) break;
+    __syncthreads();
+    // Z[k] = A[k] + i B[k];  Z[N-k] = conj(A[k]) + i conj(B[k])
+    for (int k = threadIdx.x; k <= pl.Sx / 2; k += blockDim.x) {
+      const float2* src = specT + (int64_t)k * pl.ld + ra;
+      const float2 A = src[0];
+      const float2 B = rb < nrows ? src[1] : make_float2(0.f, 0.f);
+      bx[k] = make_float2(A.x - B.y, A.y + B.x);
+      if (k > 0 && k < pl.Sx / 2) bx[pl.Sx - k] = make_float2(A.x + B.y, B.x - A.y);
+    }
+    __syncthreads();
+    float2* z = fft_pow2<true>(bx, by, tw, pl.Sx, pl.logSx);
+    for (int j = threadIdx.x; j < ncols; j += blockDim.x) {
+      const float2 v = z[(j + off) & (pl.Sx - 1)];
+      int64_t oa = (int64_t)ra * ncols + j, ob = (int64_t)rb * ncols + j;
+      if (OUT_MODE == 0) {
+        out[oa] = v.x;
+        if (rb < nrows) out[ob] = v.y;
+      } else {
+        float xa = v.x * (scale ? scale[oa] : 1.f);
+        out[oa] = accumulate ? out[oa] + xa : xa;
+        if (rb < nrows) {
+          float xb = v.y * (scale ? scale[ob] : 1.f);
+          out[ob] = accumulate ? out[ob] + xb : xb;
+        }
+      }
+    }
+    // bx/by are rewritten at the top of the next iteration after a barrier
+  }
+}
+
+static int next_pow2(int v, int* lg) {
+  int p = 1, l = 0;
+  while (p < v) {
+    p <<= 1;
+    ++l;
+  }
+  *lg = l;
+  return p;
+}
+
+static int make_plan(const char* name, int fH, int fW, int kh, int kw, Plan* pl) {
+  JD_CHECK_ARG(fH > 0 && fW > 0 && kh > 0 && kw > 0, "%s: bad shape", name);
+  pl->fH = fH;
+  pl->fW = fW;
+  pl->Sy = next_pow2(fH + kh - 1, &pl->logSy);
+  pl->Sx = next_pow2(fW + kw - 1, &pl->logSx);
+  if (pl->Sx < 2) pl->Sx = 2, pl->logSx = 1;
+  if (pl->Sy < 2) pl->Sy = 2, pl->logSy = 1;
+  JD_CHECK_ARG(pl->Sy <= 8192 && pl->Sx <= 8192, "%s: padded FFT size %dx%d exceeds 8192", name, pl->Sy, pl->Sx);
+  pl->ld = (fH + 7) & ~7;
+  return JD_OK;
+}
+
+static size_t smem_for(int S) { return (size_t)(2 * S + S / 2) * sizeof(float2); }
+static int threads_for(int S) {
+  int t = S / 4;
+  return t < 64 ? 64 : (t > 512 ? 512 : t);
+}
+
+template <typename Kern>
+static void opt_in_smem(Kern kern, size_t bytes) {
+  if (bytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
+}  // namespace fft
+}  // namespace jd
+
+using namespace jd;
+using namespace jd::fft;
+
+extern "C" {
+
+int jd_fftconv_sizes(int fH, int fW, int kh, int kw, int64_t* psf_hat_elems, int64_t* workspace_elems) {
+  Plan pl;
+  int rc = make_plan("jd_fftconv_sizes", fH, fW, kh, kw, &pl);
+  if (rc) return rc;
+  if (psf_hat_elems) *psf_hat_elems = (int64_t)(pl.Sx / 2 + 1) * pl.Sy * 2;      // floats
+  if (workspace_elems) *workspace_elems = (int64_t)(pl.Sx / 2 + 1) * pl.ld * 2;  // floats
+  return JD_OK;
+}
+
+int jd_fftconv_prepare_psf(const float* psf, int kh, int kw, int fH, int fW, float* psf_hat, float* workspace,
+                           jd_stream_t stream) {
+  JD_CHECK_ARG(psf && psf_hat && workspace, "jd_fftconv_prepare_psf: null pointer");
+  Plan pl;
+  int rc = make_plan("jd_fftconv_prepare_psf", fH, fW, kh, kw, &pl);
+  if (rc) return rc;
+  JD_CHECK_ARG(kh <= pl.ld, "jd_fftconv_prepare_psf: PSF taller than the image is not supported (kh=%d, fH=%d)", kh, fH);
+  cudaStream_t st = to_stream(stream);
+  const int pairs = 1;
+  size_t smx = smem_for(pl.Sx), smy = smem_for(pl.Sy);
+  opt_in_smem(rows_fwd_kernel<IN_PSF>, smx);
+  opt_in_smem(cols_kernel<2>, smy);
+  rows_fwd_kernel<IN_PSF><<<(kh + 2 * pairs - 1) / (2 * pairs), threads_for(pl.Sx), smx, st>>>(
+      psf, nullptr, pl, kh, kw, 1, kh, kw, reinterpret_cast<float2*>(workspace), pairs);
+  JD_CHECK_LAUNCH("jd_fftconv_prepare_psf(rows)");
+  cols_kernel<2><<<pl.Sx / 2 + 1, threads_for(pl.Sy), smy, st>>>(reinterpret_cast<float2*>(workspace), nullptr, pl, kh, 0,
+                                                                 0, 1.f, reinterpret_cast<float2*>(psf_hat));
+  JD_CHECK_LAUNCH("jd_fftconv_prepare_psf(cols)");
+  return JD_OK;
+}
+
+static int run_fftconv(const char* name, int mode, const float* in, const float* exposure, const float* psf_hat,
+                       float* workspace, float* out, int accumulate, int fH, int fW, int kh, int kw, int f, int H, int W,
+                       cudaStream_t st) {
+  Plan pl;
+  int rc = make_plan(name, fH, fW, kh, kw, &pl);
+  if (rc) return rc;
+  const int sy = (kh - 1) / 2, sx = (kw - 1) / 2;
+  const float norm = 1.0f / ((float)pl.Sy * (float)pl.Sx);
+  size_t smx = smem_for(pl.Sx), smy = smem_for(pl.Sy);
+  JD_CHECK_ARG(smx <= 200 * 1024 && smy <= 200 * 1024, "%s: FFT size too large for shared memory", name);
+  const int pairs = 2;
+  const int grid_rows = (fH + 2 * pairs - 1) / (2 * pairs);
+  float2* spec = reinterpret_cast<float2*>(workspace);
+  const float2* ph = reinterpret_cast<const float2*>(psf_hat);
+  if (mode == 0) {
+    opt_in_smem(rows_fwd_kernel<IN_FLUX>, smx);
+    opt_in_smem(cols_kernel<0>, smy);
+    opt_in_smem(rows_inv_kernel<0>, smx);
+    rows_fwd_kernel<IN_FLUX><<<grid_rows, threads_for(pl.Sx), smx, st>>>(in, exposure, pl, fH, fW, 1, fH, fW, spec, pairs);
+    JD_CHECK_LAUNCH(name);
+    cols_kernel<0><<<pl.Sx / 2 + 1, threads_for(pl.Sy), smy, st>>>(spec, ph, pl, fH, fH, sy, norm, nullptr);
+    JD_CHECK_LAUNCH(name);
+    rows_inv_kernel<0><<<grid_rows, threads_for(pl.Sx), smx, st>>>(spec, pl, fH, fW, sx, nullptr, out, 0, pairs);
+    JD_CHECK_LAUNCH(name);
+  } else {
+    opt_in_smem(rows_fwd_kernel<IN_DPOOL>, smx);
+    opt_in_smem(cols_kernel<1>, smy);
+    opt_in_smem(rows_inv_kernel<1>, smx);
+    rows_fwd_kernel<IN_DPOOL><<<grid_rows, threads_for(pl.Sx), smx, st>>>(in, nullptr, pl, fH, fW, f, H, W, spec, pairs);
+    JD_CHECK_LAUNCH(name);
+    cols_kernel<1><<<pl.Sx / 2 + 1, threads_for(pl.Sy), smy, st>>>(spec, ph, pl, fH, fH, pl.Sy - sy, norm, nullptr);
+    JD_CHECK_LAUNCH(name);
+    rows_inv_kernel<1><<<grid_rows, threads_for(pl.Sx), smx, st>>>(spec, pl, fH, fW, pl.Sx - sx, exposure, out,
+                                                                    accumulate, pairs);
+    JD_CHECK_LAUNCH(name);
+  }
+  return JD_OK;
+}
+
+int jd_conv_forward_fft(const float* flux, const float* exposure, const float* psf_hat, float* workspace, float* conv,
+                        int fH, int fW, int kh, int kw, jd_stream_t stream) {
+  JD_CHECK_ARG(flux && psf_hat && workspace && conv, "jd_conv_forward_fft: null pointer");
+  return run_fftconv("jd_conv_forward_fft", 0, flux, exposure, psf_hat, workspace, conv, 0, fH, fW, kh, kw, 1, fH, fW,
+                     to_stream(stream));
+}
+
+int jd_conv_backward_fft(const float* dpool, const float* exposure, const float* psf_hat, float* workspace,
+                         float* dflux, int accumulate, int fH, int fW, int kh, int kw, int f, int H, int W,
+                         jd_stream_t stream) {
+  JD_CHECK_ARG(dpool && psf_hat && workspace && dflux, "jd_conv_backward_fft: null pointer");
+  JD_CHECK_ARG(f >= 1 && H * f <= fH && W * f <= fW, "jd_conv_backward_fft: bad shape");
+  return run_fftconv("jd_conv_backward_fft", 1, dpool, exposure, psf_hat, workspace, dflux, accumulate, fH, fW, kh, kw, f,
+                     H, W, to_stream(stream));
+}
+
+}  // extern "C"

@@ -41,9 +41,9 @@ constexpr int A_COLS = 128;             // TMEM columns [0,64) = A hi, [64,128) 
 constexpr int TMEM_COLS = 512;          // A_COLS + NSLOT * SLOT_COLS
 constexpr int KBLOCK_BYTES_B = 64 * 128;      // 64 rows x 128 B = 8 KB
 constexpr int B_BYTES = 4 * KBLOCK_BYTES_B;   // hi(kb0,kb1) lo(kb0,kb1) = 32 KB per component
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;           // producer, MMA, 2 x 4 epilogue warps
 constexpr int MW_BYTES = 64 * 4;        // mw_k staged per accumulator slot
-constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + NSTAGE * B_BYTES + NSLOT * MW_BYTES + 1024 /*barriers etc.*/;
+constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + NSTAGE * B_BYTES + NSLOT * MW_BYTES + 4096 /*barriers etc.*/;
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -200,7 +200,7 @@ __global__ void pack_b_kernel(const float* __restrict__ Lw, int K, uint8_t* __re
 }
 
 // ---------------------------------------------------------------- the forward kernel
-template <bool TRI>
+template <bool TRI, bool ZERO_MEAN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restrict__ shift_yx,
                   const uint8_t* __restrict__ Bt, const float* __restrict__ mw, const float* __restrict__ ck, int K,
@@ -215,6 +215,9 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 3 * NSLOT);
   int* s_valid = reinterpret_cast<int*>(s_tmem + 4);       // 128 ints
   double* s_red = reinterpret_cast<double*>(s_valid + TM);  // 4 doubles
+  float* s_mm = reinterpret_cast<float*>(s_red + 4);        // merge buffers of epilogue group B: max,
+  float* s_ms = s_mm + TM;                                  //   sum-exp,
+  int* s_mk = reinterpret_cast<int*>(s_ms + TM);            //   argmax
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
@@ -260,22 +263,25 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
 
   if (warp == 0) {
     // ===================== bulk-TMA producer (whole warp waits, one elected lane issues) ==========
+    int kc = k0;  // component handled at position k
     for (int k = 0; k < K; ++k) {
       const int s = k % NSTAGE, t = k % NSLOT;
-      const int kc = (k + k0) % K;  // component handled at position k
       mbar_wait(empty_bar(s), ((k / NSTAGE) & 1) ^ 1);
       // mw_k rides with accumulator slot t: free once the epilogue of component k - NSLOT is done
-      mbar_wait(tempty_bar(t), ((k / NSLOT) & 1) ^ 1);
+      if (!ZERO_MEAN) mbar_wait(tempty_bar(t), ((k / NSLOT) & 1) ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(full_bar(s), B_BYTES);
         bulk_g2s(smem_u32(sB + s * B_BYTES), Bt + (size_t)kc * B_BYTES, B_BYTES, full_bar(s));
-        mbar_arrive_expect_tx(mwfull_bar(t), MW_BYTES);
-        bulk_g2s(smem_u32(sMW + t * 64), mw + (size_t)kc * 64, MW_BYTES, mwfull_bar(t));
+        if (!ZERO_MEAN) {
+          mbar_arrive_expect_tx(mwfull_bar(t), MW_BYTES);
+          bulk_g2s(smem_u32(sMW + t * 64), mw + (size_t)kc * 64, MW_BYTES, mwfull_bar(t));
+        }
       }
       __syncwarp();
+      kc = kc + 1 == K ? 0 : kc + 1;
     }
-  } else if (warp >= 2) {
-    // ---- gather: thread = patch row; 64 loads, mean, hi/lo split, tcgen05.st into TMEM lane `row`
+  } else if (warp >= 2 && warp < 6) {
+    // ---- gather (epilogue group A): thread = patch row; 64 loads, mean, hi/lo split, tcgen05.st into TMEM lane `row`
     float vals[64];
     float s = 0.f;
     bool ok = p < g.P;
@@ -355,15 +361,16 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
       __syncwarp();
     }
   } else if (warp >= 2) {
-    // ===================== epilogue =====================
+    // ===================== epilogue: group A (warps 2-5) takes even positions, group B odd =========
+    const int grp = warp >= 6 ? 1 : 0;
     float run_m = -CUDART_INF_F, run_s = 0.f;
-    int run_k = 0;
-    for (int k = 0; k < K; ++k) {
+    int run_k = 0x7fffffff;
+    int kc = k0 + grp;
+    kc = kc >= K ? kc - K : kc;
+    for (int k = grp; k < K; k += 2) {
       const int t = k % NSLOT;
-      const int kc = (k + k0) % K;
-      const float4* mwk = reinterpret_cast<const float4*>(sMW + t * 64);
       const float c_k = __ldg(ck + kc);
-      mbar_wait(mwfull_bar(t), (k / NSLOT) & 1);
+      if (!ZERO_MEAN) mbar_wait(mwfull_bar(t), (k / NSLOT) & 1);
       mbar_wait(tfull_bar(t), (k / NSLOT) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + A_COLS + t * SLOT_COLS;
@@ -371,26 +378,37 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
       tmem_ld32(taddr, y0);
       tmem_ld32(taddr + 32, y1);
       tmem_ld_wait();
-      float qa = 0.f, qb = 0.f;
+      float qa = 0.f, qb = 0.f, qc = 0.f, qd = 0.f;
+      if (ZERO_MEAN) {
 #pragma unroll
-      for (int c4 = 0; c4 < 8; ++c4) {
-        float4 b0 = mwk[c4], b1 = mwk[8 + c4];
-        float d0 = y0[4 * c4] - b0.x, d1 = y0[4 * c4 + 1] - b0.y, d2 = y0[4 * c4 + 2] - b0.z, d3 = y0[4 * c4 + 3] - b0.w;
-        float e0 = y1[4 * c4] - b1.x, e1 = y1[4 * c4 + 1] - b1.y, e2 = y1[4 * c4 + 2] - b1.z, e3 = y1[4 * c4 + 3] - b1.w;
-        qa = fmaf(d0, d0, qa);
-        qb = fmaf(e0, e0, qb);
-        qa = fmaf(d1, d1, qa);
-        qb = fmaf(e1, e1, qb);
-        qa = fmaf(d2, d2, qa);
-        qb = fmaf(e2, e2, qb);
-        qa = fmaf(d3, d3, qa);
-        qb = fmaf(e3, e3, qb);
+        for (int i = 0; i < 32; i += 2) {
+          qa = fmaf(y0[i], y0[i], qa);
+          qb = fmaf(y1[i], y1[i], qb);
+          qc = fmaf(y0[i + 1], y0[i + 1], qc);
+          qd = fmaf(y1[i + 1], y1[i + 1], qd);
+        }
+      } else {
+        const float4* mwk = reinterpret_cast<const float4*>(sMW + t * 64);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          float4 b0 = mwk[c4], b1 = mwk[8 + c4];
+          float d0 = y0[4 * c4] - b0.x, d1 = y0[4 * c4 + 1] - b0.y, d2 = y0[4 * c4 + 2] - b0.z, d3 = y0[4 * c4 + 3] - b0.w;
+          float e0 = y1[4 * c4] - b1.x, e1 = y1[4 * c4 + 1] - b1.y, e2 = y1[4 * c4 + 2] - b1.z, e3 = y1[4 * c4 + 3] - b1.w;
+          qa = fmaf(d0, d0, qa);
+          qb = fmaf(e0, e0, qb);
+          qc = fmaf(d1, d1, qc);
+          qd = fmaf(e1, e1, qd);
+          qa = fmaf(d2, d2, qa);
+          qb = fmaf(e2, e2, qb);
+          qc = fmaf(d3, d3, qc);
+          qd = fmaf(e3, e3, qd);
+        }
       }
       // accumulator slot and mw row are free once both are consumed
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(t));
-      const float lp = fmaf(-0.5f, qa + qb, c_k);
+      const float lp = fmaf(-0.5f, (qa + qb) + (qc + qd), c_k);
       if (logp && p < g.P) logp[p * K + kc] = lp;
       if (marginalize) {
         if (lp > run_m) {
@@ -404,18 +422,40 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
         run_m = lp;
         run_k = kc;
       }
+      kc += 2;
+      kc = kc >= K ? kc - K : kc;
     }
-    double part = 0.0;
-    if (p < g.P) {
-      const bool ok = s_valid[row] != 0;
-      float v = marginalize ? run_m + logf(run_s) : run_m;
-      v = ok ? v : 0.f;
-      if (value) value[p] = v;
-      if (argmax) argmax[p] = ok ? run_k : -1;
-      part = (double)v;
+    // merge group B into group A (named barrier 2 over the 256 epilogue threads)
+    if (grp == 1) {
+      s_mm[row] = run_m;
+      s_ms[row] = run_s;
+      s_mk[row] = run_k;
+      asm volatile("bar.arrive 2, 256;" ::: "memory");
+    } else {
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      const float om = s_mm[row], os = s_ms[row];
+      const int ok_ = s_mk[row];
+      if (marginalize) {
+        const float m = fmaxf(run_m, om);
+        run_s = run_s * expf(run_m - m) + (om == -CUDART_INF_F ? 0.f : os * expf(om - m));
+        run_k = om > run_m ? ok_ : run_k;
+        run_m = m;
+      } else if (om > run_m || (om == run_m && ok_ < run_k)) {
+        run_m = om;
+        run_k = ok_;
+      }
+      double part = 0.0;
+      if (p < g.P) {
+        const bool ok = s_valid[row] != 0;
+        float v = marginalize ? run_m + logf(run_s) : run_m;
+        v = ok ? v : 0.f;
+        if (value) value[p] = v;
+        if (argmax) argmax[p] = ok ? run_k : -1;
+        part = (double)v;
+      }
+      part = warp_sum(part);
+      if (lane == 0) s_red[q] = part;
     }
-    part = warp_sum(part);
-    if (lane == 0) s_red[q] = part;
   }
 
   tc_fence_before();
@@ -446,7 +486,7 @@ int jd_gmm_tc_pack(const float* Lw, int K, void* Bt, jd_stream_t stream) {
 
 int jd_gmm_prior_forward_tc(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
                             int row_end, const void* Bt, const float* mw, const float* ck, int K, int upper_tri,
-                            int marginalize, float* value, int32_t* argmax, float* logp, double* sum,
+                            int zero_mean, int marginalize, float* value, int32_t* argmax, float* logp, double* sum,
                             jd_stream_t stream) {
   JD_CHECK_ARG(flux && Bt && mw && ck && K > 0, "jd_gmm_prior_forward_tc: null pointer");
   JD_CHECK_ARG(fH >= PATCH && fW >= PATCH && stride >= 1 && stride <= PATCH, "jd_gmm_prior_forward_tc: bad geometry");
@@ -458,11 +498,11 @@ int jd_gmm_prior_forward_tc(const float* flux, int fH, int fW, const int32_t* sh
   tc::Geom g{fH, fW, 0, 0, stride, nx, row_begin, (row_end - row_begin) * nx};
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc::gmm_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)tc::SMEM_BYTES);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tc::gmm_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)tc::SMEM_BYTES);
+    cudaError_t e = cudaSuccess;
+    const void* kerns[4] = {(const void*)tc::gmm_fwd_tc_kernel<false, false>, (const void*)tc::gmm_fwd_tc_kernel<false, true>,
+                            (const void*)tc::gmm_fwd_tc_kernel<true, false>, (const void*)tc::gmm_fwd_tc_kernel<true, true>};
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i)
+      e = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("jd_gmm_prior_forward_tc: cannot reserve %zu B of shared memory: %s", tc::SMEM_BYTES,
                 cudaGetErrorString(e));
@@ -471,7 +511,8 @@ int jd_gmm_prior_forward_tc(const float* flux, int fH, int fW, const int32_t* sh
     attr_set = true;
   }
   int grid = (g.P + tc::TM - 1) / tc::TM;
-  auto kern = upper_tri ? tc::gmm_fwd_tc_kernel<true> : tc::gmm_fwd_tc_kernel<false>;
+  auto kern = upper_tri ? (zero_mean ? tc::gmm_fwd_tc_kernel<true, true> : tc::gmm_fwd_tc_kernel<true, false>)
+                        : (zero_mean ? tc::gmm_fwd_tc_kernel<false, true> : tc::gmm_fwd_tc_kernel<false, false>);
   kern<<<grid, tc::NTHREADS, tc::SMEM_BYTES, to_stream(stream)>>>(
       flux, g, shift_yx, reinterpret_cast<const uint8_t*>(Bt), mw, ck, K, marginalize, value, argmax, logp, sum);
   JD_CHECK_LAUNCH("jd_gmm_prior_forward_tc");

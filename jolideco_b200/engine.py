@@ -50,6 +50,8 @@ class DatasetBuffers:
         self.kh, self.kw = int(psf.shape[-2]), int(psf.shape[-1])
         for t in (counts, exposure, psf, background):
             ops._check(t, "dataset buffer")
+        # large PSFs: cached PSF spectrum + scratch for the shared-memory FFT path
+        self.fft = ops.FFTConvPlan(psf, self.fH, self.fW) if self.kh * self.kw >= ops.FFT_MIN_PSF_AREA else None
 
 
 class MapEngine:
@@ -140,10 +142,18 @@ class MapEngine:
 
     def _likelihood(self, d, loss_acc, want_grad, accumulate=False):
         s = self._s()
-        _call("jd_conv_forward_direct", _p(self.flux), _p(d.exposure), _p(d.psf), _p(self.conv), d.fH, d.fW, d.kh, d.kw, s)
+        if d.fft is not None:
+            _call("jd_conv_forward_fft", _p(self.flux), _p(d.exposure), _p(d.fft.psf_hat), _p(d.fft.workspace),
+                  _p(self.conv), d.fH, d.fW, d.kh, d.kw, s)
+        else:
+            _call("jd_conv_forward_direct", _p(self.flux), _p(d.exposure), _p(d.psf), _p(self.conv), d.fH, d.fW, d.kh,
+                  d.kw, s)
         _call("jd_poisson_forward_backward", _p(self.conv), _p(d.background), _p(d.bkg_log_norm), _p(d.counts), None,
               _p(self.dpool) if want_grad else None, loss_acc, None, d.H, d.W, d.f, d.fW, 1e-25, 1.0 / (d.H * d.W), s)
-        if want_grad:
+        if want_grad and d.fft is not None:
+            _call("jd_conv_backward_fft", _p(self.dpool), _p(d.exposure), _p(d.fft.psf_hat), _p(d.fft.workspace),
+                  _p(self.dflux_l), int(accumulate), d.fH, d.fW, d.kh, d.kw, d.f, d.H, d.W, s)
+        elif want_grad:
             _call("jd_conv_backward_direct", _p(self.dpool), _p(d.exposure), _p(d.psf), _p(self.dflux_l),
                   int(accumulate), d.fH, d.fW, d.kh, d.kw, d.f, d.H, d.W, s)
 
@@ -153,7 +163,7 @@ class MapEngine:
         if self.backend == 1:
             _call("jd_gmm_prior_forward_tc", _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride,
                   self.rows[0], self.rows[1], _p(self.packed.Bt), _p(self.packed.mw), _p(self.packed.ck), self.packed.K,
-                  int(self.packed.upper_tri), int(self.marginalize), _p(self.value), _p(self.argmax), _p(self.logp),
+                  int(self.packed.upper_tri), int(self.packed.zero_mean), int(self.marginalize), _p(self.value), _p(self.argmax), _p(self.logp),
                   sum_acc, self._s())
             return
         _call("jd_gmm_prior_forward", _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride, self.rows[0],

@@ -64,6 +64,47 @@ def conv_forward(flux, exposure, psf, out=None):
     return out
 
 
+FFT_MIN_PSF_AREA = 24 * 24  # PSFs at least this large take the shared-memory FFT path
+
+
+class FFTConvPlan:
+    """Cached PSF spectrum + scratch workspace of one dataset for the FFT convolution path."""
+
+    def __init__(self, psf, fH, fW):
+        import ctypes
+
+        _check(psf, "psf")
+        self.kh, self.kw = _hw(psf)
+        self.fH, self.fW = int(fH), int(fW)
+        n_hat, n_ws = ctypes.c_int64(0), ctypes.c_int64(0)
+        _lib.call("jd_fftconv_sizes", self.fH, self.fW, self.kh, self.kw, ctypes.addressof(n_hat), ctypes.addressof(n_ws))
+        self.psf_hat = torch.empty(n_hat.value, dtype=torch.float32, device=psf.device)
+        self.workspace = torch.empty(n_ws.value, dtype=torch.float32, device=psf.device)
+        with torch.cuda.device(psf.device):
+            _lib.call("jd_fftconv_prepare_psf", _ptr(psf), self.kh, self.kw, self.fH, self.fW, _ptr(self.psf_hat),
+                      _ptr(self.workspace), _stream())
+
+
+def conv_forward_fft(flux, exposure, plan, out=None):
+    _check(flux, "flux"), _check(exposure, "exposure")
+    out = torch.empty_like(flux) if out is None else _check(out, "out")
+    _lib.call("jd_conv_forward_fft", _ptr(flux), _ptr(exposure), _ptr(plan.psf_hat), _ptr(plan.workspace), _ptr(out),
+              plan.fH, plan.fW, plan.kh, plan.kw, _stream())
+    return out
+
+
+def conv_backward_fft(dpool, exposure, plan, f, out=None, accumulate=False):
+    _check(dpool, "dpool"), _check(exposure, "exposure")
+    H, W = _hw(dpool)
+    if out is None:
+        out = torch.empty_like(exposure)
+        accumulate = False
+    _check(out, "out")
+    _lib.call("jd_conv_backward_fft", _ptr(dpool), _ptr(exposure), _ptr(plan.psf_hat), _ptr(plan.workspace), _ptr(out),
+              int(accumulate), plan.fH, plan.fW, plan.kh, plan.kw, int(f), H, W, _stream())
+    return out
+
+
 def conv_backward(dpool, exposure, psf, f, out=None, accumulate=False):
     _check(dpool, "dpool"), _check(exposure, "exposure"), _check(psf, "psf")
     H, W = _hw(dpool)
@@ -143,6 +184,7 @@ class GMMPacked:
         self.device = torch.device(device)
         self._Bt = None
         self.upper_tri = bool(np.all(np.tril(L, -1) == 0))
+        self.zero_mean = bool(np.all(mw == 0))
 
     @property
     def Bt(self):
@@ -210,7 +252,7 @@ def gmm_prior_forward(flux, shift_yx, packed, stride=4, marginalize=False, rows=
         sum_out = torch.zeros(1, dtype=torch.float64, device=flux.device)
     if int(backend) == 1:
         _lib.call("jd_gmm_prior_forward_tc", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(packed.Bt),
-                  _ptr(packed.mw), _ptr(packed.ck), packed.K, int(packed.upper_tri), int(bool(marginalize)), _ptr(value),
+                  _ptr(packed.mw), _ptr(packed.ck), packed.K, int(packed.upper_tri), int(packed.zero_mean), int(bool(marginalize)), _ptr(value),
                   _ptr(argmax), _ptr(logp), _ptr(sum_out), _stream())
     else:
         _lib.call("jd_gmm_prior_forward", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(packed.Lw),

@@ -27,7 +27,7 @@ def synthetic_gmm(K, seed=0, mean_scale=0.01):
     rng = np.random.default_rng(seed)
     A = rng.normal(0, 0.05, size=(K, 64, 64))
     cov = A @ A.transpose(0, 2, 1) + 0.01 * np.eye(64)
-    means = rng.normal(0, mean_scale, size=(K, 64))
+    means = rng.normal(0, mean_scale, size=(K, 64)) if mean_scale else np.zeros((K, 64))
     w = rng.uniform(0.5, 1.5, size=K)
     return means, cov, w / w.sum()
 
@@ -65,6 +65,41 @@ def test_conv_forward_and_adjoint(shape, kshape):
     ref_b = O.correlate_adjoint(d, psf) * E
     out_b = ops.conv_backward(t(d), t(E), t(psf), 1).cpu().numpy()
     assert rel_max(out_b, ref_b) < 5e-6
+
+
+@pytest.mark.parametrize("shape,kshape", [((37, 45), (5, 4)), ((64, 64), (17, 17)), ((130, 70), (34, 34)),
+                                          ((96, 96), (64, 64)), ((50, 40), (41, 67)), ((256, 256), (201, 201)),
+                                          ((512, 512), (34, 34))])
+def test_fft_conv_forward_and_adjoint(shape, kshape):
+    """Shared-memory FFT path against the oracle (and hence against the direct path)."""
+    rng = np.random.default_rng(11)
+    flux = rng.gamma(2.0, size=shape) * np.exp(rng.normal(0, 1, size=shape))
+    E = rng.uniform(0.5, 1.5, size=shape)
+    psf = rng.uniform(size=kshape) * np.outer(np.hanning(kshape[0] + 2)[1:-1], np.hanning(kshape[1] + 2)[1:-1])
+    psf /= psf.sum()
+    plan = ops.FFTConvPlan(t(psf), *shape)
+    ref = O.convolve_fft(flux * E, psf)
+    out = ops.conv_forward_fft(t(flux), t(E), plan).cpu().numpy()
+    assert rel_max(out, ref) < 5e-6
+    d = rng.normal(size=shape)
+    ref_b = O.correlate_adjoint(d, psf) * E
+    out_b = ops.conv_backward_fft(t(d), t(E), plan, 1).cpu().numpy()
+    assert rel_max(out_b, ref_b) < 5e-6
+    acc = t(np.ones(shape))
+    ops.conv_backward_fft(t(d), t(E), plan, 1, out=acc, accumulate=True)
+    assert rel_max(acc.cpu().numpy(), ref_b + 1) < 5e-6
+
+
+def test_fft_conv_backward_upsampled():
+    rng = np.random.default_rng(12)
+    H, W, f = 21, 17, 2
+    psf = rng.uniform(size=(6, 6))
+    E = rng.uniform(0.5, 1.5, size=(H * f, W * f))
+    dn = rng.normal(size=(H, W))
+    ref = O.npred_backward(dn, np.ones((H, W)), np.ones((H * f, W * f)), E, psf, f)
+    plan = ops.FFTConvPlan(t(psf), H * f, W * f)
+    out = ops.conv_backward_fft(t(dn), t(E), plan, f).cpu().numpy()
+    assert rel_max(out, ref) < 5e-6
 
 
 def test_conv_golden_even_kernel():
@@ -214,14 +249,16 @@ def test_gmm_prior_row_blocks_sum_to_whole():
     assert rel_max(sum(p[1] for p in parts), gr) < 1e-6
 
 
+@pytest.mark.parametrize("mean_scale", [0.05, 0.0])
 @pytest.mark.parametrize("marginalize", [False, True])
-def test_gmm_prior_tensor_core_vs_cuda_core_full_size(marginalize):
+def test_gmm_prior_tensor_core_vs_cuda_core_full_size(marginalize, mean_scale):
     """tcgen05 split-TF32 forward against the FP32 CUDA-core forward at the BASELINE config-2 size
     (512x512 flux, 16129 patches), K=32 with non-zero means: per-patch values to FP32 accuracy,
     identical argmax except near-ties."""
     rng = np.random.default_rng(9)
     flux = t(rng.gamma(2.0, size=(512, 512)) * np.exp(rng.normal(0, 1.0, size=(512, 512))))
-    packed = pack(O.GMM(*synthetic_gmm(32, seed=5, mean_scale=0.05)))
+    packed = pack(O.GMM(*synthetic_gmm(33, seed=5, mean_scale=mean_scale)))
+    assert packed.zero_mean == (mean_scale == 0.0) and packed.upper_tri
     v0, k0, lp0, s0 = ops.gmm_prior_forward(flux, (1, -2), packed, 4, marginalize, want_logp=True, backend=0)
     v1, k1, lp1, s1 = ops.gmm_prior_forward(flux, (1, -2), packed, 4, marginalize, want_logp=True, backend=1)
     lp0, lp1 = lp0.cpu().numpy().astype(np.float64), lp1.cpu().numpy().astype(np.float64)
