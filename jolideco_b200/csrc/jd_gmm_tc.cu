@@ -22,6 +22,7 @@
 //               the SM; only value/argmax (and optionally logp) are written.
 #include <cuda_runtime.h>
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "jd_common.cuh"
 
@@ -41,6 +42,7 @@ constexpr int A_COLS = 128;             // TMEM columns [0,64) = A hi, [64,128) 
 constexpr int TMEM_COLS = 512;          // A_COLS + NSLOT * SLOT_COLS
 constexpr int KBLOCK_BYTES_B = 64 * 128;      // 64 rows x 128 B = 8 KB
 constexpr int B_BYTES = 4 * KBLOCK_BYTES_B;   // hi(kb0,kb1) lo(kb0,kb1) = 32 KB per component
+constexpr int CLUSTER = 2;              // CTA pair: each CTA fetches half of every B image and multicasts it
 constexpr int NTHREADS = 320;           // producer, MMA, 2 x 4 epilogue warps
 constexpr int MW_BYTES = 64 * 4;        // mw_k staged per accumulator slot
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + NSTAGE * B_BYTES + NSLOT * MW_BYTES + 4096 /*barriers etc.*/;
@@ -77,6 +79,27 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+// multicast variant: the same CTA-relative dst / mbarrier offsets are written in every CTA of ctaMask
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::
+          "r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols));
@@ -220,6 +243,8 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
   int* s_mk = reinterpret_cast<int*>(s_ms + TM);            //   argmax
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dbg = marginalize >> 8;  // profiling knobs (JD_TC_DEBUG): 1 = no epilogue TMEM loads, 2 = one MMA per component
+  marginalize &= 1;
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
@@ -230,7 +255,10 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
   // CTAs stream different B images / mw rows, which spreads the L2 reads over the slices instead
   // of 148 SMs hammering the same lines in lockstep.  max / logsumexp do not depend on the order
   // (ties in max resolve to the lowest component index, as torch.max does).
-  const int k0 = (int)(((long long)blockIdx.x * K) / gridDim.x);
+  // The two CTAs of a cluster share every B image (each loads one half and multicasts it to both),
+  // which halves the L2 -> SM traffic; they therefore walk the components in the same order.
+  const uint32_t crank = cluster_ctarank();
+  const int k0 = (int)(((long long)(blockIdx.x / CLUSTER) * K) / (gridDim.x / CLUSTER));
 
   if (shift_yx) {
     g.sy = shift_yx[0];
@@ -241,7 +269,7 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CLUSTER);  // released by the MMA commits of both CTAs of the pair
     }
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -253,6 +281,7 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
   if (warp == 1) tmem_alloc(smem_u32(s_tmem), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // peer barriers are initialised before any remote arrive / multicast write
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
@@ -270,8 +299,11 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
       // mw_k rides with accumulator slot t: free once the epilogue of component k - NSLOT is done
       if (!ZERO_MEAN) mbar_wait(tempty_bar(t), ((k / NSLOT) & 1) ^ 1);
       if (elect_one()) {
+        // this CTA fetches half `crank` (hi or lo, 16 KB) of the image for both CTAs of the pair
         mbar_arrive_expect_tx(full_bar(s), B_BYTES);
-        bulk_g2s(smem_u32(sB + s * B_BYTES), Bt + (size_t)kc * B_BYTES, B_BYTES, full_bar(s));
+        bulk_g2s_mc(smem_u32(sB + s * B_BYTES) + crank * (B_BYTES / CLUSTER),
+                    Bt + (size_t)kc * B_BYTES + crank * (B_BYTES / CLUSTER), B_BYTES / CLUSTER, full_bar(s),
+                    (uint16_t)((1u << CLUSTER) - 1));
         if (!ZERO_MEAN) {
           mbar_arrive_expect_tx(mwfull_bar(t), MW_BYTES);
           bulk_g2s(smem_u32(sMW + t * 64), mw + (size_t)kc * 64, MW_BYTES, mwfull_bar(t));
@@ -348,6 +380,7 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
           const uint32_t b_base = pass == 1 ? b_lo : b_hi;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
+            if ((dbg & 2) && (pass > 0 || kk > 0)) continue;
             // upper-triangular Lw: input features [8kk, 8kk+8) only reach whitened features >= 8kk
             const uint32_t n0 = TRI ? 16u * (kk >> 1) : 0u;
             const uint32_t off16 = ((kk >> 2) * KBLOCK_BYTES_B + (kk & 3) * 32 + n0 * 128) >> 4;
@@ -355,7 +388,7 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
             acc = 1;
           }
         }
-        umma_commit(empty_bar(s));  // smem stage reusable once these MMAs have read it
+        umma_commit_mc(empty_bar(s), (uint16_t)((1u << CLUSTER) - 1));  // stage free in both CTAs of the pair
         umma_commit(tfull_bar(t));  // accumulator slot complete
       }
       __syncwarp();
@@ -375,9 +408,14 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + A_COLS + t * SLOT_COLS;
       float y0[32], y1[32];
-      tmem_ld32(taddr, y0);
-      tmem_ld32(taddr + 32, y1);
-      tmem_ld_wait();
+      if (dbg & 1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) y0[i] = y1[i] = (float)lane;
+      } else {
+        tmem_ld32(taddr, y0);
+        tmem_ld32(taddr + 32, y1);
+        tmem_ld_wait();
+      }
       float qa = 0.f, qb = 0.f, qc = 0.f, qd = 0.f;
       if (ZERO_MEAN) {
 #pragma unroll
@@ -460,6 +498,7 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // the peer may still multicast into / arrive on this CTA's shared memory until here
   if (threadIdx.x == 0 && sum) atomicAdd(sum, s_red[0] + s_red[1] + s_red[2] + s_red[3]);
   if (warp == 1) {
     tc_fence_after();
@@ -511,10 +550,35 @@ int jd_gmm_prior_forward_tc(const float* flux, int fH, int fW, const int32_t* sh
     attr_set = true;
   }
   int grid = (g.P + tc::TM - 1) / tc::TM;
+  grid = (grid + tc::CLUSTER - 1) / tc::CLUSTER * tc::CLUSTER;  // whole clusters; surplus CTAs own no patch
   auto kern = upper_tri ? (zero_mean ? tc::gmm_fwd_tc_kernel<true, true> : tc::gmm_fwd_tc_kernel<true, false>)
                         : (zero_mean ? tc::gmm_fwd_tc_kernel<false, true> : tc::gmm_fwd_tc_kernel<false, false>);
-  kern<<<grid, tc::NTHREADS, tc::SMEM_BYTES, to_stream(stream)>>>(
-      flux, g, shift_yx, reinterpret_cast<const uint8_t*>(Bt), mw, ck, K, marginalize, value, argmax, logp, sum);
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("JD_TC_DEBUG");
+    dbg = e ? atoi(e) : 0;
+  }
+  if (dbg & 4) kern = zero_mean ? tc::gmm_fwd_tc_kernel<false, true> : tc::gmm_fwd_tc_kernel<false, false>;
+  marginalize = (marginalize ? 1 : 0) | (dbg << 8);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(tc::NTHREADS);
+  cfg.dynamicSmemBytes = tc::SMEM_BYTES;
+  cfg.stream = to_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = tc::CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const uint8_t* bt8 = reinterpret_cast<const uint8_t*>(Bt);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, flux, g, shift_yx, bt8, mw, ck, K, marginalize, value, argmax, logp, sum);
+  if (le != cudaSuccess) {
+    set_error("jd_gmm_prior_forward_tc: launch failed: %s", cudaGetErrorString(le));
+    cudaGetLastError();
+    return JD_ERR_CUDA;
+  }
   JD_CHECK_LAUNCH("jd_gmm_prior_forward_tc");
   return JD_OK;
 }
