@@ -36,7 +36,8 @@ class MAPDeconvolver:
 
     def __init__(self, n_epochs=1_000, beta=1, learning_rate=0.1, compute_error=False, stop_early=False,
                  stop_early_n_average=10, device="cuda", display_progress=True, optimizer_type="adam",
-                 optimizer_kwargs=None, checkpoint_path=None, use_cuda_graph=True, fused=True):
+                 optimizer_kwargs=None, checkpoint_path=None, use_cuda_graph=True, fused=True, mode="sequential",
+                 process_group=None):
         self.n_epochs = n_epochs
         self.beta = beta
         self.learning_rate = learning_rate
@@ -58,6 +59,14 @@ class MAPDeconvolver:
         self.checkpoint_path = checkpoint_path
         self.use_cuda_graph = use_cuda_graph
         self.fused = fused
+        # "sequential": the reference's loop, one Adam step per dataset with the full prior (core.py:214-229).
+        # "joint": one Adam step per epoch on sum_d L_d - beta * prior (TotalLoss.__call__, loss.py:257-261);
+        #          with torch.distributed initialised the datasets are sharded over the ranks of `process_group`,
+        #          the prior over patch-row blocks, and the flux gradient is all-reduced (NCCL over NVLink).
+        if mode not in ("sequential", "joint"):
+            raise ValueError(f"Unknown mode: {mode}, must be 'sequential' or 'joint'")
+        self.mode = mode
+        self.process_group = process_group
 
     def to_dict(self):
         data = {}
@@ -66,6 +75,8 @@ class MAPDeconvolver:
         data["checkpoint_path"] = str(self.checkpoint_path)
         data.pop("optimizer", None)
         data.pop("optimizer_kwargs", None)
+        data.pop("process_group", None)
+        data.pop("engine", None)
         return data
 
     def __str__(self):
@@ -85,7 +96,16 @@ class MAPDeconvolver:
             return True
         return isinstance(prior, GMMPatchPrior) and prior.norm is None and prior.gmm.n_features == ops.PD
 
-    def _build_engine(self, total_loss, components, n_draws):
+    def _group(self):
+        if self.mode != "joint" or not torch.distributed.is_available() or not torch.distributed.is_initialized():
+            return None, 0, 1
+        pg = self.process_group or torch.distributed.group.WORLD
+        world = torch.distributed.get_world_size(pg)
+        if world == 1:
+            return None, 0, 1
+        return pg, torch.distributed.get_rank(pg), world
+
+    def _build_engine(self, total_loss, components, n_draws, shard=None):
         (name, comp), = components.items()
         theta = comp._flux_upsampled.data[0, 0]
         mask = comp.mask[0, 0].contiguous() if comp.mask is not None else None
@@ -107,11 +127,21 @@ class MAPDeconvolver:
                              backend=backend)
             table = np.array([prior.draw_shifts() for _ in range(n_draws)], dtype=np.int32).reshape(-1, 2)
         validation = buffers(total_loss.poisson_loss_validation) if total_loss.poisson_loss_validation else []
+        kwargs = {}
+        if shard is not None:  # datasets sharded over ranks: global trace layout, identical shifts on every rank
+            if table is not None:
+                tab = torch.from_numpy(table).to(self.device)
+                torch.distributed.broadcast(tab, src=torch.distributed.get_global_rank(shard["pg"], 0), group=shard["pg"])
+                table = tab.cpu().numpy()
+            f = comp.upsampling_factor or 1
+            kwargs = dict(process_group=shard["pg"], dataset_index=shard["index"], n_datasets_global=shard["n"],
+                          validation_index=shard["vindex"], n_validation_global=shard["nv"],
+                          counts_shape=(theta.shape[0] // f, theta.shape[1] // f))
         return MapEngine(theta, buffers(total_loss.poisson_loss), prior=prior_cfg, mask=mask,
                          use_log_flux=comp.use_log_flux, beta=self.beta, lr=self.optimizer_kwargs["lr"],
                          betas=self.optimizer_kwargs.get("betas", (0.9, 0.999)),
                          eps=self.optimizer_kwargs.get("eps", 1e-8), shift_table=table,
-                         datasets_validation=validation, use_graph=self.use_cuda_graph)
+                         datasets_validation=validation, use_graph=self.use_cuda_graph, **kwargs)
 
     def _early_stop(self, trace):
         if self.stop_early and len(trace) > self.stop_early_n_average:
@@ -143,11 +173,30 @@ class MAPDeconvolver:
         if calibrations:
             calibrations = calibrations.to(self.device)
 
+        pg, rank, world = self._group()
+        shard = None
+        names, vnames = list(datasets), list(datasets_validation or {})
+        if pg is not None:  # this rank only uploads and evaluates its own datasets
+            from . import dist
+
+            shard = dict(pg=pg, index=dist.shard_indices(len(names), rank, world), n=len(names),
+                         vindex=dist.shard_indices(len(vnames), rank, world), nv=len(vnames))
+            datasets = {names[i]: datasets[names[i]] for i in shard["index"]}
+            if datasets_validation:
+                datasets_validation = {vnames[i]: datasets_validation[vnames[i]] for i in shard["vindex"]}
+
         with torch.cuda.device(self.device):
             total_loss = TotalLoss.from_datasets_and_components(
                 datasets=datasets, datasets_validation=datasets_validation, components=components,
                 calibrations=calibrations, beta=self.beta, device=self.device)
-            if self._engine_supported(components, calibrations):
+            total_loss.dataset_names = names
+            if vnames and total_loss.poisson_loss_validation is None:
+                total_loss.poisson_loss_validation = False  # no local validation shard; the trace column still exists
+            if self.mode == "joint":
+                if not self._engine_supported(components, calibrations):
+                    raise NotImplementedError("mode='joint' needs a configuration the fused engine supports")
+                self._run_joint(total_loss, components, shard)
+            elif self._engine_supported(components, calibrations):
                 self._run_fused(total_loss, components, len(datasets))
             else:
                 self._run_autograd(total_loss, components, calibrations)
@@ -164,6 +213,20 @@ class MAPDeconvolver:
         for epoch in range(self.n_epochs):
             for i in range(n_datasets):
                 engine.step(i)
+            filename = self._checkpoint(epoch, total_loss, components)
+            ld, lp, lv = engine.trace_losses()
+            total_loss.append_trace_values(ld, [lp] * len(prior_names), filename, lv if lv else None)
+            if self._early_stop(total_loss.trace):
+                break
+        torch.cuda.synchronize(self.device)
+
+    def _run_joint(self, total_loss, components, shard):
+        """One joint Adam step per epoch (+ trace); dataset- and prior-sharded when `shard` is given."""
+        engine = self._build_engine(total_loss, components, self.n_epochs * 2, shard)
+        self.engine = engine
+        prior_names = list(total_loss.prior_loss.priors)
+        for epoch in range(self.n_epochs):
+            engine.joint_step()
             filename = self._checkpoint(epoch, total_loss, components)
             ld, lp, lv = engine.trace_losses()
             total_loss.append_trace_values(ld, [lp] * len(prior_names), filename, lv if lv else None)

@@ -16,7 +16,7 @@ Two step semantics (SURVEY.md §7 "semantics of iteration"):
 import numpy as np
 import torch
 
-from . import _lib, ops
+from . import _lib, dist, ops
 
 _p = ops._ptr
 
@@ -57,7 +57,8 @@ class DatasetBuffers:
 class MapEngine:
     def __init__(self, theta, datasets, prior=None, mask=None, use_log_flux=True, beta=1.0, lr=0.1, betas=(0.9, 0.999),
                  eps=1e-8, shift_table=None, datasets_validation=(), use_graph=True, process_group=None,
-                 prior_weight=None):
+                 prior_weight=None, dataset_index=None, n_datasets_global=None, validation_index=None,
+                 n_validation_global=None, counts_shape=None):
         """theta: 2-D CUDA fp32 tensor updated in place (the component's parameter storage).
         prior: None (uniform) or dict(packed=GMMPacked, stride, marginalize, backend).
         shift_table: (N, 2) int array of pre-drawn (row, col) cycle-spin shifts in consumption order."""
@@ -72,7 +73,17 @@ class MapEngine:
         self.datasets = list(datasets)
         self.datasets_validation = list(datasets_validation)
         self.D = len(self.datasets)
-        self.prior_weight = self.D if prior_weight is None else prior_weight
+        # multi-GPU: this rank holds datasets `dataset_index` of `n_datasets_global` (dist.shard_indices)
+        self.dataset_index = list(range(self.D)) if dataset_index is None else list(dataset_index)
+        self.Dg = self.D if n_datasets_global is None else int(n_datasets_global)
+        self.validation_index = (list(range(len(self.datasets_validation))) if validation_index is None
+                                 else list(validation_index))
+        self.Vg = len(self.datasets_validation) if n_validation_global is None else int(n_validation_global)
+        if counts_shape is None:
+            ref = (self.datasets + self.datasets_validation)[0]
+            counts_shape = (ref.H, ref.W)
+        self.counts_shape = tuple(counts_shape)
+        self.prior_weight = self.Dg if prior_weight is None else prior_weight
         self.beta, self.lr, self.b1, self.b2, self.eps = float(beta), float(lr), float(betas[0]), float(betas[1]), float(eps)
         self.prior = prior
         self.pg = process_group
@@ -92,7 +103,7 @@ class MapEngine:
         self.adam_scalars = torch.zeros(2, **f32)
         # acc[0] = Poisson loss sum of the last step, acc[1] = sum_p v_p of the last prior evaluation
         self.acc = torch.zeros(2, dtype=torch.float64, device=self.dev)
-        self.n_trace = self.D + 1 + len(self.datasets_validation)
+        self.n_trace = self.Dg + 1 + self.Vg
         self.acc_trace = torch.zeros(self.n_trace, dtype=torch.float64, device=self.dev)
         self.shift_table = None
         self.n_shifts = 0
@@ -125,9 +136,7 @@ class MapEngine:
 
     # ------------------------------------------------------------------------------------------
     def _row_block(self, rank, world):
-        lo = (self.ny * rank) // world
-        hi = (self.ny * (rank + 1)) // world
-        return lo, hi
+        return dist.row_block(self.ny, rank, world)
 
     def _s(self):
         return torch.cuda.current_stream().cuda_stream
@@ -265,27 +274,31 @@ class MapEngine:
             if refresh_flux:
                 self._flux()
             base = self.acc_trace.data_ptr()
-            for j, d in enumerate(self.datasets):
+            for j, d in zip(self.dataset_index, self.datasets):
                 self._likelihood(d, base + 8 * j, want_grad=False)
             if self.prior is not None:
-                self._prior_forward(base + 8 * self.D)
-            for j, d in enumerate(self.datasets_validation):
-                self._likelihood(d, base + 8 * (self.D + 1 + j), want_grad=False)
+                self._prior_forward(base + 8 * self.Dg)  # this rank's patch-row block
+            for j, d in zip(self.validation_index, self.datasets_validation):
+                self._likelihood(d, base + 8 * (self.Dg + 1 + j), want_grad=False)
 
         self._run(("trace", bool(refresh_flux)), body)
-        if self.world > 1:
+        if self.world > 1:  # every slot is written by exactly one rank (prior: partial sums): one all-reduce
             torch.distributed.all_reduce(self.acc_trace, group=self.pg)
         vals = self.acc_trace.cpu().numpy()
-        ld = [vals[j] / (d.H * d.W) for j, d in enumerate(self.datasets)]
-        lp = float(vals[self.D] * self.c) if self.prior is not None else 0.0
-        lv = [vals[self.D + 1 + j] / (d.H * d.W) for j, d in enumerate(self.datasets_validation)]
+        npix = self.counts_shape[0] * self.counts_shape[1]
+        ld = [vals[j] / npix for j in range(self.Dg)]
+        lp = float(vals[self.Dg] * self.c) if self.prior is not None else 0.0
+        lv = [vals[self.Dg + 1 + j] / npix for j in range(self.Vg)]
         return [float(x) for x in ld], lp, [float(x) for x in lv]
 
     def last_step_losses(self):
         """(Poisson mean loss, prior value) of the most recent step; syncs."""
-        vals = self.acc.cpu().numpy()
-        d = self.datasets[0]
-        return float(vals[0] / (d.H * d.W)), float(vals[1] * self.c) if self.prior is not None else 0.0
+        vals = self.acc.clone()
+        if self.world > 1:
+            torch.distributed.all_reduce(vals, group=self.pg)
+        vals = vals.cpu().numpy()
+        npix = self.counts_shape[0] * self.counts_shape[1]
+        return float(vals[0] / npix), float(vals[1] * self.c) if self.prior is not None else 0.0
 
     def flux_numpy(self):
         self._flux()

@@ -93,14 +93,17 @@ class TotalLoss:
         self.prior_loss = prior_loss
         self.beta = beta
         self._trace = None
+        # names of ALL datasets of the run (differs from poisson_loss.names_all when the datasets are sharded
+        # over ranks: each rank only holds its own)
+        self.dataset_names = list(poisson_loss.names_all)
 
     @property
     def trace(self):
         if self._trace is None:
             names = ["total", "datasets-total", "priors-total"]
             names += [f"prior-{name}" for name in self.prior_loss.priors]
-            names += [f"dataset-{name}" for name in self.poisson_loss.names_all]
-            if self.poisson_loss_validation:
+            names += [f"dataset-{name}" for name in self.dataset_names]
+            if self.poisson_loss_validation or self.poisson_loss_validation is False:
                 names += ["datasets-validation-total"]
             names += ["filename"]
             self._trace = TraceTable(names=names, dtype=[float] * (len(names) - 1) + [str])
@@ -114,7 +117,7 @@ class TotalLoss:
                "priors-total": -loss_priors_total, "filename": filename}
         for name, value in zip(self.prior_loss.priors, loss_priors):
             row[f"prior-{name}"] = -self.beta * value
-        for name, value in zip(self.poisson_loss.names_all, loss_datasets):
+        for name, value in zip(self.dataset_names, loss_datasets):
             row[f"dataset-{name}"] = value
         if loss_datasets_validation is not None:
             row["datasets-validation-total"] = sum(loss_datasets_validation)

@@ -412,3 +412,47 @@ def map_run(flux_init_up, datasets, n_epochs, lr=0.1, beta=1.0, gmm=None, shifts
         trace.append({"total": sum(ld) - beta * lp, "datasets-total": sum(ld), "priors-total": -beta * lp,
                       "datasets": ld})
     return flux_from_theta(theta), trace
+
+
+def joint_loss_and_grad(theta, datasets, beta, gmm=None, shifts=None, stride=4, marginalize=False,
+                        dataset_index=None, rows=None):
+    """Value and gradient (w.r.t. theta) of the joint objective sum_d L_d - beta * prior
+    (TotalLoss.__call__, loss.py:257-261).  `dataset_index` / `rows` restrict to a shard (subset of
+    datasets, block of prior patch rows): shard values / gradients sum to the whole."""
+    idx = range(len(datasets)) if dataset_index is None else dataset_index
+    flux = flux_from_theta(theta)
+    total = theta.dtype.type(0)
+    dtheta = np.zeros_like(theta)
+    for i in idx:
+        loss, dth, _ = dataset_loss_and_grad(theta, datasets[i])
+        total += loss
+        dtheta += dth
+    if gmm is not None:
+        r0, r1 = (None, None) if rows is None else rows
+        if rows is None or r1 > r0:
+            prior, dflux_p, _ = gmm_patch_prior(flux, gmm, shifts[0], shifts[1], stride, marginalize, True, r0, r1)
+            total -= beta * prior
+            dtheta -= theta.dtype.type(beta) * dflux_p * flux
+    return total, dtheta
+
+
+def map_run_joint(flux_init_up, datasets, n_epochs, lr=0.1, beta=1.0, gmm=None, shifts=None, stride=4,
+                  marginalize=False, dtype=np.float32):
+    """Joint-step MAP: one Adam step per epoch on the joint objective; shifts[2*e] is consumed by the
+    step of epoch e and shifts[2*e+1] by its trace evaluation (at the pre-step flux, like core.py:245)."""
+    theta = np.log(np.asarray(flux_init_up, dtype=dtype))
+    adam = Adam(theta.shape, lr=lr, dtype=dtype)
+    trace = []
+    for epoch in range(n_epochs):
+        flux = flux_from_theta(theta)
+        sh = shifts[2 * epoch] if gmm is not None else None
+        _, dtheta = joint_loss_and_grad(theta, datasets, beta, gmm, sh, stride, marginalize)
+        theta = adam.step(theta, dtheta)
+        ld = [float(poisson_nll(npred_forward(flux, d["exposure_up"], d["psf_up"], d["background"], d["f"]),
+                                d["counts"])) for d in datasets]
+        lp = 0.0
+        if gmm is not None:
+            sh = shifts[2 * epoch + 1]
+            lp = float(gmm_patch_prior(flux, gmm, sh[0], sh[1], stride, marginalize))
+        trace.append({"total": sum(ld) - beta * lp, "datasets": ld, "priors-total": -beta * lp})
+    return flux_from_theta(theta), trace
