@@ -27,18 +27,21 @@ template <int MODE, int TY, int TX>
 __global__ void __launch_bounds__(TY * TX)
 conv_kernel(const float* __restrict__ in, const float* __restrict__ scale, const float* __restrict__ psf,
             float* __restrict__ out, int fH, int fW, int kh, int kw, int oy, int ox, int f, int H, int W,
-            int accumulate) {
+            int accumulate, int kchunk) {
   constexpr int TH = R * TY, TW = C * TX;
+  constexpr int NT = TY * TX;
   extern __shared__ __align__(16) float smem[];
   const int kwp = (kw + 3) & ~3;            // kernel row padded to a multiple of 4
   const int iw = TW + kwp;                  // staged input row length (multiple of 4)
-  const int ih = TH + KC - 1;
+  const int ih = TH + kchunk - 1;
   float* s_in = smem;                       // ih x iw
-  float* s_k = smem + ih * iw;              // (KC + 2(R-1)) x kwp, rows [R-1, R-1+KC) hold the chunk
+  float* s_k = smem + ih * iw;              // (kchunk + 2(R-1)) x kwp, rows [R-1, R-1+kchunk) hold the chunk
 
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int tile_y = blockIdx.y * TH, tile_x = blockIdx.x * TW;
-  const int nthreads = TY * TX;
+  // staging layout: 32 consecutive threads walk a row (coalesced), NT/32 rows at a time
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  constexpr int LROWS = NT / 32;
 
   float acc[R][C];
 #pragma unroll
@@ -47,37 +50,51 @@ conv_kernel(const float* __restrict__ in, const float* __restrict__ scale, const
     for (int c = 0; c < C; ++c) acc[r][c] = 0.f;
 
   // zero the kernel staging buffer once: pad rows/cols stay zero for every chunk
-  for (int i = threadIdx.x; i < (KC + 2 * (R - 1)) * kwp; i += nthreads) s_k[i] = 0.f;
+  for (int i = threadIdx.x; i < (kchunk + 2 * (R - 1)) * kwp; i += NT) s_k[i] = 0.f;
 
-  for (int a0 = 0; a0 < kh; a0 += KC) {
-    const int kc = min(KC, kh - a0);
+  for (int a0 = 0; a0 < kh; a0 += kchunk) {
+    const int kc = min(kchunk, kh - a0);
     __syncthreads();
-    // stage kernel chunk (MODE fwd: flipped psf)
-    for (int i = threadIdx.x; i < KC * kwp; i += nthreads) {
-      int a = i / kwp, b = i - a * kwp;
-      float val = 0.f;
-      if (a < kc && b < kw) {
-        int aa = a0 + a;
-        val = MODE == CONV_FWD ? psf[(kh - 1 - aa) * kw + (kw - 1 - b)] : psf[aa * kw + b];
+    // stage kernel chunk (MODE fwd: flipped psf); rows >= kc of the chunk are zeroed
+    for (int a = ly; a < kchunk; a += LROWS)
+      for (int b = lx; b < kwp; b += 32) {
+        float val = 0.f;
+        if (a < kc && b < kw) {
+          int aa = a0 + a;
+          val = MODE == CONV_FWD ? __ldg(psf + (kh - 1 - aa) * kw + (kw - 1 - b)) : __ldg(psf + aa * kw + b);
+        }
+        s_k[(a + R - 1) * kwp + b] = val;
       }
-      s_k[(a + R - 1) * kwp + b] = val;
-    }
-    // stage input tile rows [tile_y + oy + a0, +TH+kc-1), cols [tile_x + ox, +iw)
+    // stage input tile rows [tile_y + oy + a0, +TH+kc-1), cols [tile_x + ox, +iw): 4 rows per pass so that
+    // 4 (8 with the exposure) independent global loads are in flight per thread
     const int rows = TH + kc - 1;
-    for (int i = threadIdx.x; i < rows * iw; i += nthreads) {
-      int ry = i / iw, rx = i - ry * iw;
-      int y = tile_y + oy + a0 + ry, x = tile_x + ox + rx;
-      float val = 0.f;
-      if (y >= 0 && y < fH && x >= 0 && x < fW) {
-        if (MODE == CONV_FWD) {
-          val = in[(int64_t)y * fW + x];
-          if (scale) val *= scale[(int64_t)y * fW + x];
-        } else {
-          int py = y / f, px = x / f;
-          if (py < H && px < W) val = in[(int64_t)py * W + px];
+    const int y0 = tile_y + oy + a0, x0 = tile_x + ox;
+    for (int rb = ly; rb < rows; rb += 4 * LROWS) {
+      for (int rx = lx; rx < iw; rx += 32) {
+        const int x = x0 + rx;
+        const bool xin = x >= 0 && x < fW;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int ry = rb + j * LROWS, y = y0 + ry;
+          float val = 0.f;
+          if (ry < rows && xin && y >= 0 && y < fH) {
+            if (MODE == CONV_FWD) {
+              val = __ldg(in + (int64_t)y * fW + x);
+              if (scale) val *= __ldg(scale + (int64_t)y * fW + x);
+            } else {
+              int py = y / f, px = x / f;
+              if (py < H && px < W) val = __ldg(in + (int64_t)py * W + px);
+            }
+          }
+          v[j] = val;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int ry = rb + j * LROWS;
+          if (ry < rows) s_in[ry * iw + rx] = v[j];
         }
       }
-      s_in[i] = val;
     }
     __syncthreads();
 
@@ -86,6 +103,7 @@ conv_kernel(const float* __restrict__ in, const float* __restrict__ scale, const
       const float* in_row = s_in + (ty * R + t) * iw + tx * C;
       const float* k_rows = s_k + (t + R - 1) * kwp;   // row for r = 0; row for r is k_rows - r*kwp
       float4 lo = *reinterpret_cast<const float4*>(in_row);
+#pragma unroll 2
       for (int b0 = 0; b0 < kwp; b0 += 4) {
         float4 hi = *reinterpret_cast<const float4*>(in_row + b0 + 4);
         float win[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
@@ -107,55 +125,68 @@ conv_kernel(const float* __restrict__ in, const float* __restrict__ scale, const
   for (int r = 0; r < R; ++r) {
     int y = tile_y + ty * R + r;
     if (y >= fH) continue;
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      int x = tile_x + tx * C + c;
-      if (x >= fW) continue;
-      int64_t o = (int64_t)y * fW + x;
-      float val = acc[r][c];
+    int x = tile_x + tx * C;
+    int64_t o = (int64_t)y * fW + x;
+    if (x + C <= fW && (fW & 3) == 0) {
+      float4 val = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
       if (MODE == CONV_BWD) {
-        if (scale) val *= scale[o];
-        if (accumulate) val += out[o];
+        if (scale) {
+          float4 sc = *reinterpret_cast<const float4*>(scale + o);
+          val.x *= sc.x, val.y *= sc.y, val.z *= sc.z, val.w *= sc.w;
+        }
+        if (accumulate) {
+          float4 old = *reinterpret_cast<const float4*>(out + o);
+          val.x += old.x, val.y += old.y, val.z += old.z, val.w += old.w;
+        }
       }
-      out[o] = val;
+      *reinterpret_cast<float4*>(out + o) = val;
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        if (x + c >= fW) continue;
+        float val = acc[r][c];
+        if (MODE == CONV_BWD) {
+          if (scale) val *= scale[o + c];
+          if (accumulate) val += out[o + c];
+        }
+        out[o + c] = val;
+      }
     }
   }
+}
+
+template <int MODE, int TY, int TX>
+static int launch_conv_t(const float* in, const float* scale, const float* psf, float* out, int fH, int fW, int kh,
+                         int kw, int oy, int ox, int f, int H, int W, int accumulate, cudaStream_t st,
+                         const char* name) {
+  const int kwp = (kw + 3) & ~3;
+  // whole PSF in one chunk when it fits ~44 KB of shared memory (several CTAs stay resident per SM);
+  // otherwise chunks of KC rows
+  auto smem_for = [&](int kc) {
+    return ((size_t)(R * TY + kc - 1) * (C * TX + kwp) + (size_t)(kc + 2 * (R - 1)) * kwp) * sizeof(float);
+  };
+  int kchunk = kh;
+  if (smem_for(kchunk) > 44 * 1024) kchunk = KC;
+  size_t sm = smem_for(kchunk);
+  JD_CHECK_ARG(sm <= 200 * 1024, "%s: PSF too wide for the direct kernel (kw=%d)", name, kw);
+  auto kern = conv_kernel<MODE, TY, TX>;
+  static bool attr_set = false;  // once per process and instantiation: opt in to the 200 KB limit checked above
+  if (!attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  dim3 grid((fW + C * TX - 1) / (C * TX), (fH + R * TY - 1) / (R * TY));
+  kern<<<grid, TY * TX, sm, st>>>(in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, kchunk);
+  JD_CHECK_LAUNCH(name);
+  return JD_OK;
 }
 
 template <int MODE>
 static int launch_conv(const float* in, const float* scale, const float* psf, float* out, int fH, int fW, int kh,
                        int kw, int oy, int ox, int f, int H, int W, int accumulate, cudaStream_t st,
                        const char* name) {
-  // 8x8 threads -> 32x32 tiles for small images (fills 148 SMs sooner), 16x16 -> 64x64 otherwise
-  const bool small = (int64_t)fH * fW <= 1024 * 1024;
-  const int kwp = (kw + 3) & ~3;
-  if (small) {
-    constexpr int TY = 8, TX = 8;
-    size_t sm = ((size_t)(R * TY + KC - 1) * (C * TX + kwp) + (size_t)(KC + 2 * (R - 1)) * kwp) * sizeof(float);
-    JD_CHECK_ARG(sm <= 200 * 1024, "%s: PSF too wide for the direct kernel (kw=%d)", name, kw);
-    auto kern = conv_kernel<MODE, TY, TX>;
-    static bool attr_set = false;  // once per process and instantiation: opt in to the 200 KB limit checked above
-    if (!attr_set) {
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr_set = true;
-    }
-    dim3 grid((fW + C * TX - 1) / (C * TX), (fH + R * TY - 1) / (R * TY));
-    kern<<<grid, TY * TX, sm, st>>>(in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate);
-  } else {
-    constexpr int TY = 16, TX = 16;
-    size_t sm = ((size_t)(R * TY + KC - 1) * (C * TX + kwp) + (size_t)(KC + 2 * (R - 1)) * kwp) * sizeof(float);
-    JD_CHECK_ARG(sm <= 200 * 1024, "%s: PSF too wide for the direct kernel (kw=%d)", name, kw);
-    auto kern = conv_kernel<MODE, TY, TX>;
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr_set = true;
-    }
-    dim3 grid((fW + C * TX - 1) / (C * TX), (fH + R * TY - 1) / (R * TY));
-    kern<<<grid, TY * TX, sm, st>>>(in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate);
-  }
-  JD_CHECK_LAUNCH(name);
-  return JD_OK;
+  // 8x16 threads -> 32x64 tiles: >= 2 CTAs per SM already at 512x512, 4 warps per CTA to overlap staging
+  return launch_conv_t<MODE, 8, 16>(in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
 }
 
 }  // namespace jd

@@ -45,32 +45,56 @@ __global__ void flux_kernel(const float* __restrict__ theta, const uint8_t* __re
 // a3/a4/a6: sum-pool, clip, background, Poisson NLL (full Stirling term) and gradient.
 // One thread per counts pixel; warp-shuffle + shared block reduction, one double atomic per block.
 // ------------------------------------------------------------------------------------------
-__global__ void poisson_kernel(const float* __restrict__ conv, const float* __restrict__ background,
-                               const float* __restrict__ bkg_log_norm, const float* __restrict__ counts,
-                               float* __restrict__ npred_out, float* __restrict__ dpool_out,
-                               double* __restrict__ loss_sum, double* __restrict__ dlogb, int H, int W, int f,
-                               int fW, float eps, float grad_scale) {
+__device__ __forceinline__ void poisson_pixel(float pool, float bkg, float c, float eps, float grad_scale,
+                                              float& np_, float& dpool, double& acc, double& accb) {
+  np_ = fmaxf(pool, 0.f) + bkg;
+  const float ne = np_ + eps;
+  float loss = np_ - c * logf(ne);
+  if (c > 1.f) loss += c * logf(c) - c + 0.5f * logf(6.283185307179586f * c);
+  acc += (double)loss;
+  const float d = (1.f - c / ne) * grad_scale;
+  accb += (double)(d * bkg);
+  dpool = pool >= 0.f ? d : 0.f;
+}
+
+// VEC: f == 1 and W % 4 == 0 -> four pixels per thread per pass with 128-bit loads/stores
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+poisson_kernel(const float* __restrict__ conv, const float* __restrict__ background,
+               const float* __restrict__ bkg_log_norm, const float* __restrict__ counts,
+               float* __restrict__ npred_out, float* __restrict__ dpool_out, double* __restrict__ loss_sum,
+               double* __restrict__ dlogb, int H, int W, int f, int fW, float eps, float grad_scale) {
   __shared__ double red[32];
   const float bnorm = bkg_log_norm ? expf(bkg_log_norm[0]) : 1.0f;
   const int64_t n = (int64_t)H * W;
   double acc = 0.0, accb = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    int y = (int)(i / W), x = (int)(i - (int64_t)y * W);
-    float pool = 0.f;
-    const float* src = conv + (int64_t)y * f * fW + (int64_t)x * f;
-    for (int u = 0; u < f; ++u)
-      for (int v = 0; v < f; ++v) pool += src[(int64_t)u * fW + v];
-    float bkg = background[i] * bnorm;
-    float np_ = fmaxf(pool, 0.f) + bkg;
-    float c = counts[i];
-    float ne = np_ + eps;
-    float loss = np_ - c * logf(ne);
-    if (c > 1.f) loss += c * logf(c) - c + 0.5f * logf(6.283185307179586f * c);
-    acc += (double)loss;
-    float d = (1.f - c / ne) * grad_scale;
-    accb += (double)(d * bkg);
-    if (npred_out) npred_out[i] = np_;
-    if (dpool_out) dpool_out[i] = pool >= 0.f ? d : 0.f;
+  if (VEC) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t row = (i * 4) / W, col = (i * 4) - row * W;
+      const float4 pv = *reinterpret_cast<const float4*>(conv + row * fW + col);
+      const float4 bv = *reinterpret_cast<const float4*>(background + i * 4);
+      const float4 cv = *reinterpret_cast<const float4*>(counts + i * 4);
+      float4 nv, dv;
+      poisson_pixel(pv.x, bv.x * bnorm, cv.x, eps, grad_scale, nv.x, dv.x, acc, accb);
+      poisson_pixel(pv.y, bv.y * bnorm, cv.y, eps, grad_scale, nv.y, dv.y, acc, accb);
+      poisson_pixel(pv.z, bv.z * bnorm, cv.z, eps, grad_scale, nv.z, dv.z, acc, accb);
+      poisson_pixel(pv.w, bv.w * bnorm, cv.w, eps, grad_scale, nv.w, dv.w, acc, accb);
+      if (npred_out) *reinterpret_cast<float4*>(npred_out + i * 4) = nv;
+      if (dpool_out) *reinterpret_cast<float4*>(dpool_out + i * 4) = dv;
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      int y = (int)(i / W), x = (int)(i - (int64_t)y * W);
+      float pool = 0.f;
+      const float* src = conv + (int64_t)y * f * fW + (int64_t)x * f;
+      for (int u = 0; u < f; ++u)
+        for (int v = 0; v < f; ++v) pool += src[(int64_t)u * fW + v];
+      float np_, d;
+      poisson_pixel(pool, background[i] * bnorm, counts[i], eps, grad_scale, np_, d, acc, accb);
+      if (npred_out) npred_out[i] = np_;
+      if (dpool_out) dpool_out[i] = d;
+    }
   }
   double s = block_sum(acc, red);
   if (threadIdx.x == 0 && loss_sum) atomicAdd(loss_sum, s);
@@ -237,9 +261,16 @@ int jd_poisson_forward_backward(const float* conv, const float* background, cons
   JD_CHECK_ARG(H > 0 && W > 0 && f >= 1 && fW >= W * f, "jd_poisson_forward_backward: bad shape H=%d W=%d f=%d fW=%d",
                H, W, f, fW);
   int64_t n = (int64_t)H * W;
-  poisson_kernel<<<grid_for(n, 256), 256, 0, to_stream(stream)>>>(conv, background, bkg_log_norm, counts, npred,
-                                                                   dpool, loss_sum, dlogb, H, W, f, fW, eps,
-                                                                   grad_scale);
+  // few, fat blocks: one double atomic per block on the same accumulator would otherwise serialise
+  const bool vec = f == 1 && (W & 3) == 0 && (fW & 3) == 0;
+  int64_t want = ((vec ? n / 4 : n) + 255) / 256;
+  int grid = (int)(want < 1 ? 1 : (want > 2 * num_sms() ? 2 * num_sms() : want));
+  if (vec)
+    poisson_kernel<true><<<grid, 256, 0, to_stream(stream)>>>(conv, background, bkg_log_norm, counts, npred, dpool,
+                                                              loss_sum, dlogb, H, W, f, fW, eps, grad_scale);
+  else
+    poisson_kernel<false><<<grid, 256, 0, to_stream(stream)>>>(conv, background, bkg_log_norm, counts, npred, dpool,
+                                                               loss_sum, dlogb, H, W, f, fW, eps, grad_scale);
   JD_CHECK_LAUNCH("jd_poisson_forward_backward");
   return JD_OK;
 }
