@@ -139,6 +139,16 @@ int jd_gmm_prior_forward_tc(const float* flux, int fH, int fW, const int32_t* sh
                             int K, int upper_tri, int zero_mean, int marginalize, float* value,
                             int32_t* argmax, float* logp, double* sum, jd_stream_t stream);
 
+/* Same forward with SPLIT-FP16 operands (kind::f16, FP32 accumulation): hi/lo FP16 pairs with power-of-two
+ * row / component scales carry the same 22 significand bits as the TF32 pairs at half the operand bytes and
+ * twice the tensor rate.  Bt: K x 16 KB image from jd_gmm_tc16_pack, binv[k] = 1 / component scale. */
+size_t jd_gmm_tc16_packed_bytes(int K);
+int jd_gmm_tc16_pack(const float* Lw, int K, void* Bt, float* binv, jd_stream_t stream);
+int jd_gmm_prior_forward_tc16(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride,
+                              int row_begin, int row_end, const void* Bt, const float* binv, const float* mw,
+                              const float* ck, int K, int upper_tri, int zero_mean, int marginalize,
+                              float* value, int32_t* argmax, float* logp, double* sum, jd_stream_t stream);
+
 /* Per-patch gradient  G[p',:] = scale * sum_k R[p',k] (xc_p Lam_k - bk_k),  minus its row mean,
  * R = one-hot(argmax) or softmax_k(logp) (marginalize=1; needs logp and value from the forward);
  * Lam_k = Lw_k Lw_k^T, bk_k = mw_k Lw_k^T.  (Autograd mirror of gmm.py:270-272 + norms.py:97-103.)

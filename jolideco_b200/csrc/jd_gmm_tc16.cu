@@ -1,25 +1,14 @@
-// GMM patch prior forward on the 5th-generation tensor cores (tcgen05 / TMEM / bulk-TMA), sm_100a.
+// GMM patch prior forward on tcgen05 with SPLIT-FP16 operands (kind::f16, FP32 accumulation in TMEM).
 //
-// The K-component Mahalanobis evaluation is one dense contraction (patches x 64) . (64 x 64 K).  It
-// runs as split-TF32 ("3xTF32": x = hi + lo with both halves exactly representable in TF32,
-// D += lo.hi + hi.lo + hi.hi, FP32 accumulation in TMEM) so that the result keeps FP32 accuracy
-// (the per-iteration parity bar is 1e-5, single-pass TF32 gives 1e-3).
-//
-// CTA = 128 patches (UMMA M = 128), 6 warps:
-//   warp 0      bulk-TMA producer: streams the pre-packed B image of component k
-//               (Lw_k^T split hi/lo, 128B-swizzled K-major, 32 KB) into a 4-stage smem ring;
-//   warp 1      TMEM allocator + MMA issuer: 24 tcgen05.mma (M128 N<=64 K8, kind::tf32, A from TMEM,
-//               B from smem) per component into one of 6 accumulator slots (64 TMEM columns each).
-//               Lw_k is upper triangular (a Cholesky factor), so k-step kk only feeds whitened
-//               features j >= 8 kk: the MMA N extent shrinks 64,64,48,48,32,32,16,16 (62.5 % of
-//               the dense tensor work);
-//   warps 2..5  gather the 128 patches from the flux image at rolled coordinates, subtract the
-//               patch mean, split hi/lo and store the A operand straight into TMEM (tcgen05.st,
-//               thread = patch row = TMEM lane; 128 columns) so the MMA never re-reads A from shared
-//               memory; then act as the epilogue: tcgen05.ld the 128x64 accumulator of each component
-//               (thread = patch row), subtract mw_k, square, reduce over the 64 whitened features,
-//               add ck_k and fold into a running max/argmax or online logsumexp.  Y never leaves
-//               the SM; only value/argmax (and optionally logp) are written.
+// Same kernel structure, pipeline and epilogue as jd_gmm_tc.cu (split-TF32); only the operand encoding
+// differs.  x = s^-1 (hi + lo) with hi, lo FP16 and s a power-of-two scale (per patch row for A, per
+// component for B) chosen so that max |s x| lies in [2^13, 2^14): the pair carries 22 significand bits, the
+// same as a TF32 hi/lo pair, elements far below the row maximum keep an absolute error < 2^-38 max.  The three
+// products lo.hi + hi.lo + hi.hi then run at the FP16 tensor rate (2x TF32) on operands half the size:
+// 16 KB of B per component instead of 32 KB through the TMA ring and the MMA's shared-memory reads, which is
+// what bounds the TF32 kernel.  The epilogue undoes the scales (one multiply per value,
+// fused into the mean subtraction).
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdlib.h>
@@ -28,22 +17,19 @@
 #include "jd_tc_ptx.cuh"
 
 namespace jd {
+namespace tc16 {
 
-int gmm_prior_forward_simt(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
-                           int row_end, const float* Lw, const float* mw, const float* ck, int K, int marginalize,
-                           float* value, int32_t* argmax, float* logp, double* sum, cudaStream_t st);
-
-namespace tc {
+using namespace tcx;
 
 constexpr int TM = 128;                 // patches per CTA
-constexpr int NSTAGE = 6;               // B ring depth (multiple of NPROD)
+constexpr int NSTAGE = 8;               // B ring depth (multiple of NPROD)
 constexpr int NSLOT = 6;                // TMEM accumulator slots (multiple of NMMA and of the 2 epilogue groups)
 constexpr int SLOT_COLS = 64;
-constexpr int A_COLS = 128;             // TMEM columns [0,64) = A hi, [64,128) = A lo
+constexpr int A_COLS = 64;              // TMEM columns [0,32) = A hi (half2 packed), [32,64) = A lo
 constexpr int TMEM_COLS = 512;          // A_COLS + NSLOT * SLOT_COLS
-constexpr int KBLOCK_BYTES_B = 64 * 128;      // 64 rows x 128 B = 8 KB
-constexpr int B_BYTES = 4 * KBLOCK_BYTES_B;   // hi(kb0,kb1) lo(kb0,kb1) = 32 KB per component
-constexpr int CLUSTER = 2;              // CTA pair: each CTA fetches half of every B image and multicasts it
+constexpr int MAT_BYTES = 64 * 128;     // one 64 x 64 FP16 matrix: 64 rows x 128 B, one swizzle atom wide
+constexpr int B_BYTES = 2 * MAT_BYTES;  // hi, lo = 16 KB per component
+constexpr int CLUSTER = 2;
 constexpr int NMMA = 3;                 // MMA-issuing warps: component position k is issued by warp M0 + k % NMMA
 constexpr int NPROD = 2;                // bulk-TMA producer warps: position k is loaded by warp k % NPROD
 // Every mbarrier is waited on by ONE fixed warp (group) across its successive uses: a waiter may be at most one
@@ -53,42 +39,60 @@ static_assert(NSLOT % NMMA == 0 && NSLOT % 2 == 0, "a TMEM slot must always belo
 constexpr int M0 = NPROD;                // first MMA-issuer warp (also owns the TMEM allocation)
 constexpr int E0 = NPROD + NMMA;         // first epilogue warp
 constexpr int NTHREADS = 32 * (NPROD + NMMA + 8);  // producers, MMA issuers, 2 x 4 epilogue warps
-constexpr int MW_BYTES = 64 * 4;        // mw_k staged per accumulator slot
-constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + NSTAGE * B_BYTES + NSLOT * MW_BYTES + 4096 /*barriers etc.*/;
+constexpr int MW_BYTES = 64 * 4;
+constexpr size_t SMEM_BYTES = 1024 + NSTAGE * B_BYTES + NSLOT * MW_BYTES + 4096;
 
-using namespace tcx;
-
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128, N = n
-__device__ __host__ constexpr uint32_t idesc_n(uint32_t n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
-// byte offset of element (row, d) inside a [rows x 64 tf32] operand stored as two 128B-swizzled k-blocks
-__device__ __host__ __forceinline__ uint32_t sw128_offset(int row, int d, int kblock_bytes) {
-  int kb = d >> 5, c = (d & 31) >> 2, e = d & 3;
-  return kb * kblock_bytes + (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4) + e * 4;
+// D = F32, A = B = F16, both K-major, M = 128, N = n
+__device__ __host__ constexpr uint32_t idesc16_n(uint32_t n) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
-// ---------------------------------------------------------------- setup: pack Lw_k^T into the smem image
-// Bt[k] (32 KB): hi kb0, hi kb1, lo kb0, lo kb1; row n = whitened feature j, K index = input feature i.
-__global__ void pack_b_kernel(const float* __restrict__ Lw, int K, uint8_t* __restrict__ out) {
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)K * 4096) return;
-  int k = (int)(idx >> 12), rem = (int)(idx & 4095), i = rem >> 6, j = rem & 63;
-  float v = Lw[idx];  // Lw[k][i][j]
-  float hi = tf32_rna(v);
-  float lo = tf32_rna(v - hi);
+// ---------------------------------------------------------------- setup: pack Lw_k^T as scaled FP16 hi/lo
+// One CTA per component.  Image (16 KB): hi then lo, row n = whitened feature j (128 B = 64 halfs over the input
+// feature i), 128B-swizzled.  binv[k] = 1 / scale_k.
+__global__ void pack_b16_kernel(const float* __restrict__ Lw, int K, uint8_t* __restrict__ out,
+                                float* __restrict__ binv) {
+  __shared__ float s_max[32];
+  const int k = blockIdx.x;
+  const float* L = Lw + (size_t)k * 4096;
+  float m = 0.f;
+  for (int i = threadIdx.x; i < 4096; i += blockDim.x) m = fmaxf(m, fabsf(L[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, s_max[w]);
+  int e = m > 0.f ? ilogbf(m) : 13;
+  e = max(-100, min(100, e));
+  const float sB = ldexpf(1.f, 13 - e);
+  if (threadIdx.x == 0) binv[k] = ldexpf(1.f, e - 13);
   uint8_t* base = out + (size_t)k * B_BYTES;
-  uint32_t off = sw128_offset(j, i, KBLOCK_BYTES_B);
-  *reinterpret_cast<float*>(base + off) = hi;
-  *reinterpret_cast<float*>(base + 2 * KBLOCK_BYTES_B + off) = lo;
+  for (int idx = threadIdx.x; idx < 4096; idx += blockDim.x) {
+    const int i = idx >> 6, j = idx & 63;  // Lw[k][i][j]
+    const float v = L[idx] * sB;
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    const uint32_t off = (j >> 3) * 1024 + (j & 7) * 128 + (((i >> 3) ^ (j & 7)) << 4) + (i & 7) * 2;
+    *reinterpret_cast<__half*>(base + off) = h;
+    *reinterpret_cast<__half*>(base + MAT_BYTES + off) = l;
+  }
 }
 
 // ---------------------------------------------------------------- the forward kernel
 template <bool TRI, bool ZERO_MEAN>
 __global__ void __launch_bounds__(NTHREADS, 1)
-gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restrict__ shift_yx,
-                  const uint8_t* __restrict__ Bt, const float* __restrict__ mw, const float* __restrict__ ck, int K,
+gmm_fwd_tc16_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restrict__ shift_yx,
+                  const uint8_t* __restrict__ Bt, const float* __restrict__ mw, const float* __restrict__ ck, const float* __restrict__ binv, int K,
                   int marginalize, float* __restrict__ value, int32_t* __restrict__ argmax, float* __restrict__ logp,
                   double* __restrict__ sum) {
   extern __shared__ uint8_t smem_raw[];
@@ -103,6 +107,7 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
   float* s_mm = reinterpret_cast<float*>(s_red + 4);        // merge buffers of epilogue group B: max,
   float* s_ms = s_mm + TM;                                  //   sum-exp,
   int* s_mk = reinterpret_cast<int*>(s_ms + TM);            //   argmax
+  float* s_rinv = reinterpret_cast<float*>(s_mk + TM);      // 1 / (row scale) per patch row
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dbg = marginalize >> 8;  // profiling knobs (JD_TC_DEBUG): 1 = no epilogue TMEM loads, 2 = one MMA per component
@@ -151,6 +156,7 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
   const int q = warp & 3;
   const int row = q * 32 + lane;
   const int64_t p = p0 + row;
+  float row_inv = 1.f;  // 1 / (row scale): written to s_rinv by the gather, read by both epilogue groups
 
   if (warp < NPROD) {
     // ===================== bulk-TMA producers (whole warp waits, one elected lane issues) ==========
@@ -164,8 +170,8 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
       if (elect_one()) {
         // this CTA fetches half `crank` (hi or lo, 16 KB) of the image for both CTAs of the pair
         mbar_arrive_expect_tx(full_bar(s), B_BYTES);
-        bulk_g2s_mc(smem_u32(sB + s * B_BYTES) + crank * (B_BYTES / CLUSTER),
-                    Bt + (size_t)kc * B_BYTES + crank * (B_BYTES / CLUSTER), B_BYTES / CLUSTER, full_bar(s),
+        bulk_g2s_mc(smem_u32(sB + s * B_BYTES) + crank * ((B_BYTES / CLUSTER)),
+                    Bt + (size_t)kc * B_BYTES + crank * ((B_BYTES / CLUSTER)), (B_BYTES / CLUSTER), full_bar(s),
                     (uint16_t)((1u << CLUSTER) - 1));
         if (!ZERO_MEAN) {
           mbar_arrive_expect_tx(mwfull_bar(t), MW_BYTES);
@@ -202,29 +208,41 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
       for (int i = 0; i < 64; ++i) vals[i] = 0.f;
     }
     const float mean = s * (1.f / 64.f);
+    // per-row power-of-two scale: max |x| lands in [2^13, 2^14) so that the FP16 hi/lo pair keeps 22 bits
+    float amax = 0.f;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+      vals[i] = ok ? vals[i] - mean : 0.f;
+      amax = fmaxf(amax, fabsf(vals[i]));
+    }
+    int e = amax > 0.f ? ilogbf(amax) : 13;
+    e = max(-100, min(100, e));
+    const float sA = ldexpf(1.f, 13 - e);
+    s_rinv[row] = ldexpf(1.f, e - 13);
     const uint32_t a_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    {
+      float hi[32], lo[32];  // 32 packed half2 words each (64 features)
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      float hi[32], lo[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float x = ok ? vals[h * 32 + i] - mean : 0.f;
-        hi[i] = tf32_rna(x);
-        lo[i] = tf32_rna(x - hi[i]);
+      for (int c = 0; c < 32; ++c) {
+        const float x0 = vals[2 * c] * sA, x1 = vals[2 * c + 1] * sA;
+        const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+        const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
+        hi[c] = __uint_as_float((uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16));
+        lo[c] = __uint_as_float((uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16));
       }
-      tmem_st32(a_lane + h * 32, hi);
-      tmem_st32(a_lane + 64 + h * 32, lo);
+      tmem_st32(a_lane, hi);
+      tmem_st32(a_lane + 32, lo);
     }
     tmem_st_wait();
     s_valid[row] = ok ? 1 : 0;
     tc_fence_before();
     // the 4 gather warps -> MMA warp: named barrier 1 (128 gather threads + 32 MMA-warp threads)
-    asm volatile("bar.arrive 1, %0;" ::"n"(128 + 32 * NMMA) : "memory");
+    asm volatile("bar.arrive 1, %0;" ::"n"(128 + 32 * NMMA + 128) : "memory");
   }
 
   if (warp >= M0 && warp < M0 + NMMA) {
     // ===================== MMA issuers (warp-uniform control flow, one elected lane issues) =========
-    asm volatile("bar.sync 1, %0;" ::"n"(128 + 32 * NMMA) : "memory");  // A operand is in TMEM
+    asm volatile("bar.sync 1, %0;" ::"n"(128 + 32 * NMMA + 128) : "memory");  // A operand is in TMEM
     tc_fence_after();
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t sB_lo0 = desc_lo(smem_u32(sB));
@@ -234,21 +252,21 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
       mbar_wait(full_bar(s), (k / NSTAGE) & 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t b_hi = sB_lo0 + s * (B_BYTES >> 4), b_lo = b_hi + ((2 * KBLOCK_BYTES_B) >> 4);
+        const uint32_t b_hi = sB_lo0 + s * (B_BYTES >> 4), b_lo = b_hi + (MAT_BYTES >> 4);
         const uint32_t d = tmem_u + A_COLS + t * SLOT_COLS;
         uint32_t acc = 0;
         // small terms first: lo.hi, hi.lo, then hi.hi
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t a_col = pass == 0 ? 64u : 0u;
+          const uint32_t a_col = pass == 0 ? 32u : 0u;
           const uint32_t b_base = pass == 1 ? b_lo : b_hi;
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
+          for (int kk = 0; kk < 4; ++kk) {
             if ((dbg & 2) && (pass > 0 || kk > 0)) continue;
-            // upper-triangular Lw: input features [8kk, 8kk+8) only reach whitened features >= 8kk
-            const uint32_t n0 = TRI ? 16u * (kk >> 1) : 0u;
-            const uint32_t off16 = ((kk >> 2) * KBLOCK_BYTES_B + (kk & 3) * 32 + n0 * 128) >> 4;
-            umma_tf32_ts(d + n0, tmem_u + a_col + kk * 8, desc_from_lo(b_base + off16), idesc_n(64 - n0), acc);
+            // upper-triangular Lw: input features [16kk, 16kk+16) only reach whitened features >= 16kk
+            const uint32_t n0 = TRI ? 16u * kk : 0u;
+            const uint32_t off16 = (kk * 32 + n0 * 128) >> 4;
+            umma_f16_ts(d + n0, tmem_u + a_col + kk * 8, desc_from_lo(b_base + off16), idesc16_n(64 - n0), acc);
             acc = 1;
           }
         }
@@ -260,6 +278,8 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
   } else if (warp >= E0) {
     // ===================== epilogue: group A (warps 2-5) takes even positions, group B odd =========
     const int grp = warp >= E0 + 4 ? 1 : 0;
+    if (grp == 1) asm volatile("bar.sync 1, %0;" ::"n"(128 + 32 * NMMA + 128) : "memory");  // row scales written by the gather warps
+    row_inv = s_rinv[row];
     float run_m = -CUDART_INF_F, run_s = 0.f;
     int run_k = 0x7fffffff;
     int kc = k0 + grp;
@@ -267,6 +287,7 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
     for (int k = grp; k < K; k += 2) {
       const int t = k % NSLOT;
       const float c_k = __ldg(ck + kc);
+      const float inv = row_inv * __ldg(binv + kc);  // undo the row and component scales
       if (!ZERO_MEAN) mbar_wait(mwfull_bar(t), (k / NSLOT) & 1);
       mbar_wait(tfull_bar(t), (k / NSLOT) & 1);
       tc_fence_after();
@@ -294,8 +315,10 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
           float4 b0 = mwk[c4], b1 = mwk[8 + c4];
-          float d0 = y0[4 * c4] - b0.x, d1 = y0[4 * c4 + 1] - b0.y, d2 = y0[4 * c4 + 2] - b0.z, d3 = y0[4 * c4 + 3] - b0.w;
-          float e0 = y1[4 * c4] - b1.x, e1 = y1[4 * c4 + 1] - b1.y, e2 = y1[4 * c4 + 2] - b1.z, e3 = y1[4 * c4 + 3] - b1.w;
+          float d0 = fmaf(y0[4 * c4], inv, -b0.x), d1 = fmaf(y0[4 * c4 + 1], inv, -b0.y);
+          float d2 = fmaf(y0[4 * c4 + 2], inv, -b0.z), d3 = fmaf(y0[4 * c4 + 3], inv, -b0.w);
+          float e0 = fmaf(y1[4 * c4], inv, -b1.x), e1 = fmaf(y1[4 * c4 + 1], inv, -b1.y);
+          float e2 = fmaf(y1[4 * c4 + 2], inv, -b1.z), e3 = fmaf(y1[4 * c4 + 3], inv, -b1.w);
           qa = fmaf(d0, d0, qa);
           qb = fmaf(e0, e0, qb);
           qc = fmaf(d1, d1, qc);
@@ -310,7 +333,8 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(t));
-      const float lp = fmaf(-0.5f, (qa + qb) + (qc + qd), c_k);
+      const float qsum = ZERO_MEAN ? ((qa + qb) + (qc + qd)) * (inv * inv) : (qa + qb) + (qc + qd);
+      const float lp = fmaf(-0.5f, qsum, c_k);
       if (logp && p < g.P) logp[p * K + kc] = lp;
       if (marginalize) {
         if (lp > run_m) {
@@ -370,92 +394,82 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
   }
 }
 
-}  // namespace tc
+}  // namespace tc16
 }  // namespace jd
 
 using namespace jd;
 
 extern "C" {
 
-size_t jd_gmm_tc_packed_bytes(int K) { return (size_t)K * tc::B_BYTES; }
+size_t jd_gmm_tc16_packed_bytes(int K) { return (size_t)K * tc16::B_BYTES; }
 
-int jd_gmm_tc_pack(const float* Lw, int K, void* Bt, jd_stream_t stream) {
-  JD_CHECK_ARG(Lw && Bt && K > 0, "jd_gmm_tc_pack: bad arguments");
-  int64_t n = (int64_t)K * 4096;
-  tc::pack_b_kernel<<<(int)((n + 255) / 256), 256, 0, to_stream(stream)>>>(Lw, K, reinterpret_cast<uint8_t*>(Bt));
-  JD_CHECK_LAUNCH("jd_gmm_tc_pack");
+int jd_gmm_tc16_pack(const float* Lw, int K, void* Bt, float* binv, jd_stream_t stream) {
+  JD_CHECK_ARG(Lw && Bt && binv && K > 0, "jd_gmm_tc16_pack: bad arguments");
+  tc16::pack_b16_kernel<<<K, 256, 0, to_stream(stream)>>>(Lw, K, reinterpret_cast<uint8_t*>(Bt), binv);
+  JD_CHECK_LAUNCH("jd_gmm_tc16_pack");
   return JD_OK;
 }
 
-int jd_gmm_prior_forward_tc(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
-                            int row_end, const void* Bt, const float* mw, const float* ck, int K, int upper_tri,
-                            int zero_mean, int marginalize, float* value, int32_t* argmax, float* logp, double* sum,
-                            jd_stream_t stream) {
-  JD_CHECK_ARG(flux && Bt && mw && ck && K > 0, "jd_gmm_prior_forward_tc: null pointer");
-  JD_CHECK_ARG(fH >= PATCH && fW >= PATCH && stride >= 1 && stride <= PATCH, "jd_gmm_prior_forward_tc: bad geometry");
+int jd_gmm_prior_forward_tc16(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
+                              int row_end, const void* Bt, const float* binv, const float* mw, const float* ck, int K,
+                              int upper_tri, int zero_mean, int marginalize, float* value, int32_t* argmax,
+                              float* logp, double* sum, jd_stream_t stream) {
+  JD_CHECK_ARG(flux && Bt && binv && mw && ck && K > 0, "jd_gmm_prior_forward_tc16: null pointer");
+  JD_CHECK_ARG(fH >= PATCH && fW >= PATCH && stride >= 1 && stride <= PATCH, "jd_gmm_prior_forward_tc16: bad geometry");
   int ny = (fH - PATCH) / stride + 1, nx = (fW - PATCH) / stride + 1;
   JD_CHECK_ARG(row_begin >= 0 && row_end <= ny && row_begin < row_end,
-               "jd_gmm_prior_forward_tc: bad patch-row block [%d,%d) of %d", row_begin, row_end, ny);
+               "jd_gmm_prior_forward_tc16: bad patch-row block [%d,%d) of %d", row_begin, row_end, ny);
   JD_CHECK_ARG((reinterpret_cast<uintptr_t>(Bt) & 15) == 0 && (reinterpret_cast<uintptr_t>(mw) & 15) == 0,
-               "jd_gmm_prior_forward_tc: Bt and mw must be 16-byte aligned");
-  tc::Geom g{fH, fW, 0, 0, stride, nx, row_begin, (row_end - row_begin) * nx};
+               "jd_gmm_prior_forward_tc16: Bt and mw must be 16-byte aligned");
+  tcx::Geom g{fH, fW, 0, 0, stride, nx, row_begin, (row_end - row_begin) * nx};
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaSuccess;
-    const void* kerns[4] = {(const void*)tc::gmm_fwd_tc_kernel<false, false>, (const void*)tc::gmm_fwd_tc_kernel<false, true>,
-                            (const void*)tc::gmm_fwd_tc_kernel<true, false>, (const void*)tc::gmm_fwd_tc_kernel<true, true>};
+    const void* kerns[4] = {(const void*)tc16::gmm_fwd_tc16_kernel<false, false>,
+                            (const void*)tc16::gmm_fwd_tc16_kernel<false, true>,
+                            (const void*)tc16::gmm_fwd_tc16_kernel<true, false>,
+                            (const void*)tc16::gmm_fwd_tc16_kernel<true, true>};
     for (int i = 0; i < 4 && e == cudaSuccess; ++i)
-      e = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+      e = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc16::SMEM_BYTES);
     if (e != cudaSuccess) {
-      set_error("jd_gmm_prior_forward_tc: cannot reserve %zu B of shared memory: %s", tc::SMEM_BYTES,
+      set_error("jd_gmm_prior_forward_tc16: cannot reserve %zu B of shared memory: %s", tc16::SMEM_BYTES,
                 cudaGetErrorString(e));
       return JD_ERR_CUDA;
     }
     attr_set = true;
   }
-  int grid = (g.P + tc::TM - 1) / tc::TM;
-  grid = (grid + tc::CLUSTER - 1) / tc::CLUSTER * tc::CLUSTER;  // whole clusters; surplus CTAs own no patch
-  auto kern = upper_tri ? (zero_mean ? tc::gmm_fwd_tc_kernel<true, true> : tc::gmm_fwd_tc_kernel<true, false>)
-                        : (zero_mean ? tc::gmm_fwd_tc_kernel<false, true> : tc::gmm_fwd_tc_kernel<false, false>);
+  int grid = (g.P + tc16::TM - 1) / tc16::TM;
+  grid = (grid + tc16::CLUSTER - 1) / tc16::CLUSTER * tc16::CLUSTER;
+  auto kern = upper_tri ? (zero_mean ? tc16::gmm_fwd_tc16_kernel<true, true> : tc16::gmm_fwd_tc16_kernel<true, false>)
+                        : (zero_mean ? tc16::gmm_fwd_tc16_kernel<false, true> : tc16::gmm_fwd_tc16_kernel<false, false>);
   static int dbg = -1;
   if (dbg < 0) {
     const char* e = getenv("JD_TC_DEBUG");
     dbg = e ? atoi(e) : 0;
   }
-  if (dbg & 4) kern = zero_mean ? tc::gmm_fwd_tc_kernel<false, true> : tc::gmm_fwd_tc_kernel<false, false>;
   marginalize = (marginalize ? 1 : 0) | (dbg << 8);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(tc::NTHREADS);
-  cfg.dynamicSmemBytes = tc::SMEM_BYTES;
+  cfg.blockDim = dim3(tc16::NTHREADS);
+  cfg.dynamicSmemBytes = tc16::SMEM_BYTES;
   cfg.stream = to_stream(stream);
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = tc::CLUSTER;
+  attr[0].val.clusterDim.x = tc16::CLUSTER;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const uint8_t* bt8 = reinterpret_cast<const uint8_t*>(Bt);
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, flux, g, shift_yx, bt8, mw, ck, K, marginalize, value, argmax, logp, sum);
+  cudaError_t le =
+      cudaLaunchKernelEx(&cfg, kern, flux, g, shift_yx, bt8, mw, ck, binv, K, marginalize, value, argmax, logp, sum);
   if (le != cudaSuccess) {
-    set_error("jd_gmm_prior_forward_tc: launch failed: %s", cudaGetErrorString(le));
+    set_error("jd_gmm_prior_forward_tc16: launch failed: %s", cudaGetErrorString(le));
     cudaGetLastError();
     return JD_ERR_CUDA;
   }
-  JD_CHECK_LAUNCH("jd_gmm_prior_forward_tc");
+  JD_CHECK_LAUNCH("jd_gmm_prior_forward_tc16");
   return JD_OK;
-}
-
-int jd_gmm_prior_forward(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
-                         int row_end, const float* Lw, const float* mw, const float* ck, int K, int marginalize,
-                         float* value, int32_t* argmax, float* logp, double* sum, int backend, jd_stream_t stream) {
-  JD_CHECK_ARG(flux && Lw && mw && ck && K > 0, "jd_gmm_prior_forward: null pointer");
-  if (backend == 0)
-    return gmm_prior_forward_simt(flux, fH, fW, shift_yx, stride, row_begin, row_end, Lw, mw, ck, K, marginalize,
-                                  value, argmax, logp, sum, to_stream(stream));
-  set_error("jd_gmm_prior_forward: backend %d takes the packed operand: call jd_gmm_prior_forward_tc", backend);
-  return JD_ERR_UNSUPPORTED;
 }
 
 }  // extern "C"

@@ -114,6 +114,8 @@ class MapEngine:
             self.packed = prior["packed"]
             if self.backend == 1:
                 self.packed.Bt  # pack the tensor-core operand before any graph capture
+            elif self.backend == 2:
+                ops._bt16(self.packed)
             self.ny, self.nx = ops.patch_grid(self.fH, self.fW, self.stride)
             self.c = self.stride**2 / ops.PD / self.n
             # row-block shard of the prior (whole grid on one GPU)
@@ -168,6 +170,13 @@ class MapEngine:
 
     def _prior_forward(self, sum_acc):
         if self.P <= 0:
+            return
+        if self.backend == 2:
+            bt, binv = ops._bt16(self.packed)
+            _call("jd_gmm_prior_forward_tc16", _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride,
+                  self.rows[0], self.rows[1], _p(bt), _p(binv), _p(self.packed.mw), _p(self.packed.ck), self.packed.K,
+                  int(self.packed.upper_tri), int(self.packed.zero_mean), int(self.marginalize), _p(self.value),
+                  _p(self.argmax), _p(self.logp), sum_acc, self._s())
             return
         if self.backend == 1:
             _call("jd_gmm_prior_forward_tc", _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride,

@@ -183,6 +183,7 @@ class GMMPacked:
         self.Lw, self.mw, self.ck, self.Lam, self.bk = dev(Lw), dev(mw), dev(ck), dev(Lam), dev(bk)
         self.device = torch.device(device)
         self._Bt = None
+        self._Bt16 = None
         self.upper_tri = bool(np.all(np.tril(L, -1) == 0))
         self.zero_mean = bool(np.all(mw == 0))
 
@@ -198,6 +199,20 @@ class GMMPacked:
                 _lib.call("jd_gmm_tc_pack", _ptr(self.Lw), self.K, _ptr(bt), _stream())
             self._Bt = bt
         return self._Bt
+
+
+def _bt16(packed):
+    """Split-FP16 operand image + inverse component scales, packed once on the device."""
+    if packed._Bt16 is None:
+        if packed.D != PD:
+            raise _lib.JolidecoB200Error("the tcgen05 prior kernels support 8x8 patches (D=64) only")
+        nbytes = _lib.load().jd_gmm_tc16_packed_bytes(packed.K)
+        with torch.cuda.device(packed.device):
+            bt = torch.empty(nbytes, dtype=torch.uint8, device=packed.device)
+            binv = torch.empty(packed.K, dtype=torch.float32, device=packed.device)
+            _lib.call("jd_gmm_tc16_pack", _ptr(packed.Lw), packed.K, _ptr(bt), _ptr(binv), _stream())
+        packed._Bt16 = (bt, binv)
+    return packed._Bt16
 
 
 def gmm_log_prob(x, packed):
@@ -250,7 +265,12 @@ def gmm_prior_forward(flux, shift_yx, packed, stride=4, marginalize=False, rows=
     logp = torch.empty((P, packed.K), dtype=torch.float32, device=flux.device) if want_logp else None
     if sum_out is None:
         sum_out = torch.zeros(1, dtype=torch.float64, device=flux.device)
-    if int(backend) == 1:
+    if int(backend) == 2:
+        bt, binv = _bt16(packed)
+        _lib.call("jd_gmm_prior_forward_tc16", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(bt), _ptr(binv),
+                  _ptr(packed.mw), _ptr(packed.ck), packed.K, int(packed.upper_tri), int(packed.zero_mean),
+                  int(bool(marginalize)), _ptr(value), _ptr(argmax), _ptr(logp), _ptr(sum_out), _stream())
+    elif int(backend) == 1:
         _lib.call("jd_gmm_prior_forward_tc", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(packed.Bt),
                   _ptr(packed.mw), _ptr(packed.ck), packed.K, int(packed.upper_tri), int(packed.zero_mean), int(bool(marginalize)), _ptr(value),
                   _ptr(argmax), _ptr(logp), _ptr(sum_out), _stream())

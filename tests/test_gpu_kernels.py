@@ -206,7 +206,7 @@ def prior_cuda(flux, gmm_packed, sy, sx, marginalize, rows=None, backend=0):
     return s.item() * c, dflux.cpu().numpy(), argmax.cpu().numpy()
 
 
-@pytest.mark.parametrize("backend", [0, 1])
+@pytest.mark.parametrize("backend", [0, 1, 2])
 @pytest.mark.parametrize("marginalize", [False, True])
 @pytest.mark.parametrize("shape,shift", [((38, 46), (0, 0)), ((38, 46), (-2, 1)), ((64, 80), (2, -2)), ((24, 24), (1, 2))])
 def test_gmm_prior_value_and_grad(marginalize, shape, shift, backend):
@@ -225,7 +225,7 @@ def test_gmm_prior_value_and_grad(marginalize, shape, shift, backend):
         assert rel_max(gr, ref_g) < 2e-5
 
 
-@pytest.mark.parametrize("backend", [0, 1])
+@pytest.mark.parametrize("backend", [0, 1, 2])
 @pytest.mark.parametrize("case", range(8))
 def test_gmm_prior_golden(case, backend):
     g = load_golden("prior_step.npz")
@@ -249,9 +249,10 @@ def test_gmm_prior_row_blocks_sum_to_whole():
     assert rel_max(sum(p[1] for p in parts), gr) < 1e-6
 
 
+@pytest.mark.parametrize("backend", [1, 2])
 @pytest.mark.parametrize("mean_scale", [0.05, 0.0])
 @pytest.mark.parametrize("marginalize", [False, True])
-def test_gmm_prior_tensor_core_vs_cuda_core_full_size(marginalize, mean_scale):
+def test_gmm_prior_tensor_core_vs_cuda_core_full_size(marginalize, mean_scale, backend):
     """tcgen05 split-TF32 forward against the FP32 CUDA-core forward at the BASELINE config-2 size
     (512x512 flux, 16129 patches), K=32 with non-zero means: per-patch values to FP32 accuracy,
     identical argmax except near-ties."""
@@ -260,7 +261,7 @@ def test_gmm_prior_tensor_core_vs_cuda_core_full_size(marginalize, mean_scale):
     packed = pack(O.GMM(*synthetic_gmm(33, seed=5, mean_scale=mean_scale)))
     assert packed.zero_mean == (mean_scale == 0.0) and packed.upper_tri
     v0, k0, lp0, s0 = ops.gmm_prior_forward(flux, (1, -2), packed, 4, marginalize, want_logp=True, backend=0)
-    v1, k1, lp1, s1 = ops.gmm_prior_forward(flux, (1, -2), packed, 4, marginalize, want_logp=True, backend=1)
+    v1, k1, lp1, s1 = ops.gmm_prior_forward(flux, (1, -2), packed, 4, marginalize, want_logp=True, backend=backend)
     lp0, lp1 = lp0.cpu().numpy().astype(np.float64), lp1.cpu().numpy().astype(np.float64)
     scale = np.abs(lp0).max(axis=1, keepdims=True)
     assert (np.abs(lp1 - lp0) / scale).max() < 2e-6
@@ -279,10 +280,12 @@ def test_gmm_prior_tensor_core_dense_precision_factors():
     assert not packed.upper_tri
     flux = t(rng.gamma(2.0, size=(100, 84)))
     v0, k0, lp0, s0 = ops.gmm_prior_forward(flux, (0, 1), packed, 4, False, want_logp=True, backend=0)
-    v1, k1, lp1, s1 = ops.gmm_prior_forward(flux, (0, 1), packed, 4, False, want_logp=True, backend=1)
-    lp0, lp1 = lp0.cpu().numpy().astype(np.float64), lp1.cpu().numpy().astype(np.float64)
-    assert (np.abs(lp1 - lp0) / np.abs(lp0).max(axis=1, keepdims=True)).max() < 2e-6
-    assert (k0 != k1).sum().item() == 0
+    for backend in (1, 2):
+        v1, k1, lp1, s1 = ops.gmm_prior_forward(flux, (0, 1), packed, 4, False, want_logp=True, backend=backend)
+        lp1 = lp1.cpu().numpy().astype(np.float64)
+        ref = lp0.cpu().numpy().astype(np.float64)
+        assert (np.abs(lp1 - ref) / np.abs(ref).max(axis=1, keepdims=True)).max() < 2e-6
+        assert (k0 != k1).sum().item() == 0
 
 
 def test_gmm_prior_nan_patch_is_skipped():
