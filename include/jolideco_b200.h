@@ -152,11 +152,15 @@ int jd_gmm_prior_forward_tc16(const float* flux, int fH, int fW, const int32_t* 
 /* Per-patch gradient  G[p',:] = scale * sum_k R[p',k] (xc_p Lam_k - bk_k),  minus its row mean,
  * R = one-hot(argmax) or softmax_k(logp) (marginalize=1; needs logp and value from the forward);
  * Lam_k = Lw_k Lw_k^T, bk_k = mw_k Lw_k^T.  (Autograd mirror of gmm.py:270-272 + norms.py:97-103.)
- * For d prior/d flux pass scale = -stride^2/64/(fH fW). */
+ * For d prior/d flux pass scale = -stride^2/64/(fH fW).
+ * workspace (optional, marginalize=0): jd_gmm_backward_workspace_elems(P', K) int32; when given, patches are
+ * bucketed by winning component so that each Lam_k is staged in shared memory once per <= 32 patches instead of
+ * being re-read from L2 for every patch. */
+int64_t jd_gmm_backward_workspace_elems(int64_t P, int K);
 int jd_gmm_prior_backward(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride,
                           int row_begin, int row_end, const float* Lam, const float* bk, int K,
                           int marginalize, const int32_t* argmax, const float* logp, const float* value,
-                          float scale, float* G, jd_stream_t stream);
+                          float scale, float* G, int32_t* workspace, jd_stream_t stream);
 
 /* col2im of the per-patch gradients, gather form (deterministic, no atomics): for every pixel
  * sum the <= (8/s)^2 patch entries covering it at the rolled coordinates

@@ -51,8 +51,9 @@ PROTOTYPES = {
     "jd_gmm_tc16_pack": [c_f32p, c_int, ctypes.c_void_p, c_f32p, c_stream],
     "jd_gmm_prior_forward_tc16": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, ctypes.c_void_p, c_f32p, c_f32p,
                                   c_f32p, c_int, c_int, c_int, c_int, c_f32p, c_i32p, c_f32p, c_f64p, c_stream],
+    "jd_gmm_backward_workspace_elems": [c_i64, c_int],
     "jd_gmm_prior_backward": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, c_f32p, c_f32p, c_int, c_int,
-                              c_i32p, c_f32p, c_f32p, c_float, c_f32p, c_stream],
+                              c_i32p, c_f32p, c_f32p, c_float, c_f32p, c_i32p, c_stream],
     "jd_patch_fold": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, c_f32p, c_int, c_stream],
     "jd_adam_step": [c_f32p, c_f32p, c_f32p, c_f32p, c_u8p, c_f32p, c_f32p, c_float, c_int, c_i64, c_int, c_float,
                      c_float, c_float, c_float, c_stream],
@@ -81,7 +82,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
         fn.restype = {"jd_last_error": ctypes.c_char_p, "jd_gmm_tc_packed_bytes": ctypes.c_size_t,
-                      "jd_gmm_tc16_packed_bytes": ctypes.c_size_t}.get(
+                      "jd_gmm_tc16_packed_bytes": ctypes.c_size_t,
+                      "jd_gmm_backward_workspace_elems": ctypes.c_int64}.get(
             name, ctypes.c_int)
     if lib.jd_abi_version() != 1:
         raise JolidecoB200Error(f"ABI version mismatch: library {lib.jd_abi_version()}, binding 1")

@@ -210,14 +210,28 @@ class MAPDeconvolver:
         self.engine = engine
         engine.warmup()
         prior_names = list(total_loss.prior_loss.priors)
+        # Without early stopping nothing on the host depends on the per-epoch trace: the accumulator rows stay
+        # on the device and are read back once at the end (the reference syncs with .item() every epoch).
+        deferred = not self.stop_early
+        rows = torch.zeros((self.n_epochs, engine.n_trace), dtype=torch.float64, device=self.device) if deferred else None
+        filenames = []
         for epoch in range(self.n_epochs):
             for i in range(n_datasets):
                 engine.step(i)
             filename = self._checkpoint(epoch, total_loss, components)
+            if deferred:
+                engine.trace_enqueue(rows[epoch])
+                filenames.append(filename)
+                continue
             ld, lp, lv = engine.trace_losses()
             total_loss.append_trace_values(ld, [lp] * len(prior_names), filename, lv if lv else None)
             if self._early_stop(total_loss.trace):
                 break
+        if deferred:
+            host = rows.cpu().numpy()  # one synchronising read-back
+            for vals, filename in zip(host, filenames):
+                ld, lp, lv = engine.trace_decode(vals)
+                total_loss.append_trace_values(ld, [lp] * len(prior_names), filename, lv if lv else None)
         torch.cuda.synchronize(self.device)
 
     def _run_joint(self, total_loss, components, shard):

@@ -298,6 +298,103 @@ gmm_bwd_max_kernel(const float* __restrict__ flux, PatchGeom g, const int32_t* _
   }
 }
 
+// ---- max-mode backward, bucketed by winning component ------------------------------------------------
+// Patches are grouped by argmax (histogram -> scan -> scatter), then one CTA per (component, chunk of <= CH
+// patches) stages Lam_k once in shared memory and runs the 64x64 GEMVs of its patches from there: the
+// per-patch 16 KB reads of Lam_k* from L2 (P x 16 KB per launch) become one read per work item.
+constexpr int CH = 32;  // patches per work item
+
+__global__ void bwd_hist_kernel(const int32_t* __restrict__ argmax, int P, int K, int32_t* __restrict__ counts,
+                                float* __restrict__ G) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+    int k = argmax[p];
+    if (k >= 0 && k < K) {
+      atomicAdd(counts + k, 1);
+    } else {  // filtered patch: zero gradient row
+      float4* row = reinterpret_cast<float4*>(G + (int64_t)p * PD);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) row[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+// one block: exclusive scan of the K counts -> offsets / cursors, and the work-item list (k, start, count)
+__global__ void bwd_scan_kernel(int K, const int32_t* __restrict__ counts, int32_t* __restrict__ cursor,
+                                int32_t* __restrict__ items, int32_t* __restrict__ n_items) {
+  // K is small (<= a few hundred): a serial scan by one thread is cheaper than a parallel one + syncs
+  if (threadIdx.x == 0) {
+    int off = 0, ni = 0;
+    for (int k = 0; k < K; ++k) {
+      int c = counts[k];
+      cursor[k] = off;
+      for (int s0 = 0; s0 < c; s0 += CH) {
+        items[3 * ni + 0] = k;
+        items[3 * ni + 1] = off + s0;
+        items[3 * ni + 2] = min(CH, c - s0);
+        ++ni;
+      }
+      off += c;
+    }
+    n_items[0] = ni;
+  }
+}
+
+__global__ void bwd_scatter_kernel(const int32_t* __restrict__ argmax, int P, int K, int32_t* __restrict__ cursor,
+                                   int32_t* __restrict__ perm) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+    int k = argmax[p];
+    if (k >= 0 && k < K) perm[atomicAdd(cursor + k, 1)] = p;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gmm_bwd_bucket_kernel(const float* __restrict__ flux, PatchGeom g, const int32_t* __restrict__ shift_yx,
+                      const float* __restrict__ Lam, const float* __restrict__ bk, const int32_t* __restrict__ perm,
+                      const int32_t* __restrict__ items, const int32_t* __restrict__ n_items, float scale,
+                      float* __restrict__ G) {
+  __shared__ __align__(16) float Ls[PD * PD];
+  __shared__ float bs[PD];
+  __shared__ float xs[4][PD];
+  __shared__ float red[4][2];
+  if ((int)blockIdx.x >= n_items[0]) return;
+  if (shift_yx) {
+    g.sy = shift_yx[0];
+    g.sx = shift_yx[1];
+  }
+  const int k = items[3 * blockIdx.x], start = items[3 * blockIdx.x + 1], cnt = items[3 * blockIdx.x + 2];
+  const float4* Lsrc = reinterpret_cast<const float4*>(Lam + (int64_t)k * PD * PD);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(Ls)[threadIdx.x + i * 256] = __ldg(Lsrc + threadIdx.x + i * 256);
+  if (threadIdx.x < PD) bs[threadIdx.x] = bk[(int64_t)k * PD + threadIdx.x];
+  const int grp = threadIdx.x >> 6, j = threadIdx.x & 63, half = (threadIdx.x >> 5) & 1, lane = threadIdx.x & 31;
+  for (int it = 0; it < cnt; it += 4) {
+    const bool act = it + grp < cnt;
+    int64_t p = 0;
+    float x = 0.f;
+    if (act) {
+      p = perm[start + it + grp];
+      int iy = (int)(p / g.nx) + g.row_begin, ix = (int)(p % g.nx);
+      x = __ldg(flux + (int64_t)patch_src_row(g, iy, j >> 3) * g.fW + patch_src_col(g, ix, j & 7));
+    }
+    float sx_ = warp_sum(x);
+    if (lane == 0) red[grp][half] = sx_;
+    __syncthreads();  // also orders the Ls / bs staging before the first use
+    x -= (red[grp][0] + red[grp][1]) * (1.f / 64.f);
+    xs[grp][j] = x;
+    __syncthreads();
+    float acc = -bs[j];
+#pragma unroll 16
+    for (int i = 0; i < PD; ++i) acc = fmaf(xs[grp][i], Ls[i * PD + j], acc);
+    float sg = warp_sum(acc);
+    __syncthreads();  // red / xs reuse
+    if (lane == 0) red[grp][half] = sg;
+    __syncthreads();
+    const float gm = (red[grp][0] + red[grp][1]) * (1.f / 64.f);
+    if (act) G[p * PD + j] = scale * (acc - gm);
+    __syncthreads();
+  }
+}
+
 // Raw patch extraction (cycle_spin roll + view_as_overlapping_patches_torch): X[p', 8u+v].
 __global__ void extract_patches_kernel(const float* __restrict__ flux, PatchGeom g,
                                        const int32_t* __restrict__ shift_yx, float* __restrict__ X) {
@@ -406,10 +503,15 @@ int jd_extract_patches(const float* flux, int fH, int fW, const int32_t* shift_y
   return JD_OK;
 }
 
+int64_t jd_gmm_backward_workspace_elems(int64_t P, int K) {
+  // counts[K] cursor[K] n_items[1] items[3 (K + P/CH + 1)] perm[P]
+  return 2 * (int64_t)K + 1 + 3 * ((int64_t)K + P / CH + 1) + P;
+}
+
 int jd_gmm_prior_backward(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
                           int row_end, const float* Lam, const float* bk, int K, int marginalize,
                           const int32_t* argmax, const float* logp, const float* value, float scale, float* G,
-                          jd_stream_t stream) {
+                          int32_t* workspace, jd_stream_t stream) {
   JD_CHECK_ARG(flux && Lam && bk && G && K > 0, "jd_gmm_prior_backward: null pointer");
   PatchGeom g;
   int rc = make_geom("jd_gmm_prior_backward", fH, fW, stride, row_begin, row_end, &g);
@@ -428,9 +530,25 @@ int jd_gmm_prior_backward(const float* flux, int fH, int fW, const int32_t* shif
                                       const_cast<float*>(logp), nullptr, scale, G);
   } else {
     JD_CHECK_ARG(argmax, "jd_gmm_prior_backward: marginalize=0 needs argmax from the forward");
-    int64_t blocks = ((int64_t)g.P + 7) / 8;
-    int64_t cap = (int64_t)num_sms() * 16;
-    gmm_bwd_max_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, st>>>(flux, g, shift_yx, Lam, bk, argmax, scale, G);
+    if (workspace) {
+      int32_t* counts = workspace;
+      int32_t* cursor = counts + K;
+      int32_t* n_items = cursor + K;
+      int32_t* items = n_items + 1;
+      const int max_items = K + g.P / CH + 1;
+      int32_t* perm = items + 3 * (int64_t)max_items;
+      cudaMemsetAsync(counts, 0, sizeof(int32_t) * K, st);
+      int blocks = (g.P + 255) / 256;
+      bwd_hist_kernel<<<blocks, 256, 0, st>>>(argmax, g.P, K, counts, G);
+      bwd_scan_kernel<<<1, 32, 0, st>>>(K, counts, cursor, items, n_items);
+      bwd_scatter_kernel<<<blocks, 256, 0, st>>>(argmax, g.P, K, cursor, perm);
+      gmm_bwd_bucket_kernel<<<max_items, 256, 0, st>>>(flux, g, shift_yx, Lam, bk, perm, items, n_items, scale, G);
+    } else {
+      int64_t blocks = ((int64_t)g.P + 7) / 8;
+      int64_t cap = (int64_t)num_sms() * 16;
+      gmm_bwd_max_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, st>>>(flux, g, shift_yx, Lam, bk, argmax, scale,
+                                                                             G);
+    }
   }
   JD_CHECK_LAUNCH("jd_gmm_prior_backward");
   return JD_OK;

@@ -25,8 +25,15 @@ _p = ops._ptr
 _STATS = {"launches": 0, "timed": None, "events": []}
 
 
+# kernels launched by entry points that launch more than one
+_KERNELS_PER_CALL = {"jd_conv_forward_fft": 3, "jd_conv_backward_fft": 3}
+
+
 def _call(name, *args):
-    _STATS["launches"] += 1
+    n = _KERNELS_PER_CALL.get(name, 1)
+    if name == "jd_gmm_prior_backward" and args[-2] is not None:
+        n = 4  # histogram, scan, scatter, bucketed GEMV
+    _STATS["launches"] += n
     if _STATS["timed"] == name:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -126,6 +133,9 @@ class MapEngine:
             self.argmax = torch.empty(max(P, 1), dtype=torch.int32, device=self.dev)
             self.logp = torch.empty((max(P, 1), self.packed.K), **f32) if self.marginalize else None
             self.G = torch.empty((max(P, 1), ops.PD), **f32)
+            # bucketed max-mode backward (ops.gmm_backward_workspace) measured slower than the warp-per-patch
+            # kernel at K=256 (profiles/r01_summary.md): not used
+            self.bwd_ws = None
             self.dflux_p = torch.zeros_like(theta)
             if shift_table is None:
                 shift_table = np.zeros((1, 2), dtype=np.int32)
@@ -196,7 +206,7 @@ class MapEngine:
         s = self._s()
         _call("jd_gmm_prior_backward", _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride, self.rows[0],
               self.rows[1], _p(self.packed.Lam), _p(self.packed.bk), self.packed.K, int(self.marginalize),
-              _p(self.argmax), _p(self.logp), _p(self.value), float(scale), _p(self.G), s)
+              _p(self.argmax), _p(self.logp), _p(self.value), float(scale), _p(self.G), _p(self.bwd_ws), s)
         _call("jd_patch_fold", _p(self.G), self.fH, self.fW, _p(self.cur_shift), self.stride, self.rows[0], self.rows[1],
               _p(out), int(accumulate), s)
 
@@ -273,32 +283,41 @@ class MapEngine:
         self._run(("joint",), self._joint_body)
 
     # ------------------------------------------------------------------------------------------
+    def trace_enqueue(self, out_row, refresh_flux=False):
+        """Same evaluation as `trace_losses` but asynchronous: the raw accumulators are copied on the
+        stream into `out_row` (a device double tensor of n_trace entries); decode with `trace_decode`."""
+        self._run(("trace", bool(refresh_flux)), lambda: self._trace_body(refresh_flux))
+        out_row.copy_(self.acc_trace, non_blocking=True)
+
+    def trace_decode(self, vals):
+        """Raw accumulator row(s) (host numpy, already summed over ranks) -> (datasets, prior, validation)."""
+        npix = self.counts_shape[0] * self.counts_shape[1]
+        ld = [float(vals[j] / npix) for j in range(self.Dg)]
+        lp = float(vals[self.Dg] * self.c) if self.prior is not None else 0.0
+        lv = [float(vals[self.Dg + 1 + j] / npix) for j in range(self.Vg)]
+        return ld, lp, lv
+
+    def _trace_body(self, refresh_flux):
+        self._begin(advance_adam=0, zero_acc=self.acc_trace, with_shift=True)
+        if refresh_flux:
+            self._flux()
+        base = self.acc_trace.data_ptr()
+        for j, d in zip(self.dataset_index, self.datasets):
+            self._likelihood(d, base + 8 * j, want_grad=False)
+        if self.prior is not None:
+            self._prior_forward(base + 8 * self.Dg)  # this rank's patch-row block
+        for j, d in zip(self.validation_index, self.datasets_validation):
+            self._likelihood(d, base + 8 * (self.Dg + 1 + j), want_grad=False)
+
     def trace_losses(self, refresh_flux=False):
         """Per-epoch trace (loss.py:212-250): every dataset's Poisson loss and one more prior draw,
         evaluated at the flux of the LAST step's start (the reference hands the stale `fluxes` tuple
         to append_trace, core.py:217/245).  One host sync.  Returns (datasets, prior, validation)."""
 
-        def body():
-            self._begin(advance_adam=0, zero_acc=self.acc_trace, with_shift=True)
-            if refresh_flux:
-                self._flux()
-            base = self.acc_trace.data_ptr()
-            for j, d in zip(self.dataset_index, self.datasets):
-                self._likelihood(d, base + 8 * j, want_grad=False)
-            if self.prior is not None:
-                self._prior_forward(base + 8 * self.Dg)  # this rank's patch-row block
-            for j, d in zip(self.validation_index, self.datasets_validation):
-                self._likelihood(d, base + 8 * (self.Dg + 1 + j), want_grad=False)
-
-        self._run(("trace", bool(refresh_flux)), body)
+        self._run(("trace", bool(refresh_flux)), lambda: self._trace_body(refresh_flux))
         if self.world > 1:  # every slot is written by exactly one rank (prior: partial sums): one all-reduce
             torch.distributed.all_reduce(self.acc_trace, group=self.pg)
-        vals = self.acc_trace.cpu().numpy()
-        npix = self.counts_shape[0] * self.counts_shape[1]
-        ld = [vals[j] / npix for j in range(self.Dg)]
-        lp = float(vals[self.Dg] * self.c) if self.prior is not None else 0.0
-        lv = [vals[self.Dg + 1 + j] / npix for j in range(self.Vg)]
-        return [float(x) for x in ld], lp, [float(x) for x in lv]
+        return self.trace_decode(self.acc_trace.cpu().numpy())
 
     def last_step_losses(self):
         """(Poisson mean loss, prior value) of the most recent step; syncs."""

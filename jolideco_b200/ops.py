@@ -281,8 +281,13 @@ def gmm_prior_forward(flux, shift_yx, packed, stride=4, marginalize=False, rows=
     return value, argmax, logp, sum_out
 
 
+def gmm_backward_workspace(P, K, device):
+    n = _lib.load().jd_gmm_backward_workspace_elems(int(P), int(K))
+    return torch.empty(n, dtype=torch.int32, device=device)
+
+
 def gmm_prior_backward(flux, shift_yx, packed, scale, stride=4, marginalize=False, rows=None, argmax=None, logp=None,
-                       value=None, out=None):
+                       value=None, out=None, workspace=None, bucketed=False):
     _check(flux, "flux")
     fH, fW = _hw(flux)
     ny, nx = patch_grid(fH, fW, stride)
@@ -290,9 +295,12 @@ def gmm_prior_backward(flux, shift_yx, packed, scale, stride=4, marginalize=Fals
     P = (r1 - r0) * nx
     shift = as_shift_tensor(shift_yx, flux.device)
     G = torch.empty((P, PD), dtype=torch.float32, device=flux.device) if out is None else _check(out, "out")
+    if workspace is None and bucketed and not marginalize:
+        workspace = gmm_backward_workspace(P, packed.K, flux.device)
     _lib.call("jd_gmm_prior_backward", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(packed.Lam),
               _ptr(packed.bk), packed.K, int(bool(marginalize)), _ptr(_check(argmax, "argmax", torch.int32)),
-              _ptr(_check(logp, "logp")), _ptr(_check(value, "value")), float(scale), _ptr(G), _stream())
+              _ptr(_check(logp, "logp")), _ptr(_check(value, "value")), float(scale), _ptr(G),
+              _ptr(_check(workspace, "workspace", torch.int32)), _stream())
     return G
 
 

@@ -201,7 +201,9 @@ def prior_cuda(flux, gmm_packed, sy, sx, marginalize, rows=None, backend=0):
     c = 16.0 / 64.0 / (fH * fW)
     fl = t(flux)
     value, argmax, logp, s = ops.gmm_prior_forward(fl, (sy, sx), gmm_packed, 4, marginalize, rows, backend=backend)
-    G = ops.gmm_prior_backward(fl, (sy, sx), gmm_packed, -c, 4, marginalize, rows, argmax, logp, value)
+    # backend 2 also exercises the bucketed max-mode backward, the others the warp-per-patch one
+    G = ops.gmm_prior_backward(fl, (sy, sx), gmm_packed, -c, 4, marginalize, rows, argmax, logp, value,
+                               bucketed=backend == 2)
     dflux = ops.patch_fold(G, fH, fW, (sy, sx), 4, rows)
     return s.item() * c, dflux.cpu().numpy(), argmax.cpu().numpy()
 
@@ -286,6 +288,17 @@ def test_gmm_prior_tensor_core_dense_precision_factors():
         ref = lp0.cpu().numpy().astype(np.float64)
         assert (np.abs(lp1 - ref) / np.abs(ref).max(axis=1, keepdims=True)).max() < 2e-6
         assert (k0 != k1).sum().item() == 0
+
+
+def test_gmm_backward_bucketed_equals_per_patch_full_size():
+    rng = np.random.default_rng(13)
+    flux = t(rng.gamma(2.0, size=(512, 512)))
+    packed = pack(O.GMM(*synthetic_gmm(40, seed=6)))
+    value, argmax, _, _ = ops.gmm_prior_forward(flux, (2, -1), packed, 4, False, backend=1)
+    Ga = ops.gmm_prior_backward(flux, (2, -1), packed, -1e-3, 4, False, None, argmax, None, value, bucketed=False)
+    Gb = ops.gmm_prior_backward(flux, (2, -1), packed, -1e-3, 4, False, None, argmax, None, value, bucketed=True)
+    a, b = Ga.cpu().numpy(), Gb.cpu().numpy()
+    assert np.abs(a - b).max() <= 2e-6 * np.abs(a).max()
 
 
 def test_gmm_prior_nan_patch_is_skipped():
