@@ -149,7 +149,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def build_run(J, workload, args, device, n_epochs, seed=0):
+def build_run(J, workload, args, device, n_epochs, seed=0, mode="sequential"):
     """(MAPDeconvolver, components) for the workload through the public API."""
     import torch
 
@@ -162,7 +162,7 @@ def build_run(J, workload, args, device, n_epochs, seed=0):
     comps["flux"] = J.SpatialFluxComponent.from_numpy(flux=workload["flux_init"], upsampling_factor=workload["f"],
                                                       prior=prior)
     deco = J.MAPDeconvolver(n_epochs=n_epochs, learning_rate=0.1, display_progress=False, device=device,
-                            use_cuda_graph=not args.no_graph)
+                            use_cuda_graph=not args.no_graph, mode=mode)
     return deco, comps
 
 
@@ -267,15 +267,15 @@ def main():
 
     # ------------------------------------------------------------------ roofline of the dominant kernel
     roofline = None
-    if rank == 0:
+    if rank == 0 or joint:  # joint steps contain a collective: every rank has to take part
         roofline = measure_roofline(E, eng, run_step, args, workload, flush)
 
     # ------------------------------------------------------------------ e2e through MAPDeconvolver.run (host buffers)
     e2e = None
-    if rank == 0 or not joint:
-        e2e_local = measure_e2e(J, workload, args, device, rank)
+    if True:
+        e2e_local = measure_e2e(J, workload, args, device, rank, joint)
         t = torch.tensor([e2e_local["seconds"]], dtype=torch.float64, device=device)
-        if world > 1 and not joint:
+        if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         n_runs = world if not joint else 1
         e2e = {"value": n_runs * e2e_local["iters"] / float(t.item()), "unit": UNIT,
@@ -362,32 +362,35 @@ def measure_roofline(E, eng, run_step, args, workload, flush):
             "peak_source": src}
 
 
-def measure_e2e(J, workload, args, device, rank):
+def measure_e2e(J, workload, args, device, rank, joint=False):
     """MAPDeconvolver(n_epochs=E).run(datasets, components) with host (numpy) datasets: includes the
     host->device copies of every dataset, GMM constants and flux init, the per-epoch trace read-back
     and the final flux device->host copy."""
     import torch
 
     D = workload["cfg"]["D"]
-    epochs = max(1, args.steps // D)
+    mode = "joint" if joint else "sequential"
+    epochs = max(1, args.steps if joint else args.steps // D)
+    seed = 0 if joint else rank  # joint: every rank must draw the same shifts
     # one short call first so that context / module load is not billed to the timed call
-    deco, comps = build_run(J, workload, args, device, n_epochs=2, seed=rank)
+    deco, comps = build_run(J, workload, args, device, n_epochs=2, seed=seed, mode=mode)
     deco.run(datasets=workload["datasets"], components=comps)
-    deco, comps = build_run(J, workload, args, device, n_epochs=epochs, seed=rank)
+    deco, comps = build_run(J, workload, args, device, n_epochs=epochs, seed=seed, mode=mode)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     res = deco.run(datasets=workload["datasets"], components=comps)
     flux = res.flux_upsampled_total
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    iters = epochs * D
+    iters = epochs if joint else epochs * D
     h2d = sum(a.nbytes for d in workload["datasets"].values() for a in d.values()) + comps["flux"]._flux_upsampled.numel() * 4
     if workload["gmm_arrays"] is not None:
         K = workload["cfg"]["K"]
         h2d += K * (2 * 64 * 64 + 2 * 64 + 1) * 4
     d2h = epochs * 8 * (D + 1) + flux.nbytes
     return {"seconds": dt, "iters": iters, "h2d": h2d / iters, "d2h": d2h / iters,
-            "what": f"MAPDeconvolver(n_epochs={epochs}).run(numpy datasets) incl. setup, H2D, per-epoch trace D2H, final flux D2H"}
+            "what": f"MAPDeconvolver(n_epochs={epochs}, mode={mode!r}).run(numpy datasets) incl. setup, H2D of all inputs, "
+                    "trace D2H and final flux D2H"}
 
 
 if __name__ == "__main__":

@@ -192,6 +192,18 @@ int jd_step_begin(int32_t* counters, const int32_t* shift_table, int n_shifts, i
                   int advance_adam, float lr, float beta1, float beta2, float* adam_scalars, double* zero_acc,
                   int n_acc, jd_stream_t stream);
 
+/* Fused variants used by the graph-captured step (one launch each instead of two):
+ * jd_step_begin_flux = jd_step_begin + jd_flux_forward;
+ * jd_adam_fold_step_dev = jd_patch_fold (gather col2im of G, scaled by scale_b) + jd_adam_step_dev. */
+int jd_step_begin_flux(int32_t* counters, const int32_t* shift_table, int n_shifts, int32_t* shift_out,
+                       int advance_adam, float lr, float beta1, float beta2, float* adam_scalars,
+                       double* zero_acc, int n_acc, const float* theta, const uint8_t* mask, float* flux,
+                       int64_t n, int use_log_flux, jd_stream_t stream);
+int jd_adam_fold_step_dev(float* theta, float* m, float* v, const float* flux, const uint8_t* mask,
+                          const float* dflux_a, const float* G, float scale_b, int use_log_flux, int fH, int fW,
+                          const int32_t* shift_yx, int stride, int row_begin, int row_end,
+                          const float* adam_scalars, float beta1, float beta2, float eps, jd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

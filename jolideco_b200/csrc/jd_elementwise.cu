@@ -218,6 +218,66 @@ __global__ void adam_dev_kernel(float* __restrict__ theta, float* __restrict__ m
   }
 }
 
+// step_begin + flux in one launch: block 0 does the bookkeeping, every block its share of exp(theta)
+__global__ void step_begin_flux_kernel(int32_t* __restrict__ counters, const int32_t* __restrict__ shift_table,
+                                       int n_shifts, int32_t* __restrict__ shift_out, int advance_adam, float lr,
+                                       float b1, float b2, float* __restrict__ adam_scalars,
+                                       double* __restrict__ zero_acc, int n_acc, const float* __restrict__ theta,
+                                       const uint8_t* __restrict__ mask, float* __restrict__ flux, int64_t n,
+                                       int use_log) {
+  if (blockIdx.x == 0) {
+    if (threadIdx.x == 0) {
+      if (shift_table && shift_out) {
+        int d = counters[0];
+        int idx = d < n_shifts ? d : n_shifts - 1;
+        shift_out[0] = shift_table[2 * idx];
+        shift_out[1] = shift_table[2 * idx + 1];
+        counters[0] = d + 1;
+      }
+      if (advance_adam) {
+        int t = counters[1] + 1;
+        counters[1] = t;
+        double bc1 = 1.0 - pow((double)b1, (double)t);
+        double bc2 = 1.0 - pow((double)b2, (double)t);
+        adam_scalars[0] = (float)((double)lr / bc1);
+        adam_scalars[1] = (float)sqrt(bc2);
+      }
+    }
+    for (int i = threadIdx.x; i < n_acc; i += blockDim.x) zero_acc[i] = 0.0;
+  }
+  if (!flux) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float t = theta[i];
+    float f = use_log ? expf(t) : t;
+    if (mask) f *= (float)mask[i];
+    flux[i] = f;
+  }
+}
+
+// fold (gather col2im of the patch gradients) + gradient sum + chain rule + Adam in one pass
+__global__ void adam_fold_kernel(float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v,
+                                 const float* __restrict__ flux, const uint8_t* __restrict__ mask,
+                                 const float* __restrict__ da, const float* __restrict__ G, float scale_b, int use_log,
+                                 int fH, int fW, const int32_t* __restrict__ shift_yx, int stride, int row_begin,
+                                 int row_end, const float* __restrict__ scalars, float b1, float b2, float eps) {
+  const float lr_over_bc1 = scalars[0], sqrt_bc2 = scalars[1];
+  const int sy = shift_yx ? shift_yx[0] : 0, sx = shift_yx ? shift_yx[1] : 0;
+  const int ny = (fH - PATCH) / stride + 1, nx = (fW - PATCH) / stride + 1;
+  const int64_t n = (int64_t)fH * fW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int y = (int)(i / fW), x = (int)(i - (int64_t)y * fW);
+    float g = da[i] + scale_b * fold_gather(G, y, x, fH, fW, sy, sx, stride, ny, nx, row_begin, row_end);
+    g *= use_log ? flux[i] : (mask ? (float)mask[i] : 1.f);
+    float mi = m[i], vi = v[i];
+    mi = mi + (g - mi) * (1.f - b1);
+    vi = vi * b2 + (1.f - b2) * g * g;
+    float denom = sqrtf(vi) / sqrt_bc2 + eps;
+    theta[i] = theta[i] - lr_over_bc1 * (mi / denom);
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+
 static inline int grid_for(int64_t n, int block) {
   int64_t g = (n + block - 1) / block;
   int64_t cap = (int64_t)num_sms() * 8;
@@ -292,6 +352,38 @@ int jd_step_begin(int32_t* counters, const int32_t* shift_table, int n_shifts, i
   step_begin_kernel<<<1, 32, 0, to_stream(stream)>>>(counters, shift_table, n_shifts, shift_out, advance_adam, lr,
                                                      beta1, beta2, adam_scalars, zero_acc, n_acc);
   JD_CHECK_LAUNCH("jd_step_begin");
+  return JD_OK;
+}
+
+int jd_step_begin_flux(int32_t* counters, const int32_t* shift_table, int n_shifts, int32_t* shift_out,
+                       int advance_adam, float lr, float beta1, float beta2, float* adam_scalars, double* zero_acc,
+                       int n_acc, const float* theta, const uint8_t* mask, float* flux, int64_t n, int use_log_flux,
+                       jd_stream_t stream) {
+  JD_CHECK_ARG(counters && theta && flux && n > 0, "jd_step_begin_flux: null pointer");
+  JD_CHECK_ARG(!advance_adam || adam_scalars, "jd_step_begin_flux: adam_scalars required");
+  JD_CHECK_ARG(!shift_table || n_shifts > 0, "jd_step_begin_flux: empty shift table");
+  JD_CHECK_ARG(n_acc == 0 || zero_acc, "jd_step_begin_flux: null accumulator block");
+  step_begin_flux_kernel<<<grid_for(n, 256), 256, 0, to_stream(stream)>>>(counters, shift_table, n_shifts, shift_out,
+                                                                           advance_adam, lr, beta1, beta2, adam_scalars,
+                                                                           zero_acc, n_acc, theta, mask, flux, n,
+                                                                           use_log_flux);
+  JD_CHECK_LAUNCH("jd_step_begin_flux");
+  return JD_OK;
+}
+
+int jd_adam_fold_step_dev(float* theta, float* m, float* v, const float* flux, const uint8_t* mask,
+                          const float* dflux_a, const float* G, float scale_b, int use_log_flux, int fH, int fW,
+                          const int32_t* shift_yx, int stride, int row_begin, int row_end, const float* adam_scalars,
+                          float beta1, float beta2, float eps, jd_stream_t stream) {
+  JD_CHECK_ARG(theta && m && v && dflux_a && G && adam_scalars, "jd_adam_fold_step_dev: null pointer");
+  JD_CHECK_ARG(!use_log_flux || flux, "jd_adam_fold_step_dev: flux required for the log parameterisation");
+  JD_CHECK_ARG(fH >= PATCH && fW >= PATCH && stride >= 1 && stride <= PATCH, "jd_adam_fold_step_dev: bad geometry");
+  int ny = (fH - PATCH) / stride + 1;
+  JD_CHECK_ARG(row_begin >= 0 && row_end <= ny && row_begin <= row_end, "jd_adam_fold_step_dev: bad row block");
+  adam_fold_kernel<<<grid_for((int64_t)fH * fW, 256), 256, 0, to_stream(stream)>>>(
+      theta, m, v, flux, mask, dflux_a, G, scale_b, use_log_flux, fH, fW, shift_yx, stride, row_begin, row_end,
+      adam_scalars, beta1, beta2, eps);
+  JD_CHECK_LAUNCH("jd_adam_fold_step_dev");
   return JD_OK;
 }
 

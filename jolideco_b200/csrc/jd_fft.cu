@@ -5,7 +5,8 @@
 //   * the PSF spectrum is computed ONCE per dataset (jd_fftconv_prepare_psf); the reference recomputes it on
 //     every call;
 //   * any FFT size >= the linear-convolution support gives the same answer, so both axes are padded to the
-//     next power of two and a radix-2 Stockham autosort FFT runs entirely in shared memory;
+//     next power of two and a radix-4 (+ one radix-2 stage for odd log2) Stockham autosort FFT runs entirely in
+//     shared memory;
 //   * three kernels instead of rfft2 / multiply / irfft2 / slice:
 //       rows   : [input transform] 2 real rows per complex FFT (even/odd split), half spectrum written
 //                transposed  specT[kx][row]
@@ -34,28 +35,54 @@ __device__ __forceinline__ void make_twiddles(float2* tw, int N) {
   }
 }
 
-// Radix-2 Stockham autosort FFT of length N = 2^logN in shared memory (ping-pong x <-> y).
-// INV conjugates the twiddles (no scaling).  Returns the buffer holding the result (natural order).
-// All threads of the block must call it; x must be fully written and synchronised by the caller.
+// Stockham autosort FFT of length N = 2^logN in shared memory (ping-pong x <-> y): radix-4 stages, plus one
+// radix-2 stage when logN is odd.  INV conjugates the twiddles (no scaling).  Returns the buffer holding the
+// result (natural order).  All threads of the block must call it; x must be fully written and synchronised.
 template <bool INV>
 __device__ __forceinline__ float2* fft_pow2(float2* x, float2* y, const float2* tw, int N, int logN) {
-  int n = N, ls = 0;  // s = 1 << ls
-  for (int stage = 0; stage < logN; ++stage) {
-    const int m = n >> 1, s = 1 << ls;
-    for (int t = threadIdx.x; t < N / 2; t += blockDim.x) {
+  int n = N, ls = 0, done = 0;  // s = 1 << ls; n = N >> done
+  // radix-4 stages
+  while (logN - done >= 2) {
+    const int m = n >> 2, s = 1 << ls;
+    for (int t = threadIdx.x; t < N / 4; t += blockDim.x) {
       const int q = t & (s - 1), p = t >> ls;
-      float2 w = tw[p << stage];  // exp(-2 pi i p / n), n = N >> stage
-      if (INV) w.y = -w.y;
-      const float2 a = x[q + s * p], b = x[q + s * (p + m)];
-      y[q + s * (2 * p)] = make_float2(a.x + b.x, a.y + b.y);
-      y[q + s * (2 * p + 1)] = cmul(make_float2(a.x - b.x, a.y - b.y), w);
+      float2 w1 = tw[p << done];        // exp(-2 pi i p / n)
+      float2 w2 = tw[(2 * p) << done];  // exp(-2 pi i 2p / n), 2p < n/2
+      if (INV) {
+        w1.y = -w1.y;
+        w2.y = -w2.y;
+      }
+      const float2 w3 = cmul(w1, w2);
+      const float2 a = x[q + s * p], b = x[q + s * (p + m)], c = x[q + s * (p + 2 * m)], d = x[q + s * (p + 3 * m)];
+      const float2 apc = make_float2(a.x + c.x, a.y + c.y), amc = make_float2(a.x - c.x, a.y - c.y);
+      const float2 bpd = make_float2(b.x + d.x, b.y + d.y), bmd = make_float2(b.x - d.x, b.y - d.y);
+      // forward: -i (b - d) = (bmd.y, -bmd.x); inverse: +i (b - d) = (-bmd.y, bmd.x)
+      const float2 jb = INV ? make_float2(-bmd.y, bmd.x) : make_float2(bmd.y, -bmd.x);
+      float2* o = y + q + s * (4 * p);
+      o[0] = make_float2(apc.x + bpd.x, apc.y + bpd.y);
+      o[s] = cmul(make_float2(amc.x + jb.x, amc.y + jb.y), w1);
+      o[2 * s] = cmul(make_float2(apc.x - bpd.x, apc.y - bpd.y), w2);
+      o[3 * s] = cmul(make_float2(amc.x - jb.x, amc.y - jb.y), w3);
     }
     __syncthreads();
     float2* tmp = x;
     x = y;
     y = tmp;
     n = m;
-    ++ls;
+    ls += 2;
+    done += 2;
+  }
+  if (logN - done == 1) {  // final radix-2 stage: n == 2, twiddle 1
+    const int s = 1 << ls;
+    for (int t = threadIdx.x; t < N / 2; t += blockDim.x) {
+      const float2 a = x[t], b = x[t + s];  // p = 0, q = t
+      y[t] = make_float2(a.x + b.x, a.y + b.y);
+      y[t + s] = make_float2(a.x - b.x, a.y - b.y);
+    }
+    __syncthreads();
+    float2* tmp = x;
+    x = y;
+    y = tmp;
   }
   return x;
 }
@@ -270,7 +297,7 @@ static int run_fftconv(const char* name, int mode, const float* in, const float*
   const float norm = 1.0f / ((float)pl.Sy * (float)pl.Sx);
   size_t smx = smem_for(pl.Sx), smy = smem_for(pl.Sy);
   JD_CHECK_ARG(smx <= 200 * 1024 && smy <= 200 * 1024, "%s: FFT size too large for shared memory", name);
-  const int pairs = 2;
+  const int pairs = 1;  // one row pair per CTA: >= 2 CTAs per SM already at 512 rows, phases of different CTAs overlap
   const int grid_rows = (fH + 2 * pairs - 1) / (2 * pairs);
   float2* spec = reinterpret_cast<float2*>(workspace);
   const float2* ph = reinterpret_cast<const float2*>(psf_hat);

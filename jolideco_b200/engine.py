@@ -158,6 +158,19 @@ class MapEngine:
         _call("jd_step_begin", _p(self.counters), _p(tab), self.n_shifts, _p(self.cur_shift), int(advance_adam),
               self.lr, self.b1, self.b2, _p(self.adam_scalars), _p(zero_acc), int(zero_acc.numel()), self._s())
 
+    def _begin_flux(self, advance_adam, zero_acc):
+        """step bookkeeping + flux = exp(theta) in one launch"""
+        tab = self.shift_table if self.prior is not None else None
+        _call("jd_step_begin_flux", _p(self.counters), _p(tab), self.n_shifts, _p(self.cur_shift), int(advance_adam),
+              self.lr, self.b1, self.b2, _p(self.adam_scalars), _p(zero_acc), int(zero_acc.numel()), _p(self.theta),
+              _p(self.mask), _p(self.flux), self.n, int(self.use_log_flux), self._s())
+
+    def _adam_fold(self, scale_b):
+        """col2im of the patch gradients + gradient sum + Adam in one launch"""
+        _call("jd_adam_fold_step_dev", _p(self.theta), _p(self.m), _p(self.v), _p(self.flux), _p(self.mask),
+              _p(self.dflux_l), _p(self.G), float(scale_b), int(self.use_log_flux), self.fH, self.fW, _p(self.cur_shift),
+              self.stride, self.rows[0], self.rows[1], _p(self.adam_scalars), self.b1, self.b2, self.eps, self._s())
+
     def _flux(self):
         _call("jd_flux_forward", _p(self.theta), _p(self.mask), _p(self.flux), self.n, int(self.use_log_flux), self._s())
 
@@ -198,6 +211,12 @@ class MapEngine:
               self.rows[1], _p(self.packed.Lw), _p(self.packed.mw), _p(self.packed.ck), self.packed.K,
               int(self.marginalize), _p(self.value), _p(self.argmax), _p(self.logp), sum_acc, self.backend, self._s())
 
+    def _prior_gradient(self, scale):
+        """per-patch gradient rows G (consumed by _adam_fold)"""
+        _call("jd_gmm_prior_backward", _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride, self.rows[0],
+              self.rows[1], _p(self.packed.Lam), _p(self.packed.bk), self.packed.K, int(self.marginalize),
+              _p(self.argmax), _p(self.logp), _p(self.value), float(scale), _p(self.G), _p(self.bwd_ws), self._s())
+
     def _prior_backward(self, scale, out, accumulate):
         if self.P <= 0:
             if not accumulate:
@@ -219,13 +238,12 @@ class MapEngine:
     def _step_body(self, i):
         """Reference step for dataset i: total = L_i - beta * prior / D  (core.py:214-229)."""
         d = self.datasets[i]
-        self._begin(advance_adam=1, zero_acc=self.acc, with_shift=True)
-        self._flux()
+        self._begin_flux(advance_adam=1, zero_acc=self.acc)
         self._likelihood(d, self.acc.data_ptr(), want_grad=True)
-        if self.prior is not None:
+        if self.prior is not None and self.P > 0:
             self._prior_forward(self.acc.data_ptr() + 8)
-            self._prior_backward(-self.c, self.dflux_p, accumulate=False)
-            self._adam(self.dflux_p, -self.beta / self.prior_weight)
+            self._prior_gradient(-self.c)
+            self._adam_fold(-self.beta / self.prior_weight)
         else:
             self._adam(None, 0.0)
 
