@@ -2,6 +2,7 @@
 drop-in behind the reference's Python API.  All arithmetic runs in `libjolideco_b200.so`
 (hand-written CUDA, C ABI in include/jolideco_b200.h); there is no CPU or PyTorch fallback."""
 from ._lib import JolidecoB200Error  # noqa: F401
+from .batch import BatchedRuns, run_many  # noqa: F401
 from .core import MAPDeconvolver, MAPDeconvolverResult  # noqa: F401
 from .loss import PoissonLoss, PriorLoss, TotalLoss  # noqa: F401
 from .models import (  # noqa: F401
