@@ -224,7 +224,7 @@ def main():
     eng = deco._build_engine(total_loss, comps, n_draws)
     if pg is not None:
         eng = rebuild_with_group(E, eng, pg)
-    eng.warmup()
+    eng.warmup(joint=joint)
     D_local = len(eng.datasets)
 
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=device)
@@ -392,7 +392,7 @@ def rebuild_with_group(E, eng, pg):
     new = E.MapEngine(eng.theta, eng.datasets, prior=prior, mask=eng.mask, use_log_flux=eng.use_log_flux, beta=eng.beta,
                       lr=eng.lr, betas=(eng.b1, eng.b2), eps=eng.eps,
                       shift_table=eng.shift_table.cpu().numpy() if eng.shift_table is not None else None,
-                      use_graph=False, process_group=pg)
+                      use_graph=eng.use_graph, process_group=pg)
     return new
 
 

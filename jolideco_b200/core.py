@@ -238,14 +238,29 @@ class MAPDeconvolver:
         """One joint Adam step per epoch (+ trace); dataset- and prior-sharded when `shard` is given."""
         engine = self._build_engine(total_loss, components, self.n_epochs * 2, shard)
         self.engine = engine
+        engine.warmup(joint=True)
         prior_names = list(total_loss.prior_loss.priors)
+        deferred = not self.stop_early
+        rows = torch.zeros((self.n_epochs, engine.n_trace), dtype=torch.float64, device=self.device) if deferred else None
+        filenames = []
         for epoch in range(self.n_epochs):
             engine.joint_step()
             filename = self._checkpoint(epoch, total_loss, components)
+            if deferred:
+                engine.trace_enqueue(rows[epoch])
+                filenames.append(filename)
+                continue
             ld, lp, lv = engine.trace_losses()
             total_loss.append_trace_values(ld, [lp] * len(prior_names), filename, lv if lv else None)
             if self._early_stop(total_loss.trace):
                 break
+        if deferred:
+            if engine.world > 1:  # every slot is written by one rank (prior: partial sums): one all-reduce for all epochs
+                torch.distributed.all_reduce(rows, group=engine.pg)
+            host = rows.cpu().numpy()
+            for vals, filename in zip(host, filenames):
+                ld, lp, lv = engine.trace_decode(vals)
+                total_loss.append_trace_values(ld, [lp] * len(prior_names), filename, lv if lv else None)
         torch.cuda.synchronize(self.device)
 
     def _run_autograd(self, total_loss, components, calibrations):

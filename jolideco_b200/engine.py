@@ -142,6 +142,8 @@ class MapEngine:
             tab = np.ascontiguousarray(np.asarray(shift_table, dtype=np.int32).reshape(-1, 2))
             self.shift_table = torch.from_numpy(tab).to(self.dev)
             self.n_shifts = int(tab.shape[0])
+        # multi-rank joint steps are launched eagerly: capturing the NCCL all-reduce together with the kernels in
+        # one CUDA graph hung with uneven dataset shards (2-GPU test) and gained < 4 % when it worked
         self.use_graph = bool(use_graph) and process_group is None
         self._graphs = {}
         self._graph_nodes = {}
@@ -281,14 +283,17 @@ class MapEngine:
             self._graphs[key] = g
         g.replay()
 
-    def warmup(self):
-        """Run every kernel once outside graph capture (function attributes, module load), then
-        restore the optimiser state so that training starts from step 0."""
+    def warmup(self, joint=False):
+        """Run every kernel once outside graph capture (function attributes, module load, NCCL
+        communicator), then restore the optimiser state so that training starts from step 0."""
         state = [t.clone() for t in (self.theta, self.m, self.v, self.counters, self.acc)]
         graph = self.use_graph
         self.use_graph = False
-        for i in range(min(self.D, 1)):
-            self._step_body(i)
+        if joint:
+            self._joint_body()  # collective: every rank calls warmup(joint=True)
+        else:
+            for i in range(min(self.D, 1)):
+                self._step_body(i)
         self.use_graph = graph
         torch.cuda.synchronize(self.dev)
         for t, s in zip((self.theta, self.m, self.v, self.counters, self.acc), state):

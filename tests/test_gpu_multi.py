@@ -47,5 +47,5 @@ def test_joint_mode_single_gpu_matches_oracle(marginalize):
 def test_dataset_sharded_joint_run_two_ranks_nccl():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
            "127.0.0.1", "--master-port", str(29600 + os.getpid() % 300), os.path.join(ROOT, "tests", "dist_worker.py")]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=150)
     assert res.returncode == 0 and "DIST_WORKER_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
