@@ -192,6 +192,12 @@ int jd_step_begin(int32_t* counters, const int32_t* shift_table, int n_shifts, i
                   int advance_adam, float lr, float beta1, float beta2, float* adam_scalars, double* zero_acc,
                   int n_acc, jd_stream_t stream);
 
+/* Adam on the scalar calibration parameters of one dataset (NPredCalibration._background_norm, models/npred.py:
+ * 298-333): grad[i] are the double accumulators written by jd_poisson_forward_backward (dlogb), counter is the
+ * parameter's own step count (torch.optim.Adam only advances it when the parameter received a gradient). */
+int jd_adam_scalar_step_dev(float* param, float* m, float* v, const double* grad, int32_t* counter, int n,
+                            float lr, float beta1, float beta2, float eps, jd_stream_t stream);
+
 /* Fused variants used by the graph-captured step (one launch each instead of two):
  * jd_step_begin_flux = jd_step_begin + jd_flux_forward;
  * jd_adam_fold_step_dev = jd_patch_fold (gather col2im of G, scaled by scale_b) + jd_adam_step_dev. */

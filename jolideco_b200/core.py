@@ -83,8 +83,22 @@ class MAPDeconvolver:
         return f"{self.__class__.__name__}\n" + "\n".join(f"  {k:24s}: {v}" for k, v in self.to_dict().items())
 
     # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _calibrations_fusable(calibrations):
+        """Calibrations the engine covers: background norm (trained or frozen); shifts at 0 never train in the
+        reference (`shift_image_torch` returns early, utils/torch.py:211) and psf_scale ~ 1 is the identity."""
+        for cal in calibrations.values():
+            shift = cal.shift_xy.detach().cpu()
+            if not bool(torch.all(torch.isclose(shift, torch.zeros_like(shift)))):
+                return False
+            if not bool(torch.isclose(cal.psf_scale.detach().cpu(), torch.tensor(1.0)).all()):
+                return False
+        return True
+
     def _engine_supported(self, components, calibrations):
-        if not self.fused or self.optimizer_type != "adam" or calibrations:
+        if not self.fused or self.optimizer_type != "adam":
+            return False
+        if calibrations and not self._calibrations_fusable(calibrations):
             return False
         if set(self.optimizer_kwargs) - {"lr", "betas", "eps"}:
             return False
@@ -115,8 +129,11 @@ class MAPDeconvolver:
             for ds_name, counts, models in zip(poisson_loss.names_all, poisson_loss.counts_all,
                                                poisson_loss.npred_models_all):
                 model = models[name]
+                cal = models.calibration
                 out.append(DatasetBuffers(counts[0, 0].contiguous(), model.exposure[0, 0], model.psf[0, 0],
-                                          models.background[0, 0].contiguous(), model.upsampling_factor, name=ds_name))
+                                          models.background[0, 0].contiguous(), model.upsampling_factor, name=ds_name,
+                                          bkg_log_norm=None if cal is None else cal._background_norm.data,
+                                          train_bkg_norm=cal is not None and not cal.frozen))
             return out
 
         prior_cfg, table = None, None

@@ -278,6 +278,30 @@ __global__ void adam_fold_kernel(float* __restrict__ theta, float* __restrict__ 
   }
 }
 
+// Adam on a handful of scalar calibration parameters (log background norm) whose gradients were accumulated in
+// double by the Poisson kernel.  torch.optim.Adam keeps one step counter per parameter and only advances it when
+// the parameter has a gradient (core.py:197-204, 229): `counter` is that per-parameter count.
+__global__ void adam_scalar_kernel(float* __restrict__ param, float* __restrict__ m, float* __restrict__ v,
+                                   const double* __restrict__ grad, int32_t* __restrict__ counter, int n, float lr,
+                                   float b1, float b2, float eps) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const int t = counter[0] + 1;
+    counter[0] = t;
+    const double bc1 = 1.0 - pow((double)b1, (double)t), bc2 = 1.0 - pow((double)b2, (double)t);
+    const float step_size = (float)((double)lr / bc1), sqrt_bc2 = (float)sqrt(bc2);
+    for (int i = 0; i < n; ++i) {
+      const float g = (float)grad[i];
+      float mi = m[i], vi = v[i];
+      mi = mi + (g - mi) * (1.f - b1);
+      vi = vi * b2 + (1.f - b2) * g * g;
+      const float denom = sqrtf(vi) / sqrt_bc2 + eps;
+      param[i] = param[i] - step_size * (mi / denom);
+      m[i] = mi;
+      v[i] = vi;
+    }
+  }
+}
+
 static inline int grid_for(int64_t n, int block) {
   int64_t g = (n + block - 1) / block;
   int64_t cap = (int64_t)num_sms() * 8;
@@ -384,6 +408,14 @@ int jd_adam_fold_step_dev(float* theta, float* m, float* v, const float* flux, c
       theta, m, v, flux, mask, dflux_a, G, scale_b, use_log_flux, fH, fW, shift_yx, stride, row_begin, row_end,
       adam_scalars, beta1, beta2, eps);
   JD_CHECK_LAUNCH("jd_adam_fold_step_dev");
+  return JD_OK;
+}
+
+int jd_adam_scalar_step_dev(float* param, float* m, float* v, const double* grad, int32_t* counter, int n, float lr,
+                            float beta1, float beta2, float eps, jd_stream_t stream) {
+  JD_CHECK_ARG(param && m && v && grad && counter && n > 0 && n <= 64, "jd_adam_scalar_step_dev: bad arguments");
+  adam_scalar_kernel<<<1, 32, 0, to_stream(stream)>>>(param, m, v, grad, counter, n, lr, beta1, beta2, eps);
+  JD_CHECK_LAUNCH("jd_adam_scalar_step_dev");
   return JD_OK;
 }
 

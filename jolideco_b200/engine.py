@@ -47,10 +47,17 @@ def _call(name, *args):
 class DatasetBuffers:
     """Device-resident arrays of one dataset (loss.py:104-118, npred.py:281-295)."""
 
-    def __init__(self, counts, exposure, psf, background, f, bkg_log_norm=None, name=""):
+    def __init__(self, counts, exposure, psf, background, f, bkg_log_norm=None, name="", train_bkg_norm=False):
         self.counts, self.exposure, self.psf, self.background = counts, exposure, psf, background
         self.f = int(f) if f else 1
+        # log background norm (NPredCalibration._background_norm, a (1,) CUDA float tensor sharing the
+        # parameter's storage) and, when it is trained, its private Adam state
         self.bkg_log_norm = bkg_log_norm
+        self.train_bkg_norm = bool(train_bkg_norm) and bkg_log_norm is not None
+        if self.train_bkg_norm:
+            self.cal_m = torch.zeros_like(bkg_log_norm)
+            self.cal_v = torch.zeros_like(bkg_log_norm)
+            self.cal_t = torch.zeros(1, dtype=torch.int32, device=bkg_log_norm.device)
         self.name = name
         self.H, self.W = int(counts.shape[-2]), int(counts.shape[-1])
         self.fH, self.fW = int(exposure.shape[-2]), int(exposure.shape[-1])
@@ -108,8 +115,9 @@ class MapEngine:
         self.counters = torch.zeros(2, dtype=torch.int32, device=self.dev)
         self.cur_shift = torch.zeros(2, dtype=torch.int32, device=self.dev)
         self.adam_scalars = torch.zeros(2, **f32)
-        # acc[0] = Poisson loss sum of the last step, acc[1] = sum_p v_p of the last prior evaluation
-        self.acc = torch.zeros(2, dtype=torch.float64, device=self.dev)
+        # acc[0] = Poisson loss sum of the last step, acc[1] = sum_p v_p of the last prior evaluation,
+        # acc[2] = d loss / d log(background norm) of the last step
+        self.acc = torch.zeros(3, dtype=torch.float64, device=self.dev)
         self.n_trace = self.Dg + 1 + self.Vg
         self.acc_trace = torch.zeros(self.n_trace, dtype=torch.float64, device=self.dev)
         self.shift_table = None
@@ -184,8 +192,13 @@ class MapEngine:
         else:
             _call("jd_conv_forward_direct", _p(self.flux), _p(d.exposure), _p(d.psf), _p(self.conv), d.fH, d.fW, d.kh,
                   d.kw, s)
+        train_cal = want_grad and d.train_bkg_norm
         _call("jd_poisson_forward_backward", _p(self.conv), _p(d.background), _p(d.bkg_log_norm), _p(d.counts), None,
-              _p(self.dpool) if want_grad else None, loss_acc, None, d.H, d.W, d.f, d.fW, 1e-25, 1.0 / (d.H * d.W), s)
+              _p(self.dpool) if want_grad else None, loss_acc, self.acc.data_ptr() + 16 if train_cal else None, d.H, d.W,
+              d.f, d.fW, 1e-25, 1.0 / (d.H * d.W), s)
+        if train_cal:  # Adam on log(background norm) with the parameter's own step counter
+            _call("jd_adam_scalar_step_dev", _p(d.bkg_log_norm), _p(d.cal_m), _p(d.cal_v), self.acc.data_ptr() + 16,
+                  _p(d.cal_t), 1, self.lr, self.b1, self.b2, self.eps, s)
         if want_grad and d.fft is not None:
             _call("jd_conv_backward_fft", _p(self.dpool), _p(d.exposure), _p(d.fft.psf_hat), _p(d.fft.workspace),
                   _p(self.dflux_l), int(accumulate), d.fH, d.fW, d.kh, d.kw, d.f, d.H, d.W, s)
@@ -286,7 +299,11 @@ class MapEngine:
     def warmup(self, joint=False):
         """Run every kernel once outside graph capture (function attributes, module load, NCCL
         communicator), then restore the optimiser state so that training starts from step 0."""
-        state = [t.clone() for t in (self.theta, self.m, self.v, self.counters, self.acc)]
+        tensors = [self.theta, self.m, self.v, self.counters, self.acc]
+        for d in self.datasets:
+            if d.train_bkg_norm:
+                tensors += [d.bkg_log_norm, d.cal_m, d.cal_v, d.cal_t]
+        state = [t.clone() for t in tensors]
         graph = self.use_graph
         self.use_graph = False
         if joint:
@@ -296,7 +313,7 @@ class MapEngine:
                 self._step_body(i)
         self.use_graph = graph
         torch.cuda.synchronize(self.dev)
-        for t, s in zip((self.theta, self.m, self.v, self.counters, self.acc), state):
+        for t, s in zip(tensors, state):
             t.copy_(s)
 
     def step(self, i):

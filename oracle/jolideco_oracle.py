@@ -346,21 +346,33 @@ class Adam:
 # --------------------------------------------------------------------------------------
 # the MAP step / run                                              core.py:209-230
 # --------------------------------------------------------------------------------------
-def dataset_loss_and_grad(theta, ds, mask=None):
-    """Poisson loss of one dataset and its gradient w.r.t. theta (log flux).
+def dataset_loss_and_grad(theta, ds, mask=None, logb=None, return_dlogb=False):
+    """Poisson loss of one dataset and its gradient w.r.t. theta (log flux) [and w.r.t. the log background
+    norm `logb` of an NPredCalibration, models/npred.py:234-237, 329-337].
 
     ds: dict(counts, exposure_up, psf_up, background, f)."""
     flux = flux_from_theta(theta, mask)
-    npred, pool = npred_forward(flux, ds["exposure_up"], ds["psf_up"], ds["background"], ds["f"], return_pool=True)
+    bnorm = None if logb is None else np.exp(theta.dtype.type(logb))
+    npred, pool = npred_forward(flux, ds["exposure_up"], ds["psf_up"], ds["background"], ds["f"], bnorm, return_pool=True)
     loss = poisson_nll(npred, ds["counts"])
     dn = poisson_nll_grad(npred, ds["counts"])
     dflux = npred_backward(dn, pool, flux, ds["exposure_up"], ds["psf_up"], ds["f"])
+    if return_dlogb:
+        dlogb = float((dn * ds["background"] * (1 if bnorm is None else bnorm)).sum(dtype=np.float64))
+        return loss, dflux * flux, npred, dlogb
     return loss, dflux * flux, npred
 
 
-def map_step(theta, adam, ds, n_datasets, beta, gmm=None, shifts=None, stride=4, marginalize=False, mask=None):
-    """One reference step: total = L_d - beta * prior / D, backward, Adam (core.py:214-229)."""
-    loss, dtheta, _ = dataset_loss_and_grad(theta, ds, mask)
+def map_step(theta, adam, ds, n_datasets, beta, gmm=None, shifts=None, stride=4, marginalize=False, mask=None,
+             cal=None):
+    """One reference step: total = L_d - beta * prior / D, backward, Adam (core.py:214-229).
+    cal: None or dict(logb=array(1), adam=Adam) — the dataset's trainable log background norm, stepped by its
+    own Adam state (torch.optim.Adam keeps a step counter per parameter)."""
+    if cal is None:
+        loss, dtheta, _ = dataset_loss_and_grad(theta, ds, mask)
+    else:
+        loss, dtheta, _, dlogb = dataset_loss_and_grad(theta, ds, mask, cal["logb"][0], return_dlogb=True)
+        cal["logb"] = cal["adam"].step(cal["logb"], np.array([dlogb], dtype=theta.dtype))
     prior = theta.dtype.type(0)
     if gmm is not None:
         flux = flux_from_theta(theta, mask)
@@ -384,7 +396,7 @@ def prepare_dataset(dataset, f=1, dtype=np.float32):
 
 
 def map_run(flux_init_up, datasets, n_epochs, lr=0.1, beta=1.0, gmm=None, shifts=None, stride=4,
-            marginalize=False, dtype=np.float32, trace_shifts=None):
+            marginalize=False, dtype=np.float32, trace_shifts=None, background_norms=None):
     """MAPDeconvolver.run restated: sequential per-dataset Adam steps (core.py:209-230) and the
     per-epoch trace (loss.py:212-250).  `shifts[step]` are the injected cycle-spin draws of the
     training steps; `trace_shifts[epoch]` those consumed by `append_trace`'s extra prior call.
@@ -394,23 +406,31 @@ def map_run(flux_init_up, datasets, n_epochs, lr=0.1, beta=1.0, gmm=None, shifts
     D = len(datasets)
     trace = []
     step = 0
+    cals = None
+    if background_norms is not None:
+        cals = [dict(logb=np.log(np.array([b], dtype=dtype)), adam=Adam((1,), lr=lr, dtype=dtype)) for b in background_norms]
     for epoch in range(n_epochs):
-        for ds in datasets:
+        for i_ds, ds in enumerate(datasets):
             sh = shifts[step] if gmm is not None else None
             # `fluxes` is evaluated before the step (core.py:217) and the same (by then stale)
             # tuple is handed to append_trace after the loop (core.py:245): the trace of an
             # epoch is the loss at the parameters *before* the epoch's last Adam step.
             flux = flux_from_theta(theta)
-            theta, *_ = map_step(theta, adam, ds, D, beta, gmm, sh, stride, marginalize)
+            theta, *_ = map_step(theta, adam, ds, D, beta, gmm, sh, stride, marginalize,
+                                 cal=None if cals is None else cals[i_ds])
             step += 1
-        ld = [float(poisson_nll(npred_forward(flux, d["exposure_up"], d["psf_up"], d["background"], d["f"]),
-                                d["counts"])) for d in datasets]
+        # the calibration parameters are read live by append_trace (only the flux tuple is stale)
+        bn = [None] * D if cals is None else [np.exp(c["logb"][0]) for c in cals]
+        ld = [float(poisson_nll(npred_forward(flux, d["exposure_up"], d["psf_up"], d["background"], d["f"], b),
+                                d["counts"])) for d, b in zip(datasets, bn)]
         lp = 0.0
         if gmm is not None:
             sh = trace_shifts[epoch]
             lp = float(gmm_patch_prior(flux, gmm, sh[0], sh[1], stride, marginalize))
         trace.append({"total": sum(ld) - beta * lp, "datasets-total": sum(ld), "priors-total": -beta * lp,
                       "datasets": ld})
+    if cals is not None:
+        return flux_from_theta(theta), trace, [float(np.exp(c["logb"][0])) for c in cals]
     return flux_from_theta(theta), trace
 
 

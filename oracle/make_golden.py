@@ -282,8 +282,54 @@ def golden_runs():
     print("run_gmm_up2.npz total", out["trace_total"][-1])
 
 
+def golden_calibration():
+    """GMM prior + NPredCalibrations with trainable background norms (shifts 0, as in the Chandra example)."""
+    from jolideco.models import NPredCalibration, NPredCalibrations
+
+    rng = np.random.default_rng(21)
+    datasets = {str(i): synthetic_dataset(rng, 40, 36, 7, 7) for i in range(2)}
+    flux_init = rng.gamma(20, size=(40, 36)) / 10
+    gmm_arrays = synthetic_gmm_arrays(8, seed=9)
+    n_epochs, norms = 8, [1.3, 0.7]
+    gmm = GaussianMixtureModel.from_numpy(*gmm_arrays, meta=GaussianMixtureModelMeta(stride=4))
+    gen = torch.Generator().manual_seed(6)
+    prior = GMMPatchPrior(gmm=gmm, stride=4, generator=gen)
+    g = torch.Generator()
+    g.set_state(gen.get_state())
+    shifts, trace_shifts = [], []
+    for _ in range(n_epochs):
+        for _ in range(2):
+            shifts.append(peek_and_advance(g))
+        trace_shifts.append(peek_and_advance(g))
+    comps = FluxComponents()
+    comps["flux-1"] = SpatialFluxComponent.from_numpy(flux=flux_init, upsampling_factor=1, prior=prior)
+    flux_init_up = comps["flux-1"].flux_upsampled.detach().numpy()[0, 0].copy()
+    cals = NPredCalibrations()
+    for name, b in zip(datasets, norms):
+        cals[name] = NPredCalibration(background_norm=b)
+    res = MAPDeconvolver(n_epochs=n_epochs, learning_rate=0.1, display_progress=False).run(
+        datasets=datasets, components=comps, calibrations=cals)
+    out = {}
+    pack_datasets(datasets, "ds", out)
+    out["flux_init"], out["flux_init_up"] = flux_init, flux_init_up
+    out["gmm_means"], out["gmm_cov"], out["gmm_w"] = gmm_arrays
+    out["marginalize"] = False
+    out["background_norm_init"] = np.array(norms)
+    out["background_norm"] = np.array([float(c.background_norm) for c in res.calibrations.values()])
+    out["flux_up"] = res.flux_upsampled_total
+    tr = res.trace_loss
+    out["trace_total"] = np.asarray(tr["total"])
+    out["trace_datasets"] = np.stack([np.asarray(tr[f"dataset-{n}"]) for n in datasets], axis=1)
+    out["trace_prior"] = np.asarray(tr["priors-total"])
+    out["shifts"] = np.array(shifts).reshape(-1, 2)
+    out["trace_shifts"] = np.array(trace_shifts).reshape(-1, 2)
+    np.savez_compressed(os.path.join(OUT, "run_gmm_calib.npz"), **out)
+    print("run_gmm_calib.npz norms", out["background_norm"], "total", out["trace_total"][-1])
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     golden_kat()
     golden_prior_step()
     golden_runs()
+    golden_calibration()

@@ -155,3 +155,21 @@ def test_batched_independent_runs_equal_single_runs():
     # dealing jobs to ranks: rank 1 of 2 gets job 1 only
     part = J.run_many(jobs, n_epochs=1, rank=1, world=2, device=DEV)
     assert sorted(part) == [1]
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_background_norm_calibration_matches_imported_reference(fused):
+    """NPredCalibrations with trainable background norms: fused engine (scalar Adam kernel) and autograd path."""
+    g = load_golden("run_gmm_calib.npz")
+    prior = make_prior(g, 6)
+    comps = J.FluxComponents()
+    comps["flux-1"] = J.SpatialFluxComponent.from_numpy(flux=g["flux_init"], upsampling_factor=1, prior=prior)
+    cals = J.NPredCalibrations()
+    for name, b in zip(as_datasets(g), g["background_norm_init"]):
+        cals[name] = J.NPredCalibration(background_norm=float(b))
+    deco = J.MAPDeconvolver(n_epochs=8, learning_rate=0.1, display_progress=False, device=DEV, fused=fused)
+    res = deco.run(datasets=as_datasets(g), components=comps, calibrations=cals)
+    assert hasattr(deco, "engine") == fused
+    check(res, g, 8)
+    norms = [float(c.background_norm) for c in res.calibrations.values()]
+    assert_allclose(norms, g["background_norm"], rtol=1e-4)

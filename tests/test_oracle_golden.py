@@ -214,3 +214,15 @@ def test_torch_port_matches_imported_reference(name, f, n):
         assert_allclose(tr["total"], g["trace_total"][epoch], rtol=1e-5)
     if n == len(g["trace_total"]):
         assert_allclose(loop.flux_numpy(), g["flux_up"], rtol=1e-4)
+
+
+def test_run_with_background_norm_calibration_matches_imported_reference():
+    """NPredCalibrations with trainable background norms (shifts 0): flux, trace and fitted norms."""
+    g = load_golden("run_gmm_calib.npz")
+    datasets = [O.prepare_dataset(d, f=1) for d in unpack_datasets(g)]
+    gmm = O.GMM(g["gmm_means"], g["gmm_cov"], g["gmm_w"])
+    flux_up, trace, norms = O.map_run(g["flux_init_up"], datasets, 8, gmm=gmm, shifts=g["shifts"],
+                                      trace_shifts=g["trace_shifts"], background_norms=g["background_norm_init"])
+    assert np.linalg.norm(flux_up - g["flux_up"]) / np.linalg.norm(g["flux_up"]) < 1e-3
+    assert_allclose([t["total"] for t in trace], g["trace_total"], rtol=1e-5)
+    assert_allclose(norms, g["background_norm"], rtol=1e-5)
