@@ -131,13 +131,22 @@ int jd_gmm_prior_forward(const float* flux, int fH, int fW, const int32_t* shift
  * upper_tri != 0 asserts that every Lw_k is upper triangular (true for precision Cholesky factors,
  * utils/numpy.py:16-34): the kernel then skips the structurally-zero part of the product.
  * zero_mean != 0 asserts mw == 0 (zero-mean mixtures such as zoran-weiss): the epilogue skips the
- * mean subtraction. */
+ * mean subtraction.
+ * NOTE: the tensor-core forwards write logp COMPONENT-MAJOR (K x P', coalesced over patch rows), unlike the
+ * CUDA-core forward (P' x K); jd_gmm_prior_backward_lse_tc consumes that layout. */
 size_t jd_gmm_tc_packed_bytes(int K);
 int jd_gmm_tc_pack(const float* Lw, int K, void* Bt, jd_stream_t stream);
 int jd_gmm_prior_forward_tc(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride,
                             int row_begin, int row_end, const void* Bt, const float* mw, const float* ck,
                             int K, int upper_tri, int zero_mean, int marginalize, float* value,
                             int32_t* argmax, float* logp, double* sum, jd_stream_t stream);
+
+/* logsumexp (marginalize=1) backward on the tensor cores: G[p',:] = scale * sum_k r[p',k] (xc_p Lam_k - bk_k) minus
+ * its row mean, r = exp(logpT[k,p'] - lse[p']).  Bt_lam = jd_gmm_tc_pack(Lam) (any 64x64 matrices pack), logpT and
+ * lse (= value) come from a tensor-core forward with marginalize=1. */
+int jd_gmm_prior_backward_lse_tc(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride,
+                                 int row_begin, int row_end, const void* Bt_lam, const float* bk, int K,
+                                 const float* logpT, const float* lse, float scale, float* G, jd_stream_t stream);
 
 /* Same forward with SPLIT-FP16 operands (kind::f16, FP32 accumulation): hi/lo FP16 pairs with power-of-two
  * row / component scales carry the same 22 significand bits as the TF32 pairs at half the operand bytes and

@@ -53,6 +53,8 @@ PROTOTYPES = {
     "jd_gmm_tc_pack": [c_f32p, c_int, ctypes.c_void_p, c_stream],
     "jd_gmm_prior_forward_tc": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, ctypes.c_void_p, c_f32p, c_f32p,
                                 c_int, c_int, c_int, c_int, c_f32p, c_i32p, c_f32p, c_f64p, c_stream],
+    "jd_gmm_prior_backward_lse_tc": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, ctypes.c_void_p, c_f32p, c_int,
+                                     c_f32p, c_f32p, c_float, c_f32p, c_stream],
     "jd_gmm_tc16_packed_bytes": [c_int],
     "jd_gmm_tc16_pack": [c_f32p, c_int, ctypes.c_void_p, c_f32p, c_stream],
     "jd_gmm_prior_forward_tc16": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, ctypes.c_void_p, c_f32p, c_f32p,

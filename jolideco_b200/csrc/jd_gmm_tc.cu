@@ -54,7 +54,10 @@ constexpr int M0 = NPROD;                // first MMA-issuer warp (also owns the
 constexpr int E0 = NPROD + NMMA;         // first epilogue warp
 constexpr int NTHREADS = 32 * (NPROD + NMMA + 8);  // producers, MMA issuers, 2 x 4 epilogue warps
 constexpr int MW_BYTES = 64 * 4;        // mw_k staged per accumulator slot
+constexpr int NSTAGE_BWD = 4;           // B ring depth of the logsumexp backward (room for the merge buffer)
+constexpr int MERGE_BYTES = 64 * TM * 4; // gradient rows of epilogue group B
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + NSTAGE * B_BYTES + NSLOT * MW_BYTES + 4096 /*barriers etc.*/;
+constexpr size_t SMEM_BYTES_BWD = 1024 + NSTAGE_BWD * B_BYTES + NSLOT * MW_BYTES + MERGE_BYTES + 4096;
 
 using namespace tcx;
 
@@ -311,7 +314,7 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(t));
       const float lp = fmaf(-0.5f, (qa + qb) + (qc + qd), c_k);
-      if (logp && p < g.P) logp[p * K + kc] = lp;
+      if (logp && p < g.P) logp[(size_t)kc * g.P + p] = lp;  // component-major (K x P'): coalesced over patch rows
       if (marginalize) {
         if (lp > run_m) {
           run_s = run_s * expf(run_m - lp) + 1.f;
@@ -364,6 +367,262 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
   __syncthreads();
   cluster_sync_all();  // the peer may still multicast into / arrive on this CTA's shared memory until here
   if (threadIdx.x == 0 && sum) atomicAdd(sum, s_red[0] + s_red[1] + s_red[2] + s_red[3]);
+  if (warp == M0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------- logsumexp backward on the tensor cores
+// G[p,:] = scale * sum_k r[p,k] (xc_p Lam_k - bk_k) - row mean,  r = exp(logp[p,k] - lse[p]).
+// Same pipeline as the forward kernel with B = Lam_k (dense schedule: Lam is symmetric, not triangular) and
+// bk staged per slot; the epilogue scales each accumulator row by its responsibility and adds it to a
+// 64-register gradient row per thread; the two epilogue groups merge through shared memory.
+// logpT is component-major (K x P'), as the tensor-core forward writes it.
+__global__ void __launch_bounds__(NTHREADS, 1)
+gmm_bwd_lse_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restrict__ shift_yx,
+                      const uint8_t* __restrict__ Bt, const float* __restrict__ mw, const float* __restrict__ logpT,
+                      const float* __restrict__ lse, int K, float scale, float* __restrict__ G) {
+  constexpr bool TRI = false, ZERO_MEAN = false;
+  constexpr int NSTAGE = NSTAGE_BWD;
+  const int marginalize = 1;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sB = smem;                          // NSTAGE x 32 KB
+  float* sMW = reinterpret_cast<float*>(sB + NSTAGE * B_BYTES);  // NSLOT x 64 floats
+  float* s_merge = reinterpret_cast<float*>(sB + NSTAGE * B_BYTES + NSLOT * MW_BYTES);  // 64 x 128 floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + NSTAGE * B_BYTES + NSLOT * MW_BYTES + MERGE_BYTES);
+  // barrier indices: full[NSTAGE], empty[NSTAGE], tfull[NSLOT], tempty[NSLOT], mwfull[NSLOT]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 3 * NSLOT);
+  int* s_valid = reinterpret_cast<int*>(s_tmem + 4);       // 128 ints
+  double* s_red = reinterpret_cast<double*>(s_valid + TM);  // 4 doubles
+  float* s_mm = reinterpret_cast<float*>(s_red + 4);        // merge buffers of epilogue group B: max,
+  float* s_ms = s_mm + TM;                                  //   sum-exp,
+  int* s_mk = reinterpret_cast<int*>(s_ms + TM);            //   argmax
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dbg = 0;
+  (void)marginalize;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + NSLOT + s); };
+  auto mwfull_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 * NSLOT + s); };
+  // Every CTA walks the components in a different cyclic order (start k0): at any instant the
+  // CTAs stream different B images / mw rows, which spreads the L2 reads over the slices instead
+  // of 148 SMs hammering the same lines in lockstep.  max / logsumexp do not depend on the order
+  // (ties in max resolve to the lowest component index, as torch.max does).
+  // The two CTAs of a cluster share every B image (each loads one half and multicasts it to both),
+  // which halves the L2 -> SM traffic; they therefore walk the components in the same order.
+  const uint32_t crank = cluster_ctarank();
+  const int k0 = (int)(((long long)(blockIdx.x / CLUSTER) * K) / (gridDim.x / CLUSTER));
+
+  if (shift_yx) {
+    g.sy = shift_yx[0];
+    g.sx = shift_yx[1];
+  }
+  const int64_t p0 = (int64_t)blockIdx.x * TM;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), CLUSTER);  // released by the MMA commits of both CTAs of the pair
+    }
+    for (int s = 0; s < NSLOT; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+      mbar_init(mwfull_bar(s), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == M0) tmem_alloc(smem_u32(s_tmem), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // peer barriers are initialised before any remote arrive / multicast write
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  // TMEM lane quarter of an epilogue/gather warp, and the patch row (= TMEM lane) of its threads
+  const int q = warp & 3;
+  const int row = q * 32 + lane;
+  const int64_t p = p0 + row;
+
+  if (warp < NPROD) {
+    // ===================== bulk-TMA producers (whole warp waits, one elected lane issues) ==========
+    int kc = k0 + warp;  // component handled at position k
+    kc = kc >= K ? kc - K : kc;
+    for (int k = warp; k < K; k += NPROD) {
+      const int s = k % NSTAGE, t = k % NSLOT;
+      mbar_wait(empty_bar(s), ((k / NSTAGE) & 1) ^ 1);
+      // mw_k rides with accumulator slot t: free once the epilogue of component k - NSLOT is done
+      if (!ZERO_MEAN) mbar_wait(tempty_bar(t), ((k / NSLOT) & 1) ^ 1);
+      if (elect_one()) {
+        // this CTA fetches half `crank` (hi or lo, 16 KB) of the image for both CTAs of the pair
+        mbar_arrive_expect_tx(full_bar(s), B_BYTES);
+        bulk_g2s_mc(smem_u32(sB + s * B_BYTES) + crank * (B_BYTES / CLUSTER),
+                    Bt + (size_t)kc * B_BYTES + crank * (B_BYTES / CLUSTER), B_BYTES / CLUSTER, full_bar(s),
+                    (uint16_t)((1u << CLUSTER) - 1));
+        if (!ZERO_MEAN) {
+          mbar_arrive_expect_tx(mwfull_bar(t), MW_BYTES);
+          bulk_g2s(smem_u32(sMW + t * 64), mw + (size_t)kc * 64, MW_BYTES, mwfull_bar(t));
+        }
+      }
+      __syncwarp();
+      kc += NPROD;
+      kc = kc >= K ? kc - K : kc;
+    }
+  } else if (warp >= E0 && warp < E0 + 4) {
+    // ---- gather (epilogue group A): thread = patch row; 64 loads, mean, hi/lo split, tcgen05.st into TMEM lane `row`
+    float vals[64];
+    float s = 0.f;
+    bool ok = p < g.P;
+    if (ok) {
+      int iy = (int)(p / g.nx) + g.row_begin, ix = (int)(p % g.nx);
+      int cols[8];
+#pragma unroll
+      for (int v = 0; v < 8; ++v) cols[v] = src_col(g, ix, v);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float* src = flux + (int64_t)src_row(g, iy, u) * g.fW;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          float x = __ldg(src + cols[v]);
+          vals[u * 8 + v] = x;
+          s += x;
+          ok = ok && (x > -1e5f);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) vals[i] = 0.f;
+    }
+    const float mean = s * (1.f / 64.f);
+    const uint32_t a_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float hi[32], lo[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float x = ok ? vals[h * 32 + i] - mean : 0.f;
+        hi[i] = tf32_rna(x);
+        lo[i] = tf32_rna(x - hi[i]);
+      }
+      tmem_st32(a_lane + h * 32, hi);
+      tmem_st32(a_lane + 64 + h * 32, lo);
+    }
+    tmem_st_wait();
+    s_valid[row] = ok ? 1 : 0;
+    tc_fence_before();
+    // the 4 gather warps -> MMA warp: named barrier 1 (128 gather threads + 32 MMA-warp threads)
+    asm volatile("bar.arrive 1, %0;" ::"n"(128 + 32 * NMMA) : "memory");
+  }
+
+  if (warp >= M0 && warp < M0 + NMMA) {
+    // ===================== MMA issuers (warp-uniform control flow, one elected lane issues) =========
+    asm volatile("bar.sync 1, %0;" ::"n"(128 + 32 * NMMA) : "memory");  // A operand is in TMEM
+    tc_fence_after();
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t sB_lo0 = desc_lo(smem_u32(sB));
+    for (int k = warp - M0; k < K; k += NMMA) {
+      const int s = k % NSTAGE, t = k % NSLOT;
+      mbar_wait(tempty_bar(t), ((k / NSLOT) & 1) ^ 1);
+      mbar_wait(full_bar(s), (k / NSTAGE) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t b_hi = sB_lo0 + s * (B_BYTES >> 4), b_lo = b_hi + ((2 * KBLOCK_BYTES_B) >> 4);
+        const uint32_t d = tmem_u + A_COLS + t * SLOT_COLS;
+        uint32_t acc = 0;
+        // small terms first: lo.hi, hi.lo, then hi.hi
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t a_col = pass == 0 ? 64u : 0u;
+          const uint32_t b_base = pass == 1 ? b_lo : b_hi;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            if ((dbg & 2) && (pass > 0 || kk > 0)) continue;
+            // upper-triangular Lw: input features [8kk, 8kk+8) only reach whitened features >= 8kk
+            const uint32_t n0 = TRI ? 16u * (kk >> 1) : 0u;
+            const uint32_t off16 = ((kk >> 2) * KBLOCK_BYTES_B + (kk & 3) * 32 + n0 * 128) >> 4;
+            umma_tf32_ts(d + n0, tmem_u + a_col + kk * 8, desc_from_lo(b_base + off16), idesc_n(64 - n0), acc);
+            acc = 1;
+          }
+        }
+        umma_commit_mc(empty_bar(s), (uint16_t)((1u << CLUSTER) - 1));  // stage free in both CTAs of the pair
+        umma_commit(tfull_bar(t));  // accumulator slot complete
+      }
+      __syncwarp();
+    }
+  } else if (warp >= E0) {
+    // ===================== epilogue: group A (warps 2-5) takes even positions, group B odd =========
+    const int grp = warp >= E0 + 4 ? 1 : 0;
+    float gacc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) gacc[i] = 0.f;
+    const float lse_p = p < g.P ? __ldg(lse + p) : 0.f;
+    int kc = k0 + grp;
+    kc = kc >= K ? kc - K : kc;
+    for (int k = grp; k < K; k += 2) {
+      const int t = k % NSLOT;
+      const float r = p < g.P ? expf(__ldg(logpT + (size_t)kc * g.P + p) - lse_p) : 0.f;
+      mbar_wait(mwfull_bar(t), (k / NSLOT) & 1);
+      mbar_wait(tfull_bar(t), (k / NSLOT) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + A_COLS + t * SLOT_COLS;
+      const float4* bkk = reinterpret_cast<const float4*>(sMW + t * 64);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float y[32];
+        tmem_ld32(taddr + 32 * h, y);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 b = bkk[8 * h + c4];
+          gacc[32 * h + 4 * c4 + 0] = fmaf(r, y[4 * c4 + 0] - b.x, gacc[32 * h + 4 * c4 + 0]);
+          gacc[32 * h + 4 * c4 + 1] = fmaf(r, y[4 * c4 + 1] - b.y, gacc[32 * h + 4 * c4 + 1]);
+          gacc[32 * h + 4 * c4 + 2] = fmaf(r, y[4 * c4 + 2] - b.z, gacc[32 * h + 4 * c4 + 2]);
+          gacc[32 * h + 4 * c4 + 3] = fmaf(r, y[4 * c4 + 3] - b.w, gacc[32 * h + 4 * c4 + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(t));
+      kc += 2;
+      kc = kc >= K ? kc - K : kc;
+    }
+    // merge group B into group A (feature-major buffer: conflict-free), then mean-subtract, scale, store
+    if (grp == 1) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) s_merge[j * TM + row] = gacc[j];
+      asm volatile("bar.arrive 2, 256;" ::: "memory");
+    } else {
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      float rs = 0.f;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        gacc[j] += s_merge[j * TM + row];
+        rs += gacc[j];
+      }
+      const float mean = rs * (1.f / 64.f);
+      if (p < g.P) {
+        const bool ok = s_valid[row] != 0;
+        float4* out = reinterpret_cast<float4*>(G + (size_t)p * 64);
+#pragma unroll
+        for (int c4 = 0; c4 < 16; ++c4) {
+          float4 o;
+          o.x = ok ? scale * (gacc[4 * c4 + 0] - mean) : 0.f;
+          o.y = ok ? scale * (gacc[4 * c4 + 1] - mean) : 0.f;
+          o.z = ok ? scale * (gacc[4 * c4 + 2] - mean) : 0.f;
+          o.w = ok ? scale * (gacc[4 * c4 + 3] - mean) : 0.f;
+          out[c4] = o;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer may still multicast into / arrive on this CTA's shared memory until here
   if (warp == M0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -444,6 +703,54 @@ int jd_gmm_prior_forward_tc(const float* flux, int fH, int fW, const int32_t* sh
     return JD_ERR_CUDA;
   }
   JD_CHECK_LAUNCH("jd_gmm_prior_forward_tc");
+  return JD_OK;
+}
+
+int jd_gmm_prior_backward_lse_tc(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
+                                 int row_end, const void* Bt_lam, const float* bk, int K, const float* logpT,
+                                 const float* lse, float scale, float* G, jd_stream_t stream) {
+  JD_CHECK_ARG(flux && Bt_lam && bk && logpT && lse && G && K > 0, "jd_gmm_prior_backward_lse_tc: null pointer");
+  JD_CHECK_ARG(fH >= PATCH && fW >= PATCH && stride >= 1 && stride <= PATCH, "jd_gmm_prior_backward_lse_tc: bad geometry");
+  int ny = (fH - PATCH) / stride + 1, nx = (fW - PATCH) / stride + 1;
+  JD_CHECK_ARG(row_begin >= 0 && row_end <= ny && row_begin < row_end,
+               "jd_gmm_prior_backward_lse_tc: bad patch-row block [%d,%d) of %d", row_begin, row_end, ny);
+  JD_CHECK_ARG((reinterpret_cast<uintptr_t>(Bt_lam) & 15) == 0 && (reinterpret_cast<uintptr_t>(bk) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(G) & 15) == 0,
+               "jd_gmm_prior_backward_lse_tc: Bt_lam, bk and G must be 16-byte aligned");
+  tcx::Geom g{fH, fW, 0, 0, stride, nx, row_begin, (row_end - row_begin) * nx};
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc::gmm_bwd_lse_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)tc::SMEM_BYTES_BWD);
+    if (e != cudaSuccess) {
+      set_error("jd_gmm_prior_backward_lse_tc: cannot reserve %zu B of shared memory: %s", tc::SMEM_BYTES_BWD,
+                cudaGetErrorString(e));
+      return JD_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  int grid = (g.P + tc::TM - 1) / tc::TM;
+  grid = (grid + tc::CLUSTER - 1) / tc::CLUSTER * tc::CLUSTER;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(tc::NTHREADS);
+  cfg.dynamicSmemBytes = tc::SMEM_BYTES_BWD;
+  cfg.stream = to_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = tc::CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const uint8_t* bt8 = reinterpret_cast<const uint8_t*>(Bt_lam);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, tc::gmm_bwd_lse_tc_kernel, flux, g, shift_yx, bt8, bk, logpT, lse, K, scale, G);
+  if (le != cudaSuccess) {
+    set_error("jd_gmm_prior_backward_lse_tc: launch failed: %s", cudaGetErrorString(le));
+    cudaGetLastError();
+    return JD_ERR_CUDA;
+  }
+  JD_CHECK_LAUNCH("jd_gmm_prior_backward_lse_tc");
   return JD_OK;
 }
 

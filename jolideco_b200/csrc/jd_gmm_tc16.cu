@@ -335,7 +335,7 @@ gmm_fwd_tc16_kernel(const float* __restrict__ flux, Geom g, const int32_t* __res
       if (lane == 0) mbar_arrive(tempty_bar(t));
       const float qsum = ZERO_MEAN ? ((qa + qb) + (qc + qd)) * (inv * inv) : (qa + qb) + (qc + qd);
       const float lp = fmaf(-0.5f, qsum, c_k);
-      if (logp && p < g.P) logp[p * K + kc] = lp;
+      if (logp && p < g.P) logp[(size_t)kc * g.P + p] = lp;  // component-major (K x P'): coalesced over patch rows
       if (marginalize) {
         if (lp > run_m) {
           run_s = run_s * expf(run_m - lp) + 1.f;

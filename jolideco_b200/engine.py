@@ -139,7 +139,10 @@ class MapEngine:
             self.P = P
             self.value = torch.empty(max(P, 1), **f32)
             self.argmax = torch.empty(max(P, 1), dtype=torch.int32, device=self.dev)
+            # logsumexp mode keeps logp for the backward; the tensor-core kernels use a component-major layout
             self.logp = torch.empty((max(P, 1), self.packed.K), **f32) if self.marginalize else None
+            if self.marginalize and self.backend in (1, 2):
+                ops._bt_lam(self.packed)
             self.G = torch.empty((max(P, 1), ops.PD), **f32)
             # bucketed max-mode backward (ops.gmm_backward_workspace) measured slower than the warp-per-patch
             # kernel at K=256 (profiles/r01_summary.md): not used
@@ -228,6 +231,11 @@ class MapEngine:
 
     def _prior_gradient(self, scale):
         """per-patch gradient rows G (consumed by _adam_fold)"""
+        if self.marginalize and self.backend in (1, 2):
+            _call("jd_gmm_prior_backward_lse_tc", _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride,
+                  self.rows[0], self.rows[1], _p(ops._bt_lam(self.packed)), _p(self.packed.bk), self.packed.K,
+                  _p(self.logp), _p(self.value), float(scale), _p(self.G), self._s())
+            return
         _call("jd_gmm_prior_backward", _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride, self.rows[0],
               self.rows[1], _p(self.packed.Lam), _p(self.packed.bk), self.packed.K, int(self.marginalize),
               _p(self.argmax), _p(self.logp), _p(self.value), float(scale), _p(self.G), _p(self.bwd_ws), self._s())
@@ -238,9 +246,7 @@ class MapEngine:
                 out.zero_()
             return
         s = self._s()
-        _call("jd_gmm_prior_backward", _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride, self.rows[0],
-              self.rows[1], _p(self.packed.Lam), _p(self.packed.bk), self.packed.K, int(self.marginalize),
-              _p(self.argmax), _p(self.logp), _p(self.value), float(scale), _p(self.G), _p(self.bwd_ws), s)
+        self._prior_gradient(scale)
         _call("jd_patch_fold", _p(self.G), self.fH, self.fW, _p(self.cur_shift), self.stride, self.rows[0], self.rows[1],
               _p(out), int(accumulate), s)
 

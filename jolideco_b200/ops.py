@@ -184,6 +184,7 @@ class GMMPacked:
         self.device = torch.device(device)
         self._Bt = None
         self._Bt16 = None
+        self._Bt_lam = None
         self.upper_tri = bool(np.all(np.tril(L, -1) == 0))
         self.zero_mean = bool(np.all(mw == 0))
 
@@ -199,6 +200,17 @@ class GMMPacked:
                 _lib.call("jd_gmm_tc_pack", _ptr(self.Lw), self.K, _ptr(bt), _stream())
             self._Bt = bt
         return self._Bt
+
+
+def _bt_lam(packed):
+    """Tensor-core operand image of Lam_k (for the logsumexp backward)."""
+    if packed._Bt_lam is None:
+        nbytes = _lib.load().jd_gmm_tc_packed_bytes(packed.K)
+        with torch.cuda.device(packed.device):
+            bt = torch.empty(nbytes, dtype=torch.uint8, device=packed.device)
+            _lib.call("jd_gmm_tc_pack", _ptr(packed.Lam), packed.K, _ptr(bt), _stream())
+        packed._Bt_lam = bt
+    return packed._Bt_lam
 
 
 def _bt16(packed):
@@ -262,7 +274,11 @@ def gmm_prior_forward(flux, shift_yx, packed, stride=4, marginalize=False, rows=
     argmax = torch.empty(P, dtype=torch.int32, device=flux.device)
     if want_logp is None:
         want_logp = bool(marginalize)
-    logp = torch.empty((P, packed.K), dtype=torch.float32, device=flux.device) if want_logp else None
+    # the tensor-core forwards write logp component-major (K x P'): returned as the transposed (P', K) view
+    tc = int(backend) in (1, 2)
+    logp = None
+    if want_logp:
+        logp = torch.empty((packed.K, P) if tc else (P, packed.K), dtype=torch.float32, device=flux.device)
     if sum_out is None:
         sum_out = torch.zeros(1, dtype=torch.float64, device=flux.device)
     if int(backend) == 2:
@@ -278,6 +294,8 @@ def gmm_prior_forward(flux, shift_yx, packed, stride=4, marginalize=False, rows=
         _lib.call("jd_gmm_prior_forward", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(packed.Lw),
                   _ptr(packed.mw), _ptr(packed.ck), packed.K, int(bool(marginalize)), _ptr(value), _ptr(argmax),
                   _ptr(logp), _ptr(sum_out), int(backend), _stream())
+    if tc and logp is not None:
+        logp = logp.t()
     return value, argmax, logp, sum_out
 
 
@@ -295,6 +313,12 @@ def gmm_prior_backward(flux, shift_yx, packed, scale, stride=4, marginalize=Fals
     P = (r1 - r0) * nx
     shift = as_shift_tensor(shift_yx, flux.device)
     G = torch.empty((P, PD), dtype=torch.float32, device=flux.device) if out is None else _check(out, "out")
+    if marginalize and logp is not None and not logp.is_contiguous() and logp.t().is_contiguous():
+        # component-major logp from a tensor-core forward: tensor-core backward
+        _lib.call("jd_gmm_prior_backward_lse_tc", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1,
+                  _ptr(_bt_lam(packed)), _ptr(packed.bk), packed.K, _ptr(logp.t()), _ptr(_check(value, "value")),
+                  float(scale), _ptr(G), _stream())
+        return G
     if workspace is None and bucketed and not marginalize:
         workspace = gmm_backward_workspace(P, packed.K, flux.device)
     _lib.call("jd_gmm_prior_backward", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(packed.Lam),
