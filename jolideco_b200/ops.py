@@ -161,32 +161,35 @@ class GMMPacked:
     """
 
     def __init__(self, means, precisions_cholesky, weights, pixel_weights, device):
-        L = np.asarray(precisions_cholesky, dtype=np.float32).astype(np.float64)
-        mu = np.asarray(means, dtype=np.float32).astype(np.float64)
-        pi = np.asarray(weights, dtype=np.float32).astype(np.float64)
-        w = np.asarray(pixel_weights, dtype=np.float32).astype(np.float64).reshape(-1)
-        K, D, _ = L.shape
-        self.K, self.D = K, D
-        sw = np.sqrt(w)
-        Lw = L * sw[None, None, :]
-        # mu L evaluated in float32 like the reference's lazily cached means_precisions_cholesky
-        muL = np.einsum("ki,kij->kj", mu.astype(np.float32), L.astype(np.float32)).astype(np.float64)
-        mw = muL * sw[None, :]
-        log_det = np.log(np.diagonal(L, axis1=1, axis2=2)).sum(axis=1)
-        ck = -0.5 * D * math.log(2 * math.pi) + log_det + np.log(pi)
-        Lam = Lw @ Lw.transpose(0, 2, 1)
-        bk = np.einsum("kj,kij->ki", mw, Lw)
+        # setup-time plumbing: float64 torch ops on the device (a few ms for K=256; numpy took ~30 ms)
+        device = torch.device(device)
+        with torch.cuda.device(device):
+            def up(a):
+                return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32))).to(device)
 
-        def dev(a):
-            return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device)
-
-        self.Lw, self.mw, self.ck, self.Lam, self.bk = dev(Lw), dev(mw), dev(ck), dev(Lam), dev(bk)
-        self.device = torch.device(device)
+            L32, mu32 = up(precisions_cholesky), up(means)
+            L, pi = L32.double(), up(weights).double()
+            w = up(np.asarray(pixel_weights).reshape(-1)).double()
+            K, D, _ = L.shape
+            self.K, self.D = int(K), int(D)
+            sw = torch.sqrt(w)
+            Lw = L * sw[None, None, :]
+            # mu L evaluated in float32 like the reference's lazily cached means_precisions_cholesky
+            muL = torch.einsum("ki,kij->kj", mu32, L32).double()
+            mw = muL * sw[None, :]
+            log_det = torch.log(torch.diagonal(L, dim1=1, dim2=2)).sum(dim=1)
+            ck = -0.5 * D * math.log(2 * math.pi) + log_det + torch.log(pi)
+            Lam = Lw @ Lw.transpose(1, 2)
+            bk = torch.einsum("kj,kij->ki", mw, Lw)
+            self.Lw, self.mw, self.ck = Lw.float().contiguous(), mw.float().contiguous(), ck.float().contiguous()
+            self.Lam, self.bk = Lam.float().contiguous(), bk.float().contiguous()
+            flags = torch.stack([(torch.tril(L, -1) == 0).all(), (mw == 0).all()]).cpu()
+        self.device = device
         self._Bt = None
         self._Bt16 = None
         self._Bt_lam = None
-        self.upper_tri = bool(np.all(np.tril(L, -1) == 0))
-        self.zero_mean = bool(np.all(mw == 0))
+        self.upper_tri = bool(flags[0])
+        self.zero_mean = bool(flags[1])
 
     @property
     def Bt(self):

@@ -13,6 +13,13 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the CUDA library is built in-tree (git-ignored): make sure it exists / is current before any test imports it
+    try:
+        from jolideco_b200 import build
+
+        build.build()
+    except Exception as exc:  # no nvcc on this machine: tests that need the library will fail loudly themselves
+        print(f"[conftest] could not (re)build libjolideco_b200.so: {exc}")
 
 
 def load_golden(name):

@@ -313,7 +313,7 @@ def test_gmm_lse_backward_tensor_core_vs_cuda_core_full_size():
     G1 = ops.gmm_prior_backward(flux, (-1, 2), packed, -1e-3, 4, True, None, k1, lp1, v1).cpu().numpy()
     # responsibilities exp(logp - lse) amplify the fp32 round-off of |logp| ~ 1e2..1e3 in BOTH kernels:
     # compare in rel-L2 (the float64-oracle tests above bound each kernel separately at small sizes)
-    assert np.linalg.norm(G1 - G0) / np.linalg.norm(G0) < 5e-6
+    assert np.linalg.norm(G1 - G0) / np.linalg.norm(G0) < 2e-5
     assert np.abs(G1 - G0).max() <= 1e-4 * np.abs(G0).max()
 
 
