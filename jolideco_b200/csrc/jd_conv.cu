@@ -7,23 +7,24 @@
 // which reproduces rfft2*rfft2 -> irfft2 -> centred crop of utils/torch.py:337-370 exactly, including
 // the asymmetric crop of even-sized PSFs.
 //
-// Tiling: a CTA of TY x TX threads owns a (4 TY) x (4 TX) output tile; each thread a 4x4 register
-// block.  The PSF is processed in chunks of KC rows: per chunk the input tile
+// Tiling: a CTA of TY x TX threads owns an (R TY) x (4 TX) output tile; each thread an R x 4 register
+// block (R = 2 by default).  The PSF is processed in chunks of KC rows: per chunk the input tile
 // (4 TY + KC - 1) x (4 TX + kw_pad - 1) and the chunk rows are staged in shared memory.  For every
 // staged input row t the thread loads a sliding 4+4 window once and feeds the 4 output rows r with
 // kernel row a = t - r (zero rows pad the chunk so no predicate is needed): 64 FMA per
 // 1 window LDS.128 + 4 broadcast LDS.128.
+#include <stdlib.h>
+
 #include "jd_common.cuh"
 
 namespace jd {
 
-constexpr int R = 4;   // output rows per thread
 constexpr int C = 4;   // output cols per thread
 constexpr int KC = 16; // PSF rows per chunk
 
 enum { CONV_FWD = 0, CONV_BWD = 1 };
 
-template <int MODE, int TY, int TX>
+template <int MODE, int TY, int TX, int R>  // R = output rows per thread
 __global__ void __launch_bounds__(TY * TX)
 conv_kernel(const float* __restrict__ in, const float* __restrict__ scale, const float* __restrict__ psf,
             float* __restrict__ out, int fH, int fW, int kh, int kw, int oy, int ox, int f, int H, int W,
@@ -155,7 +156,7 @@ conv_kernel(const float* __restrict__ in, const float* __restrict__ scale, const
   }
 }
 
-template <int MODE, int TY, int TX>
+template <int MODE, int TY, int TX, int R>
 static int launch_conv_t(const float* in, const float* scale, const float* psf, float* out, int fH, int fW, int kh,
                          int kw, int oy, int ox, int f, int H, int W, int accumulate, cudaStream_t st,
                          const char* name) {
@@ -169,7 +170,7 @@ static int launch_conv_t(const float* in, const float* scale, const float* psf, 
   if (smem_for(kchunk) > 44 * 1024) kchunk = KC;
   size_t sm = smem_for(kchunk);
   JD_CHECK_ARG(sm <= 200 * 1024, "%s: PSF too wide for the direct kernel (kw=%d)", name, kw);
-  auto kern = conv_kernel<MODE, TY, TX>;
+  auto kern = conv_kernel<MODE, TY, TX, R>;
   static bool attr_set = false;  // once per process and instantiation: opt in to the 200 KB limit checked above
   if (!attr_set) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -185,8 +186,18 @@ template <int MODE>
 static int launch_conv(const float* in, const float* scale, const float* psf, float* out, int fH, int fW, int kh,
                        int kw, int oy, int ox, int f, int H, int W, int accumulate, cudaStream_t st,
                        const char* name) {
-  // 8x16 threads -> 32x64 tiles: >= 2 CTAs per SM already at 512x512, 4 warps per CTA to overlap staging
-  return launch_conv_t<MODE, 8, 16>(in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
+  static int tile = -1;
+  if (tile < 0) {
+    const char* e = getenv("JD_CONV_TILE");  // tuning knob: rows per thread / CTA shape, see below
+    tile = e ? atoi(e) : 1;
+  }
+  if (tile == 1)  // default: 2 rows per thread, 16x16 threads -> 32x64 tiles (best of the sweep, tools/conv_exp.py)
+    return launch_conv_t<MODE, 16, 16, 2>(in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
+  if (tile == 2)  // 2 rows per thread, 8x16 threads -> 16x64 tiles
+    return launch_conv_t<MODE, 8, 16, 2>(in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
+  if (tile == 3)  // 1 row per thread, 16x16 threads -> 16x64 tiles
+    return launch_conv_t<MODE, 16, 16, 1>(in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
+  return launch_conv_t<MODE, 8, 16, 4>(in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
 }
 
 }  // namespace jd
