@@ -153,11 +153,12 @@ class MapEngine:
             tab = np.ascontiguousarray(np.asarray(shift_table, dtype=np.int32).reshape(-1, 2))
             self.shift_table = torch.from_numpy(tab).to(self.dev)
             self.n_shifts = int(tab.shape[0])
-        # multi-rank joint steps are launched eagerly: capturing the NCCL all-reduce together with the kernels in
-        # one CUDA graph hung with uneven dataset shards (2-GPU test) and gained < 4 % when it worked
-        self.use_graph = bool(use_graph) and process_group is None
+        # multi-rank joint steps replay two graphs (before / after the gradient all-reduce) with the NCCL call
+        # launched eagerly in between: capturing the collective inside the graph hung with uneven dataset shards
+        self.use_graph = bool(use_graph)
         self._graphs = {}
         self._graph_nodes = {}
+        self._capture_stream = None
 
     # ------------------------------------------------------------------------------------------
     def _row_block(self, rank, world):
@@ -268,10 +269,10 @@ class MapEngine:
         else:
             self._adam(None, 0.0)
 
-    def _joint_body(self):
-        """Joint step on sum_d L_d - beta * prior (loss.py:257-261); prior gradient folded into dflux_l."""
-        self._begin(advance_adam=1, zero_acc=self.acc, with_shift=True)
-        self._flux()
+    def _joint_pre(self):
+        """Joint step up to the local gradient: sum_d dL_d/dflux (local datasets) - beta d prior/dflux (local
+        patch rows), folded into dflux_l (loss.py:257-261)."""
+        self._begin_flux(advance_adam=1, zero_acc=self.acc)
         if not self.datasets:
             self.dflux_l.zero_()
         for j, d in enumerate(self.datasets):
@@ -279,9 +280,16 @@ class MapEngine:
         if self.prior is not None:
             self._prior_forward(self.acc.data_ptr() + 8)
             self._prior_backward(self.c * self.beta, self.dflux_l, accumulate=True)
+
+    def _joint_post(self):
+        self._adam(None, 0.0)
+
+    def _joint_body(self):
+        """Joint step on sum_d L_d - beta * prior; with ranks: one all-reduce of the flux gradient."""
+        self._joint_pre()
         if self.world > 1:
             torch.distributed.all_reduce(self.dflux_l, group=self.pg)
-        self._adam(None, 0.0)
+        self._joint_post()
 
     def _run(self, key, body):
         if not self.use_graph:
@@ -296,8 +304,17 @@ class MapEngine:
             torch.cuda.synchronize(self.dev)
             g = torch.cuda.CUDAGraph()
             before = _STATS["launches"]
-            with torch.cuda.graph(g):
-                body()
+            # low-level capture: the torch.cuda.graph() context manager also runs gc.collect() and
+            # empty_cache() on entry (~100 ms per capture), which would dominate short runs.
+            # thread_local: the NCCL watchdog thread may query events while this thread captures.
+            if self._capture_stream is None:
+                self._capture_stream = torch.cuda.Stream(device=self.dev)
+            with torch.cuda.stream(self._capture_stream):
+                g.capture_begin(capture_error_mode="thread_local" if self.pg is not None else "global")
+                try:
+                    body()
+                finally:
+                    g.capture_end()
             self._graph_nodes[key] = _STATS["launches"] - before
             self._graphs[key] = g
         g.replay()
@@ -326,7 +343,12 @@ class MapEngine:
         self._run(("step", i), lambda: self._step_body(i))
 
     def joint_step(self):
-        self._run(("joint",), self._joint_body)
+        if self.world == 1:
+            self._run(("joint",), self._joint_body)
+            return
+        self._run(("joint-pre",), self._joint_pre)
+        torch.distributed.all_reduce(self.dflux_l, group=self.pg)  # eager NCCL between the two graphs
+        self._run(("joint-post",), self._joint_post)
 
     # ------------------------------------------------------------------------------------------
     def trace_enqueue(self, out_row, refresh_flux=False):
