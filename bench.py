@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed iterations")
+    ap.add_argument("--collective", default="nccl", choices=["nccl", "peer"],
+                    help="joint multi-GPU step: NCCL all-reduce + Adam, or the fused peer-memory reduce+Adam kernel")
     return ap.parse_args()
 
 
@@ -165,7 +167,7 @@ def build_run(J, workload, args, device, n_epochs, seed=0, mode="sequential"):
     comps["flux"] = J.SpatialFluxComponent.from_numpy(flux=workload["flux_init"], upsampling_factor=workload["f"],
                                                       prior=prior)
     deco = J.MAPDeconvolver(n_epochs=n_epochs, learning_rate=0.1, display_progress=False, device=device,
-                            use_cuda_graph=not args.no_graph, mode=mode)
+                            use_cuda_graph=not args.no_graph, mode=mode, collective=args.collective)
     return deco, comps
 
 
@@ -223,7 +225,7 @@ def main():
     n_draws = args.steps * 3 + args.warmup + 64
     eng = deco._build_engine(total_loss, comps, n_draws)
     if pg is not None:
-        eng = rebuild_with_group(E, eng, pg)
+        eng = rebuild_with_group(E, eng, pg, args.collective)
     eng.warmup(joint=joint)
     D_local = len(eng.datasets)
 
@@ -384,7 +386,7 @@ def bench_batched(args, rank, local_rank, world, n_runs=64):
         dist.destroy_process_group()
 
 
-def rebuild_with_group(E, eng, pg):
+def rebuild_with_group(E, eng, pg, collective="nccl"):
     """Same engine with the dataset shard of this rank and a process group for the gradient all-reduce."""
     prior = None
     if eng.prior is not None:
@@ -392,7 +394,7 @@ def rebuild_with_group(E, eng, pg):
     new = E.MapEngine(eng.theta, eng.datasets, prior=prior, mask=eng.mask, use_log_flux=eng.use_log_flux, beta=eng.beta,
                       lr=eng.lr, betas=(eng.b1, eng.b2), eps=eng.eps,
                       shift_table=eng.shift_table.cpu().numpy() if eng.shift_table is not None else None,
-                      use_graph=eng.use_graph, process_group=pg)
+                      use_graph=eng.use_graph, process_group=pg, collective=collective)
     return new
 
 

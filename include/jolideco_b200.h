@@ -207,6 +207,17 @@ int jd_step_begin(int32_t* counters, const int32_t* shift_table, int n_shifts, i
 int jd_adam_scalar_step_dev(float* param, float* m, float* v, const double* grad, int32_t* counter, int n,
                             float lr, float beta1, float beta2, float eps, jd_stream_t stream);
 
+/* ---- multi-GPU joint step: gradient all-reduce fused with Adam over NVLink peer memory ------------------
+ * grad_ptrs_dev / theta_ptrs_dev: device arrays of `world` pointers to every rank's partial-gradient and theta
+ * buffers (symmetric memory, peer-addressable).  Rank r sums the partial gradients of its pixel slice
+ * [n r/world, n (r+1)/world) from all peers (fixed order), applies Adam there (chain rule as jd_adam_step_dev) and
+ * stores the new theta slice into every replica.  The caller provides the cross-rank barriers before (all
+ * partial gradients written) and after (all slices stored).  n must be a multiple of 4.
+ * Replaces ncclAllReduce + jd_adam_step_dev of the NCCL variant. */
+int jd_adam_allreduce_peer(const void* grad_ptrs_dev, const void* theta_ptrs_dev, int rank, int world, float* m,
+                           float* v, const float* flux, const uint8_t* mask, int use_log_flux, int64_t n,
+                           const float* adam_scalars, float beta1, float beta2, float eps, jd_stream_t stream);
+
 /* Fused variants used by the graph-captured step (one launch each instead of two):
  * jd_step_begin_flux = jd_step_begin + jd_flux_forward;
  * jd_adam_fold_step_dev = jd_patch_fold (gather col2im of G, scaled by scale_b) + jd_adam_step_dev. */

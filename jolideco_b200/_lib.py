@@ -39,6 +39,8 @@ PROTOTYPES = {
                       c_stream],
     "jd_adam_scalar_step_dev": [c_f32p, c_f32p, c_f32p, c_f64p, c_i32p, c_int, c_float, c_float, c_float, c_float,
                                 c_stream],
+    "jd_adam_allreduce_peer": [ctypes.c_void_p, ctypes.c_void_p, c_int, c_int, c_f32p, c_f32p, c_f32p, c_u8p, c_int,
+                               c_i64, c_f32p, c_float, c_float, c_float, c_stream],
     "jd_step_begin_flux": [c_i32p, c_i32p, c_int, c_i32p, c_int, c_float, c_float, c_float, c_f32p, c_f64p, c_int,
                            c_f32p, c_u8p, c_f32p, c_i64, c_int, c_stream],
     "jd_adam_fold_step_dev": [c_f32p, c_f32p, c_f32p, c_f32p, c_u8p, c_f32p, c_f32p, c_float, c_int, c_int, c_int,

@@ -37,7 +37,7 @@ class MAPDeconvolver:
     def __init__(self, n_epochs=1_000, beta=1, learning_rate=0.1, compute_error=False, stop_early=False,
                  stop_early_n_average=10, device="cuda", display_progress=True, optimizer_type="adam",
                  optimizer_kwargs=None, checkpoint_path=None, use_cuda_graph=True, fused=True, mode="sequential",
-                 process_group=None):
+                 process_group=None, collective="nccl"):
         self.n_epochs = n_epochs
         self.beta = beta
         self.learning_rate = learning_rate
@@ -67,6 +67,7 @@ class MAPDeconvolver:
             raise ValueError(f"Unknown mode: {mode}, must be 'sequential' or 'joint'")
         self.mode = mode
         self.process_group = process_group
+        self.collective = collective  # "nccl" or "peer" (fused all-reduce + Adam over NVLink peer memory)
 
     def to_dict(self):
         data = {}
@@ -151,7 +152,8 @@ class MAPDeconvolver:
                 torch.distributed.broadcast(tab, src=torch.distributed.get_global_rank(shard["pg"], 0), group=shard["pg"])
                 table = tab.cpu().numpy()
             f = comp.upsampling_factor or 1
-            kwargs = dict(process_group=shard["pg"], dataset_index=shard["index"], n_datasets_global=shard["n"],
+            kwargs = dict(process_group=shard["pg"], collective=self.collective, dataset_index=shard["index"],
+                          n_datasets_global=shard["n"],
                           validation_index=shard["vindex"], n_validation_global=shard["nv"],
                           counts_shape=(theta.shape[0] // f, theta.shape[1] // f))
         return MapEngine(theta, buffers(total_loss.poisson_loss), prior=prior_cfg, mask=mask,
@@ -278,6 +280,7 @@ class MAPDeconvolver:
             for vals, filename in zip(host, filenames):
                 ld, lp, lv = engine.trace_decode(vals)
                 total_loss.append_trace_values(ld, [lp] * len(prior_names), filename, lv if lv else None)
+        engine.sync_theta()
         torch.cuda.synchronize(self.device)
 
     def _run_autograd(self, total_loss, components, calibrations):

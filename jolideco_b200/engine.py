@@ -72,7 +72,7 @@ class MapEngine:
     def __init__(self, theta, datasets, prior=None, mask=None, use_log_flux=True, beta=1.0, lr=0.1, betas=(0.9, 0.999),
                  eps=1e-8, shift_table=None, datasets_validation=(), use_graph=True, process_group=None,
                  prior_weight=None, dataset_index=None, n_datasets_global=None, validation_index=None,
-                 n_validation_global=None, counts_shape=None):
+                 n_validation_global=None, counts_shape=None, collective="nccl"):
         """theta: 2-D CUDA fp32 tensor updated in place (the component's parameter storage).
         prior: None (uniform) or dict(packed=GMMPacked, stride, marginalize, backend).
         shift_table: (N, 2) int array of pre-drawn (row, col) cycle-spin shifts in consumption order."""
@@ -156,11 +156,41 @@ class MapEngine:
         # multi-rank joint steps replay two graphs (before / after the gradient all-reduce) with the NCCL call
         # launched eagerly in between: capturing the collective inside the graph hung with uneven dataset shards
         self.use_graph = bool(use_graph)
+        # "nccl": ncclAllReduce of the flux gradient + replicated Adam; "peer": one fused kernel that reduces the
+        # gradient slices over NVLink peer memory, runs Adam on the owned slice and broadcasts theta (jd_peer.cu)
+        if collective not in ("nccl", "peer"):
+            raise ValueError(f"Unknown collective: {collective}, must be 'nccl' or 'peer'")
+        self.collective = collective if self.world > 1 else "nccl"
+        self._theta_param = None
+        if self.collective == "peer":
+            self._enable_peer()
         self._graphs = {}
         self._graph_nodes = {}
         self._capture_stream = None
 
     # ------------------------------------------------------------------------------------------
+    def _enable_peer(self):
+        """Move theta and the partial-gradient buffer into symmetric memory (peer-addressable over NVLink)."""
+        import torch.distributed._symmetric_memory as symm
+
+        if self.n % 4:
+            raise _lib.JolidecoB200Error("collective='peer' needs a flux pixel count divisible by 4")
+        with torch.cuda.device(self.dev):
+            self.sym_grad = symm.empty(self.n, dtype=torch.float32, device=self.dev)
+            self.sym_theta = symm.empty(self.n, dtype=torch.float32, device=self.dev)
+            self.h_grad = symm.rendezvous(self.sym_grad, self.pg)
+            self.h_theta = symm.rendezvous(self.sym_theta, self.pg)
+            self.sym_grad.zero_()
+            self.sym_theta.copy_(self.theta.reshape(-1))
+        self._theta_param = self.theta  # the component's parameter storage: refreshed by sync_theta()
+        self.theta = self.sym_theta.view(self.fH, self.fW)
+        self.dflux_l = self.sym_grad.view(self.fH, self.fW)
+
+    def sync_theta(self):
+        """Copy the working theta back into the component's parameter storage (peer mode only)."""
+        if self._theta_param is not None:
+            self._theta_param.copy_(self.theta)
+
     def _row_block(self, rank, world):
         return dist.row_block(self.ny, rank, world)
 
@@ -329,7 +359,11 @@ class MapEngine:
         state = [t.clone() for t in tensors]
         graph = self.use_graph
         self.use_graph = False
-        if joint:
+        if joint and self.collective == "peer":
+            self._joint_pre()
+            self.h_grad.barrier(channel=0)
+            self.h_grad.barrier(channel=1)  # communicator / signal pads warmed up; no update applied
+        elif joint:
             self._joint_body()  # collective: every rank calls warmup(joint=True)
         else:
             for i in range(min(self.D, 1)):
@@ -347,6 +381,14 @@ class MapEngine:
             self._run(("joint",), self._joint_body)
             return
         self._run(("joint-pre",), self._joint_pre)
+        if self.collective == "peer":
+            # barrier (all partial gradients written) -> fused reduce + Adam + theta broadcast -> barrier
+            self.h_grad.barrier(channel=0)
+            _call("jd_adam_allreduce_peer", self.h_grad.buffer_ptrs_dev, self.h_theta.buffer_ptrs_dev, self.rank,
+                  self.world, _p(self.m), _p(self.v), _p(self.flux), _p(self.mask), int(self.use_log_flux), self.n,
+                  _p(self.adam_scalars), self.b1, self.b2, self.eps, self._s())
+            self.h_grad.barrier(channel=1)
+            return
         torch.distributed.all_reduce(self.dflux_l, group=self.pg)  # eager NCCL between the two graphs
         self._run(("joint-post",), self._joint_post)
 

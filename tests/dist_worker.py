@@ -26,7 +26,8 @@ def main():
     raw = raw + [dict(d, counts=np.roll(d["counts"], 3, axis=1)) for d in raw] + raw[:1]  # 5 datasets: uneven shards
     datasets = {f"d{i}": d for i, d in enumerate(raw)}
     n_epochs = 6
-    for marginalize in (False, True):
+    collectives = sys.argv[1:] or ["nccl"]
+    for marginalize, collective in [(m, c) for m in (False, True) for c in collectives]:
         gmm = J.GaussianMixtureModel.from_numpy(g["gmm_means"], g["gmm_cov"], g["gmm_w"],
                                                 meta=J.GaussianMixtureModelMeta(stride=4))
         gen = torch.Generator().manual_seed(11)
@@ -37,9 +38,11 @@ def main():
         prior = J.GMMPatchPrior(gmm=gmm, stride=4, generator=gen, marginalize=marginalize)
         comps = J.FluxComponents()
         comps["flux"] = J.SpatialFluxComponent.from_numpy(flux=g["flux_init"], upsampling_factor=1, prior=prior)
-        deco = J.MAPDeconvolver(n_epochs=n_epochs, display_progress=False, device=f"cuda:{local}", mode="joint")
+        deco = J.MAPDeconvolver(n_epochs=n_epochs, display_progress=False, device=f"cuda:{local}", mode="joint",
+                                collective=collective)
         res = deco.run(datasets=datasets, components=comps)
         assert deco.engine.world == dist.get_world_size() and len(deco.engine.datasets) <= 3
+        assert deco.engine.collective == collective
         ods = [O.prepare_dataset(d, f=1) for d in raw]
         flux_ref, trace_ref = O.map_run_joint(g["flux_init_up"], ods, n_epochs, gmm=O.GMM(g["gmm_means"], g["gmm_cov"], g["gmm_w"]),
                                               shifts=shifts, marginalize=marginalize)

@@ -44,8 +44,11 @@ def test_joint_mode_single_gpu_matches_oracle(marginalize):
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-def test_dataset_sharded_joint_run_two_ranks_nccl():
+@pytest.mark.parametrize("collective", ["nccl", "peer"])
+def test_dataset_sharded_joint_run_two_ranks(collective):
+    """NCCL all-reduce + replicated Adam, and the fused peer-memory reduce + Adam + theta broadcast kernel."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
-           "127.0.0.1", "--master-port", str(29600 + os.getpid() % 300), os.path.join(ROOT, "tests", "dist_worker.py")]
+           "127.0.0.1", "--master-port", str(29600 + os.getpid() % 300), os.path.join(ROOT, "tests", "dist_worker.py"),
+           collective]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=150)
     assert res.returncode == 0 and "DIST_WORKER_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
