@@ -415,6 +415,8 @@ def measure_roofline(E, eng, run_step, args, workload, flush):
     eng.use_graph = False
     if eng.prior is not None:
         name = {1: "jd_gmm_prior_forward_tc", 2: "jd_gmm_prior_forward_tc16"}.get(eng.backend, "jd_gmm_prior_forward")
+        if eng.backend == 1 and getattr(eng, "sk_ws", None) is not None:
+            name = "jd_gmm_prior_forward_tc_sk"
         P = eng.P
         work = 2.0 * P * 64 * 64 * eng.packed.K  # useful flops, counted once
         bf16 = peaks.get("bf16_tflops_sustained")

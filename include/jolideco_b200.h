@@ -65,6 +65,11 @@ int jd_conv_backward_direct(const float* dpool, const float* exposure, const flo
                             int accumulate, int fH, int fW, int kh, int kw, int f, int H, int W,
                             jd_stream_t stream);
 
+/* Tuning / test hook of the direct kernels (process-wide; 0 = automatic): v3 = 0 selects the chunked,
+ * synchronously staged kernel instead of the cp.async one; tx = 8 | 16 forces 32- | 64-column tiles;
+ * split = 1 | 2 | 4 forces the number of thread groups the PSF rows are divided over. */
+int jd_conv_tuning(int v3, int tx, int split);
+
 /* ---- a3, large PSFs: shared-memory FFT convolution (same arithmetic contract as the direct entries) ----
  * jd_fftconv_sizes: element counts (floats) of the cached PSF spectrum and of the scratch workspace for an
  * fH x fW image and a kh x kw PSF (both axes padded to the next power of two >= n + k - 1).
@@ -140,6 +145,17 @@ int jd_gmm_prior_forward_tc(const float* flux, int fH, int fW, const int32_t* sh
                             int row_begin, int row_end, const void* Bt, const float* mw, const float* ck,
                             int K, int upper_tri, int zero_mean, int marginalize, float* value,
                             int32_t* argmax, float* logp, double* sum, jd_stream_t stream);
+
+/* Stream-K variant of jd_gmm_prior_forward_tc: the (patch tile, component) space is cut into equal chunks, one
+ * per CTA pair, so that all SMs stream the same number of components whatever the patch count is (row-block
+ * shards, image sizes that do not fill the last wave).  `workspace`: jd_gmm_tc_sk_workspace_bytes(P', K) bytes,
+ * 256-byte aligned, ZERO-INITIALISED ONCE by the caller (arrival counters; the kernel leaves them at zero),
+ * not shared between launches that may run concurrently.  Same outputs as jd_gmm_prior_forward_tc. */
+int64_t jd_gmm_tc_sk_workspace_bytes(int64_t n_patches, int K);
+int jd_gmm_prior_forward_tc_sk(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
+                               int row_end, const void* Bt, const float* mw, const float* ck, int K, int upper_tri,
+                               int zero_mean, int marginalize, void* workspace, float* value, int32_t* argmax,
+                               float* logp, double* sum, jd_stream_t stream);
 
 /* logsumexp (marginalize=1) backward on the tensor cores: G[p',:] = scale * sum_k r[p',k] (xc_p Lam_k - bk_k) minus
  * its row mean, r = exp(logpT[k,p'] - lse[p']).  Bt_lam = jd_gmm_tc_pack(Lam) (any 64x64 matrices pack), logpT and

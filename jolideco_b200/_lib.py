@@ -29,6 +29,7 @@ PROTOTYPES = {
                                 c_int, c_stream],
     "jd_fftconv_sizes": [c_int, c_int, c_int, c_int, ctypes.c_void_p, ctypes.c_void_p],
     "jd_fftconv_prepare_psf": [c_f32p, c_int, c_int, c_int, c_int, c_f32p, c_f32p, c_stream],
+    "jd_conv_tuning": [c_int, c_int, c_int],
     "jd_conv_forward_fft": [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_stream],
     "jd_conv_backward_fft": [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                              c_int, c_stream],
@@ -55,6 +56,10 @@ PROTOTYPES = {
     "jd_gmm_tc_pack": [c_f32p, c_int, ctypes.c_void_p, c_stream],
     "jd_gmm_prior_forward_tc": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, ctypes.c_void_p, c_f32p, c_f32p,
                                 c_int, c_int, c_int, c_int, c_f32p, c_i32p, c_f32p, c_f64p, c_stream],
+    "jd_gmm_tc_sk_workspace_bytes": [c_i64, c_int],
+    "jd_gmm_prior_forward_tc_sk": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, ctypes.c_void_p, c_f32p, c_f32p,
+                                   c_int, c_int, c_int, c_int, ctypes.c_void_p, c_f32p, c_i32p, c_f32p, c_f64p,
+                                   c_stream],
     "jd_gmm_prior_backward_lse_tc": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, ctypes.c_void_p, c_f32p, c_int,
                                      c_f32p, c_f32p, c_float, c_f32p, c_stream],
     "jd_gmm_tc16_packed_bytes": [c_int],
@@ -93,7 +98,8 @@ def load():
         fn.argtypes = argtypes
         fn.restype = {"jd_last_error": ctypes.c_char_p, "jd_gmm_tc_packed_bytes": ctypes.c_size_t,
                       "jd_gmm_tc16_packed_bytes": ctypes.c_size_t,
-                      "jd_gmm_backward_workspace_elems": ctypes.c_int64}.get(
+                      "jd_gmm_backward_workspace_elems": ctypes.c_int64,
+                      "jd_gmm_tc_sk_workspace_bytes": ctypes.c_int64}.get(
             name, ctypes.c_int)
     if lib.jd_abi_version() != 1:
         raise JolidecoB200Error(f"ABI version mismatch: library {lib.jd_abi_version()}, binding 1")

@@ -120,7 +120,7 @@ class MAPDeconvolver:
             return None, 0, 1
         return pg, torch.distributed.get_rank(pg), world
 
-    def _build_engine(self, total_loss, components, n_draws, shard=None):
+    def _build_engine(self, total_loss, components, n_draws, shard=None, stream_k=None):
         (name, comp), = components.items()
         theta = comp._flux_upsampled.data[0, 0]
         mask = comp.mask[0, 0].contiguous() if comp.mask is not None else None
@@ -160,7 +160,7 @@ class MAPDeconvolver:
                          use_log_flux=comp.use_log_flux, beta=self.beta, lr=self.optimizer_kwargs["lr"],
                          betas=self.optimizer_kwargs.get("betas", (0.9, 0.999)),
                          eps=self.optimizer_kwargs.get("eps", 1e-8), shift_table=table,
-                         datasets_validation=validation, use_graph=self.use_cuda_graph, **kwargs)
+                         datasets_validation=validation, use_graph=self.use_cuda_graph, stream_k=stream_k, **kwargs)
 
     def _early_stop(self, trace):
         if self.stop_early and len(trace) > self.stop_early_n_average:

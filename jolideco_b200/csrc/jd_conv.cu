@@ -182,14 +182,341 @@ static int launch_conv_t(const float* in, const float* scale, const float* psf, 
   return JD_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// v3: whole PSF in shared memory, asynchronous (cp.async, zero-filling) tile staging, 4x4 register
+// blocks, exact tap count (no zero-padded kernel rows / columns in the FMA loop) and an optional
+// split of the kernel rows over S thread groups of one CTA (small images: more warps per SM).
+//
+//   block = S groups x (TY x TX) threads; every group owns the whole (4 TY) x (4 TX) output tile for the
+//   kernel rows [q kh/S, (q+1) kh/S); the partial tiles are summed through shared memory.
+//   Staging: 16-byte cp.async when the tile origin is 16-byte aligned in global memory (the kernel is
+//   shifted right by dx = (ox mod 4) zero taps to get there), else 4-byte cp.async; out-of-image
+//   chunks are zero-filled by the copy itself (src-size 0), so the loop carries no predicates.
+//   Forward: flux and exposure tiles are both copied and multiplied in place by the copying thread.
+//   FMA loop: per staged input row t one sliding 4+4 window (LDS.128) feeds the output rows r with
+//   kernel row a = t - r (4 broadcast LDS.128): 64 FFMA per 5 LDS.  The kernel rows sit at a
+//   compile-time stride (KS) so all four are immediate offsets of one pointer; the first / last three
+//   input rows of a group (fewer than 4 output rows take part) are separate instantiations with a
+//   compile-time row range instead of predicates.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+constexpr int R3 = 4;   // output rows per thread (v3)
+constexpr int TY3 = 8;  // thread rows per group (v3): 32-row tiles
+constexpr int KS = 68;  // shared-memory stride of a kernel row (floats): kw + dx <= 68
+
+// one staged input row against the kernel rows a = t - r of the output rows r in [RLO, RHI]
+// (krow0 = kernel row t; row t - r sits r * KS floats below)
+template <int KT, int RLO, int RHI>
+__device__ __forceinline__ void conv3_row(float (&acc)[R3][C], const float* __restrict__ ip,
+                                          const float* __restrict__ kp, int ng_full) {
+  float4 lo = *reinterpret_cast<const float4*>(ip);
+#pragma unroll 2
+  for (int g = 0; g < ng_full; ++g) {
+    ip += 4;
+    const float4 hi = *reinterpret_cast<const float4*>(ip);
+    const float win[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+    for (int r = RLO; r <= RHI; ++r) {
+      const float4 kv = *reinterpret_cast<const float4*>(kp - r * KS);
+      const float kk[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+      for (int bb = 0; bb < 4; ++bb)
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[r][c] = fmaf(kk[bb], win[bb + c], acc[r][c]);
+    }
+    kp += 4;
+    lo = hi;
+  }
+  if (KT > 0) {  // last tap group holds KT (< 4) taps
+    float4 hi = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (KT > 1) hi = *reinterpret_cast<const float4*>(ip + 4);
+    const float win[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+    for (int r = RLO; r <= RHI; ++r) {
+      const float4 kv = *reinterpret_cast<const float4*>(kp - r * KS);
+      const float kk[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+      for (int bb = 0; bb < KT; ++bb)
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[r][c] = fmaf(kk[bb], win[bb + c], acc[r][c]);
+    }
+  }
+}
+
+template <int MODE, int TY, int TX, int KT>
+__global__ void __launch_bounds__(TY * TX * 4)
+conv3_kernel(const float* __restrict__ in, const float* __restrict__ scale, const float* __restrict__ psf,
+             float* __restrict__ out, int fH, int fW, int kh, int kw, int oy, int ox, int f, int H, int W,
+             int accumulate, int dx, int vec, int S) {
+  constexpr int TH = R3 * TY, TW = C * TX, NG = TY * TX;  // NG threads per group
+  extern __shared__ __align__(16) float smem[];
+  const int kwp = (kw + dx + 3) & ~3;  // kernel row: dx leading zero taps, padded to a multiple of 4
+  const int ng = kwp >> 2, ng_full = KT ? ng - 1 : ng;
+  const int iw = TW + kwp, ih = TH + kh - 1;
+  const bool has_e = MODE == CONV_FWD && scale != nullptr;
+  float* s_k = smem;                 // kh x KS
+  float* s_in = smem + kh * KS;      // ih x iw
+  float* s_e = s_in + ih * iw;       // ih x iw (forward with exposure), also the reduction buffer
+
+  const int tid = threadIdx.x, nt = NG * S;
+  const int q = tid / NG, tg = tid - q * NG;
+  const int tx = tg % TX, ty = tg / TX;
+  const int tile_y = blockIdx.y * TH, tile_x = blockIdx.x * TW;
+
+  // kernel (forward: flipped PSF), shifted right by dx, zero padded up to kwp
+  for (int i = tid; i < kh * KS; i += nt) {
+    const int a = i / KS, c = i - a * KS, b = c - dx;
+    if (c < kwp) {
+      float val = 0.f;
+      if (b >= 0 && b < kw) val = MODE == CONV_FWD ? __ldg(psf + (kh - 1 - a) * kw + (kw - 1 - b)) : __ldg(psf + a * kw + b);
+      s_k[i] = val;
+    }
+  }
+
+  // input tile rows [y0, y0 + ih), cols [x0, x0 + iw): flattened chunk index -> (row, chunk) by multiply-high
+  const int y0 = tile_y + oy, x0 = tile_x + ox - dx;
+  if (vec) {
+    const int ncx = iw >> 2, total = ih * ncx;
+    const uint32_t inv = 0xFFFFFFFFu / (uint32_t)ncx + 1u;  // exact floor(c / ncx) for c * ncx < 2^32
+    for (int c = tid; c < total; c += nt) {
+      const int ry = (int)__umulhi((uint32_t)c, inv), cx = c - ry * ncx;
+      const int y = y0 + ry, x = x0 + 4 * cx;
+      const bool ok = y >= 0 && y < fH && x >= 0 && x + 3 < fW;
+      const int64_t off = ok ? (int64_t)y * fW + x : 0;
+      cp_async16(smem_addr(s_in + ry * iw + 4 * cx), in + off, ok ? 16 : 0);
+      if (has_e) cp_async16(smem_addr(s_e + ry * iw + 4 * cx), scale + off, ok ? 16 : 0);
+    }
+    cp_async_wait_all();
+    if (has_e) {  // g = flux * exposure, in place, by the thread that copied the chunk
+      for (int c = tid; c < total; c += nt) {
+        float4* pa = reinterpret_cast<float4*>(s_in) + c;
+        const float4 a = *pa, e = reinterpret_cast<const float4*>(s_e)[c];
+        *pa = make_float4(a.x * e.x, a.y * e.y, a.z * e.z, a.w * e.w);
+      }
+    }
+  } else {
+    const int total = ih * iw;
+    const uint32_t inv = 0xFFFFFFFFu / (uint32_t)iw + 1u;
+    for (int c = tid; c < total; c += nt) {
+      const int ry = (int)__umulhi((uint32_t)c, inv), rx = c - ry * iw;
+      const int y = y0 + ry, x = x0 + rx;
+      bool ok = y >= 0 && y < fH && x >= 0 && x < fW;
+      int64_t off = 0;
+      if (MODE == CONV_FWD) {
+        off = ok ? (int64_t)y * fW + x : 0;
+      } else if (ok) {
+        const int py = y / f, px = x / f;
+        ok = py < H && px < W;
+        off = ok ? (int64_t)py * W + px : 0;
+      }
+      cp_async4(smem_addr(s_in + c), in + off, ok ? 4 : 0);
+      if (has_e) cp_async4(smem_addr(s_e + c), scale + off, ok ? 4 : 0);
+    }
+    cp_async_wait_all();
+    if (has_e) {
+      for (int c = tid; c < total; c += nt) s_in[c] *= s_e[c];
+    }
+  }
+  __syncthreads();
+
+  float acc[R3][C];
+#pragma unroll
+  for (int r = 0; r < R3; ++r)
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[r][c] = 0.f;
+
+  // this group's kernel rows [a_lo, a_hi): input rows t = a + r, t in [a_lo, a_hi + R3 - 1)
+  const int a_lo = (q * kh) / S, a_hi = ((q + 1) * kh) / S;
+  const float* ip = s_in + (ty * R3 + a_lo) * iw + tx * C;  // staged row t, this thread's first column
+  const float* kp = s_k + a_lo * KS;                        // kernel row t
+  if (a_hi - a_lo >= R3 - 1) {
+    conv3_row<KT, 0, 0>(acc, ip, kp, ng_full);
+    conv3_row<KT, 0, 1>(acc, ip + iw, kp + KS, ng_full);
+    conv3_row<KT, 0, 2>(acc, ip + 2 * iw, kp + 2 * KS, ng_full);
+    ip += 3 * iw, kp += 3 * KS;
+    for (int t = a_lo + 3; t < a_hi; ++t, ip += iw, kp += KS) conv3_row<KT, 0, 3>(acc, ip, kp, ng_full);
+    conv3_row<KT, 1, 3>(acc, ip, kp, ng_full);
+    conv3_row<KT, 2, 3>(acc, ip + iw, kp + KS, ng_full);
+    conv3_row<KT, 3, 3>(acc, ip + 2 * iw, kp + 2 * KS, ng_full);
+  } else {
+    // fewer than 3 kernel rows in this group: one output row at a time, row by row
+    for (int a = a_lo; a < a_hi; ++a) {
+      conv3_row<KT, 0, 0>(acc, s_in + (ty * R3 + a) * iw + tx * C, s_k + a * KS, ng_full);
+      conv3_row<KT, 1, 1>(acc, s_in + (ty * R3 + a + 1) * iw + tx * C, s_k + (a + 1) * KS, ng_full);
+      conv3_row<KT, 2, 2>(acc, s_in + (ty * R3 + a + 2) * iw + tx * C, s_k + (a + 2) * KS, ng_full);
+      conv3_row<KT, 3, 3>(acc, s_in + (ty * R3 + a + 3) * iw + tx * C, s_k + (a + 3) * KS, ng_full);
+    }
+  }
+
+  if (S > 1) {  // sum the groups' partial tiles (accumulator-major: conflict-free)
+    __syncthreads();
+    float* s_red = s_in;  // (S - 1) x 16 x NG floats; the host sizes s_in + s_e for it
+    if (q > 0) {
+#pragma unroll
+      for (int r = 0; r < R3; ++r)
+#pragma unroll
+        for (int c = 0; c < C; ++c) s_red[((q - 1) * (R3 * C) + r * C + c) * NG + tg] = acc[r][c];
+    }
+    __syncthreads();
+    if (q > 0) return;
+    for (int qq = 0; qq < S - 1; ++qq)
+#pragma unroll
+      for (int r = 0; r < R3; ++r)
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[r][c] += s_red[(qq * (R3 * C) + r * C + c) * NG + tg];
+  }
+
+  const bool vec_out = (fW & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                       (scale == nullptr || (reinterpret_cast<uintptr_t>(scale) & 15) == 0);
+#pragma unroll
+  for (int r = 0; r < R3; ++r) {
+    const int y = tile_y + ty * R3 + r;
+    if (y >= fH) continue;
+    const int x = tile_x + tx * C;
+    const int64_t o = (int64_t)y * fW + x;
+    if (x + C <= fW && vec_out) {
+      float4 val = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      if (MODE == CONV_BWD) {
+        if (scale) {
+          const float4 sc = *reinterpret_cast<const float4*>(scale + o);
+          val.x *= sc.x, val.y *= sc.y, val.z *= sc.z, val.w *= sc.w;
+        }
+        if (accumulate) {
+          const float4 old = *reinterpret_cast<const float4*>(out + o);
+          val.x += old.x, val.y += old.y, val.z += old.z, val.w += old.w;
+        }
+      }
+      *reinterpret_cast<float4*>(out + o) = val;
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        if (x + c >= fW) continue;
+        float val = acc[r][c];
+        if (MODE == CONV_BWD) {
+          if (scale) val *= scale[o + c];
+          if (accumulate) val += out[o + c];
+        }
+        out[o + c] = val;
+      }
+    }
+  }
+}
+
+constexpr size_t CONV3_SMEM_MAX = 200 * 1024;
+
+struct Conv3Plan {
+  int tx, S, dx, vec, kt;
+  size_t smem;
+};
+
+static size_t conv3_smem(int mode, bool has_scale, int kh, int kw, int dx, int tx, int S) {
+  const int kwp = (kw + dx + 3) & ~3, NG = TY3 * tx;
+  size_t buf = (size_t)(R3 * TY3 + kh - 1) * (C * tx + kwp) * ((mode == CONV_FWD && has_scale) ? 2 : 1);
+  const size_t red = (size_t)(S - 1) * R3 * C * NG;
+  if (buf < red) buf = red;
+  return ((size_t)kh * KS + buf) * sizeof(float);
+}
+
+// tile shape / kernel-row split: enough warps per SM for the FMA pipe, and a last wave that is not mostly idle
+static bool conv3_plan(int mode, const float* in, const float* scale, const float* out, int fH, int fW, int kh, int kw,
+                       int ox, int f, int H, int W, Conv3Plan* p) {
+  const bool aligned = (fW & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+                       (scale == nullptr || (reinterpret_cast<uintptr_t>(scale) & 15) == 0) &&
+                       (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  p->vec = aligned && (mode == CONV_FWD || (f == 1 && H == fH && W == fW));
+  p->dx = p->vec ? ((ox % 4) + 4) % 4 : 0;
+  if (kw + p->dx > KS) return false;
+  p->kt = (kw + p->dx) & 3;
+  const int nsm = num_sms();
+  constexpr int TH = R3 * TY3;
+  const long tiles64 = (long)((fW + 63) / 64) * ((fH + TH - 1) / TH);
+  p->tx = tiles64 >= 6L * nsm ? 16 : 8;
+  const int TW = C * p->tx, NG = TY3 * p->tx;
+  const long tiles = (long)((fW + TW - 1) / TW) * ((fH + TH - 1) / TH);
+  const long per_sm = (tiles + nsm - 1) / nsm;
+  const int warps_per_group = NG / 32;
+  int S = 1;
+  while (S < 4 && per_sm * warps_per_group * S < 16 && kh >= 8 * S) S *= 2;
+  p->S = S;
+  p->smem = conv3_smem(mode, scale != nullptr, kh, kw, p->dx, p->tx, p->S);
+  return p->smem <= CONV3_SMEM_MAX;
+}
+
+template <int MODE, int TX, int KT>
+static int launch_conv3_t(const Conv3Plan& p, const float* in, const float* scale, const float* psf, float* out, int fH,
+                          int fW, int kh, int kw, int oy, int ox, int f, int H, int W, int accumulate, cudaStream_t st,
+                          const char* name) {
+  constexpr int TY = TY3;
+  auto kern = conv3_kernel<MODE, TY, TX, KT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV3_SMEM_MAX);
+    if (e != cudaSuccess) {
+      set_error("%s: cannot reserve shared memory: %s", name, cudaGetErrorString(e));
+      return JD_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  dim3 grid((fW + C * TX - 1) / (C * TX), (fH + R3 * TY - 1) / (R3 * TY));
+  kern<<<grid, TY * TX * p.S, p.smem, st>>>(in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, p.dx, p.vec,
+                                            p.S);
+  JD_CHECK_LAUNCH(name);
+  return JD_OK;
+}
+
+template <int MODE, int TX>
+static int launch_conv3_kt(const Conv3Plan& p, const float* in, const float* scale, const float* psf, float* out, int fH,
+                           int fW, int kh, int kw, int oy, int ox, int f, int H, int W, int accumulate, cudaStream_t st,
+                           const char* name) {
+  switch (p.kt) {
+    case 0: return launch_conv3_t<MODE, TX, 0>(p, in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
+    case 1: return launch_conv3_t<MODE, TX, 1>(p, in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
+    case 2: return launch_conv3_t<MODE, TX, 2>(p, in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
+    default: return launch_conv3_t<MODE, TX, 3>(p, in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
+  }
+}
+
+// tuning knobs (environment at first use, or jd_conv_tuning): JD_CONV_TILE = shape of the previous kernel,
+// JD_CONV_V3 = 0 selects the previous (synchronously staged, chunked) kernel, JD_CONV_TX = 8 | 16 forces the v3
+// tile width (32 | 64 columns), JD_CONV_S = 1 | 2 | 4 forces the v3 kernel-row split
+static int g_tile = -1, g_v3 = 1, g_tx = 0, g_s = 0;
+static void conv_tuning_init() {
+  if (g_tile >= 0) return;
+  const char* e = getenv("JD_CONV_TILE");
+  g_tile = e ? atoi(e) : 1;
+  if ((e = getenv("JD_CONV_V3"))) g_v3 = atoi(e);
+  if ((e = getenv("JD_CONV_TX"))) g_tx = atoi(e);
+  if ((e = getenv("JD_CONV_S"))) g_s = atoi(e);
+}
+
 template <int MODE>
 static int launch_conv(const float* in, const float* scale, const float* psf, float* out, int fH, int fW, int kh,
                        int kw, int oy, int ox, int f, int H, int W, int accumulate, cudaStream_t st,
                        const char* name) {
-  static int tile = -1;
-  if (tile < 0) {
-    const char* e = getenv("JD_CONV_TILE");  // tuning knob: rows per thread / CTA shape, see below
-    tile = e ? atoi(e) : 1;
+  conv_tuning_init();
+  const int tile = g_tile, v3 = g_v3, force_tx = g_tx, force_s = g_s;
+  Conv3Plan p;
+  if (v3 && conv3_plan(MODE, in, scale, out, fH, fW, kh, kw, ox, f, H, W, &p)) {
+    if (force_tx == 8 || force_tx == 16 || force_s == 1 || force_s == 2 || force_s == 4) {
+      if (force_tx == 8 || force_tx == 16) p.tx = force_tx;
+      if (force_s) p.S = force_s;
+      p.smem = conv3_smem(MODE, scale != nullptr, kh, kw, p.dx, p.tx, p.S);
+    }
+    if (p.smem <= CONV3_SMEM_MAX) {
+      if (p.tx == 16)
+        return launch_conv3_kt<MODE, 16>(p, in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
+      return launch_conv3_kt<MODE, 8>(p, in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
+    }
   }
   if (tile == 1)  // default: 2 rows per thread, 16x16 threads -> 32x64 tiles (best of the sweep, tools/conv_exp.py)
     return launch_conv_t<MODE, 16, 16, 2>(in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
@@ -205,6 +532,16 @@ static int launch_conv(const float* in, const float* scale, const float* psf, fl
 using namespace jd;
 
 extern "C" {
+
+int jd_conv_tuning(int v3, int tx, int split) {
+  JD_CHECK_ARG((tx == 0 || tx == 8 || tx == 16) && (split == 0 || split == 1 || split == 2 || split == 4),
+               "jd_conv_tuning: tx must be 0, 8 or 16 and split 0, 1, 2 or 4");
+  conv_tuning_init();
+  g_v3 = v3 ? 1 : 0;
+  g_tx = tx;
+  g_s = split;
+  return JD_OK;
+}
 
 int jd_conv_forward_direct(const float* flux, const float* exposure, const float* psf, float* conv, int fH,
                            int fW, int kh, int kw, jd_stream_t stream) {

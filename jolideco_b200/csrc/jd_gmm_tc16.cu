@@ -110,6 +110,7 @@ gmm_fwd_tc16_kernel(const float* __restrict__ flux, Geom g, const int32_t* __res
   float* s_rinv = reinterpret_cast<float*>(s_mk + TM);      // 1 / (row scale) per patch row
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rt_zero = (uint32_t)K >> 30;  // 0 at run time (K < 2^30), opaque to the compiler
   const int dbg = marginalize >> 8;  // profiling knobs (JD_TC_DEBUG): 1 = no epilogue TMEM loads, 2 = one MMA per component
   marginalize &= 1;
   const uint32_t bar0 = smem_u32(bars);
@@ -329,12 +330,12 @@ gmm_fwd_tc16_kernel(const float* __restrict__ flux, Geom g, const int32_t* __res
           qd = fmaf(e3, e3, qd);
         }
       }
-      // accumulator slot and mw row are free once both are consumed
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(t));
       const float qsum = ZERO_MEAN ? ((qa + qb) + (qc + qd)) * (inv * inv) : (qa + qb) + (qc + qd);
       const float lp = fmaf(-0.5f, qsum, c_k);
+      // accumulator slot and mw row are free once both are consumed (lp depends on every load, see mbar_arrive_after)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_after(tempty_bar(t), lp, rt_zero);
       if (logp && p < g.P) logp[(size_t)kc * g.P + p] = lp;  // component-major (K x P'): coalesced over patch rows
       if (marginalize) {
         if (lp > run_m) {

@@ -18,6 +18,16 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Arrive that cannot be issued before `dep` is available.  ptxas treats the arrive as independent of earlier
+// shared-memory / TMEM loads whose values are still unconsumed and hoists it above their consumers (seen in SASS:
+// the slot-release arrive sat in the middle of the epilogue's FMA chain, and the bulk copy refilling the mw row then
+// raced with the tail of those loads: a few rows of one component off by 1e-3, once in ~20 launches).  Making the
+// barrier ADDRESS depend on a value computed from everything that was loaded (rt_zero is 0 at run time, unknown at
+// compile time) pins the arrive behind the loads through the register scoreboard.
+__device__ __forceinline__ void mbar_arrive_after(uint32_t bar, float dep, uint32_t rt_zero) {
+  mbar_arrive(bar + (__float_as_uint(dep) & rt_zero));
+}
+__device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }

@@ -72,10 +72,12 @@ class MapEngine:
     def __init__(self, theta, datasets, prior=None, mask=None, use_log_flux=True, beta=1.0, lr=0.1, betas=(0.9, 0.999),
                  eps=1e-8, shift_table=None, datasets_validation=(), use_graph=True, process_group=None,
                  prior_weight=None, dataset_index=None, n_datasets_global=None, validation_index=None,
-                 n_validation_global=None, counts_shape=None, collective="nccl"):
+                 n_validation_global=None, counts_shape=None, collective="nccl", stream_k=None):
         """theta: 2-D CUDA fp32 tensor updated in place (the component's parameter storage).
         prior: None (uniform) or dict(packed=GMMPacked, stride, marginalize, backend).
-        shift_table: (N, 2) int array of pre-drawn (row, col) cycle-spin shifts in consumption order."""
+        shift_table: (N, 2) int array of pre-drawn (row, col) cycle-spin shifts in consumption order.
+        stream_k: stream-K decomposition of the tcgen05 prior forward (None = ops.use_stream_k: only when the
+        patch tiles do not fill the SMs; it buys latency of ONE run, not throughput of concurrent runs)."""
         ops.require_device(theta.device)
         self.theta = ops._check(theta, "theta")
         assert theta.ndim == 2
@@ -127,6 +129,7 @@ class MapEngine:
             self.marginalize = bool(prior["marginalize"])
             self.backend = int(prior.get("backend", 0))
             self.packed = prior["packed"]
+            self.sk_ws = None
             if self.backend == 1:
                 self.packed.Bt  # pack the tensor-core operand before any graph capture
             elif self.backend == 2:
@@ -137,6 +140,8 @@ class MapEngine:
             self.rows = self._row_block(self.rank, self.world)
             P = (self.rows[1] - self.rows[0]) * self.nx
             self.P = P
+            if self.backend == 1 and P > 0 and (ops.use_stream_k(P, self.dev) if stream_k is None else stream_k):
+                self.sk_ws = ops.tc_sk_workspace(P, self.packed.K, self.dev)
             self.value = torch.empty(max(P, 1), **f32)
             self.argmax = torch.empty(max(P, 1), dtype=torch.int32, device=self.dev)
             # logsumexp mode keeps logp for the backward; the tensor-core kernels use a component-major layout
@@ -249,6 +254,12 @@ class MapEngine:
                   self.rows[0], self.rows[1], _p(bt), _p(binv), _p(self.packed.mw), _p(self.packed.ck), self.packed.K,
                   int(self.packed.upper_tri), int(self.packed.zero_mean), int(self.marginalize), _p(self.value),
                   _p(self.argmax), _p(self.logp), sum_acc, self._s())
+            return
+        if self.backend == 1 and self.sk_ws is not None:
+            _call("jd_gmm_prior_forward_tc_sk", _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride,
+                  self.rows[0], self.rows[1], _p(self.packed.Bt), _p(self.packed.mw), _p(self.packed.ck), self.packed.K,
+                  int(self.packed.upper_tri), int(self.packed.zero_mean), int(self.marginalize), _p(self.sk_ws),
+                  _p(self.value), _p(self.argmax), _p(self.logp), sum_acc, self._s())
             return
         if self.backend == 1:
             _call("jd_gmm_prior_forward_tc", _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride,

@@ -1,6 +1,7 @@
 """Tensor-level wrappers over the C ABI: validate, allocate outputs with torch, pass raw device
 pointers and the current CUDA stream.  No arithmetic happens in Python/PyTorch here."""
 import math
+import os
 
 import numpy as np
 import torch
@@ -64,7 +65,10 @@ def conv_forward(flux, exposure, psf, out=None):
     return out
 
 
-FFT_MIN_PSF_AREA = 24 * 24  # PSFs at least this large take the shared-memory FFT path
+# PSFs at least this large take the shared-memory FFT path.  tools/conv_exp.py (back-to-back launches) puts the
+# cross-over of the cp.async direct kernel near 36 x 36 on a 512^2 grid, but inside the cfg2 step (cold L2) the FFT
+# path is still 7 us ahead at 34 x 34: the threshold sits between the 23 x 23 and 34 x 34 measurements.
+FFT_MIN_PSF_AREA = 30 * 30
 
 
 class FFTConvPlan:
@@ -230,6 +234,27 @@ def _bt16(packed):
     return packed._Bt16
 
 
+# tcgen05 prior forward: stream-K work decomposition (jd_gmm_prior_forward_tc_sk).  JD_TC_STREAMK = 0 | 1 forces it
+# off / on; default "auto": only when the one-tile-per-CTA kernel would leave more than a quarter of the SMs idle
+# (row-block shards of a multi-GPU run, small images) - with every SM busy the per-segment overhead of stream-K
+# (pipeline drain + gather at each tile boundary) outweighs the balance (profiles/r01_summary.md).
+TC_STREAMK = {"0": False, "1": True}.get(os.environ.get("JD_TC_STREAMK", "auto"), None)
+
+
+def use_stream_k(P, device):
+    if TC_STREAMK is not None:
+        return TC_STREAMK
+    n_pairs = ((int(P) + 127) // 128 + 1) // 2
+    clusters = torch.cuda.get_device_properties(device).multi_processor_count // 2
+    return 0 < n_pairs <= 0.75 * clusters
+
+
+def tc_sk_workspace(P, K, device):
+    """Zero-initialised workspace of the stream-K forward (arrival counters + per-segment partials)."""
+    n = int(_lib.load().jd_gmm_tc_sk_workspace_bytes(int(P), int(K)))
+    return torch.zeros(max(n, 256), dtype=torch.uint8, device=device)
+
+
 def gmm_log_prob(x, packed):
     _check(x, "x")
     P, D = x.shape
@@ -289,6 +314,11 @@ def gmm_prior_forward(flux, shift_yx, packed, stride=4, marginalize=False, rows=
         _lib.call("jd_gmm_prior_forward_tc16", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(bt), _ptr(binv),
                   _ptr(packed.mw), _ptr(packed.ck), packed.K, int(packed.upper_tri), int(packed.zero_mean),
                   int(bool(marginalize)), _ptr(value), _ptr(argmax), _ptr(logp), _ptr(sum_out), _stream())
+    elif int(backend) == 1 and use_stream_k(P, flux.device):
+        ws = tc_sk_workspace(P, packed.K, flux.device)
+        _lib.call("jd_gmm_prior_forward_tc_sk", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(packed.Bt),
+                  _ptr(packed.mw), _ptr(packed.ck), packed.K, int(packed.upper_tri), int(packed.zero_mean),
+                  int(bool(marginalize)), _ptr(ws), _ptr(value), _ptr(argmax), _ptr(logp), _ptr(sum_out), _stream())
     elif int(backend) == 1:
         _lib.call("jd_gmm_prior_forward_tc", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(packed.Bt),
                   _ptr(packed.mw), _ptr(packed.ck), packed.K, int(packed.upper_tri), int(packed.zero_mean), int(bool(marginalize)), _ptr(value),

@@ -125,6 +125,72 @@ def test_conv_backward_upsampled(f):
     assert rel_max(acc.cpu().numpy(), ref + 1) < 5e-6
 
 
+@pytest.mark.parametrize("tx,split", [(0, 0), (8, 1), (8, 2), (8, 4), (16, 1), (16, 2), (16, 4)])
+@pytest.mark.parametrize("shape,kshape", [((96, 128), (17, 17)), ((64, 192), (18, 19)), ((80, 64), (34, 34)),
+                                          ((72, 100), (5, 20)), ((64, 64), (3, 2)), ((50, 70), (9, 9)),
+                                          ((40, 48), (23, 1))])
+def test_conv_v3_variants(shape, kshape, tx, split):
+    """cp.async kernel: every tile width / PSF-row split, vector (16 B) and scalar (4 B) staging, all tap tails
+    (kw + dx mod 4), against the oracle; and identical to the previous kernel to rounding."""
+    from jolideco_b200 import _lib
+
+    rng = np.random.default_rng(21)
+    flux = rng.gamma(2.0, size=shape)
+    E = rng.uniform(0.5, 1.5, size=shape)
+    psf = rng.uniform(size=kshape)
+    psf /= psf.sum()
+    d = rng.normal(size=shape)
+    ref = O.convolve_fft(flux * E, psf)
+    ref_b = O.correlate_adjoint(d, psf) * E
+    _lib.call("jd_conv_tuning", 1, tx, split)
+    try:
+        out = ops.conv_forward(t(flux), t(E), t(psf)).cpu().numpy()
+        out_b = ops.conv_backward(t(d), t(E), t(psf), 1).cpu().numpy()
+        acc = t(np.ones(shape))
+        ops.conv_backward(t(d), t(E), t(psf), 1, out=acc, accumulate=True)
+    finally:
+        _lib.call("jd_conv_tuning", 1, 0, 0)
+    assert rel_max(out, ref) < 5e-6
+    assert rel_max(out_b, ref_b) < 5e-6
+    assert rel_max(acc.cpu().numpy(), ref_b + 1) < 5e-6
+
+
+@pytest.mark.parametrize("f", [2, 3])
+@pytest.mark.parametrize("split", [1, 4])
+def test_conv_v3_backward_upsampled_multi_tile(f, split):
+    from jolideco_b200 import _lib
+
+    rng = np.random.default_rng(22)
+    H, W = 40, 36
+    fH, fW = H * f, W * f
+    psf = rng.uniform(size=(7 * f, 7 * f))
+    E = rng.uniform(0.5, 1.5, size=(fH, fW))
+    dn = rng.normal(size=(H, W))
+    ref = O.npred_backward(dn, np.ones((H, W)), np.ones((fH, fW)), E, psf, f)
+    _lib.call("jd_conv_tuning", 1, 8, split)
+    try:
+        out = ops.conv_backward(t(dn), t(E), t(psf), f).cpu().numpy()
+    finally:
+        _lib.call("jd_conv_tuning", 1, 0, 0)
+    assert rel_max(out, ref) < 5e-6
+
+
+def test_conv_previous_kernel_still_matches():
+    from jolideco_b200 import _lib
+
+    rng = np.random.default_rng(23)
+    shape, kshape = (96, 128), (17, 17)
+    flux, E = rng.gamma(2.0, size=shape), rng.uniform(0.5, 1.5, size=shape)
+    psf = rng.uniform(size=kshape)
+    ref = O.convolve_fft(flux * E, psf)
+    _lib.call("jd_conv_tuning", 0, 0, 0)
+    try:
+        out = ops.conv_forward(t(flux), t(E), t(psf)).cpu().numpy()
+    finally:
+        _lib.call("jd_conv_tuning", 1, 0, 0)
+    assert rel_max(out, ref) < 5e-6
+
+
 @pytest.mark.parametrize("f", [1, 2])
 def test_poisson_forward_backward(f):
     rng = np.random.default_rng(3)
@@ -270,6 +336,42 @@ def test_gmm_prior_tensor_core_vs_cuda_core_full_size(marginalize, mean_scale, b
     assert_allclose(s1.item(), s0.item(), rtol=1e-6)
     assert_allclose(v1.cpu().numpy(), v0.cpu().numpy(), rtol=1e-5, atol=1e-3)
     assert (k0 != k1).sum().item() <= 3
+
+
+@pytest.mark.parametrize("marginalize", [False, True])
+@pytest.mark.parametrize("shape,rows,K", [((512, 512), None, 256), ((1024, 1024), (31, 63), 256), ((200, 328), None, 40),
+                                          ((64, 80), None, 3), ((1024, 1024), None, 64)])
+def test_gmm_prior_stream_k_equals_tile_per_cta(monkeypatch, shape, rows, K, marginalize):
+    """Stream-K decomposition (segments merged through the workspace) against the one-tile-per-CTA kernel:
+    identical per-component log-probabilities, hence bit-identical max / argmax; logsumexp to rounding.
+    Run twice on the same workspace-free path to check the arrival counters are left at zero."""
+    rng = np.random.default_rng(15)
+    flux = t(rng.gamma(2.0, size=shape) * np.exp(rng.normal(0, 0.7, size=shape)))
+    packed = pack(O.GMM(*synthetic_gmm(K, seed=9, mean_scale=0.02)))
+    monkeypatch.setattr(ops, "TC_STREAMK", False)
+    v0, k0, lp0, s0 = ops.gmm_prior_forward(flux, (2, -1), packed, 4, marginalize, rows=rows, want_logp=True, backend=1)
+    monkeypatch.setattr(ops, "TC_STREAMK", True)
+    P = v0.numel()
+    ws = ops.tc_sk_workspace(P, packed.K, flux.device)
+    monkeypatch.setattr(ops, "tc_sk_workspace", lambda *a: ws)
+    for _ in range(2):
+        v1, k1, lp1, s1 = ops.gmm_prior_forward(flux, (2, -1), packed, 4, marginalize, rows=rows, want_logp=True,
+                                                backend=1)
+        diff = lp0 != lp1
+        if bool(diff.any()):
+            idx = diff.nonzero().cpu().numpy()
+            a, b = lp0[diff].cpu().numpy(), lp1[diff].cpu().numpy()
+            raise AssertionError(f"logp differs in {idx.shape[0]} entries: tiles {np.unique(idx[:, 0] // 128)[:16]}, rows "
+                                 f"{np.unique(idx[:, 0] % 128)[:16]}, components {np.unique(idx[:, 1])[:32]}, "
+                                 f"max |diff| {np.abs(a - b).max()}, samples {a[:4]} vs {b[:4]}")
+        assert torch.equal(k0, k1)
+        if marginalize:
+            assert_allclose(v1.cpu().numpy(), v0.cpu().numpy(), rtol=2e-6)
+        else:
+            assert torch.equal(v0, v1)
+        assert_allclose(s1.item(), s0.item(), rtol=1e-9 if not marginalize else 1e-6)
+    n_tiles2 = ((P + 127) // 128 + 1) // 2 * 2  # arrival counters: one per tile, whole CTA pairs
+    assert int(ws[:4 * n_tiles2].view(torch.int32).abs().sum()) == 0
 
 
 def test_gmm_prior_tensor_core_dense_precision_factors():

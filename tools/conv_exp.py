@@ -1,17 +1,41 @@
-"""Timing of the direct convolution kernel (tuning aid): JD_CONV_TILE=0|1|2 python tools/conv_exp.py"""
+"""Timing sweep of the direct convolution kernels against the FFT path (tuning aid):
+    python tools/conv_exp.py > gpurun_out/conv_exp.txt"""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from jolideco_b200 import ops
-for n, k in [(1024, 17), (512, 17), (256, 17), (512, 9), (1024, 23)]:
-    flux = torch.rand(n, n, device="cuda"); E = torch.rand(n, n, device="cuda") + 0.5
-    psf = torch.rand(k, k, device="cuda"); out = torch.empty_like(flux)
+from jolideco_b200 import _lib, ops
+
+
+def timeit(fn, reps=30):
     for _ in range(3):
-        ops.conv_forward(flux, E, psf, out=out)
+        fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(50):
-        ops.conv_forward(flux, E, psf, out=out)
-    e1.record(); torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) / 50 * 1e3
-    print(f"tile {os.environ.get('JD_CONV_TILE','0')} n={n} k={k}: {us:7.1f} us  {2*n*n*k*k/us/1e6:6.1f} TFLOP/s")
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3
+
+
+cases = [(1024, 17), (512, 34), (512, 17), (256, 17), (1024, 34), (1024, 23), (512, 48), (512, 64), (2048, 17), (1024, 9)]
+variants = [("auto", 1, 0, 0), ("old", 0, 0, 0)] + [(f"tx{tx}s{s}", 1, tx, s) for tx in (8, 16) for s in (1, 2, 4)]
+for n, k in cases:
+    flux = torch.rand(n, n, device="cuda"); E = torch.rand(n, n, device="cuda") + 0.5
+    psf = torch.rand(k, k, device="cuda"); out = torch.empty_like(flux); d = torch.randn(n, n, device="cuda")
+    flop = 2.0 * n * n * k * k
+    row = []
+    for name, v3, tx, s in variants:
+        _lib.call("jd_conv_tuning", v3, tx, s)
+        try:
+            uf = timeit(lambda: ops.conv_forward(flux, E, psf, out=out))
+            ub = timeit(lambda: ops.conv_backward(d, E, psf, 1, out=out))
+            row.append(f"{name}: {uf:6.1f}/{ub:6.1f} us ({flop / uf / 1e6:5.1f} TF/s)")
+        except Exception as exc:
+            row.append(f"{name}: failed ({str(exc)[:40]})")
+    _lib.call("jd_conv_tuning", 1, 0, 0)
+    plan = ops.FFTConvPlan(psf, n, n)
+    uf = timeit(lambda: ops.conv_forward_fft(flux, E, plan, out=out))
+    ub = timeit(lambda: ops.conv_backward_fft(d, E, plan, 1, out=out))
+    row.append(f"fft: {uf:6.1f}/{ub:6.1f} us")
+    print(f"n={n} k={k}: " + " | ".join(row), flush=True)
