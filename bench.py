@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed iterations")
+    ap.add_argument("--breakdown", action="store_true",
+                    help="add per-entry-point device times (CUDA events around every C-ABI call of eager steps)")
     ap.add_argument("--collective", default="nccl", choices=["nccl", "peer"],
                     help="joint multi-GPU step: NCCL all-reduce + Adam, or the fused peer-memory reduce+Adam kernel")
     return ap.parse_args()
@@ -277,6 +279,10 @@ def main():
     if rank == 0 or joint:  # joint steps contain a collective: every rank has to take part
         roofline = measure_roofline(E, eng, run_step, args, workload, flush)
 
+    breakdown = None
+    if args.breakdown and rank == 0 and not (joint and world > 1):
+        breakdown = measure_breakdown(E, eng, run_step, flush)
+
     # ------------------------------------------------------------------ e2e through MAPDeconvolver.run (host buffers)
     e2e = None
     if True:
@@ -306,9 +312,32 @@ def main():
                                                      "cuda_graph": eng.use_graph,
                                                      "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps}),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        if breakdown:
+            line["breakdown_us_per_step"] = breakdown
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_breakdown(E, eng, run_step, flush, n=10):
+    """Device time per C-ABI entry point and step: CUDA events around every call of eager steps (L2 flushed before
+    each step like the timed loop; kernels run back to back, so inter-kernel gaps are not included)."""
+    import torch
+
+    graph = eng.use_graph
+    eng.use_graph = False
+    E._STATS["timed"], E._STATS["events"] = "*", []
+    for i in range(n):
+        if flush is not None:
+            flush.fill_(i & 0xFF)
+        run_step(i)
+    torch.cuda.synchronize()
+    out = {}
+    for name, a, b in E._STATS["events"]:
+        out[name] = out.get(name, 0.0) + a.elapsed_time(b) * 1e3 / n
+    E._STATS["timed"], E._STATS["events"] = None, []
+    eng.use_graph = graph
+    return {k: round(v, 2) for k, v in sorted(out.items(), key=lambda kv: -kv[1])}
 
 
 def bench_batched(args, rank, local_rank, world, n_runs=64):
@@ -413,6 +442,7 @@ def measure_roofline(E, eng, run_step, args, workload, flush):
         pass
     graph = eng.use_graph
     eng.use_graph = False
+    extra = {}
     if eng.prior is not None:
         name = {1: "jd_gmm_prior_forward_tc", 2: "jd_gmm_prior_forward_tc16"}.get(eng.backend, "jd_gmm_prior_forward")
         if eng.backend == 1 and getattr(eng, "sk_ws", None) is not None:
@@ -420,9 +450,15 @@ def measure_roofline(E, eng, run_step, args, workload, flush):
         P = eng.P
         work = 2.0 * P * 64 * 64 * eng.packed.K  # useful flops, counted once
         bf16 = peaks.get("bf16_tflops_sustained")
-        peak, src = (bf16 / 2.0, "measured (1/2 x sustained cuBLAS bf16, MEASURED_PEAKS.json)") if bf16 else (
-            1590.0 / 2, "fallback (1/2 x 1.59 PFLOP/s)")
+        # split-TF32 runs on the TF32 pipe (half the bf16 rate); the split-FP16 kernel on the f16 pipe (= bf16 rate)
+        div, what = (1.0, "sustained cuBLAS bf16") if eng.backend == 2 else (2.0, "1/2 x sustained cuBLAS bf16")
+        peak, src = (bf16 / div, f"measured ({what}, MEASURED_PEAKS.json)") if bf16 else (
+            1590.0 / div, f"fallback ({what} = 1.59 PFLOP/s)")
         bound, unit = "tensor", "TFLOP/s"
+        # the 3-term split issues 3 products per useful one; the triangular trim keeps 320/512 of each
+        issued = 3.0 * ((320.0 / 512.0) if eng.packed.upper_tri else 1.0)
+        extra = {"issued_over_useful_flops": issued,
+                 "ncu": ncu_reference(name, workload["name"])}
     else:
         name = "jd_conv_forward_direct"
         k = cfg["psf"] * cfg["f"]
@@ -441,9 +477,26 @@ def measure_roofline(E, eng, run_step, args, workload, flush):
     eng.use_graph = graph
     avg_ms = float(np.mean(durs))
     achieved = work / (avg_ms * 1e-3) / 1e12
-    return {"bound": bound, "kernel": name, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
-            "traffic": None, "avg_launch_ms": avg_ms, "launches_timed": len(durs), "algorithmic_work": work,
-            "peak_source": src}
+    out = {"bound": bound, "kernel": name, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+           "traffic": None, "avg_launch_ms": avg_ms, "launches_timed": len(durs), "algorithmic_work": work,
+           "peak_source": src}
+    if extra:
+        out["issued_frac"] = achieved * extra["issued_over_useful_flops"] / peak
+        out["issued_over_useful_flops"] = extra["issued_over_useful_flops"]
+        ncu = extra["ncu"]
+        if ncu:  # one committed `ncu --set full` capture of this kernel on this workload (profiles/)
+            out["traffic"] = ncu.get("dram_bytes")
+            out["ncu"] = ncu
+    return out
+
+
+def ncu_reference(kernel, workload):
+    """DRAM traffic / pipe utilisation of the kernel from the committed ncu capture (profiles/ncu_reference.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_reference.json")) as fh:
+            return json.load(fh).get(f"{kernel}:{workload}")
+    except Exception:
+        return None
 
 
 def measure_e2e(J, workload, args, device, rank, joint=False):

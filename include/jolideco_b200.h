@@ -66,7 +66,7 @@ int jd_conv_backward_direct(const float* dpool, const float* exposure, const flo
                             jd_stream_t stream);
 
 /* Tuning / test hook of the direct kernels (process-wide; 0 = automatic): v3 = 0 selects the chunked,
- * synchronously staged kernel instead of the cp.async one; tx = 8 | 16 forces 32- | 64-column tiles;
+ * synchronously staged kernel instead of the cp.async one; tx = 8 | 16 | 28 forces 32- | 64-column tiles | 64-column tiles with two column groups per thread;
  * split = 1 | 2 | 4 forces the number of thread groups the PSF rows are divided over. */
 int jd_conv_tuning(int v3, int tx, int split);
 
@@ -186,6 +186,13 @@ int jd_gmm_prior_backward(const float* flux, int fH, int fW, const int32_t* shif
                           int row_begin, int row_end, const float* Lam, const float* bk, int K,
                           int marginalize, const int32_t* argmax, const float* logp, const float* value,
                           float scale, float* G, int32_t* workspace, jd_stream_t stream);
+
+/* Max-mode backward for upper-triangular factors (precision Cholesky factors are): same G as
+ * jd_gmm_prior_backward(marginalize = 0), computed as (xc Lw_k* - mw_k*) Lw_k*^T from the triangular factor
+ * (12 KB of L2 reads per patch instead of the 16 KB of Lam_k*).  Lw must be upper triangular. */
+int jd_gmm_prior_backward_max_tri(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
+                                  int row_end, const float* Lw, const float* mw, int K, const int32_t* argmax,
+                                  float scale, float* G, jd_stream_t stream);
 
 /* col2im of the per-patch gradients, gather form (deterministic, no atomics): for every pixel
  * sum the <= (8/s)^2 patch entries covering it at the rolled coordinates

@@ -69,6 +69,8 @@ PROTOTYPES = {
     "jd_gmm_backward_workspace_elems": [c_i64, c_int],
     "jd_gmm_prior_backward": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, c_f32p, c_f32p, c_int, c_int,
                               c_i32p, c_f32p, c_f32p, c_float, c_f32p, c_i32p, c_stream],
+    "jd_gmm_prior_backward_max_tri": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, c_f32p, c_f32p, c_int, c_i32p,
+                                      c_float, c_f32p, c_stream],
     "jd_patch_fold": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, c_f32p, c_int, c_stream],
     "jd_adam_step": [c_f32p, c_f32p, c_f32p, c_f32p, c_u8p, c_f32p, c_f32p, c_float, c_int, c_i64, c_int, c_float,
                      c_float, c_float, c_float, c_stream],

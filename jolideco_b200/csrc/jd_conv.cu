@@ -215,50 +215,68 @@ constexpr int TY3 = 8;  // thread rows per group (v3): 32-row tiles
 constexpr int KS = 68;  // shared-memory stride of a kernel row (floats): kw + dx <= 68
 
 // one staged input row against the kernel rows a = t - r of the output rows r in [RLO, RHI]
-// (krow0 = kernel row t; row t - r sits r * KS floats below)
-template <int KT, int RLO, int RHI>
-__device__ __forceinline__ void conv3_row(float (&acc)[R3][C], const float* __restrict__ ip,
+// (krow0 = kernel row t; row t - r sits r * KS floats below).  CG column groups of 4 outputs, GS floats apart:
+// every kernel vector feeds CG x 16 FFMA.
+template <int KT, int RLO, int RHI, int CG, int GS>
+__device__ __forceinline__ void conv3_row(float (&acc)[R3][CG][C], const float* __restrict__ ip,
                                           const float* __restrict__ kp, int ng_full) {
-  float4 lo = *reinterpret_cast<const float4*>(ip);
+  float4 lo[CG];
+#pragma unroll
+  for (int cg = 0; cg < CG; ++cg) lo[cg] = *reinterpret_cast<const float4*>(ip + cg * GS);
 #pragma unroll 2
   for (int g = 0; g < ng_full; ++g) {
     ip += 4;
-    const float4 hi = *reinterpret_cast<const float4*>(ip);
-    const float win[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    float win[CG][8];
+#pragma unroll
+    for (int cg = 0; cg < CG; ++cg) {
+      const float4 hi = *reinterpret_cast<const float4*>(ip + cg * GS);
+      win[cg][0] = lo[cg].x, win[cg][1] = lo[cg].y, win[cg][2] = lo[cg].z, win[cg][3] = lo[cg].w;
+      win[cg][4] = hi.x, win[cg][5] = hi.y, win[cg][6] = hi.z, win[cg][7] = hi.w;
+      lo[cg] = hi;
+    }
 #pragma unroll
     for (int r = RLO; r <= RHI; ++r) {
       const float4 kv = *reinterpret_cast<const float4*>(kp - r * KS);
       const float kk[4] = {kv.x, kv.y, kv.z, kv.w};
 #pragma unroll
-      for (int bb = 0; bb < 4; ++bb)
+      for (int cg = 0; cg < CG; ++cg)
 #pragma unroll
-        for (int c = 0; c < C; ++c) acc[r][c] = fmaf(kk[bb], win[bb + c], acc[r][c]);
+        for (int bb = 0; bb < 4; ++bb)
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[r][cg][c] = fmaf(kk[bb], win[cg][bb + c], acc[r][cg][c]);
     }
     kp += 4;
-    lo = hi;
   }
   if (KT > 0) {  // last tap group holds KT (< 4) taps
-    float4 hi = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (KT > 1) hi = *reinterpret_cast<const float4*>(ip + 4);
-    const float win[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    float win[CG][8];
+#pragma unroll
+    for (int cg = 0; cg < CG; ++cg) {
+      float4 hi = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (KT > 1) hi = *reinterpret_cast<const float4*>(ip + 4 + cg * GS);
+      win[cg][0] = lo[cg].x, win[cg][1] = lo[cg].y, win[cg][2] = lo[cg].z, win[cg][3] = lo[cg].w;
+      win[cg][4] = hi.x, win[cg][5] = hi.y, win[cg][6] = hi.z, win[cg][7] = hi.w;
+    }
 #pragma unroll
     for (int r = RLO; r <= RHI; ++r) {
       const float4 kv = *reinterpret_cast<const float4*>(kp - r * KS);
       const float kk[4] = {kv.x, kv.y, kv.z, kv.w};
 #pragma unroll
-      for (int bb = 0; bb < KT; ++bb)
+      for (int cg = 0; cg < CG; ++cg)
 #pragma unroll
-        for (int c = 0; c < C; ++c) acc[r][c] = fmaf(kk[bb], win[bb + c], acc[r][c]);
+        for (int bb = 0; bb < KT; ++bb)
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[r][cg][c] = fmaf(kk[bb], win[cg][bb + c], acc[r][cg][c]);
     }
   }
 }
 
-template <int MODE, int TY, int TX, int KT>
+template <int MODE, int TY, int TX, int CG, int KT>
 __global__ void __launch_bounds__(TY * TX * 4)
 conv3_kernel(const float* __restrict__ in, const float* __restrict__ scale, const float* __restrict__ psf,
              float* __restrict__ out, int fH, int fW, int kh, int kw, int oy, int ox, int f, int H, int W,
              int accumulate, int dx, int vec, int S) {
-  constexpr int TH = R3 * TY, TW = C * TX, NG = TY * TX;  // NG threads per group
+  constexpr int GS = C * TX;                                   // column-group stride (floats)
+  constexpr int TH = R3 * TY, TW = GS * CG, NG = TY * TX;      // NG threads per group
   extern __shared__ __align__(16) float smem[];
   const int kwp = (kw + dx + 3) & ~3;  // kernel row: dx leading zero taps, padded to a multiple of 4
   const int ng = kwp >> 2, ng_full = KT ? ng - 1 : ng;
@@ -329,43 +347,48 @@ conv3_kernel(const float* __restrict__ in, const float* __restrict__ scale, cons
   }
   __syncthreads();
 
-  float acc[R3][C];
+  float acc[R3][CG][C];
 #pragma unroll
   for (int r = 0; r < R3; ++r)
 #pragma unroll
-    for (int c = 0; c < C; ++c) acc[r][c] = 0.f;
+    for (int cg = 0; cg < CG; ++cg)
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[r][cg][c] = 0.f;
 
   // this group's kernel rows [a_lo, a_hi): input rows t = a + r, t in [a_lo, a_hi + R3 - 1)
   const int a_lo = (q * kh) / S, a_hi = ((q + 1) * kh) / S;
   const float* ip = s_in + (ty * R3 + a_lo) * iw + tx * C;  // staged row t, this thread's first column
   const float* kp = s_k + a_lo * KS;                        // kernel row t
   if (a_hi - a_lo >= R3 - 1) {
-    conv3_row<KT, 0, 0>(acc, ip, kp, ng_full);
-    conv3_row<KT, 0, 1>(acc, ip + iw, kp + KS, ng_full);
-    conv3_row<KT, 0, 2>(acc, ip + 2 * iw, kp + 2 * KS, ng_full);
+    conv3_row<KT, 0, 0, CG, GS>(acc, ip, kp, ng_full);
+    conv3_row<KT, 0, 1, CG, GS>(acc, ip + iw, kp + KS, ng_full);
+    conv3_row<KT, 0, 2, CG, GS>(acc, ip + 2 * iw, kp + 2 * KS, ng_full);
     ip += 3 * iw, kp += 3 * KS;
-    for (int t = a_lo + 3; t < a_hi; ++t, ip += iw, kp += KS) conv3_row<KT, 0, 3>(acc, ip, kp, ng_full);
-    conv3_row<KT, 1, 3>(acc, ip, kp, ng_full);
-    conv3_row<KT, 2, 3>(acc, ip + iw, kp + KS, ng_full);
-    conv3_row<KT, 3, 3>(acc, ip + 2 * iw, kp + 2 * KS, ng_full);
+    for (int t = a_lo + 3; t < a_hi; ++t, ip += iw, kp += KS) conv3_row<KT, 0, 3, CG, GS>(acc, ip, kp, ng_full);
+    conv3_row<KT, 1, 3, CG, GS>(acc, ip, kp, ng_full);
+    conv3_row<KT, 2, 3, CG, GS>(acc, ip + iw, kp + KS, ng_full);
+    conv3_row<KT, 3, 3, CG, GS>(acc, ip + 2 * iw, kp + 2 * KS, ng_full);
   } else {
     // fewer than 3 kernel rows in this group: one output row at a time, row by row
     for (int a = a_lo; a < a_hi; ++a) {
-      conv3_row<KT, 0, 0>(acc, s_in + (ty * R3 + a) * iw + tx * C, s_k + a * KS, ng_full);
-      conv3_row<KT, 1, 1>(acc, s_in + (ty * R3 + a + 1) * iw + tx * C, s_k + (a + 1) * KS, ng_full);
-      conv3_row<KT, 2, 2>(acc, s_in + (ty * R3 + a + 2) * iw + tx * C, s_k + (a + 2) * KS, ng_full);
-      conv3_row<KT, 3, 3>(acc, s_in + (ty * R3 + a + 3) * iw + tx * C, s_k + (a + 3) * KS, ng_full);
+      conv3_row<KT, 0, 0, CG, GS>(acc, s_in + (ty * R3 + a) * iw + tx * C, s_k + a * KS, ng_full);
+      conv3_row<KT, 1, 1, CG, GS>(acc, s_in + (ty * R3 + a + 1) * iw + tx * C, s_k + (a + 1) * KS, ng_full);
+      conv3_row<KT, 2, 2, CG, GS>(acc, s_in + (ty * R3 + a + 2) * iw + tx * C, s_k + (a + 2) * KS, ng_full);
+      conv3_row<KT, 3, 3, CG, GS>(acc, s_in + (ty * R3 + a + 3) * iw + tx * C, s_k + (a + 3) * KS, ng_full);
     }
   }
 
   if (S > 1) {  // sum the groups' partial tiles (accumulator-major: conflict-free)
+    constexpr int NA = R3 * CG * C;
     __syncthreads();
-    float* s_red = s_in;  // (S - 1) x 16 x NG floats; the host sizes s_in + s_e for it
+    float* s_red = s_in;  // (S - 1) x NA x NG floats; the host sizes s_in + s_e for it
     if (q > 0) {
 #pragma unroll
       for (int r = 0; r < R3; ++r)
 #pragma unroll
-        for (int c = 0; c < C; ++c) s_red[((q - 1) * (R3 * C) + r * C + c) * NG + tg] = acc[r][c];
+        for (int cg = 0; cg < CG; ++cg)
+#pragma unroll
+          for (int c = 0; c < C; ++c) s_red[((q - 1) * NA + (r * CG + cg) * C + c) * NG + tg] = acc[r][cg][c];
     }
     __syncthreads();
     if (q > 0) return;
@@ -373,7 +396,9 @@ conv3_kernel(const float* __restrict__ in, const float* __restrict__ scale, cons
 #pragma unroll
       for (int r = 0; r < R3; ++r)
 #pragma unroll
-        for (int c = 0; c < C; ++c) acc[r][c] += s_red[(qq * (R3 * C) + r * C + c) * NG + tg];
+        for (int cg = 0; cg < CG; ++cg)
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[r][cg][c] += s_red[(qq * NA + (r * CG + cg) * C + c) * NG + tg];
   }
 
   const bool vec_out = (fW & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
@@ -382,31 +407,34 @@ conv3_kernel(const float* __restrict__ in, const float* __restrict__ scale, cons
   for (int r = 0; r < R3; ++r) {
     const int y = tile_y + ty * R3 + r;
     if (y >= fH) continue;
-    const int x = tile_x + tx * C;
-    const int64_t o = (int64_t)y * fW + x;
-    if (x + C <= fW && vec_out) {
-      float4 val = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-      if (MODE == CONV_BWD) {
-        if (scale) {
-          const float4 sc = *reinterpret_cast<const float4*>(scale + o);
-          val.x *= sc.x, val.y *= sc.y, val.z *= sc.z, val.w *= sc.w;
-        }
-        if (accumulate) {
-          const float4 old = *reinterpret_cast<const float4*>(out + o);
-          val.x += old.x, val.y += old.y, val.z += old.z, val.w += old.w;
-        }
-      }
-      *reinterpret_cast<float4*>(out + o) = val;
-    } else {
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        if (x + c >= fW) continue;
-        float val = acc[r][c];
+    for (int cg = 0; cg < CG; ++cg) {
+      const int x = tile_x + cg * GS + tx * C;
+      const int64_t o = (int64_t)y * fW + x;
+      if (x + C <= fW && vec_out) {
+        float4 val = make_float4(acc[r][cg][0], acc[r][cg][1], acc[r][cg][2], acc[r][cg][3]);
         if (MODE == CONV_BWD) {
-          if (scale) val *= scale[o + c];
-          if (accumulate) val += out[o + c];
+          if (scale) {
+            const float4 sc = *reinterpret_cast<const float4*>(scale + o);
+            val.x *= sc.x, val.y *= sc.y, val.z *= sc.z, val.w *= sc.w;
+          }
+          if (accumulate) {
+            const float4 old = *reinterpret_cast<const float4*>(out + o);
+            val.x += old.x, val.y += old.y, val.z += old.z, val.w += old.w;
+          }
         }
-        out[o + c] = val;
+        *reinterpret_cast<float4*>(out + o) = val;
+      } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          if (x + c >= fW) continue;
+          float val = acc[r][cg][c];
+          if (MODE == CONV_BWD) {
+            if (scale) val *= scale[o + c];
+            if (accumulate) val += out[o + c];
+          }
+          out[o + c] = val;
+        }
       }
     }
   }
@@ -415,19 +443,44 @@ conv3_kernel(const float* __restrict__ in, const float* __restrict__ scale, cons
 constexpr size_t CONV3_SMEM_MAX = 200 * 1024;
 
 struct Conv3Plan {
-  int tx, S, dx, vec, kt;
+  int tx, cg, S, dx, vec, kt;
   size_t smem;
 };
 
-static size_t conv3_smem(int mode, bool has_scale, int kh, int kw, int dx, int tx, int S) {
+static size_t conv3_smem(int mode, bool has_scale, int kh, int kw, int dx, int tx, int cg, int S) {
   const int kwp = (kw + dx + 3) & ~3, NG = TY3 * tx;
-  size_t buf = (size_t)(R3 * TY3 + kh - 1) * (C * tx + kwp) * ((mode == CONV_FWD && has_scale) ? 2 : 1);
-  const size_t red = (size_t)(S - 1) * R3 * C * NG;
+  size_t buf = (size_t)(R3 * TY3 + kh - 1) * (C * tx * cg + kwp) * ((mode == CONV_FWD && has_scale) ? 2 : 1);
+  const size_t red = (size_t)(S - 1) * R3 * C * cg * NG;
   if (buf < red) buf = red;
   return ((size_t)kh * KS + buf) * sizeof(float);
 }
 
 // tile shape / kernel-row split: enough warps per SM for the FMA pipe, and a last wave that is not mostly idle
+static void conv3_auto(int mode, bool has_scale, int fH, int fW, int kh, int kw, Conv3Plan* p) {
+  const int nsm = num_sms();
+  constexpr int TH = R3 * TY3;
+  const long rows = (fH + TH - 1) / TH;
+  const long tiles64 = (long)((fW + 63) / 64) * rows, tiles32 = (long)((fW + 31) / 32) * rows;
+  // many waves: 64-column tiles with two column groups per thread (32 outputs per thread, least staging and
+  // fewest shared-memory reads per FMA); otherwise 32-column tiles for the balance of the last wave
+  p->tx = 8;
+  p->cg = tiles64 >= 6L * nsm ? 2 : 1;
+  const long tiles = p->cg == 2 ? tiles64 : tiles32;
+  const long per_sm = (tiles + nsm - 1) / nsm;
+  const int warps_per_group = TY3 * p->tx / 32;
+  // PSF-row split S: about 24 resident warps per SM keep the FMA pipe busy (tools/conv_exp.py sweep)
+  int S = 1;
+  for (;;) {
+    const size_t smem = conv3_smem(mode, has_scale, kh, kw, p->dx, p->tx, p->cg, S) + 1024;
+    long resident = (long)(220 * 1024 / smem);
+    if (resident > per_sm) resident = per_sm;
+    if (resident < 1) resident = 1;
+    if (S >= 4 || resident * warps_per_group * S >= 24 || kh < 8 * S) break;
+    S *= 2;
+  }
+  p->S = S;
+}
+
 static bool conv3_plan(int mode, const float* in, const float* scale, const float* out, int fH, int fW, int kh, int kw,
                        int ox, int f, int H, int W, Conv3Plan* p) {
   const bool aligned = (fW & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
@@ -437,27 +490,20 @@ static bool conv3_plan(int mode, const float* in, const float* scale, const floa
   p->dx = p->vec ? ((ox % 4) + 4) % 4 : 0;
   if (kw + p->dx > KS) return false;
   p->kt = (kw + p->dx) & 3;
-  const int nsm = num_sms();
-  constexpr int TH = R3 * TY3;
-  const long tiles64 = (long)((fW + 63) / 64) * ((fH + TH - 1) / TH);
-  p->tx = tiles64 >= 6L * nsm ? 16 : 8;
-  const int TW = C * p->tx, NG = TY3 * p->tx;
-  const long tiles = (long)((fW + TW - 1) / TW) * ((fH + TH - 1) / TH);
-  const long per_sm = (tiles + nsm - 1) / nsm;
-  const int warps_per_group = NG / 32;
-  int S = 1;
-  while (S < 4 && per_sm * warps_per_group * S < 16 && kh >= 8 * S) S *= 2;
-  p->S = S;
-  p->smem = conv3_smem(mode, scale != nullptr, kh, kw, p->dx, p->tx, p->S);
+  p->tx = 8;
+  p->cg = 1;
+  p->S = 1;
+  conv3_auto(mode, scale != nullptr, fH, fW, kh, kw, p);
+  p->smem = conv3_smem(mode, scale != nullptr, kh, kw, p->dx, p->tx, p->cg, p->S);
   return p->smem <= CONV3_SMEM_MAX;
 }
 
-template <int MODE, int TX, int KT>
+template <int MODE, int TX, int CG, int KT>
 static int launch_conv3_t(const Conv3Plan& p, const float* in, const float* scale, const float* psf, float* out, int fH,
                           int fW, int kh, int kw, int oy, int ox, int f, int H, int W, int accumulate, cudaStream_t st,
                           const char* name) {
   constexpr int TY = TY3;
-  auto kern = conv3_kernel<MODE, TY, TX, KT>;
+  auto kern = conv3_kernel<MODE, TY, TX, CG, KT>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV3_SMEM_MAX);
@@ -467,28 +513,28 @@ static int launch_conv3_t(const Conv3Plan& p, const float* in, const float* scal
     }
     attr_set = true;
   }
-  dim3 grid((fW + C * TX - 1) / (C * TX), (fH + R3 * TY - 1) / (R3 * TY));
+  dim3 grid((fW + C * TX * CG - 1) / (C * TX * CG), (fH + R3 * TY - 1) / (R3 * TY));
   kern<<<grid, TY * TX * p.S, p.smem, st>>>(in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, p.dx, p.vec,
                                             p.S);
   JD_CHECK_LAUNCH(name);
   return JD_OK;
 }
 
-template <int MODE, int TX>
+template <int MODE, int TX, int CG>
 static int launch_conv3_kt(const Conv3Plan& p, const float* in, const float* scale, const float* psf, float* out, int fH,
                            int fW, int kh, int kw, int oy, int ox, int f, int H, int W, int accumulate, cudaStream_t st,
                            const char* name) {
   switch (p.kt) {
-    case 0: return launch_conv3_t<MODE, TX, 0>(p, in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
-    case 1: return launch_conv3_t<MODE, TX, 1>(p, in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
-    case 2: return launch_conv3_t<MODE, TX, 2>(p, in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
-    default: return launch_conv3_t<MODE, TX, 3>(p, in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
+    case 0: return launch_conv3_t<MODE, TX, CG, 0>(p, in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
+    case 1: return launch_conv3_t<MODE, TX, CG, 1>(p, in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
+    case 2: return launch_conv3_t<MODE, TX, CG, 2>(p, in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
+    default: return launch_conv3_t<MODE, TX, CG, 3>(p, in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
   }
 }
 
 // tuning knobs (environment at first use, or jd_conv_tuning): JD_CONV_TILE = shape of the previous kernel,
-// JD_CONV_V3 = 0 selects the previous (synchronously staged, chunked) kernel, JD_CONV_TX = 8 | 16 forces the v3
-// tile width (32 | 64 columns), JD_CONV_S = 1 | 2 | 4 forces the v3 kernel-row split
+// JD_CONV_V3 = 0 selects the previous (synchronously staged, chunked) kernel, JD_CONV_TX = 8 | 16 | 28 forces the v3
+// tile (32 | 64 columns with one column group per thread | 64 columns with two), JD_CONV_S = 1 | 2 | 4 forces the v3 kernel-row split
 static int g_tile = -1, g_v3 = 1, g_tx = 0, g_s = 0;
 static void conv_tuning_init() {
   if (g_tile >= 0) return;
@@ -507,15 +553,18 @@ static int launch_conv(const float* in, const float* scale, const float* psf, fl
   const int tile = g_tile, v3 = g_v3, force_tx = g_tx, force_s = g_s;
   Conv3Plan p;
   if (v3 && conv3_plan(MODE, in, scale, out, fH, fW, kh, kw, ox, f, H, W, &p)) {
-    if (force_tx == 8 || force_tx == 16 || force_s == 1 || force_s == 2 || force_s == 4) {
-      if (force_tx == 8 || force_tx == 16) p.tx = force_tx;
+    if (force_tx == 8 || force_tx == 16 || force_tx == 28 || force_s == 1 || force_s == 2 || force_s == 4) {
+      if (force_tx == 8 || force_tx == 16) p.tx = force_tx, p.cg = 1;
+      if (force_tx == 28) p.tx = 8, p.cg = 2;
       if (force_s) p.S = force_s;
-      p.smem = conv3_smem(MODE, scale != nullptr, kh, kw, p.dx, p.tx, p.S);
+      p.smem = conv3_smem(MODE, scale != nullptr, kh, kw, p.dx, p.tx, p.cg, p.S);
     }
     if (p.smem <= CONV3_SMEM_MAX) {
+      if (p.cg == 2)
+        return launch_conv3_kt<MODE, 8, 2>(p, in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
       if (p.tx == 16)
-        return launch_conv3_kt<MODE, 16>(p, in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
-      return launch_conv3_kt<MODE, 8>(p, in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
+        return launch_conv3_kt<MODE, 16, 1>(p, in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
+      return launch_conv3_kt<MODE, 8, 1>(p, in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, st, name);
     }
   }
   if (tile == 1)  // default: 2 rows per thread, 16x16 threads -> 32x64 tiles (best of the sweep, tools/conv_exp.py)
@@ -534,8 +583,8 @@ using namespace jd;
 extern "C" {
 
 int jd_conv_tuning(int v3, int tx, int split) {
-  JD_CHECK_ARG((tx == 0 || tx == 8 || tx == 16) && (split == 0 || split == 1 || split == 2 || split == 4),
-               "jd_conv_tuning: tx must be 0, 8 or 16 and split 0, 1, 2 or 4");
+  JD_CHECK_ARG((tx == 0 || tx == 8 || tx == 16 || tx == 28) && (split == 0 || split == 1 || split == 2 || split == 4),
+               "jd_conv_tuning: tx must be 0, 8, 16 or 28 and split 0, 1, 2 or 4");
   conv_tuning_init();
   g_v3 = v3 ? 1 : 0;
   g_tx = tx;

@@ -46,14 +46,17 @@ __global__ void flux_kernel(const float* __restrict__ theta, const uint8_t* __re
 // One thread per counts pixel; warp-shuffle + shared block reduction, one double atomic per block.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void poisson_pixel(float pool, float bkg, float c, float eps, float grad_scale,
-                                              float& np_, float& dpool, double& acc, double& accb) {
+                                              float& np_, float& dpool, float& acc, float& accb) {
   np_ = fmaxf(pool, 0.f) + bkg;
   const float ne = np_ + eps;
   float loss = np_ - c * logf(ne);
-  if (c > 1.f) loss += c * logf(c) - c + 0.5f * logf(6.283185307179586f * c);
-  acc += (double)loss;
+  if (c > 1.f) {  // Stirling term c log c - c + 1/2 log(2 pi c), with log(2 pi c) = log c + log 2 pi
+    const float lc = logf(c);
+    loss += fmaf(c, lc, -c) + 0.5f * (lc + 1.8378770664093453f);
+  }
+  acc += loss;
   const float d = (1.f - c / ne) * grad_scale;
-  accb += (double)(d * bkg);
+  accb = fmaf(d, bkg, accb);
   dpool = pool >= 0.f ? d : 0.f;
 }
 
@@ -67,14 +70,34 @@ poisson_kernel(const float* __restrict__ conv, const float* __restrict__ backgro
   __shared__ double red[32];
   const float bnorm = bkg_log_norm ? expf(bkg_log_norm[0]) : 1.0f;
   const int64_t n = (int64_t)H * W;
-  double acc = 0.0, accb = 0.0;
+  // per-thread partial sums in FP32 (a thread sees at most a few dozen pixels), FP64 from the block reduction on
+  float acc = 0.f, accb = 0.f;
   if (VEC) {
-    const int64_t n4 = n >> 2;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-      const int64_t row = (i * 4) / W, col = (i * 4) - row * W;
-      const float4 pv = *reinterpret_cast<const float4*>(conv + row * fW + col);
+    // two 4-pixel chunks per thread and pass: six independent 128-bit loads in flight per thread (the kernel is
+    // bound by memory latency x bytes in flight, not by arithmetic)
+    const int64_t n4 = n >> 2, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += 2 * stride) {
+      const int64_t j = i + stride;
+      const bool two = j < n4;
+      int64_t ci = i * 4;  // f == 1: conv row stride fW, equal to W unless the caller passes a padded buffer
+      if (fW != W) {
+        const int64_t row = ci / W;
+        ci = row * fW + (ci - row * W);
+      }
+      const float4 pv = *reinterpret_cast<const float4*>(conv + ci);
       const float4 bv = *reinterpret_cast<const float4*>(background + i * 4);
       const float4 cv = *reinterpret_cast<const float4*>(counts + i * 4);
+      float4 pv2 = pv, bv2 = bv, cv2 = cv;
+      if (two) {
+        int64_t cj = j * 4;
+        if (fW != W) {
+          const int64_t row2 = cj / W;
+          cj = row2 * fW + (cj - row2 * W);
+        }
+        pv2 = *reinterpret_cast<const float4*>(conv + cj);
+        bv2 = *reinterpret_cast<const float4*>(background + j * 4);
+        cv2 = *reinterpret_cast<const float4*>(counts + j * 4);
+      }
       float4 nv, dv;
       poisson_pixel(pv.x, bv.x * bnorm, cv.x, eps, grad_scale, nv.x, dv.x, acc, accb);
       poisson_pixel(pv.y, bv.y * bnorm, cv.y, eps, grad_scale, nv.y, dv.y, acc, accb);
@@ -82,6 +105,14 @@ poisson_kernel(const float* __restrict__ conv, const float* __restrict__ backgro
       poisson_pixel(pv.w, bv.w * bnorm, cv.w, eps, grad_scale, nv.w, dv.w, acc, accb);
       if (npred_out) *reinterpret_cast<float4*>(npred_out + i * 4) = nv;
       if (dpool_out) *reinterpret_cast<float4*>(dpool_out + i * 4) = dv;
+      if (two) {
+        poisson_pixel(pv2.x, bv2.x * bnorm, cv2.x, eps, grad_scale, nv.x, dv.x, acc, accb);
+        poisson_pixel(pv2.y, bv2.y * bnorm, cv2.y, eps, grad_scale, nv.y, dv.y, acc, accb);
+        poisson_pixel(pv2.z, bv2.z * bnorm, cv2.z, eps, grad_scale, nv.z, dv.z, acc, accb);
+        poisson_pixel(pv2.w, bv2.w * bnorm, cv2.w, eps, grad_scale, nv.w, dv.w, acc, accb);
+        if (npred_out) *reinterpret_cast<float4*>(npred_out + j * 4) = nv;
+        if (dpool_out) *reinterpret_cast<float4*>(dpool_out + j * 4) = dv;
+      }
     }
   } else {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -96,10 +127,10 @@ poisson_kernel(const float* __restrict__ conv, const float* __restrict__ backgro
       if (dpool_out) dpool_out[i] = d;
     }
   }
-  double s = block_sum(acc, red);
+  double s = block_sum((double)acc, red);
   if (threadIdx.x == 0 && loss_sum) atomicAdd(loss_sum, s);
   if (dlogb) {
-    double sb = block_sum(accb, red);
+    double sb = block_sum((double)accb, red);
     if (threadIdx.x == 0) atomicAdd(dlogb, sb);
   }
 }
@@ -348,7 +379,7 @@ int jd_poisson_forward_backward(const float* conv, const float* background, cons
   // few, fat blocks: one double atomic per block on the same accumulator would otherwise serialise
   const bool vec = f == 1 && (W & 3) == 0 && (fW & 3) == 0;
   int64_t want = ((vec ? n / 4 : n) + 255) / 256;
-  int grid = (int)(want < 1 ? 1 : (want > 2 * num_sms() ? 2 * num_sms() : want));
+  int grid = (int)(want < 1 ? 1 : (want > 4 * num_sms() ? 4 * num_sms() : want));
   if (vec)
     poisson_kernel<true><<<grid, 256, 0, to_stream(stream)>>>(conv, background, bkg_log_norm, counts, npred, dpool,
                                                               loss_sum, dlogb, H, W, f, fW, eps, grad_scale);

@@ -298,6 +298,77 @@ gmm_bwd_max_kernel(const float* __restrict__ flux, PatchGeom g, const int32_t* _
   }
 }
 
+// Max-mode backward for upper-triangular factors, from Lw_k* itself instead of Lam_k* = Lw Lw^T:
+//     y = xc Lw - mw   (y_j = sum_{i<=j}),   G = y Lw^T   (G_i = sum_{j>=i} y_j Lw[i][j]),   G -= mean(G).
+// The kernel above is bound by the L2 -> SM traffic of one 16 KB Lam matrix per patch; the triangular factor
+// is read once (rows i < 32: both 128-byte halves, rows i >= 32: the upper half only = 12 KB, its zero half-rows
+// skipped) and used for both products from registers.  Lane l owns columns l and l + 32; the 64 row sums of the
+// second product are reduced across the warp with a 62-shuffle reduce-scatter (lane l ends with rows 2l, 2l + 1).
+__global__ void __launch_bounds__(256)
+gmm_bwd_max_tri_kernel(const float* __restrict__ flux, PatchGeom g, const int32_t* __restrict__ shift_yx,
+                       const float* __restrict__ Lw, const float* __restrict__ mw, const int32_t* __restrict__ argmax,
+                       float scale, float* __restrict__ G) {
+  if (shift_yx) {
+    g.sy = shift_yx[0];
+    g.sx = shift_yx[1];
+  }
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p = warp; p < g.P; p += nwarps) {
+    const int k = argmax[p];
+    float2* out = reinterpret_cast<float2*>(G + p * PD) + lane;
+    if (k < 0) {
+      *out = make_float2(0.f, 0.f);
+      continue;
+    }
+    const int iy = (int)(p / g.nx) + g.row_begin, ix = (int)(p % g.nx);
+    // lane holds patch elements d = lane (u = lane/8, v = lane%8) and d = lane + 32 (u + 4)
+    const int u = lane >> 3, v = lane & 7;
+    const int x = patch_src_col(g, ix, v);
+    float x0 = __ldg(flux + (int64_t)patch_src_row(g, iy, u) * g.fW + x);
+    float x1 = __ldg(flux + (int64_t)patch_src_row(g, iy, u + 4) * g.fW + x);
+    const float mean = warp_sum(x0 + x1) * (1.f / 64.f);
+    x0 -= mean;
+    x1 -= mean;
+    const float* L = Lw + (int64_t)k * PD * PD;
+    float a[32], b[64];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      a[i] = __ldg(L + i * PD + lane);
+      b[i] = __ldg(L + i * PD + lane + 32);
+    }
+#pragma unroll
+    for (int i = 32; i < 64; ++i) b[i] = __ldg(L + i * PD + lane + 32);
+    float y0 = -__ldg(mw + (int64_t)k * PD + lane), y1 = -__ldg(mw + (int64_t)k * PD + lane + 32);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float xa = __shfl_sync(0xffffffffu, x0, i), xb = __shfl_sync(0xffffffffu, x1, i);
+      y0 = fmaf(xa, a[i], y0);
+      y1 = fmaf(xa, b[i], y1);
+      y1 = fmaf(xb, b[i + 32], y1);
+    }
+    // row partials r_i = Lw[i][l] y_l + Lw[i][l+32] y_{l+32}, in place
+#pragma unroll
+    for (int i = 0; i < 32; ++i) b[i] = fmaf(a[i], y0, b[i] * y1);
+#pragma unroll
+    for (int i = 32; i < 64; ++i) b[i] *= y1;
+    // reduce-scatter over the warp: after the step with mask m a lane keeps the half of its rows selected by (lane & m)
+#pragma unroll
+    for (int m = 16, c = 32; m >= 1; m >>= 1, c >>= 1) {
+      const bool up = (lane & m) != 0;
+#pragma unroll
+      for (int t = 0; t < c; ++t) {
+        const float send = up ? b[t] : b[t + c];
+        const float keep = up ? b[t + c] : b[t];
+        b[t] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+      }
+    }
+    const float gm = warp_sum(b[0] + b[1]) * (1.f / 64.f);
+    *out = make_float2(scale * (b[0] - gm), scale * (b[1] - gm));  // rows 2 lane, 2 lane + 1
+  }
+}
+
 // ---- max-mode backward, bucketed by winning component ------------------------------------------------
 // Patches are grouped by argmax (histogram -> scan -> scatter), then one CTA per (component, chunk of <= CH
 // patches) stages Lam_k once in shared memory and runs the 64x64 GEMVs of its patches from there: the
@@ -551,6 +622,22 @@ int jd_gmm_prior_backward(const float* flux, int fH, int fW, const int32_t* shif
     }
   }
   JD_CHECK_LAUNCH("jd_gmm_prior_backward");
+  return JD_OK;
+}
+
+int jd_gmm_prior_backward_max_tri(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
+                                  int row_end, const float* Lw, const float* mw, int K, const int32_t* argmax,
+                                  float scale, float* G, jd_stream_t stream) {
+  JD_CHECK_ARG(flux && Lw && mw && argmax && G && K > 0, "jd_gmm_prior_backward_max_tri: null pointer");
+  JD_CHECK_ARG((reinterpret_cast<uintptr_t>(G) & 7) == 0, "jd_gmm_prior_backward_max_tri: G must be 8-byte aligned");
+  PatchGeom g;
+  int rc = make_geom("jd_gmm_prior_backward_max_tri", fH, fW, stride, row_begin, row_end, &g);
+  if (rc) return rc;
+  int64_t blocks = ((int64_t)g.P + 7) / 8;
+  int64_t cap = (int64_t)num_sms() * 8;
+  gmm_bwd_max_tri_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, to_stream(stream)>>>(flux, g, shift_yx, Lw, mw,
+                                                                                           argmax, scale, G);
+  JD_CHECK_LAUNCH("jd_gmm_prior_backward_max_tri");
   return JD_OK;
 }
 

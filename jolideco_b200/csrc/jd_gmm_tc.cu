@@ -110,6 +110,7 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rt_zero = (uint32_t)K >> 30;  // 0 at run time (K < 2^30), opaque to the compiler
   const int dbg = marginalize >> 8;  // profiling knobs (JD_TC_DEBUG): 1 = no epilogue TMEM loads, 2 = one MMA per component
+  const bool trim8 = (dbg & 8) != 0;  // triangular trim per k-step (N = 64, 56, .., 8) instead of per pair of k-steps
   marginalize &= 1;
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -250,7 +251,7 @@ gmm_fwd_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restr
           for (int kk = 0; kk < 8; ++kk) {
             if ((dbg & 2) && (pass > 0 || kk > 0)) continue;
             // upper-triangular Lw: input features [8kk, 8kk+8) only reach whitened features >= 8kk
-            const uint32_t n0 = TRI ? 16u * (kk >> 1) : 0u;
+            const uint32_t n0 = TRI ? (trim8 ? 8u * kk : 16u * (kk >> 1)) : 0u;
             const uint32_t off16 = ((kk >> 2) * KBLOCK_BYTES_B + (kk & 3) * 32 + n0 * 128) >> 4;
             umma_tf32_ts(d + n0, tmem_u + a_col + kk * 8, desc_from_lo(b_base + off16), idesc_n(64 - n0), acc);
             acc = 1;
@@ -413,6 +414,7 @@ gmm_fwd_tc_sk_kernel(const float* __restrict__ flux, Geom g, const int32_t* __re
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rt_zero = (uint32_t)K >> 30;  // 0 at run time (K < 2^30), opaque to the compiler
+  const bool trim8 = ((marginalize >> 8) & 8) != 0;
   marginalize &= 1;
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -511,7 +513,7 @@ gmm_fwd_tc_sk_kernel(const float* __restrict__ flux, Geom g, const int32_t* __re
           const uint32_t b_base = pass == 1 ? b_lo : b_hi;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
-            const uint32_t n0 = TRI ? 16u * (kk >> 1) : 0u;
+            const uint32_t n0 = TRI ? (trim8 ? 8u * kk : 16u * (kk >> 1)) : 0u;
             const uint32_t off16 = ((kk >> 2) * KBLOCK_BYTES_B + (kk & 3) * 32 + n0 * 128) >> 4;
             umma_tf32_ts(d + n0, tmem_u + a_col + kk * 8, desc_from_lo(b_base + off16), idesc_n(64 - n0), acc);
             acc = 1;
@@ -737,6 +739,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 gmm_bwd_lse_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restrict__ shift_yx,
                       const uint8_t* __restrict__ Bt, const float* __restrict__ mw, const float* __restrict__ logpT,
                       const float* __restrict__ lse, int K, float scale, float* __restrict__ G) {
+  constexpr bool trim8 = false;
   constexpr bool TRI = false, ZERO_MEAN = false;
   constexpr int NSTAGE = NSTAGE_BWD;
   const int marginalize = 1;
@@ -897,7 +900,7 @@ gmm_bwd_lse_tc_kernel(const float* __restrict__ flux, Geom g, const int32_t* __r
           for (int kk = 0; kk < 8; ++kk) {
             if ((dbg & 2) && (pass > 0 || kk > 0)) continue;
             // upper-triangular Lw: input features [8kk, 8kk+8) only reach whitened features >= 8kk
-            const uint32_t n0 = TRI ? 16u * (kk >> 1) : 0u;
+            const uint32_t n0 = TRI ? (trim8 ? 8u * kk : 16u * (kk >> 1)) : 0u;
             const uint32_t off16 = ((kk >> 2) * KBLOCK_BYTES_B + (kk & 3) * 32 + n0 * 128) >> 4;
             umma_tf32_ts(d + n0, tmem_u + a_col + kk * 8, desc_from_lo(b_base + off16), idesc_n(64 - n0), acc);
             acc = 1;
@@ -992,6 +995,16 @@ using namespace jd;
 
 extern "C" {
 
+// JD_TC_TRIM8=1: per-k-step triangular trim (MMA N = 64, 56, .., 8; not a multiple of 16 for every step)
+static int tc_trim8() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("JD_TC_TRIM8");
+    v = e ? (atoi(e) != 0) : 0;
+  }
+  return v;
+}
+
 size_t jd_gmm_tc_packed_bytes(int K) { return (size_t)K * tc::B_BYTES; }
 
 int jd_gmm_tc_pack(const float* Lw, int K, void* Bt, jd_stream_t stream) {
@@ -1038,7 +1051,7 @@ int jd_gmm_prior_forward_tc(const float* flux, int fH, int fW, const int32_t* sh
     dbg = e ? atoi(e) : 0;
   }
   if (dbg & 4) kern = zero_mean ? tc::gmm_fwd_tc_kernel<false, true> : tc::gmm_fwd_tc_kernel<false, false>;
-  marginalize = (marginalize ? 1 : 0) | (dbg << 8);
+  marginalize = (marginalize ? 1 : 0) | (dbg << 8) | (tc_trim8() << 11);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(tc::NTHREADS);
@@ -1160,8 +1173,8 @@ int jd_gmm_prior_forward_tc_sk(const float* flux, int fH, int fW, const int32_t*
   float* ws_m = reinterpret_cast<float*>(ws + p.off_m);
   float* ws_s = reinterpret_cast<float*>(ws + p.off_s);
   int* ws_k = reinterpret_cast<int*>(ws + p.off_k);
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, flux, g, shift_yx, bt8, mw, ck, K, marginalize ? 1 : 0, p.chunk, p.smax,
-                                      rot_mul, counters, ws_m, ws_s, ws_k, value, argmax, logp, sum);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, flux, g, shift_yx, bt8, mw, ck, K, (marginalize ? 1 : 0) | (tc_trim8() << 11), p.chunk,
+                                      p.smax, rot_mul, counters, ws_m, ws_s, ws_k, value, argmax, logp, sum);
   if (le != cudaSuccess) {
     set_error("jd_gmm_prior_forward_tc_sk: launch failed: %s", cudaGetErrorString(le));
     cudaGetLastError();

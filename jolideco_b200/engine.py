@@ -34,12 +34,12 @@ def _call(name, *args):
     if name == "jd_gmm_prior_backward" and args[-2] is not None:
         n = 4  # histogram, scan, scatter, bucketed GEMV
     _STATS["launches"] += n
-    if _STATS["timed"] == name:
+    if _STATS["timed"] == name or _STATS["timed"] == "*":
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         _lib.call(name, *args)
         e1.record()
-        _STATS["events"].append((e0, e1))
+        _STATS["events"].append((e0, e1) if _STATS["timed"] == name else (name, e0, e1))
         return
     _lib.call(name, *args)
 
@@ -277,6 +277,11 @@ class MapEngine:
             _call("jd_gmm_prior_backward_lse_tc", _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride,
                   self.rows[0], self.rows[1], _p(ops._bt_lam(self.packed)), _p(self.packed.bk), self.packed.K,
                   _p(self.logp), _p(self.value), float(scale), _p(self.G), self._s())
+            return
+        if self.bwd_ws is None and ops.use_bwd_tri(self.packed, self.P, self.marginalize):
+            _call("jd_gmm_prior_backward_max_tri", _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride,
+                  self.rows[0], self.rows[1], _p(self.packed.Lw), _p(self.packed.mw), self.packed.K, _p(self.argmax),
+                  float(scale), _p(self.G), self._s())
             return
         _call("jd_gmm_prior_backward", _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride, self.rows[0],
               self.rows[1], _p(self.packed.Lam), _p(self.packed.bk), self.packed.K, int(self.marginalize),

@@ -337,8 +337,20 @@ def gmm_backward_workspace(P, K, device):
     return torch.empty(n, dtype=torch.int32, device=device)
 
 
+# max-mode backward from the triangular factor Lw (12 KB of L2 reads per patch) instead of Lam = Lw Lw^T (16 KB);
+# JD_BWD_TRI=0 keeps the Lam kernel
+BWD_TRI = os.environ.get("JD_BWD_TRI", "1") != "0"
+# ... for up to this many patches: inside the steps the triangular kernel saves 15 us of 41 at 16 129 patches (cfg2)
+# but loses 8 us of 78 at 65 025 (joint1024), where the leaner Lam kernel (64 resident warps per SM) hides latency better
+BWD_TRI_MAX_PATCHES = 32768
+
+
+def use_bwd_tri(packed, P, marginalize=False):
+    return bool(BWD_TRI and not marginalize and packed.upper_tri and packed.D == PD and P <= BWD_TRI_MAX_PATCHES)
+
+
 def gmm_prior_backward(flux, shift_yx, packed, scale, stride=4, marginalize=False, rows=None, argmax=None, logp=None,
-                       value=None, out=None, workspace=None, bucketed=False):
+                       value=None, out=None, workspace=None, bucketed=False, tri=None):
     _check(flux, "flux")
     fH, fW = _hw(flux)
     ny, nx = patch_grid(fH, fW, stride)
@@ -351,6 +363,12 @@ def gmm_prior_backward(flux, shift_yx, packed, scale, stride=4, marginalize=Fals
         _lib.call("jd_gmm_prior_backward_lse_tc", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1,
                   _ptr(_bt_lam(packed)), _ptr(packed.bk), packed.K, _ptr(logp.t()), _ptr(_check(value, "value")),
                   float(scale), _ptr(G), _stream())
+        return G
+    if tri is None:
+        tri = use_bwd_tri(packed, P, marginalize) and not bucketed
+    if not marginalize and tri and packed.upper_tri and workspace is None and packed.D == PD:
+        _lib.call("jd_gmm_prior_backward_max_tri", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(packed.Lw),
+                  _ptr(packed.mw), packed.K, _ptr(_check(argmax, "argmax", torch.int32)), float(scale), _ptr(G), _stream())
         return G
     if workspace is None and bucketed and not marginalize:
         workspace = gmm_backward_workspace(P, packed.K, flux.device)

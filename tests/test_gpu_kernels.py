@@ -125,7 +125,7 @@ def test_conv_backward_upsampled(f):
     assert rel_max(acc.cpu().numpy(), ref + 1) < 5e-6
 
 
-@pytest.mark.parametrize("tx,split", [(0, 0), (8, 1), (8, 2), (8, 4), (16, 1), (16, 2), (16, 4)])
+@pytest.mark.parametrize("tx,split", [(0, 0), (8, 1), (8, 2), (8, 4), (16, 1), (16, 2), (16, 4), (28, 1), (28, 2), (28, 4)])
 @pytest.mark.parametrize("shape,kshape", [((96, 128), (17, 17)), ((64, 192), (18, 19)), ((80, 64), (34, 34)),
                                           ((72, 100), (5, 20)), ((64, 64), (3, 2)), ((50, 70), (9, 9)),
                                           ((40, 48), (23, 1))])
@@ -401,6 +401,22 @@ def test_gmm_backward_bucketed_equals_per_patch_full_size():
     Gb = ops.gmm_prior_backward(flux, (2, -1), packed, -1e-3, 4, False, None, argmax, None, value, bucketed=True)
     a, b = Ga.cpu().numpy(), Gb.cpu().numpy()
     assert np.abs(a - b).max() <= 2e-6 * np.abs(a).max()
+
+
+@pytest.mark.parametrize("mean_scale", [0.05, 0.0])
+def test_gmm_backward_max_triangular_equals_lam_kernel_full_size(mean_scale):
+    """(xc Lw - mw) Lw^T from the triangular factor against xc Lam - bk, 16 129 patches, K = 40."""
+    rng = np.random.default_rng(16)
+    flux = t(rng.gamma(2.0, size=(512, 512)))
+    packed = pack(O.GMM(*synthetic_gmm(40, seed=6, mean_scale=mean_scale)))
+    value, argmax, _, _ = ops.gmm_prior_forward(flux, (2, -1), packed, 4, False, backend=1)
+    argmax[5] = -1  # a filtered patch: zero row
+    Ga = ops.gmm_prior_backward(flux, (2, -1), packed, -1e-3, 4, False, None, argmax, None, value, tri=False)
+    Gb = ops.gmm_prior_backward(flux, (2, -1), packed, -1e-3, 4, False, None, argmax, None, value, tri=True)
+    a, b = Ga.cpu().numpy(), Gb.cpu().numpy()
+    assert np.abs(b[5]).max() == 0
+    assert np.abs(a - b).max() <= 3e-6 * np.abs(a).max()
+    assert np.linalg.norm(a - b) <= 1e-6 * np.linalg.norm(a)
 
 
 def test_gmm_lse_backward_tensor_core_vs_cuda_core_full_size():

@@ -1,0 +1,29 @@
+"""cProfile of MAPDeconvolver.run (cfg2, host numpy inputs): where does the fixed per-run cost go?"""
+import cProfile, os, pstats, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+import jolideco_b200 as J
+from jolideco_b200 import synthetic
+
+class A: marginalize = False; backend = None; no_graph = False; collective = "nccl"
+wl = synthetic.make_workload(sys.argv[1] if len(sys.argv) > 1 else "cfg2", seed=0)
+epochs = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+deco, comps = bench.build_run(J, wl, A, "cuda:0", n_epochs=2)
+deco.run(datasets=wl["datasets"], components=comps)
+for rep in range(2):
+    deco, comps = bench.build_run(J, wl, A, "cuda:0", n_epochs=epochs)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = deco.run(datasets=wl["datasets"], components=comps)
+    flux = res.flux_upsampled_total
+    torch.cuda.synchronize()
+    print(f"run {rep}: {1e3 * (time.perf_counter() - t0):.2f} ms for {epochs} epochs")
+deco, comps = bench.build_run(J, wl, A, "cuda:0", n_epochs=epochs)
+pr = cProfile.Profile()
+pr.enable()
+res = deco.run(datasets=wl["datasets"], components=comps)
+flux = res.flux_upsampled_total
+torch.cuda.synchronize()
+pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
