@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--marginalize", action="store_true", help="logsumexp over components instead of max")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end MAPDeconvolver.run leg (profiling runs)")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed iterations")
     ap.add_argument("--breakdown", action="store_true",
@@ -285,7 +286,7 @@ def main():
 
     # ------------------------------------------------------------------ e2e through MAPDeconvolver.run (host buffers)
     e2e = None
-    if True:
+    if not args.no_e2e:
         e2e_local = measure_e2e(J, workload, args, device, rank, joint)
         t = torch.tensor([e2e_local["seconds"]], dtype=torch.float64, device=device)
         if world > 1:
