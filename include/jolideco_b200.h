@@ -152,6 +152,8 @@ int jd_gmm_prior_forward_tc(const float* flux, int fH, int fW, const int32_t* sh
  * 256-byte aligned, ZERO-INITIALISED ONCE by the caller (arrival counters; the kernel leaves them at zero),
  * not shared between launches that may run concurrently.  Same outputs as jd_gmm_prior_forward_tc. */
 int64_t jd_gmm_tc_sk_workspace_bytes(int64_t n_patches, int K);
+/* The decomposition the launch will use (host arithmetic only): CTA pairs, components per chunk, partial slots per tile. */
+int jd_gmm_tc_sk_plan(int64_t n_patches, int K, int* n_cta_pairs, int* chunk, int* max_segments_per_tile);
 int jd_gmm_prior_forward_tc_sk(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
                                int row_end, const void* Bt, const float* mw, const float* ck, int K, int upper_tri,
                                int zero_mean, int marginalize, void* workspace, float* value, int32_t* argmax,

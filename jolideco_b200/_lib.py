@@ -57,6 +57,7 @@ PROTOTYPES = {
     "jd_gmm_prior_forward_tc": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, ctypes.c_void_p, c_f32p, c_f32p,
                                 c_int, c_int, c_int, c_int, c_f32p, c_i32p, c_f32p, c_f64p, c_stream],
     "jd_gmm_tc_sk_workspace_bytes": [c_i64, c_int],
+    "jd_gmm_tc_sk_plan": [c_i64, c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p],
     "jd_gmm_prior_forward_tc_sk": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, ctypes.c_void_p, c_f32p, c_f32p,
                                    c_int, c_int, c_int, c_int, ctypes.c_void_p, c_f32p, c_i32p, c_f32p, c_f64p,
                                    c_stream],

@@ -1119,6 +1119,15 @@ int64_t jd_gmm_tc_sk_workspace_bytes(int64_t P, int K) {
   return (int64_t)tc::sk_plan(P, K).bytes;
 }
 
+int jd_gmm_tc_sk_plan(int64_t P, int K, int* n_cta_pairs, int* chunk, int* max_segments_per_tile) {
+  JD_CHECK_ARG(P > 0 && K > 0 && n_cta_pairs && chunk && max_segments_per_tile, "jd_gmm_tc_sk_plan: bad arguments");
+  const tc::SkPlan p = tc::sk_plan(P, K);
+  *n_cta_pairs = p.n_clusters;
+  *chunk = p.chunk;
+  *max_segments_per_tile = p.smax;
+  return JD_OK;
+}
+
 int jd_gmm_prior_forward_tc_sk(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
                                int row_end, const void* Bt, const float* mw, const float* ck, int K, int upper_tri,
                                int zero_mean, int marginalize, void* workspace, float* value, int32_t* argmax,
