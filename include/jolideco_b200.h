@@ -72,7 +72,7 @@ int jd_conv_tuning(int v3, int tx, int split);
 
 /* ---- a3, large PSFs: shared-memory FFT convolution (same arithmetic contract as the direct entries) ----
  * jd_fftconv_sizes: element counts (floats) of the cached PSF spectrum and of the scratch workspace for an
- * fH x fW image and a kh x kw PSF (both axes padded to the next power of two >= n + k - 1).
+ * fH x fW image and a kh x kw PSF (both axes padded to the next r * 2^L >= n + k - 1, r in {1, 3, 5}).
  * jd_fftconv_prepare_psf: PSF spectrum, computed once per dataset (the reference recomputes rfft2(psf) on every
  * call, utils/torch.py:368).  jd_conv_forward_fft / jd_conv_backward_fft: drop-in for the *_direct entries. */
 int jd_fftconv_sizes(int fH, int fW, int kh, int kw, int64_t* psf_hat_elems, int64_t* workspace_elems);

@@ -5,8 +5,9 @@
 //   * the PSF spectrum is computed ONCE per dataset (jd_fftconv_prepare_psf); the reference recomputes it on
 //     every call;
 //   * any FFT size >= the linear-convolution support gives the same answer, so both axes are padded to the
-//     next power of two and a radix-4 (+ one radix-2 stage for odd log2) Stockham autosort FFT runs entirely in
-//     shared memory;
+//     next r0 * 2^L, r0 in {1, 3, 5} (545 -> 640 instead of 1024, 1224 -> 1280 instead of 2048; JD_FFT_MIXED=0: r0 = 1)
+//     and a Stockham autosort FFT (radix-4 stages, one radix-2 stage for odd L, one final twiddle-free radix-r0
+//     stage; jd_fft_stages.cuh, checked on the host by tests/test_fft_host.py) runs entirely in shared memory;
 //   * three kernels instead of rfft2 / multiply / irfft2 / slice:
 //       rows   : [input transform] 2 real rows per complex FFT (even/odd split), half spectrum written
 //                transposed  specT[kx][row]
@@ -17,14 +18,13 @@
 //   Crop / adjoint geometry: output index i reads circular index (i + off) mod S with off = +(k-1)/2 for the
 //   forward model and off = -(k-1)/2 with conj(PSF^) for the adjoint (correlation), which reproduces the
 //   asymmetric crop of even-sized PSFs exactly.
+#include <stdlib.h>
+
 #include "jd_common.cuh"
+#include "jd_fft_stages.cuh"
 
 namespace jd {
 namespace fft {
-
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
-}
 
 // tw[j] = exp(-2 pi i j / N), j < N/2
 __device__ __forceinline__ void make_twiddles(float2* tw, int N) {
@@ -35,61 +35,22 @@ __device__ __forceinline__ void make_twiddles(float2* tw, int N) {
   }
 }
 
-// Stockham autosort FFT of length N = 2^logN in shared memory (ping-pong x <-> y): radix-4 stages, plus one
-// radix-2 stage when logN is odd.  INV conjugates the twiddles (no scaling).  Returns the buffer holding the
-// result (natural order).  All threads of the block must call it; x must be fully written and synchronised.
+// Stockham autosort FFT of length N = r0 * 2^L in shared memory (ping-pong x <-> y).  INV conjugates the twiddles (no
+// scaling).  Returns the buffer holding the result (natural order).  All threads of the block must call it; x must be
+// fully written and synchronised.
 template <bool INV>
-__device__ __forceinline__ float2* fft_pow2(float2* x, float2* y, const float2* tw, int N, int logN) {
-  int n = N, ls = 0, done = 0;  // s = 1 << ls; n = N >> done
-  // radix-4 stages
-  while (logN - done >= 2) {
-    const int m = n >> 2, s = 1 << ls;
-    for (int t = threadIdx.x; t < N / 4; t += blockDim.x) {
-      const int q = t & (s - 1), p = t >> ls;
-      float2 w1 = tw[p << done];        // exp(-2 pi i p / n)
-      float2 w2 = tw[(2 * p) << done];  // exp(-2 pi i 2p / n), 2p < n/2
-      if (INV) {
-        w1.y = -w1.y;
-        w2.y = -w2.y;
-      }
-      const float2 w3 = cmul(w1, w2);
-      const float2 a = x[q + s * p], b = x[q + s * (p + m)], c = x[q + s * (p + 2 * m)], d = x[q + s * (p + 3 * m)];
-      const float2 apc = make_float2(a.x + c.x, a.y + c.y), amc = make_float2(a.x - c.x, a.y - c.y);
-      const float2 bpd = make_float2(b.x + d.x, b.y + d.y), bmd = make_float2(b.x - d.x, b.y - d.y);
-      // forward: -i (b - d) = (bmd.y, -bmd.x); inverse: +i (b - d) = (-bmd.y, bmd.x)
-      const float2 jb = INV ? make_float2(-bmd.y, bmd.x) : make_float2(bmd.y, -bmd.x);
-      float2* o = y + q + s * (4 * p);
-      o[0] = make_float2(apc.x + bpd.x, apc.y + bpd.y);
-      o[s] = cmul(make_float2(amc.x + jb.x, amc.y + jb.y), w1);
-      o[2 * s] = cmul(make_float2(apc.x - bpd.x, apc.y - bpd.y), w2);
-      o[3 * s] = cmul(make_float2(amc.x - jb.x, amc.y - jb.y), w3);
-    }
+__device__ __forceinline__ float2* fft_smem(float2* x, float2* y, const float2* tw, int N, int L, int r0) {
+  return fft_mixed<INV>(x, y, tw, N, L, r0, [](int items, auto f) {
+    for (int t = threadIdx.x; t < items; t += blockDim.x) f(t);
     __syncthreads();
-    float2* tmp = x;
-    x = y;
-    y = tmp;
-    n = m;
-    ls += 2;
-    done += 2;
-  }
-  if (logN - done == 1) {  // final radix-2 stage: n == 2, twiddle 1
-    const int s = 1 << ls;
-    for (int t = threadIdx.x; t < N / 2; t += blockDim.x) {
-      const float2 a = x[t], b = x[t + s];  // p = 0, q = t
-      y[t] = make_float2(a.x + b.x, a.y + b.y);
-      y[t + s] = make_float2(a.x - b.x, a.y - b.y);
-    }
-    __syncthreads();
-    float2* tmp = x;
-    x = y;
-    y = tmp;
-  }
-  return x;
+  });
 }
 
 struct Plan {
-  int fH, fW, Sy, Sx, logSy, logSx, ld;  // ld = row stride (in complex) of specT: fH rounded up to 8
+  int fH, fW, Sy, Sx, logSy, logSx, ry, rx, ld;  // S = r * 2^log; ld = row stride (in complex) of specT: fH rounded up to 8
 };
+
+__device__ __forceinline__ int wrap_index(int i, int S) { return i >= S ? i - S : i; }  // i in [0, 2S)
 
 enum { IN_FLUX = 0, IN_DPOOL = 1, IN_PSF = 2 };
 
@@ -126,10 +87,10 @@ __global__ void rows_fwd_kernel(const float* __restrict__ in, const float* __res
       bx[j] = make_float2(va, vb);
     }
     __syncthreads();
-    float2* z = fft_pow2<false>(bx, by, tw, pl.Sx, pl.logSx);
+    float2* z = fft_smem<false>(bx, by, tw, pl.Sx, pl.logSx, pl.rx);
     // split: A[k] = (Z[k] + conj Z[N-k]) / 2,  B[k] = (Z[k] - conj Z[N-k]) / (2i)
     for (int k = threadIdx.x; k <= pl.Sx / 2; k += blockDim.x) {
-      const float2 zk = z[k], zn = z[(pl.Sx - k) & (pl.Sx - 1)];
+      const float2 zk = z[k], zn = z[wrap_index(pl.Sx - k, pl.Sx)];
       const float2 A = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
       const float2 B = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
       float2* dst = specT + (int64_t)k * pl.ld + ra;
@@ -153,7 +114,7 @@ __global__ void cols_kernel(float2* __restrict__ specT, const float2* __restrict
   float2* col = specT + (int64_t)k * pl.ld;
   for (int r = threadIdx.x; r < pl.Sy; r += blockDim.x) bx[r] = r < nrows_in ? col[r] : make_float2(0.f, 0.f);
   __syncthreads();
-  float2* z = fft_pow2<false>(bx, by, tw, pl.Sy, pl.logSy);
+  float2* z = fft_smem<false>(bx, by, tw, pl.Sy, pl.logSy, pl.ry);
   if (PSF_MODE == 2) {
     float2* dst = psf_out + (int64_t)k * pl.Sy;
     for (int r = threadIdx.x; r < pl.Sy; r += blockDim.x) dst[r] = z[r];
@@ -168,8 +129,8 @@ __global__ void cols_kernel(float2* __restrict__ specT, const float2* __restrict
   }
   __syncthreads();
   float2* other = z == bx ? by : bx;
-  float2* w = fft_pow2<true>(z, other, tw, pl.Sy, pl.logSy);
-  for (int i = threadIdx.x; i < nrows_out; i += blockDim.x) col[i] = w[(i + off) & (pl.Sy - 1)];
+  float2* w = fft_smem<true>(z, other, tw, pl.Sy, pl.logSy, pl.ry);
+  for (int i = threadIdx.x; i < nrows_out; i += blockDim.x) col[i] = w[wrap_index(i + off, pl.Sy)];
 }
 
 // ---- pass 3: inverse row FFTs of row pairs, column crop, output transform.
@@ -195,9 +156,9 @@ __global__ void rows_inv_kernel(const float2* __restrict__ specT, Plan pl, int n
       if (k > 0 && k < pl.Sx / 2) bx[pl.Sx - k] = make_float2(A.x + B.y, B.x - A.y);
     }
     __syncthreads();
-    float2* z = fft_pow2<true>(bx, by, tw, pl.Sx, pl.logSx);
+    float2* z = fft_smem<true>(bx, by, tw, pl.Sx, pl.logSx, pl.rx);
     for (int j = threadIdx.x; j < ncols; j += blockDim.x) {
-      const float2 v = z[(j + off) & (pl.Sx - 1)];
+      const float2 v = z[wrap_index(j + off, pl.Sx)];
       int64_t oa = (int64_t)ra * ncols + j, ob = (int64_t)rb * ncols + j;
       if (OUT_MODE == 0) {
         out[oa] = v.x;
@@ -215,24 +176,23 @@ __global__ void rows_inv_kernel(const float2* __restrict__ specT, Plan pl, int n
   }
 }
 
-static int next_pow2(int v, int* lg) {
-  int p = 1, l = 0;
-  while (p < v) {
-    p <<= 1;
-    ++l;
+// sizes 3 * 2^L and 5 * 2^L are allowed next to 2^L (2.5x less padded area for 545 or 1224 points); JD_FFT_MIXED=0
+// restricts the plan to powers of two
+static bool fft_mixed_sizes() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("JD_FFT_MIXED");
+    v = e ? (atoi(e) != 0) : 1;
   }
-  *lg = l;
-  return p;
+  return v != 0;
 }
 
 static int make_plan(const char* name, int fH, int fW, int kh, int kw, Plan* pl) {
   JD_CHECK_ARG(fH > 0 && fW > 0 && kh > 0 && kw > 0, "%s: bad shape", name);
   pl->fH = fH;
   pl->fW = fW;
-  pl->Sy = next_pow2(fH + kh - 1, &pl->logSy);
-  pl->Sx = next_pow2(fW + kw - 1, &pl->logSx);
-  if (pl->Sx < 2) pl->Sx = 2, pl->logSx = 1;
-  if (pl->Sy < 2) pl->Sy = 2, pl->logSy = 1;
+  pl->Sy = fft_size(fH + kh - 1, fft_mixed_sizes(), &pl->logSy, &pl->ry);
+  pl->Sx = fft_size(fW + kw - 1, fft_mixed_sizes(), &pl->logSx, &pl->rx);
   JD_CHECK_ARG(pl->Sy <= 8192 && pl->Sx <= 8192, "%s: padded FFT size %dx%d exceeds 8192", name, pl->Sy, pl->Sx);
   pl->ld = (fH + 7) & ~7;
   return JD_OK;
