@@ -344,32 +344,108 @@ class Adam:
 
 
 # --------------------------------------------------------------------------------------
+# calibration: sub-pixel shift of the flux                        utils/torch.py:196-223, npred.py:226-230
+# --------------------------------------------------------------------------------------
+def _shift_taps(shift_y, shift_x, scale, dtype, shape):
+    """`shift_image_torch` = affine_grid + grid_sample (bilinear, zeros padding, align_corners=False) with a pure
+    translation: output pixel (i, j) samples the input at (i + scale * shift_y, j + scale * shift_x), i.e. a
+    4-tap stencil with constant weights.  Returns (fy, fx, wy, wx, gy, gx): integer offsets, fractional weights and
+    d(sample position)/d(shift).  The reference forms the normalised translation with `2 * scale / torch.tensor(
+    [[W], [H]])`, a FLOAT32 tensor whatever the dtype of the image (utils/torch.py:216): that rounding of 2 scale / W
+    is reproduced here (it moves the sample position by ~1e-7 pixel)."""
+    H, W = shape
+    # torch evaluates scalar / tensor as scalar * reciprocal(tensor), in float32
+    gy = dtype.type(np.float32(2 * scale) * (np.float32(1) / np.float32(H))) * dtype.type(H) / dtype.type(2)
+    gx = dtype.type(np.float32(2 * scale) * (np.float32(1) / np.float32(W))) * dtype.type(W) / dtype.type(2)
+    dy, dx = gy * dtype.type(shift_y), gx * dtype.type(shift_x)
+    fy, fx = int(np.floor(dy)), int(np.floor(dx))
+    return fy, fx, dtype.type(dy - fy), dtype.type(dx - fx), gy, gx
+
+
+def _shifted(image, oy, ox):
+    """out[i, j] = image[i + oy, j + ox], zero outside."""
+    H, W = image.shape
+    out = np.zeros_like(image)
+    i0, i1 = max(0, -oy), min(H, H - oy)
+    j0, j1 = max(0, -ox), min(W, W - ox)
+    if i1 > i0 and j1 > j0:
+        out[i0:i1, j0:j1] = image[i0 + oy:i1 + oy, j0 + ox:j1 + ox]
+    return out
+
+
+def shift_image(image, shift_y, shift_x, scale=1, return_grads=False):
+    """Shifted image (utils/torch.py:196-223); with return_grads also d out / d shift_y and d out / d shift_x
+    (per pixel; the derivative of the bilinear interpolant, as grid_sample's backward gives it).
+    The reference returns the input unchanged when both shifts are ~0 (utils/torch.py:211) - callers handle that."""
+    fy, fx, wy, wx, gy, gx = _shift_taps(shift_y, shift_x, scale, image.dtype, image.shape)
+    a00, a01 = _shifted(image, fy, fx), _shifted(image, fy, fx + 1)
+    a10, a11 = _shifted(image, fy + 1, fx), _shifted(image, fy + 1, fx + 1)
+    out = (1 - wy) * ((1 - wx) * a00 + wx * a01) + wy * ((1 - wx) * a10 + wx * a11)
+    if not return_grads:
+        return out
+    d_dy = gy * ((1 - wx) * (a10 - a00) + wx * (a11 - a01))
+    d_dx = gx * ((1 - wy) * (a01 - a00) + wy * (a11 - a10))
+    return out, d_dy, d_dx
+
+
+def shift_image_adjoint(d, shift_y, shift_x, scale=1):
+    """Transpose of `shift_image` w.r.t. the image: dimage[m, n] = sum_ab w_ab d[m - fy - a, n - fx - b]."""
+    fy, fx, wy, wx, _, _ = _shift_taps(shift_y, shift_x, scale, d.dtype, d.shape)
+    return ((1 - wy) * ((1 - wx) * _shifted(d, -fy, -fx) + wx * _shifted(d, -fy, -fx - 1))
+            + wy * ((1 - wx) * _shifted(d, -fy - 1, -fx) + wx * _shifted(d, -fy - 1, -fx - 1)))
+
+
+def shift_is_identity(shift_y, shift_x):
+    """The reference's early return (utils/torch.py:211): torch.isclose(shift, 0) with default tolerances."""
+    return abs(shift_y) <= 1e-8 and abs(shift_x) <= 1e-8
+
+
+# --------------------------------------------------------------------------------------
 # the MAP step / run                                              core.py:209-230
 # --------------------------------------------------------------------------------------
-def dataset_loss_and_grad(theta, ds, mask=None, logb=None, return_dlogb=False):
+def dataset_loss_and_grad(theta, ds, mask=None, logb=None, return_dlogb=False, shift_xy=None):
     """Poisson loss of one dataset and its gradient w.r.t. theta (log flux) [and w.r.t. the log background
-    norm `logb` of an NPredCalibration, models/npred.py:234-237, 329-337].
+    norm `logb` and the sub-pixel shift `shift_xy` = (shift_x, shift_y) of an NPredCalibration,
+    models/npred.py:226-237, 329-337].
 
-    ds: dict(counts, exposure_up, psf_up, background, f)."""
+    ds: dict(counts, exposure_up, psf_up, background, f).  With `shift_xy` the return value gains a last element
+    dshift_xy (None when the shift is ~0: the reference then returns the unshifted image without a graph)."""
     flux = flux_from_theta(theta, mask)
     bnorm = None if logb is None else np.exp(theta.dtype.type(logb))
-    npred, pool = npred_forward(flux, ds["exposure_up"], ds["psf_up"], ds["background"], ds["f"], bnorm, return_pool=True)
+    shifted = shift_xy is not None and not shift_is_identity(shift_xy[1], shift_xy[0])
+    flux_in = flux
+    if shifted:
+        flux_in, d_dy, d_dx = shift_image(flux, shift_xy[1], shift_xy[0], ds["f"], return_grads=True)
+    npred, pool = npred_forward(flux_in, ds["exposure_up"], ds["psf_up"], ds["background"], ds["f"], bnorm, return_pool=True)
     loss = poisson_nll(npred, ds["counts"])
     dn = poisson_nll_grad(npred, ds["counts"])
-    dflux = npred_backward(dn, pool, flux, ds["exposure_up"], ds["psf_up"], ds["f"])
+    dflux = npred_backward(dn, pool, flux_in, ds["exposure_up"], ds["psf_up"], ds["f"])
+    dshift = None
+    if shifted:
+        dshift = np.array([(dflux * d_dx).sum(dtype=np.float64), (dflux * d_dy).sum(dtype=np.float64)], dtype=theta.dtype)
+        dflux = shift_image_adjoint(dflux, shift_xy[1], shift_xy[0], ds["f"])
+    out = (loss, dflux * flux, npred)
     if return_dlogb:
-        dlogb = float((dn * ds["background"] * (1 if bnorm is None else bnorm)).sum(dtype=np.float64))
-        return loss, dflux * flux, npred, dlogb
-    return loss, dflux * flux, npred
+        out += (float((dn * ds["background"] * (1 if bnorm is None else bnorm)).sum(dtype=np.float64)),)
+    if shift_xy is not None:
+        out += (dshift,)
+    return out
 
 
 def map_step(theta, adam, ds, n_datasets, beta, gmm=None, shifts=None, stride=4, marginalize=False, mask=None,
              cal=None):
     """One reference step: total = L_d - beta * prior / D, backward, Adam (core.py:214-229).
-    cal: None or dict(logb=array(1), adam=Adam) — the dataset's trainable log background norm, stepped by its
-    own Adam state (torch.optim.Adam keeps a step counter per parameter)."""
+    cal: None or dict(logb=array(1), adam=Adam[, shift_xy=array(2), adam_shift=Adam]) - the dataset's trainable log
+    background norm and (shift_x, shift_y), each stepped by its own Adam state (torch.optim.Adam keeps a step counter
+    per parameter; a parameter without gradient - a shift at 0 - is skipped)."""
     if cal is None:
         loss, dtheta, _ = dataset_loss_and_grad(theta, ds, mask)
+    elif "shift_xy" in cal:
+        loss, dtheta, _, dlogb, dshift = dataset_loss_and_grad(theta, ds, mask, cal["logb"][0], return_dlogb=True,
+                                                               shift_xy=cal["shift_xy"])
+        cal["logb"] = cal["adam"].step(cal["logb"], np.array([dlogb], dtype=theta.dtype))
+        if dshift is not None:
+            cal["shift_xy"] = cal["adam_shift"].step(cal["shift_xy"], dshift)
     else:
         loss, dtheta, _, dlogb = dataset_loss_and_grad(theta, ds, mask, cal["logb"][0], return_dlogb=True)
         cal["logb"] = cal["adam"].step(cal["logb"], np.array([dlogb], dtype=theta.dtype))
@@ -396,11 +472,12 @@ def prepare_dataset(dataset, f=1, dtype=np.float32):
 
 
 def map_run(flux_init_up, datasets, n_epochs, lr=0.1, beta=1.0, gmm=None, shifts=None, stride=4,
-            marginalize=False, dtype=np.float32, trace_shifts=None, background_norms=None):
+            marginalize=False, dtype=np.float32, trace_shifts=None, background_norms=None, shifts_xy=None):
     """MAPDeconvolver.run restated: sequential per-dataset Adam steps (core.py:209-230) and the
     per-epoch trace (loss.py:212-250).  `shifts[step]` are the injected cycle-spin draws of the
     training steps; `trace_shifts[epoch]` those consumed by `append_trace`'s extra prior call.
-    Returns (flux_upsampled, trace rows)."""
+    `background_norms` / `shifts_xy` (one value / (shift_x, shift_y) pair per dataset): trainable NPredCalibration
+    parameters.  Returns (flux_upsampled, trace rows[, background norms[, shifts_xy]])."""
     theta = np.log(np.asarray(flux_init_up, dtype=dtype))
     adam = Adam(theta.shape, lr=lr, dtype=dtype)
     D = len(datasets)
@@ -409,6 +486,10 @@ def map_run(flux_init_up, datasets, n_epochs, lr=0.1, beta=1.0, gmm=None, shifts
     cals = None
     if background_norms is not None:
         cals = [dict(logb=np.log(np.array([b], dtype=dtype)), adam=Adam((1,), lr=lr, dtype=dtype)) for b in background_norms]
+        if shifts_xy is not None:
+            for c, sxy in zip(cals, shifts_xy):
+                c["shift_xy"] = np.array(sxy, dtype=dtype)
+                c["adam_shift"] = Adam((2,), lr=lr, dtype=dtype)
     for epoch in range(n_epochs):
         for i_ds, ds in enumerate(datasets):
             sh = shifts[step] if gmm is not None else None
@@ -421,14 +502,21 @@ def map_run(flux_init_up, datasets, n_epochs, lr=0.1, beta=1.0, gmm=None, shifts
             step += 1
         # the calibration parameters are read live by append_trace (only the flux tuple is stale)
         bn = [None] * D if cals is None else [np.exp(c["logb"][0]) for c in cals]
-        ld = [float(poisson_nll(npred_forward(flux, d["exposure_up"], d["psf_up"], d["background"], d["f"], b),
-                                d["counts"])) for d, b in zip(datasets, bn)]
+        fl = [flux] * D
+        if cals is not None and shifts_xy is not None:
+            fl = [flux if shift_is_identity(c["shift_xy"][1], c["shift_xy"][0]) else
+                  shift_image(flux, c["shift_xy"][1], c["shift_xy"][0], d["f"]) for c, d in zip(cals, datasets)]
+        ld = [float(poisson_nll(npred_forward(f_, d["exposure_up"], d["psf_up"], d["background"], d["f"], b),
+                                d["counts"])) for f_, d, b in zip(fl, datasets, bn)]
         lp = 0.0
         if gmm is not None:
             sh = trace_shifts[epoch]
             lp = float(gmm_patch_prior(flux, gmm, sh[0], sh[1], stride, marginalize))
         trace.append({"total": sum(ld) - beta * lp, "datasets-total": sum(ld), "priors-total": -beta * lp,
                       "datasets": ld})
+    if cals is not None and shifts_xy is not None:
+        return (flux_from_theta(theta), trace, [float(np.exp(c["logb"][0])) for c in cals],
+                [c["shift_xy"].copy() for c in cals])
     if cals is not None:
         return flux_from_theta(theta), trace, [float(np.exp(c["logb"][0])) for c in cals]
     return flux_from_theta(theta), trace

@@ -27,7 +27,7 @@ from jolideco.loss import PoissonLoss, TotalLoss  # noqa: E402
 from jolideco.models import FluxComponents, NPredModels, SpatialFluxComponent  # noqa: E402
 from jolideco.priors import GMMPatchPrior, UniformPrior  # noqa: E402
 from jolideco.priors.patches.gmm import GaussianMixtureModel, GaussianMixtureModelMeta  # noqa: E402
-from jolideco.utils.torch import convolve_fft_torch, view_as_overlapping_patches_torch  # noqa: E402
+from jolideco.utils.torch import convolve_fft_torch, shift_image_torch, view_as_overlapping_patches_torch  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 os.makedirs(OUT, exist_ok=True)
@@ -327,9 +327,91 @@ def golden_calibration():
     print("run_gmm_calib.npz norms", out["background_norm"], "total", out["trace_total"][-1])
 
 
+def golden_calibration_shift():
+    """GMM prior + NPredCalibrations with trainable NON-ZERO sub-pixel shifts and background norms
+    (the Chandra example fits both, examples/chandra-e0102-filament.py:197-206), f = 1 and f = 2."""
+    from jolideco.models import NPredCalibration, NPredCalibrations
+
+    for f, tag in ((1, "run_gmm_shift.npz"), (2, "run_gmm_shift_up2.npz")):
+        rng = np.random.default_rng(41 + f)
+        datasets = {str(i): synthetic_dataset(rng, 32, 28, 6 if f == 2 else 7, 6 if f == 2 else 7) for i in range(2)}
+        flux_init = rng.gamma(20, size=(32, 28)) / 10
+        gmm_arrays = synthetic_gmm_arrays(8, seed=9)
+        n_epochs, norms, shifts_xy = 6, [1.2, 0.8], [(0.4, -0.7), (-0.25, 0.3)]
+        gmm = GaussianMixtureModel.from_numpy(*gmm_arrays, meta=GaussianMixtureModelMeta(stride=4))
+        gen = torch.Generator().manual_seed(8)
+        prior = GMMPatchPrior(gmm=gmm, stride=4, generator=gen)
+        g = torch.Generator()
+        g.set_state(gen.get_state())
+        shifts, trace_shifts = [], []
+        for _ in range(n_epochs):
+            for _ in range(2):
+                shifts.append(peek_and_advance(g))
+            trace_shifts.append(peek_and_advance(g))
+        comps = FluxComponents()
+        comps["flux-1"] = SpatialFluxComponent.from_numpy(flux=flux_init, upsampling_factor=f, prior=prior)
+        flux_init_up = comps["flux-1"].flux_upsampled.detach().numpy()[0, 0].copy()
+        cals = NPredCalibrations()
+        for name, b, (sx, sy) in zip(datasets, norms, shifts_xy):
+            cals[name] = NPredCalibration(shift_x=sx, shift_y=sy, background_norm=b)
+        res = MAPDeconvolver(n_epochs=n_epochs, learning_rate=0.1, display_progress=False).run(
+            datasets=datasets, components=comps, calibrations=cals)
+        out = {}
+        pack_datasets(datasets, "ds", out)
+        out["flux_init"], out["flux_init_up"], out["upsampling"] = flux_init, flux_init_up, f
+        out["gmm_means"], out["gmm_cov"], out["gmm_w"] = gmm_arrays
+        out["marginalize"] = False
+        out["background_norm_init"] = np.array(norms)
+        out["shift_xy_init"] = np.array(shifts_xy)
+        out["background_norm"] = np.array([float(c.background_norm) for c in res.calibrations.values()])
+        out["shift_xy"] = np.stack([c.shift_xy.detach().numpy()[0] for c in res.calibrations.values()])
+        out["flux_up"] = res.flux_upsampled_total
+        tr = res.trace_loss
+        out["trace_total"] = np.asarray(tr["total"])
+        out["trace_datasets"] = np.stack([np.asarray(tr[f"dataset-{n}"]) for n in datasets], axis=1)
+        out["trace_prior"] = np.asarray(tr["priors-total"])
+        out["shifts"] = np.array(shifts).reshape(-1, 2)
+        out["trace_shifts"] = np.array(trace_shifts).reshape(-1, 2)
+        np.savez_compressed(os.path.join(OUT, tag), **out)
+        print(tag, "norms", out["background_norm"], "shift_xy", out["shift_xy"].tolist(), "total", out["trace_total"][-1])
+
+
+def golden_shift():
+    """`shift_image_torch` (utils/torch.py:196-223) values and autograd gradients (w.r.t. the image and shift_xy)
+    for non-trivial sub-pixel shifts, fp32 and fp64; plus one whole-pixel shift (values only: the interpolant has a
+    kink there)."""
+    rng = np.random.default_rng(31)
+    out = {}
+    cases = [(0.3, -1.7, 1), (2.25, 0.6, 2), (-0.6, 0.05, 1), (-3.4, 2.2, 3)]
+    image = rng.gamma(2.0, size=(13, 17))
+    cot = rng.normal(size=(13, 17))
+    out["image"], out["cot"] = image, cot
+    out["cases"] = np.array(cases, dtype=np.float64)
+    for i, (sx, sy, scale) in enumerate(cases):
+        for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+            img = torch.tensor(image[None, None], dtype=dt, requires_grad=True)
+            shift_xy = torch.tensor([[sx, sy]], dtype=dt, requires_grad=True)
+            res = shift_image_torch(img, shift_xy, scale=scale)
+            (res * torch.tensor(cot[None, None], dtype=dt)).sum().backward()
+            out[f"c{i}_{tag}_out"] = res.detach().numpy()[0, 0]
+            out[f"c{i}_{tag}_dimage"] = img.grad.numpy()[0, 0]
+            out[f"c{i}_{tag}_dshift_xy"] = shift_xy.grad.numpy()[0]
+    img = torch.tensor(image[None, None], dtype=torch.float64)
+    out["whole_out"] = shift_image_torch(img, torch.tensor([[2.0, -1.0]], dtype=torch.float64), scale=1).numpy()[0, 0]
+    out["zero_is_identity"] = shift_image_torch(img, torch.zeros((1, 2), dtype=torch.float64)).numpy()[0, 0]
+    np.savez_compressed(os.path.join(OUT, "shift_kat.npz"), **out)
+    print("shift_kat.npz", {k: v.shape for k, v in out.items() if k.startswith("c0")})
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "shift":
+        golden_shift()
+        golden_calibration_shift()
+        sys.exit(0)
     golden_kat()
     golden_prior_step()
     golden_runs()
     golden_calibration()
+    golden_shift()
+    golden_calibration_shift()

@@ -226,3 +226,38 @@ def test_run_with_background_norm_calibration_matches_imported_reference():
     assert np.linalg.norm(flux_up - g["flux_up"]) / np.linalg.norm(g["flux_up"]) < 1e-3
     assert_allclose([t["total"] for t in trace], g["trace_total"], rtol=1e-5)
     assert_allclose(norms, g["background_norm"], rtol=1e-5)
+
+
+def test_shift_image_kat_against_imported_reference():
+    """Sub-pixel shift of the flux (utils/torch.py:196-223): values, image gradient and shift gradient of the
+    4-tap restatement against `shift_image_torch` + autograd, fp64 to round-off and fp32 to its own noise."""
+    g = load_golden("shift_kat.npz")
+    image, cot = g["image"], g["cot"]
+    for i, (sx, sy, scale) in enumerate(g["cases"]):
+        out, d_dy, d_dx = O.shift_image(image, sy, sx, scale, return_grads=True)
+        assert_allclose(out, g[f"c{i}_f64_out"], rtol=1e-9, atol=1e-12)
+        assert_allclose(O.shift_image_adjoint(cot, sy, sx, scale), g[f"c{i}_f64_dimage"], rtol=1e-9, atol=1e-12)
+        assert_allclose([(cot * d_dx).sum(), (cot * d_dy).sum()], g[f"c{i}_f64_dshift_xy"], rtol=1e-9)
+        out32 = O.shift_image(image.astype(np.float32), sy, sx, scale)
+        assert np.abs(out32 - g[f"c{i}_f32_out"]).max() <= 2e-5 * np.abs(out32).max()
+    assert_allclose(O.shift_image(image, -1.0, 2.0, 1), g["whole_out"], rtol=1e-12)
+    assert np.array_equal(g["zero_is_identity"], image) and O.shift_is_identity(0.0, 0.0)
+    # the shifted image leaves zeros where it samples outside (zeros padding)
+    assert np.all(O.shift_image(image, 0.0, 3.0, 1)[:, -3:] == 0)
+
+
+@pytest.mark.parametrize("name,f", [("run_gmm_shift.npz", 1), ("run_gmm_shift_up2.npz", 2)])
+def test_run_with_shift_calibration_matches_imported_reference(name, f):
+    """NPredCalibrations with trainable non-zero sub-pixel shifts AND background norms: flux, trace, fitted
+    norms and fitted shifts of the restated loop against the imported reference."""
+    g = load_golden(name)
+    datasets = [O.prepare_dataset(d, f=f) for d in unpack_datasets(g)]
+    gmm = O.GMM(g["gmm_means"], g["gmm_cov"], g["gmm_w"])
+    flux_up, trace, norms, shifts_xy = O.map_run(g["flux_init_up"], datasets, 6, gmm=gmm, shifts=g["shifts"],
+                                                 trace_shifts=g["trace_shifts"],
+                                                 background_norms=g["background_norm_init"],
+                                                 shifts_xy=g["shift_xy_init"])
+    assert np.linalg.norm(flux_up - g["flux_up"]) / np.linalg.norm(g["flux_up"]) < 1e-3
+    assert_allclose([t["total"] for t in trace], g["trace_total"], rtol=2e-5)
+    assert_allclose(norms, g["background_norm"], rtol=1e-4)
+    assert_allclose(np.stack(shifts_xy), g["shift_xy"], rtol=1e-3, atol=1e-4)
