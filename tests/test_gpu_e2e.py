@@ -173,3 +173,27 @@ def test_background_norm_calibration_matches_imported_reference(fused):
     check(res, g, 8)
     norms = [float(c.background_norm) for c in res.calibrations.values()]
     assert_allclose(norms, g["background_norm"], rtol=1e-4)
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("JD_TEST_PENDING"),
+                    reason="written at the end of round 1 without GPU minutes left; set JD_TEST_PENDING=1, and drop this "
+                           "mark after the first green run")
+@pytest.mark.parametrize("name,f", [("run_gmm_shift.npz", 1), ("run_gmm_shift_up2.npz", 2)])
+def test_shift_calibration_matches_imported_reference(name, f):
+    """trainable non-zero sub-pixel shifts + background norms.  Not covered by the fused engine:
+    `MAPDeconvolver.run` must route it to the autograd path (grid_sample + the CUDA kernels) and still reproduce
+    the imported reference's run (flux, trace, fitted norms and shifts)."""
+    g = load_golden(name)
+    prior = make_prior(g, 8)
+    comps = J.FluxComponents()
+    comps["flux-1"] = J.SpatialFluxComponent.from_numpy(flux=g["flux_init"], upsampling_factor=f, prior=prior)
+    cals = J.NPredCalibrations()
+    for ds_name, b, (sx, sy) in zip(as_datasets(g), g["background_norm_init"], g["shift_xy_init"]):
+        cals[ds_name] = J.NPredCalibration(shift_x=float(sx), shift_y=float(sy), background_norm=float(b))
+    deco = J.MAPDeconvolver(n_epochs=6, learning_rate=0.1, display_progress=False, device=DEV)
+    res = deco.run(datasets=as_datasets(g), components=comps, calibrations=cals)
+    assert not hasattr(deco, "engine")  # the fused engine does not cover shifts
+    check(res, g, 6)
+    assert_allclose([float(c.background_norm) for c in res.calibrations.values()], g["background_norm"], rtol=1e-4)
+    shifts = np.stack([c.shift_xy.detach().cpu().numpy()[0] for c in res.calibrations.values()])
+    assert_allclose(shifts, g["shift_xy"], rtol=1e-3, atol=1e-4)
