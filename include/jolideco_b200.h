@@ -226,6 +226,17 @@ int jd_step_begin(int32_t* counters, const int32_t* shift_table, int n_shifts, i
                   int advance_adam, float lr, float beta1, float beta2, float* adam_scalars, double* zero_acc,
                   int n_acc, jd_stream_t stream);
 
+/* ---- a5 / 8f-2: sub-pixel shift of the flux by an NPredCalibration (utils/torch.py:196-223 `shift_image_torch` =
+ * affine_grid + grid_sample, bilinear, zeros padding; npred.py:226-230 applies it with scale = upsampling factor).
+ * shift_xy: device pair (shift_x, shift_y) - the storage of NPredCalibration.shift_xy.  shifted[i,j] samples flux at
+ * (i + scale shift_y, j + scale shift_x).  jd_shift_backward: dflux (+)= shift^T dshifted and, when dshift_xy != NULL,
+ * dshift_xy[0..1] += (dL/dshift_x, dL/dshift_y) (double accumulators, zeroed by the caller).  The reference skips the
+ * operator (and never trains the shift) when both shifts are ~0 (utils/torch.py:211): callers do the same. */
+int jd_shift_forward(const float* flux, const float* shift_xy, int scale, int fH, int fW, float* shifted,
+                     jd_stream_t stream);
+int jd_shift_backward(const float* dshifted, const float* flux, const float* shift_xy, int scale, int fH, int fW,
+                      float* dflux, int accumulate, double* dshift_xy, jd_stream_t stream);
+
 /* Adam on the scalar calibration parameters of one dataset (NPredCalibration._background_norm, models/npred.py:
  * 298-333): grad[i] are the double accumulators written by jd_poisson_forward_backward (dlogb), counter is the
  * parameter's own step count (torch.optim.Adam only advances it when the parameter received a gradient). */

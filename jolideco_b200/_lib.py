@@ -38,6 +38,8 @@ PROTOTYPES = {
                          c_float, c_float, c_float, c_stream],
     "jd_step_begin": [c_i32p, c_i32p, c_int, c_i32p, c_int, c_float, c_float, c_float, c_f32p, c_f64p, c_int,
                       c_stream],
+    "jd_shift_forward": [c_f32p, c_f32p, c_int, c_int, c_int, c_f32p, c_stream],
+    "jd_shift_backward": [c_f32p, c_f32p, c_f32p, c_int, c_int, c_int, c_f32p, c_int, c_f64p, c_stream],
     "jd_adam_scalar_step_dev": [c_f32p, c_f32p, c_f32p, c_f64p, c_i32p, c_int, c_float, c_float, c_float, c_float,
                                 c_stream],
     "jd_adam_allreduce_peer": [ctypes.c_void_p, ctypes.c_void_p, c_int, c_int, c_f32p, c_f32p, c_f32p, c_u8p, c_int,

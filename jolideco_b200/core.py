@@ -9,6 +9,7 @@ There is no CPU fallback: a non-CUDA device raises.
 """
 import copy
 import logging
+import os
 from pathlib import Path
 
 import numpy as np
@@ -85,12 +86,19 @@ class MAPDeconvolver:
 
     # ------------------------------------------------------------------------------------------
     @staticmethod
-    def _calibrations_fusable(calibrations):
+    def _shift_is_zero(cal):
+        shift = cal.shift_xy.detach().cpu()
+        return bool(torch.all(torch.isclose(shift, torch.zeros_like(shift))))
+
+    @classmethod
+    def _calibrations_fusable(cls, calibrations):
         """Calibrations the engine covers: background norm (trained or frozen); shifts at 0 never train in the
-        reference (`shift_image_torch` returns early, utils/torch.py:211) and psf_scale ~ 1 is the identity."""
+        reference (`shift_image_torch` returns early, utils/torch.py:211); psf_scale ~ 1 is the identity.  Non-zero
+        (trainable) shifts run in the engine through jd_shift_forward/backward when JD_FUSED_SHIFT=1 (written at the end
+        of round 1 without GPU minutes left: the autograd path stays the default until its GPU test has run)."""
+        fused_shift = os.environ.get("JD_FUSED_SHIFT", "0") == "1"
         for cal in calibrations.values():
-            shift = cal.shift_xy.detach().cpu()
-            if not bool(torch.all(torch.isclose(shift, torch.zeros_like(shift)))):
+            if not cls._shift_is_zero(cal) and not fused_shift:
                 return False
             if not bool(torch.isclose(cal.psf_scale.detach().cpu(), torch.tensor(1.0)).all()):
                 return False
@@ -131,10 +139,13 @@ class MAPDeconvolver:
                                                poisson_loss.npred_models_all):
                 model = models[name]
                 cal = models.calibration
+                shifted = cal is not None and not self._shift_is_zero(cal)
                 out.append(DatasetBuffers(counts[0, 0].contiguous(), model.exposure[0, 0], model.psf[0, 0],
                                           models.background[0, 0].contiguous(), model.upsampling_factor, name=ds_name,
                                           bkg_log_norm=None if cal is None else cal._background_norm.data,
-                                          train_bkg_norm=cal is not None and not cal.frozen))
+                                          train_bkg_norm=cal is not None and not cal.frozen,
+                                          shift_xy=cal.shift_xy.data.view(-1) if shifted else None,
+                                          train_shift=shifted and not cal.frozen))
             return out
 
         prior_cfg, table = None, None

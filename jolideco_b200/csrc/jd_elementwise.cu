@@ -4,6 +4,7 @@
 #include <stdarg.h>
 
 #include "jd_common.cuh"
+#include "jd_shift.cuh"
 
 namespace jd {
 
@@ -333,6 +334,48 @@ __global__ void adam_scalar_kernel(float* __restrict__ param, float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// NPredCalibration sub-pixel shift (utils/torch.py:196-223): 4-tap stencil with weights derived from the
+// device-resident (shift_x, shift_y) pair; per-pixel arithmetic in jd_shift.cuh (host-checked against the oracle).
+// ------------------------------------------------------------------------------------------
+__global__ void shift_fwd_kernel(const float* __restrict__ flux, const float* __restrict__ shift_xy, int scale, int H,
+                                 int W, float* __restrict__ out) {
+  const ShiftTaps t = shift_taps(shift_xy[0], shift_xy[1], scale, H, W);
+  const int64_t n = (int64_t)H * W;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / W), j = (int)(idx - (int64_t)i * W);
+    out[idx] = shift_sample(flux, H, W, i, j, t);
+  }
+}
+
+// dflux (+)= shift^T d;  dshift_xy += (sum d * d shifted / d shift_x, sum d * d shifted / d shift_y)
+__global__ void __launch_bounds__(256)
+shift_bwd_kernel(const float* __restrict__ d, const float* __restrict__ flux, const float* __restrict__ shift_xy,
+                 int scale, int H, int W, float* __restrict__ dflux, int accumulate, double* __restrict__ dshift_xy) {
+  __shared__ double red[32];
+  const ShiftTaps t = shift_taps(shift_xy[0], shift_xy[1], scale, H, W);
+  const int64_t n = (int64_t)H * W;
+  float ax = 0.f, ay = 0.f;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / W), j = (int)(idx - (int64_t)i * W);
+    const float g = shift_adjoint(d, H, W, i, j, t);
+    dflux[idx] = accumulate ? dflux[idx] + g : g;
+    if (dshift_xy) {
+      float d_dy, d_dx;
+      shift_dshift(flux, H, W, i, j, t, &d_dy, &d_dx);
+      const float di = d[idx];
+      ax = fmaf(di, d_dx, ax);
+      ay = fmaf(di, d_dy, ay);
+    }
+  }
+  if (dshift_xy) {
+    const double sx = block_sum((double)ax, red);
+    if (threadIdx.x == 0) atomicAdd(dshift_xy, sx);
+    const double sy = block_sum((double)ay, red);
+    if (threadIdx.x == 0) atomicAdd(dshift_xy + 1, sy);
+  }
+}
+
 static inline int grid_for(int64_t n, int block) {
   int64_t g = (n + block - 1) / block;
   int64_t cap = (int64_t)num_sms() * 8;
@@ -439,6 +482,25 @@ int jd_adam_fold_step_dev(float* theta, float* m, float* v, const float* flux, c
       theta, m, v, flux, mask, dflux_a, G, scale_b, use_log_flux, fH, fW, shift_yx, stride, row_begin, row_end,
       adam_scalars, beta1, beta2, eps);
   JD_CHECK_LAUNCH("jd_adam_fold_step_dev");
+  return JD_OK;
+}
+
+int jd_shift_forward(const float* flux, const float* shift_xy, int scale, int fH, int fW, float* shifted,
+                     jd_stream_t stream) {
+  JD_CHECK_ARG(flux && shift_xy && shifted && flux != shifted, "jd_shift_forward: bad pointers");
+  JD_CHECK_ARG(scale >= 1 && fH > 0 && fW > 0, "jd_shift_forward: bad shape");
+  shift_fwd_kernel<<<grid_for((int64_t)fH * fW, 256), 256, 0, to_stream(stream)>>>(flux, shift_xy, scale, fH, fW, shifted);
+  JD_CHECK_LAUNCH("jd_shift_forward");
+  return JD_OK;
+}
+
+int jd_shift_backward(const float* dshifted, const float* flux, const float* shift_xy, int scale, int fH, int fW,
+                      float* dflux, int accumulate, double* dshift_xy, jd_stream_t stream) {
+  JD_CHECK_ARG(dshifted && flux && shift_xy && dflux && dflux != dshifted, "jd_shift_backward: bad pointers");
+  JD_CHECK_ARG(scale >= 1 && fH > 0 && fW > 0, "jd_shift_backward: bad shape");
+  shift_bwd_kernel<<<grid_for((int64_t)fH * fW, 256), 256, 0, to_stream(stream)>>>(dshifted, flux, shift_xy, scale, fH, fW,
+                                                                                  dflux, accumulate, dshift_xy);
+  JD_CHECK_LAUNCH("jd_shift_backward");
   return JD_OK;
 }
 

@@ -47,7 +47,8 @@ def _call(name, *args):
 class DatasetBuffers:
     """Device-resident arrays of one dataset (loss.py:104-118, npred.py:281-295)."""
 
-    def __init__(self, counts, exposure, psf, background, f, bkg_log_norm=None, name="", train_bkg_norm=False):
+    def __init__(self, counts, exposure, psf, background, f, bkg_log_norm=None, name="", train_bkg_norm=False,
+                 shift_xy=None, train_shift=False):
         self.counts, self.exposure, self.psf, self.background = counts, exposure, psf, background
         self.f = int(f) if f else 1
         # log background norm (NPredCalibration._background_norm, a (1,) CUDA float tensor sharing the
@@ -58,6 +59,16 @@ class DatasetBuffers:
             self.cal_m = torch.zeros_like(bkg_log_norm)
             self.cal_v = torch.zeros_like(bkg_log_norm)
             self.cal_t = torch.zeros(1, dtype=torch.int32, device=bkg_log_norm.device)
+        # non-zero sub-pixel shift (NPredCalibration.shift_xy, a (2,) CUDA float view of the parameter's storage:
+        # shift_x, shift_y) and, when it is trained, its private Adam state (one step counter for the pair, as
+        # torch.optim.Adam keeps one per parameter tensor).  None = no shift operator (the reference skips it, and
+        # never trains the shift, when it is ~0: utils/torch.py:211)
+        self.shift_xy = shift_xy
+        self.train_shift = bool(train_shift) and shift_xy is not None
+        if self.train_shift:
+            self.shift_m = torch.zeros_like(shift_xy)
+            self.shift_v = torch.zeros_like(shift_xy)
+            self.shift_t = torch.zeros(1, dtype=torch.int32, device=shift_xy.device)
         self.name = name
         self.H, self.W = int(counts.shape[-2]), int(counts.shape[-1])
         self.fH, self.fW = int(exposure.shape[-2]), int(exposure.shape[-1])
@@ -118,8 +129,12 @@ class MapEngine:
         self.cur_shift = torch.zeros(2, dtype=torch.int32, device=self.dev)
         self.adam_scalars = torch.zeros(2, **f32)
         # acc[0] = Poisson loss sum of the last step, acc[1] = sum_p v_p of the last prior evaluation,
-        # acc[2] = d loss / d log(background norm) of the last step
-        self.acc = torch.zeros(3, dtype=torch.float64, device=self.dev)
+        # acc[2] = d loss / d log(background norm) of the last step, acc[3:5] = d loss / d (shift_x, shift_y)
+        self.acc = torch.zeros(5, dtype=torch.float64, device=self.dev)
+        self.flux_s = self.dflux_s = None
+        if any(d.shift_xy is not None for d in self.datasets + self.datasets_validation):
+            self.flux_s = torch.empty_like(theta)   # shifted flux of the current dataset
+            self.dflux_s = torch.empty_like(theta)  # gradient w.r.t. the shifted flux
         self.n_trace = self.Dg + 1 + self.Vg
         self.acc_trace = torch.zeros(self.n_trace, dtype=torch.float64, device=self.dev)
         self.shift_table = None
@@ -225,11 +240,15 @@ class MapEngine:
 
     def _likelihood(self, d, loss_acc, want_grad, accumulate=False):
         s = self._s()
+        src = self.flux
+        if d.shift_xy is not None:  # calibration shift: the NPred model sees the shifted flux (npred.py:226-230)
+            _call("jd_shift_forward", _p(self.flux), _p(d.shift_xy), d.f, d.fH, d.fW, _p(self.flux_s), s)
+            src = self.flux_s
         if d.fft is not None:
-            _call("jd_conv_forward_fft", _p(self.flux), _p(d.exposure), _p(d.fft.psf_hat), _p(d.fft.workspace),
+            _call("jd_conv_forward_fft", _p(src), _p(d.exposure), _p(d.fft.psf_hat), _p(d.fft.workspace),
                   _p(self.conv), d.fH, d.fW, d.kh, d.kw, s)
         else:
-            _call("jd_conv_forward_direct", _p(self.flux), _p(d.exposure), _p(d.psf), _p(self.conv), d.fH, d.fW, d.kh,
+            _call("jd_conv_forward_direct", _p(src), _p(d.exposure), _p(d.psf), _p(self.conv), d.fH, d.fW, d.kh,
                   d.kw, s)
         train_cal = want_grad and d.train_bkg_norm
         _call("jd_poisson_forward_backward", _p(self.conv), _p(d.background), _p(d.bkg_log_norm), _p(d.counts), None,
@@ -238,12 +257,23 @@ class MapEngine:
         if train_cal:  # Adam on log(background norm) with the parameter's own step counter
             _call("jd_adam_scalar_step_dev", _p(d.bkg_log_norm), _p(d.cal_m), _p(d.cal_v), self.acc.data_ptr() + 16,
                   _p(d.cal_t), 1, self.lr, self.b1, self.b2, self.eps, s)
-        if want_grad and d.fft is not None:
+        if not want_grad:
+            return
+        # gradient w.r.t. the NPred model's input: straight into dflux_l, or via dflux_s when that input was shifted
+        out, acc_flag = (self.dflux_l, int(accumulate)) if d.shift_xy is None else (self.dflux_s, 0)
+        if d.fft is not None:
             _call("jd_conv_backward_fft", _p(self.dpool), _p(d.exposure), _p(d.fft.psf_hat), _p(d.fft.workspace),
-                  _p(self.dflux_l), int(accumulate), d.fH, d.fW, d.kh, d.kw, d.f, d.H, d.W, s)
-        elif want_grad:
-            _call("jd_conv_backward_direct", _p(self.dpool), _p(d.exposure), _p(d.psf), _p(self.dflux_l),
-                  int(accumulate), d.fH, d.fW, d.kh, d.kw, d.f, d.H, d.W, s)
+                  _p(out), acc_flag, d.fH, d.fW, d.kh, d.kw, d.f, d.H, d.W, s)
+        else:
+            _call("jd_conv_backward_direct", _p(self.dpool), _p(d.exposure), _p(d.psf), _p(out),
+                  acc_flag, d.fH, d.fW, d.kh, d.kw, d.f, d.H, d.W, s)
+        if d.shift_xy is not None:
+            dshift = self.acc.data_ptr() + 24 if d.train_shift else None
+            _call("jd_shift_backward", _p(self.dflux_s), _p(self.flux), _p(d.shift_xy), d.f, d.fH, d.fW, _p(self.dflux_l),
+                  int(accumulate), dshift, s)
+            if d.train_shift:  # Adam on (shift_x, shift_y): one parameter tensor, one step counter
+                _call("jd_adam_scalar_step_dev", _p(d.shift_xy), _p(d.shift_m), _p(d.shift_v), dshift, _p(d.shift_t), 2,
+                      self.lr, self.b1, self.b2, self.eps, s)
 
     def _prior_forward(self, sum_acc):
         if self.P <= 0:
@@ -322,6 +352,10 @@ class MapEngine:
         if not self.datasets:
             self.dflux_l.zero_()
         for j, d in enumerate(self.datasets):
+            if j > 0 and (d.train_bkg_norm or d.train_shift):
+                # the calibration-gradient accumulators acc[2:5] are per dataset: clear what the previous one left
+                _call("jd_step_begin", _p(self.counters), None, 0, None, 0, self.lr, self.b1, self.b2,
+                      _p(self.adam_scalars), self.acc.data_ptr() + 16, 3, self._s())
             self._likelihood(d, self.acc.data_ptr(), want_grad=True, accumulate=j > 0)
         if self.prior is not None:
             self._prior_forward(self.acc.data_ptr() + 8)
@@ -372,6 +406,8 @@ class MapEngine:
         for d in self.datasets:
             if d.train_bkg_norm:
                 tensors += [d.bkg_log_norm, d.cal_m, d.cal_v, d.cal_t]
+            if d.train_shift:
+                tensors += [d.shift_xy, d.shift_m, d.shift_v, d.shift_t]
         state = [t.clone() for t in tensors]
         graph = self.use_graph
         self.use_graph = False

@@ -197,3 +197,54 @@ def test_shift_calibration_matches_imported_reference(name, f):
     assert_allclose([float(c.background_norm) for c in res.calibrations.values()], g["background_norm"], rtol=1e-4)
     shifts = np.stack([c.shift_xy.detach().cpu().numpy()[0] for c in res.calibrations.values()])
     assert_allclose(shifts, g["shift_xy"], rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("JD_TEST_PENDING"),
+                    reason="written at the end of round 1 without GPU minutes left; set JD_TEST_PENDING=1, and drop this "
+                           "mark after the first green run")
+@pytest.mark.parametrize("name,f", [("run_gmm_shift.npz", 1), ("run_gmm_shift_up2.npz", 2)])
+def test_shift_calibration_fused_engine_matches_imported_reference(monkeypatch, name, f):
+    """The same runs through the fused engine (jd_shift_forward / jd_shift_backward + scalar Adam on the shift pair,
+    opt-in with JD_FUSED_SHIFT=1)."""
+    monkeypatch.setenv("JD_FUSED_SHIFT", "1")
+    g = load_golden(name)
+    prior = make_prior(g, 8)
+    comps = J.FluxComponents()
+    comps["flux-1"] = J.SpatialFluxComponent.from_numpy(flux=g["flux_init"], upsampling_factor=f, prior=prior)
+    cals = J.NPredCalibrations()
+    for ds_name, b, (sx, sy) in zip(as_datasets(g), g["background_norm_init"], g["shift_xy_init"]):
+        cals[ds_name] = J.NPredCalibration(shift_x=float(sx), shift_y=float(sy), background_norm=float(b))
+    deco = J.MAPDeconvolver(n_epochs=6, learning_rate=0.1, display_progress=False, device=DEV)
+    res = deco.run(datasets=as_datasets(g), components=comps, calibrations=cals)
+    assert hasattr(deco, "engine")
+    check(res, g, 6)
+    assert_allclose([float(c.background_norm) for c in res.calibrations.values()], g["background_norm"], rtol=1e-4)
+    shifts = np.stack([c.shift_xy.detach().cpu().numpy()[0] for c in res.calibrations.values()])
+    assert_allclose(shifts, g["shift_xy"], rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("JD_TEST_PENDING"),
+                    reason="written at the end of round 1 without GPU minutes left; set JD_TEST_PENDING=1, and drop this "
+                           "mark after the first green run")
+def test_shift_kernels_match_oracle():
+    """jd_shift_forward / jd_shift_backward against the oracle's 4-tap restatement (pinned to shift_image_torch)."""
+    from jolideco_b200 import _lib
+
+    g = load_golden("shift_kat.npz")
+    image, cot = g["image"].astype(np.float32), g["cot"].astype(np.float32)
+    H, W = image.shape
+    dev = lambda a, dt=torch.float32: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(DEV)  # noqa: E731
+    s = torch.cuda.current_stream().cuda_stream
+    for sx, sy, scale in g["cases"]:
+        shift = dev(np.array([sx, sy]))
+        img, d = dev(image), dev(cot)
+        out, dflux = torch.empty_like(img), torch.ones_like(img)
+        dshift = torch.zeros(2, dtype=torch.float64, device=DEV)
+        _lib.call("jd_shift_forward", img.data_ptr(), shift.data_ptr(), int(scale), H, W, out.data_ptr(), s)
+        _lib.call("jd_shift_backward", d.data_ptr(), img.data_ptr(), shift.data_ptr(), int(scale), H, W, dflux.data_ptr(), 1,
+                  dshift.data_ptr(), s)
+        ref, d_dy, d_dx = O.shift_image(image.astype(np.float64), sy, sx, int(scale), return_grads=True)
+        assert np.abs(out.cpu().numpy() - ref).max() <= 3e-6 * np.abs(ref).max()
+        adj = O.shift_image_adjoint(cot.astype(np.float64), sy, sx, int(scale)) + 1
+        assert np.abs(dflux.cpu().numpy() - adj).max() <= 3e-6 * np.abs(adj).max()
+        assert_allclose(dshift.cpu().numpy(), [(cot * d_dx).sum(), (cot * d_dy).sum()], rtol=2e-5)
