@@ -104,6 +104,10 @@ class SpatialFluxComponent(nn.Module):
         return self._flux_upsampled_error
 
     @property
+    def flux_upsampled_error_numpy(self):
+        return self.flux_upsampled_error.detach().cpu().numpy()[0, 0]
+
+    @property
     def flux_numpy(self):
         return self.flux.detach().cpu().numpy()[0, 0]
 
@@ -143,6 +147,15 @@ class FluxComponents(nn.ModuleDict):
     @property
     def fluxes_upsampled_numpy(self):
         return self.to_numpy()
+
+    @property
+    def flux_upsampled_total(self):
+        """Total summed flux as a tensor (models/core.py:746-757)."""
+        values = list(self.values())
+        flux = torch.zeros_like(values[0].flux_upsampled)
+        for component in values:
+            flux = flux + component.flux_upsampled
+        return flux
 
     @property
     def flux_upsampled_total_numpy(self):

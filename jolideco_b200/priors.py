@@ -155,6 +155,54 @@ class GaussianMixtureModel(nn.Module):
         return self.means.detach().cpu().numpy()
 
     @property
+    def covariances_numpy(self):
+        return self.covariances.detach().cpu().numpy()
+
+    @property
+    def weights_numpy(self):
+        return self.weights.detach().cpu().numpy()
+
+    @property
+    def precisions_cholesky_numpy(self):
+        return self.precisions_cholesky.detach().cpu().numpy()
+
+    @property
+    def log_weights_numpy(self):
+        return np.log(self.weights_numpy)
+
+    @property
+    def log_det_cholesky_numpy(self):
+        return np.log(np.diagonal(self.precisions_cholesky_numpy, axis1=1, axis2=2)).sum(axis=1)
+
+    @property
+    def covariance_det(self):
+        """Determinant of the first component's covariance (gmm.py:414-417)."""
+        return np.linalg.det(self.covariances_numpy[0])
+
+    def is_equal(self, other):
+        """Same shapes and close covariances (gmm.py:447-452)."""
+        if self.covariances.shape != other.covariances.shape:
+            return False
+        return bool(np.allclose(self.covariances_numpy, other.covariances_numpy))
+
+    def reduce_to_topk(self, k):
+        """The k components with the largest weights (gmm.py:391-412)."""
+        idx = np.argsort(self.weights_numpy)[::-1][:k]
+        return self.from_numpy(means=self.means_numpy[idx], covariances=self.covariances_numpy[idx],
+                               weights=self.weights_numpy[idx], meta=self.meta)
+
+    def estimate_log_prob_numpy(self, x):
+        """Host (float64 numpy) evaluation of the per-component log likelihood (gmm.py:242-260) - setup-time
+        inspection only; the MAP path uses the CUDA kernels."""
+        x = np.asarray(x, dtype=np.float64)
+        out = np.empty((x.shape[0], self.n_components))
+        for k, (mu, L) in enumerate(zip(self.means_numpy.astype(np.float64), self.precisions_cholesky_numpy.astype(np.float64))):
+            y = x @ L - mu @ L
+            out[:, k] = np.sum(np.square(y) * self.pixel_weights_numpy, axis=1)
+        return (-0.5 * (self.n_features * np.log(2 * np.pi) + out) + self.log_det_cholesky_numpy
+                + self.log_weights_numpy)
+
+    @property
     def pixel_weights_numpy(self):
         if self.meta.stride is None:
             weights = np.ones(self.patch_shape)
@@ -237,6 +285,10 @@ class GMMPatchPrior(Prior):
     @property
     def log_like_weight(self):
         return self.stride**2 / (self.patch_shape[0] * self.patch_shape[1])
+
+    @property
+    def overlap(self):
+        return max(self.patch_shape) - self.stride
 
     def draw_shifts(self):
         """The two randint draws of `cycle_spin` (utils/torch.py:108-116): (row shift, col shift)."""

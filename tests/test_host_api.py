@@ -112,3 +112,26 @@ def test_trace_table_indexing_like_the_reference():
     np.testing.assert_array_equal(t["dataset-0"], [0.0, 2.0, 4.0, 6.0])
     assert len(t[-2:]) == 2 and t[-2:][0]["total"] == 2.0
     assert t.to_dict()["total"] == [0.0, 1.0, 2.0, 3.0]
+
+
+def test_gmm_numpy_accessors_and_host_log_prob():
+    means, cov, w = small_gmm(K=6, seed=3)
+    gmm = J.GaussianMixtureModel.from_numpy(means, cov, w, meta=J.GaussianMixtureModelMeta(stride=4))
+    assert gmm.covariances_numpy.shape == (6, 64, 64) and gmm.weights_numpy.shape == (6,)
+    np.testing.assert_allclose(gmm.log_weights_numpy, np.log(w), rtol=1e-6)
+    np.testing.assert_allclose(gmm.log_det_cholesky_numpy, gmm.log_det_cholesky.numpy(), rtol=1e-5)
+    assert gmm.is_equal(gmm) and not gmm.is_equal(gmm.reduce_to_topk(3))
+    top = gmm.reduce_to_topk(2)
+    assert top.n_components == 2
+    np.testing.assert_allclose(np.sort(top.weights_numpy), np.sort(w)[-2:], rtol=1e-6)
+    x = np.random.default_rng(0).normal(0, 0.1, size=(7, 64))
+    lp = gmm.estimate_log_prob_numpy(x)
+    ref = O.GMM(means, cov, w, dtype=np.float64).estimate_log_prob(x.astype(np.float64))
+    assert lp.shape == (7, 6)
+    np.testing.assert_allclose(lp, ref, rtol=1e-4)
+    prior = J.GMMPatchPrior(gmm=gmm)
+    assert prior.overlap == 4
+    comps = J.FluxComponents()
+    comps["a"] = J.SpatialFluxComponent.from_numpy(flux=np.full((8, 8), 2.0), prior=J.UniformPrior())
+    comps["b"] = J.SpatialFluxComponent.from_numpy(flux=np.full((8, 8), 3.0), prior=J.UniformPrior())
+    np.testing.assert_allclose(comps.flux_upsampled_total.detach().numpy()[0, 0], 5.0, rtol=1e-6)
