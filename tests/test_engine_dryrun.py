@@ -1,0 +1,157 @@
+"""Dry run of the fused engine's HOST logic on CPU: the C-ABI calls are recorded instead of executed (no kernel runs,
+no result is checked here - parity is the GPU tests' job).  Guards the launch sequence of a step / joint step / trace
+evaluation and the Python paths around it (calibration routing, accumulator offsets) against host-side regressions."""
+import contextlib
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import jolideco_b200 as J
+from jolideco_b200 import engine as E
+from jolideco_b200 import ops
+from jolideco_b200.core import MAPDeconvolver
+
+
+@pytest.fixture
+def recorder(monkeypatch):
+    calls = []
+
+    def fake_call(name, *args):
+        calls.append((name, args))
+
+    monkeypatch.setattr(E._lib, "call", fake_call)
+    monkeypatch.setattr(ops, "require_device", lambda *a, **k: None)
+    monkeypatch.setattr(ops, "_check", lambda t, name, dtype=torch.float32: t)
+    monkeypatch.setattr(ops, "use_stream_k", lambda P, device: False)
+    monkeypatch.setattr(E.MapEngine, "_s", lambda self: 0)
+    monkeypatch.setattr(ops, "_stream", lambda: 0)
+    monkeypatch.setattr(torch.cuda, "device", lambda *a, **k: contextlib.nullcontext())
+    return calls
+
+
+def fake_packed(K=4, upper_tri=True, zero_mean=False):
+    z = torch.zeros
+    return types.SimpleNamespace(K=K, D=64, upper_tri=upper_tri, zero_mean=zero_mean, Lw=z(K, 64, 64), mw=z(K, 64),
+                                 ck=z(K), Lam=z(K, 64, 64), bk=z(K, 64), Bt=z(K * 32768, dtype=torch.uint8),
+                                 _Bt_lam=z(K * 32768, dtype=torch.uint8), _Bt16=None, device=torch.device("cpu"))
+
+
+def dataset(n=32, k=5, f=1, **kw):
+    H = n // f
+    return E.DatasetBuffers(torch.ones(H, H), torch.ones(n, n), torch.ones(k, k), torch.ones(H, H), f, **kw)
+
+
+def names(calls):
+    return [c[0] for c in calls]
+
+
+def test_reference_step_launch_sequence(recorder):
+    eng = E.MapEngine(torch.zeros(32, 32), [dataset()], prior=dict(packed=fake_packed(), stride=4, marginalize=False,
+                                                                   backend=1), use_graph=False,
+                      shift_table=np.zeros((4, 2), dtype=np.int32))
+    eng.step(0)
+    assert names(recorder) == ["jd_step_begin_flux", "jd_conv_forward_direct", "jd_poisson_forward_backward",
+                               "jd_conv_backward_direct", "jd_gmm_prior_forward_tc", "jd_gmm_prior_backward_max_tri",
+                               "jd_adam_fold_step_dev"]
+    assert E._STATS["launches"] >= 7
+    del recorder[:]
+    eng.trace_enqueue(torch.zeros(eng.n_trace, dtype=torch.float64))
+    assert names(recorder) == ["jd_step_begin", "jd_conv_forward_direct", "jd_poisson_forward_backward",
+                               "jd_gmm_prior_forward_tc"]
+
+
+def test_logsumexp_and_uniform_prior_sequences(recorder):
+    eng = E.MapEngine(torch.zeros(32, 32), [dataset()], prior=dict(packed=fake_packed(), stride=4, marginalize=True,
+                                                                   backend=1), use_graph=False)
+    eng.step(0)
+    assert names(recorder)[-3:] == ["jd_gmm_prior_forward_tc", "jd_gmm_prior_backward_lse_tc", "jd_adam_fold_step_dev"]
+    del recorder[:]
+    eng = E.MapEngine(torch.zeros(32, 32), [dataset()], prior=None, use_graph=False)
+    eng.step(0)
+    assert names(recorder) == ["jd_step_begin_flux", "jd_conv_forward_direct", "jd_poisson_forward_backward",
+                               "jd_conv_backward_direct", "jd_adam_step_dev"]
+
+
+def test_fft_path_is_taken_for_large_psfs(recorder):
+    eng = E.MapEngine(torch.zeros(64, 64), [dataset(n=64, k=31)], prior=None, use_graph=False)
+    eng.step(0)
+    assert "jd_conv_forward_fft" in names(recorder) and "jd_conv_backward_fft" in names(recorder)
+    assert "jd_conv_forward_direct" not in names(recorder)
+
+
+def test_calibration_accumulators_and_shift_sequence(recorder):
+    logb = torch.zeros(1)
+    shift = torch.tensor([0.4, -0.7])
+    ds = [dataset(bkg_log_norm=logb, train_bkg_norm=True, shift_xy=shift, train_shift=True),
+          dataset(bkg_log_norm=torch.zeros(1), train_bkg_norm=True)]
+    eng = E.MapEngine(torch.zeros(32, 32), ds, prior=None, use_graph=False)
+    assert eng.flux_s is not None and eng.acc.numel() == 5
+    eng.step(0)
+    seq = names(recorder)
+    assert seq == ["jd_step_begin_flux", "jd_shift_forward", "jd_conv_forward_direct", "jd_poisson_forward_backward",
+                   "jd_adam_scalar_step_dev", "jd_conv_backward_direct", "jd_shift_backward", "jd_adam_scalar_step_dev",
+                   "jd_adam_step_dev"]
+    base = eng.acc.data_ptr()
+    poisson = recorder[3][1]
+    assert poisson[6] == base and poisson[7] == base + 16          # loss sum -> acc[0], dlogb -> acc[2]
+    conv_b, shift_b = recorder[5][1], recorder[6][1]
+    assert conv_b[3] == eng.dflux_s.data_ptr() and conv_b[4] == 0  # conv adjoint writes the gradient of the shifted flux
+    assert shift_b[6] == eng.dflux_l.data_ptr() and shift_b[8] == base + 24  # ... folded into dflux_l, dshift -> acc[3:5]
+    assert recorder[7][1][5] == 2                                 # Adam on the (shift_x, shift_y) pair
+    # joint step: the second dataset's calibration gradients start from cleared accumulators
+    del recorder[:]
+    eng.joint_step()
+    seq = names(recorder)
+    i = seq.index("jd_step_begin")
+    assert seq[i - 1] == "jd_adam_scalar_step_dev" and recorder[i][1][9] == base + 16 and recorder[i][1][10] == 3
+    assert seq.count("jd_poisson_forward_backward") == 2 and seq[-1] == "jd_adam_step_dev"
+    # a dataset without shift keeps the direct route into dflux_l (accumulating for the second dataset)
+    conv_b2 = [c for c in recorder if c[0] == "jd_conv_backward_direct"][1][1]
+    assert conv_b2[3] == eng.dflux_l.data_ptr() and conv_b2[4] == 1
+
+
+def test_calibration_routing(monkeypatch):
+    cals = J.NPredCalibrations()
+    cals["a"] = J.NPredCalibration(background_norm=1.2)
+    assert MAPDeconvolver._calibrations_fusable(cals)            # shifts at 0: background norm only
+    cals["b"] = J.NPredCalibration(shift_x=0.3, shift_y=0.0)
+    monkeypatch.delenv("JD_FUSED_SHIFT", raising=False)
+    assert not MAPDeconvolver._calibrations_fusable(cals)        # non-zero shift: autograd path by default
+    monkeypatch.setenv("JD_FUSED_SHIFT", "1")
+    assert MAPDeconvolver._calibrations_fusable(cals)
+    cals["c"] = J.NPredCalibration(psf_scale=1.1)
+    assert not MAPDeconvolver._calibrations_fusable(cals)        # psf rescaling is not covered
+    assert MAPDeconvolver._shift_is_zero(cals["a"]) and not MAPDeconvolver._shift_is_zero(cals["b"])
+
+
+def test_deconvolver_run_builds_the_engine_with_calibrations(recorder, monkeypatch):
+    """`MAPDeconvolver.run` end to end on CPU with the kernels recorded: datasets -> TotalLoss -> DatasetBuffers (with
+    the calibration's parameter storage) -> engine steps and per-epoch traces -> result object."""
+    monkeypatch.setenv("JD_FUSED_SHIFT", "1")
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    rng = np.random.default_rng(0)
+    A = rng.normal(0, 0.05, size=(3, 64, 64))
+    gmm = J.GaussianMixtureModel.from_numpy(np.zeros((3, 64)), A @ A.transpose(0, 2, 1) + 0.01 * np.eye(64),
+                                            np.full(3, 1 / 3), meta=J.GaussianMixtureModelMeta(stride=4))
+    prior = J.GMMPatchPrior(gmm=gmm, generator=torch.Generator().manual_seed(0))
+    comp = J.SpatialFluxComponent.from_numpy(flux=np.ones((24, 24)), upsampling_factor=2, prior=prior)
+    ds = {n: dict(counts=rng.poisson(2.0, size=(24, 24)).astype(np.float32), psf=np.full((4, 4), 1 / 16.0),
+                  exposure=np.ones((24, 24)), background=np.full((24, 24), 0.5)) for n in ("a", "b")}
+    cals = J.NPredCalibrations()
+    cals["a"] = J.NPredCalibration(shift_x=0.4, shift_y=-0.2, background_norm=1.1)
+    cals["b"] = J.NPredCalibration(background_norm=0.9, frozen=True)
+    deco = MAPDeconvolver(n_epochs=2, display_progress=False, use_cuda_graph=False)
+    deco.device = torch.device("cpu")  # dry run: no kernel is executed
+    res = deco.run(datasets=ds, components=comp, calibrations=cals)
+    eng = deco.engine
+    a, b = eng.datasets
+    assert a.f == 2 and a.shift_xy is not None and a.train_shift and a.train_bkg_norm
+    assert a.shift_xy.data_ptr() == cals["a"].shift_xy.data_ptr()      # the engine updates the parameter in place
+    assert b.shift_xy is None and not b.train_bkg_norm and b.bkg_log_norm is not None
+    seq = names(recorder)
+    assert seq.count("jd_shift_forward") == 2 * (1 + 1) + 1            # warm-up + 2 steps + 2 traces for dataset a
+    assert seq.count("jd_adam_fold_step_dev") == 2 * 2 + 1            # 2 epochs x 2 datasets + warm-up
+    assert len(res.trace_loss) == 2 and set(res.trace_loss.colnames) >= {"total", "dataset-a", "dataset-b"}
+    assert res.flux_upsampled_total.shape == (48, 48)
