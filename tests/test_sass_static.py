@@ -1,0 +1,65 @@
+"""Static checks on the SASS of the built library (cuobjdump, no GPU):
+  * the tensor-core kernels really are tcgen05 / TMEM / bulk-TMA code (UTCHMMA, LDTM / STTM, UBLKCP);
+  * the direct convolution stages its tiles with zero-filling cp.async (LDGSTS ... ZFILL);
+  * in every tensor-core kernel the epilogue's slot-release `mbarrier.arrive` is issued AFTER all arithmetic that
+    consumes the shared-memory / TMEM loads of that slot.  ptxas once hoisted it above those consumers, which let the
+    producer's next bulk copy overtake loads in flight (rare corrupted rows, DESIGN.md 4.1 "Slot-release ordering");
+    `mbar_arrive_after` pins it - this test fails if a compiler or code change undoes that."""
+import re
+import shutil
+import subprocess
+
+import pytest
+
+from jolideco_b200 import build
+
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="needs cuobjdump")
+
+
+@pytest.fixture(scope="module")
+def functions():
+    lib = build.build()
+    txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
+    out = {}
+    for chunk in re.split(r"\n\s*Function : ", txt)[1:]:
+        name, body = chunk.split("\n", 1)
+        out[name.strip()] = [line for line in body.split("\n") if re.match(r"\s+/\*[0-9a-f]{4,5}\*/", line)]
+    return out
+
+
+def test_tensor_core_kernels_use_tcgen05_tmem_and_bulk_tma(functions):
+    kernels = {n: b for n, b in functions.items() if re.search(r"gmm_fwd_tc|gmm_bwd_lse_tc|gmm_fwd_tc16", n)}
+    assert len(kernels) >= 13  # 4 + 4 forward variants (tile / stream-K), 4 FP16, 1 logsumexp backward
+    for name, body in kernels.items():
+        text = "\n".join(body)
+        for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UBLKCP", "UTCBAR"):
+            assert mnemonic in text, f"{mnemonic} missing in {name}"
+
+
+def test_direct_convolution_stages_with_zero_filling_cp_async(functions):
+    kernels = {n: b for n, b in functions.items() if "conv3_kernel" in n}
+    assert len(kernels) == 24  # 2 directions x 3 tile shapes x 4 tap tails
+    for name, body in kernels.items():
+        text = "\n".join(body)
+        assert "LDGSTS" in text and "ZFILL" in text, name
+
+
+def test_slot_release_arrive_follows_the_consumers_of_the_loads(functions):
+    checked = 0
+    for name, body in functions.items():
+        if not re.search(r"gmm_fwd_tc|gmm_bwd_lse_tc|gmm_fwd_tc16", name):
+            continue
+        arrives = [i for i, line in enumerate(body)
+                   if "SYNCS.ARRIVE.TRANS64.A1T0" in line and "@" in line.split("SYNCS")[0]]
+        assert arrives, f"no predicated slot-release arrive found in {name}"
+        for i in arrives:
+            last_ld = max(k for k in range(i) if re.search(r"\bLDTM\b|LDTM\.", body[k]))
+            math_before = sum(1 for k in range(last_ld + 1, i) if re.search(r"FFMA|FADD|FMUL", body[k]))
+            math_after = 0
+            for k in range(i + 1, min(i + 200, len(body))):
+                if re.search(r"\bBRA\b|\bEXIT\b", body[k]):
+                    break
+                math_after += bool(re.search(r"FFMA|FADD|FMUL", body[k]))
+            assert math_before >= 40 and math_after == 0, (name, math_before, math_after)
+            checked += 1
+    assert checked >= 13
