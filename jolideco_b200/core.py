@@ -191,8 +191,6 @@ class MAPDeconvolver:
         """Run the MAP deconvolver (core.py:149-282); returns a `MAPDeconvolverResult`."""
         if self.stop_early and datasets_validation is None:
             raise ValueError("Early stopping requires providing test datasets")
-        if self.compute_error:
-            raise NotImplementedError("compute_error (Hessian-vector errors, loss.py:263-300) is not accelerated yet")
         ops.require_device(self.device)
         if isinstance(components, SpatialFluxComponent):
             components = {self._default_flux_component: components}
@@ -230,6 +228,16 @@ class MAPDeconvolver:
                 self._run_fused(total_loss, components, len(datasets))
             else:
                 self._run_autograd(total_loss, components, calibrations)
+
+        if self.compute_error:
+            # The reference's estimate is sqrt(1 / (H 1)) with H 1 a vector-Hessian product of TotalLoss.__call__
+            # (loss.py:263-300).  PoissonLoss.evaluate re-wraps the dataset losses in a fresh torch.tensor (loss.py:71),
+            # which cuts the graph: H 1 is identically 0 and the reference returns inf everywhere (checked with the
+            # imported reference, uniform and GMM priors, f = 1 and 2).  Reproduced as is rather than "fixed".
+            log.warning("compute_error=True: the reference's Hessian estimate is identically zero (detached dataset "
+                        "losses, loss.py:71), flux errors are inf as in the reference")
+            components.set_flux_errors({name: torch.full_like(c.flux_upsampled.detach(), float("inf"))
+                                        for name, c in components.items()})
 
         return MAPDeconvolverResult(config=self.to_dict(), components=components, components_init=components_init,
                                     trace_loss=total_loss.trace, calibrations=calibrations,

@@ -142,7 +142,7 @@ def test_deconvolver_run_builds_the_engine_with_calibrations(recorder, monkeypat
     cals = J.NPredCalibrations()
     cals["a"] = J.NPredCalibration(shift_x=0.4, shift_y=-0.2, background_norm=1.1)
     cals["b"] = J.NPredCalibration(background_norm=0.9, frozen=True)
-    deco = MAPDeconvolver(n_epochs=2, display_progress=False, use_cuda_graph=False)
+    deco = MAPDeconvolver(n_epochs=2, display_progress=False, use_cuda_graph=False, compute_error=True)
     deco.device = torch.device("cpu")  # dry run: no kernel is executed
     res = deco.run(datasets=ds, components=comp, calibrations=cals)
     eng = deco.engine
@@ -155,3 +155,5 @@ def test_deconvolver_run_builds_the_engine_with_calibrations(recorder, monkeypat
     assert seq.count("jd_adam_fold_step_dev") == 2 * 2 + 1            # 2 epochs x 2 datasets + warm-up
     assert len(res.trace_loss) == 2 and set(res.trace_loss.colnames) >= {"total", "dataset-a", "dataset-b"}
     assert res.flux_upsampled_total.shape == (48, 48)
+    err = res.components["flux"].flux_upsampled_error_numpy   # compute_error: inf everywhere, as in the reference
+    assert err.shape == (48, 48) and np.all(np.isinf(err))
