@@ -13,6 +13,18 @@ from .models import (  # noqa: F401
     NPredModels,
     SpatialFluxComponent,
 )
+from .norms import (  # noqa: F401
+    NORMS_REGISTRY,
+    ASinhImageNorm,
+    ATanImageNorm,
+    FixedMaxImageNorm,
+    IdentityImageNorm,
+    ImageNorm,
+    LogImageNorm,
+    MaxImageNorm,
+    PowerImageNorm,
+    SigmoidImageNorm,
+)
 from .priors import (  # noqa: F401
     GaussianMixtureModel,
     GaussianMixtureModelMeta,

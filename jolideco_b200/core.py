@@ -20,6 +20,7 @@ from ._lib import JolidecoB200Error
 from .engine import DatasetBuffers, MapEngine
 from .loss import TotalLoss
 from .models import FluxComponents, SpatialFluxComponent
+from .norms import IdentityImageNorm
 from .priors import GMMPatchPrior, UniformPrior, default_backend
 
 log = logging.getLogger(__name__)
@@ -117,7 +118,8 @@ class MAPDeconvolver:
         prior = comps[0].prior
         if isinstance(prior, UniformPrior):
             return True
-        return isinstance(prior, GMMPatchPrior) and prior.norm is None and prior.gmm.n_features == ops.PD
+        identity = prior.norm is None or isinstance(prior.norm, IdentityImageNorm)  # other norms: autograd path
+        return isinstance(prior, GMMPatchPrior) and identity and prior.gmm.n_features == ops.PD
 
     def _group(self):
         if self.mode != "joint" or not torch.distributed.is_available() or not torch.distributed.is_initialized():

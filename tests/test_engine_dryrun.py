@@ -157,3 +157,31 @@ def test_deconvolver_run_builds_the_engine_with_calibrations(recorder, monkeypat
     assert res.flux_upsampled_total.shape == (48, 48)
     err = res.components["flux"].flux_upsampled_error_numpy   # compute_error: inf everywhere, as in the reference
     assert err.shape == (48, 48) and np.all(np.isinf(err))
+
+
+def test_engine_support_matrix():
+    """Which configurations take the fused engine and which the autograd path (core.py `_engine_supported`)."""
+    rng = np.random.default_rng(1)
+    A = rng.normal(0, 0.05, size=(2, 64, 64))
+    gmm = J.GaussianMixtureModel.from_numpy(np.zeros((2, 64)), A @ A.transpose(0, 2, 1) + 0.01 * np.eye(64),
+                                            np.full(2, 0.5), meta=J.GaussianMixtureModelMeta(stride=4))
+
+    def comps(prior, **kw):
+        c = J.FluxComponents()
+        c["flux"] = J.SpatialFluxComponent.from_numpy(flux=np.ones((16, 16)), prior=prior, **kw)
+        return c
+
+    deco = MAPDeconvolver(display_progress=False)
+    assert deco._engine_supported(comps(J.UniformPrior()), None)
+    assert deco._engine_supported(comps(J.GMMPatchPrior(gmm=gmm)), None)
+    assert deco._engine_supported(comps(J.GMMPatchPrior(gmm=gmm, norm=J.IdentityImageNorm())), None)
+    assert not deco._engine_supported(comps(J.GMMPatchPrior(gmm=gmm, norm=J.ASinhImageNorm(alpha=0.5))), None)
+    assert not deco._engine_supported(comps(J.UniformPrior(), frozen=True), None)
+    assert not MAPDeconvolver(optimizer_type="sgd")._engine_supported(comps(J.UniformPrior()), None)
+    assert not MAPDeconvolver(fused=False)._engine_supported(comps(J.UniformPrior()), None)
+    two = comps(J.UniformPrior())
+    two["more"] = J.SpatialFluxComponent.from_numpy(flux=np.ones((16, 16)), prior=J.UniformPrior())
+    assert not deco._engine_supported(two, None)
+    # a trainable norm's parameters reach the optimiser through the component (models/core.py: components.parameters())
+    with_norm = comps(J.GMMPatchPrior(gmm=gmm, norm=J.ASinhImageNorm(alpha=0.5)))
+    assert len(list(with_norm.parameters())) == 3
