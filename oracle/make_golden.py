@@ -376,6 +376,45 @@ def golden_calibration_shift():
         print(tag, "norms", out["background_norm"], "shift_xy", out["shift_xy"].tolist(), "total", out["trace_total"][-1])
 
 
+def golden_joint_objective():
+    """The joint objective of `mode="joint"`: TotalLoss.__call__ = sum_d L_d - beta * prior (loss.py:257-261).
+    Value from the reference's own call; gradient w.r.t. the flux assembled from the reference's components with
+    autograd (per-dataset `loss_function(npred_model.evaluate(fluxes), counts)` and the prior) - `TotalLoss.__call__`
+    itself detaches the dataset terms (loss.py:71), so its own backward would miss them."""
+    rng = np.random.default_rng(51)
+    datasets = {str(i): synthetic_dataset(rng, 32, 36, 7, 7) for i in range(3)}
+    flux = rng.gamma(20, size=(32, 36)) / 10
+    gmm_arrays = synthetic_gmm_arrays(8, seed=9)
+    beta = 0.7
+    out = {}
+    pack_datasets(datasets, "ds", out)
+    out["flux"], out["beta"] = flux, beta
+    out["gmm_means"], out["gmm_cov"], out["gmm_w"] = gmm_arrays
+    for marginalize, tag in ((False, "max"), (True, "lse")):
+        gmm = GaussianMixtureModel.from_numpy(*gmm_arrays, meta=GaussianMixtureModelMeta(stride=4))
+        gen = torch.Generator().manual_seed(12)
+        prior = GMMPatchPrior(gmm=gmm, stride=4, generator=gen, marginalize=marginalize)
+        comps = FluxComponents()
+        comps["flux-1"] = SpatialFluxComponent.from_numpy(flux=flux, upsampling_factor=1, prior=prior)
+        total_loss = TotalLoss.from_datasets_and_components(datasets=datasets, components=comps, beta=beta)
+        g = torch.Generator()
+        g.set_state(gen.get_state())
+        out[f"{tag}_shift"] = np.array(peek_and_advance(g))
+        fluxes = comps.to_flux_tuple()
+        out[f"{tag}_total"] = float(total_loss(fluxes))
+        # intended gradient, from the reference's components (same shift: rewind the generator)
+        gen.manual_seed(12)
+        fl = tuple(f.detach().clone().requires_grad_(True) for f in fluxes)
+        value = -beta * total_loss.prior_loss(fluxes=fl)
+        for counts, npred_model in total_loss.poisson_loss.iter_by_dataset:
+            value = value + total_loss.poisson_loss.loss_function(npred_model.evaluate(fluxes=fl), counts)
+        value.backward()
+        out[f"{tag}_total_components"] = float(value)
+        out[f"{tag}_dflux"] = fl[0].grad.numpy()[0, 0]
+    np.savez_compressed(os.path.join(OUT, "joint_objective.npz"), **out)
+    print("joint_objective.npz", out["max_total"], out["max_total_components"], out["lse_total"])
+
+
 def golden_shift():
     """`shift_image_torch` (utils/torch.py:196-223) values and autograd gradients (w.r.t. the image and shift_xy)
     for non-trivial sub-pixel shifts, fp32 and fp64; plus one whole-pixel shift (values only: the interpolant has a
@@ -409,9 +448,13 @@ if __name__ == "__main__":
         golden_shift()
         golden_calibration_shift()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "joint":
+        golden_joint_objective()
+        sys.exit(0)
     golden_kat()
     golden_prior_step()
     golden_runs()
     golden_calibration()
     golden_shift()
     golden_calibration_shift()
+    golden_joint_objective()

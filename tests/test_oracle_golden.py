@@ -261,3 +261,28 @@ def test_run_with_shift_calibration_matches_imported_reference(name, f):
     assert_allclose([t["total"] for t in trace], g["trace_total"], rtol=2e-5)
     assert_allclose(norms, g["background_norm"], rtol=1e-4)
     assert_allclose(np.stack(shifts_xy), g["shift_xy"], rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("tag,marginalize", [("max", False), ("lse", True)])
+def test_joint_objective_matches_imported_reference(tag, marginalize):
+    """The objective of `mode="joint"` (one Adam step on sum_d L_d - beta * prior, sharded over GPUs): value against
+    the reference's `TotalLoss.__call__` (loss.py:257-261), gradient against autograd through the reference's own
+    components (its `__call__` detaches the dataset terms, loss.py:71)."""
+    g = load_golden("joint_objective.npz")
+    datasets = [O.prepare_dataset(d, f=1) for d in unpack_datasets(g)]
+    gmm = O.GMM(g["gmm_means"], g["gmm_cov"], g["gmm_w"])
+    flux = g["flux"].astype(np.float32)
+    theta = np.log(flux)
+    total, dtheta = O.joint_loss_and_grad(theta, datasets, float(g["beta"]), gmm, g[f"{tag}_shift"], 4, marginalize)
+    assert_allclose(total, g[f"{tag}_total"], rtol=2e-6)
+    assert_allclose(g[f"{tag}_total"], g[f"{tag}_total_components"], rtol=1e-6)
+    dflux = dtheta / flux  # the oracle differentiates w.r.t. theta = log flux
+    ref = g[f"{tag}_dflux"]
+    assert np.abs(dflux - ref).max() <= 2e-5 * np.abs(ref).max()
+    # shards (datasets dealt to 2 ranks, prior rows split) add up to the whole: what the all-reduce relies on
+    ny = (flux.shape[0] - 8) // 4 + 1
+    parts = [O.joint_loss_and_grad(theta, datasets, float(g["beta"]), gmm, g[f"{tag}_shift"], 4, marginalize,
+                                   dataset_index=idx, rows=rows)
+             for idx, rows in (([0, 2], (0, ny // 2)), ([1], (ny // 2, ny)))]
+    assert_allclose(sum(p[0] for p in parts), total, rtol=1e-6)
+    assert np.abs(sum(p[1] for p in parts) - dtheta).max() <= 1e-6 * np.abs(dtheta).max()
