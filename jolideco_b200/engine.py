@@ -13,6 +13,8 @@ Two step semantics (SURVEY.md §7 "semantics of iteration"):
                      `torch.distributed` the datasets are sharded over ranks, the prior is
                      row-block sharded and the flux gradient is all-reduced (NCCL / NVLink).
 """
+import os
+
 import numpy as np
 import torch
 
@@ -164,9 +166,12 @@ class MapEngine:
             if self.marginalize and self.backend in (1, 2):
                 ops._bt_lam(self.packed)
             self.G = torch.empty((max(P, 1), ops.PD), **f32)
-            # bucketed max-mode backward (ops.gmm_backward_workspace) measured slower than the warp-per-patch
-            # kernel at K=256 (profiles/r01_summary.md): not used
+            # bucketed max-mode backward (patches grouped by winning component, Lam_k staged once per 32 patches):
+            # measured slower than the warp-per-patch kernels at 16 129 patches / K = 256 (profiles/r01_summary.md);
+            # JD_BWD_BUCKETED=1 enables it for comparison at larger patch counts
             self.bwd_ws = None
+            if os.environ.get("JD_BWD_BUCKETED", "0") == "1" and not self.marginalize and P > 0:
+                self.bwd_ws = ops.gmm_backward_workspace(P, self.packed.K, self.dev)
             self.dflux_p = torch.zeros_like(theta)
             if shift_table is None:
                 shift_table = np.zeros((1, 2), dtype=np.int32)

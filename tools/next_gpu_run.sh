@@ -10,6 +10,8 @@ echo "== 3. BASELINE configs[2] and [3] (cfg3: 8 x 512^2, 64^2 PSFs; cfg4: 20 x 
 timeout 300 python bench.py --workload cfg3 --steps 30 --no-cpu-baseline --breakdown > gpurun_out/next_bench_cfg3.json 2>/dev/null
 timeout 400 python bench.py --workload cfg4 --steps 10 --no-cpu-baseline --breakdown > gpurun_out/next_bench_cfg4.json 2>/dev/null
 JD_FFT_MIXED=0 timeout 400 python bench.py --workload cfg4 --steps 10 --no-cpu-baseline --no-e2e > gpurun_out/next_bench_cfg4_pow2.json 2>/dev/null
+echo "== 3b. max-mode backward at 65 025 patches: Lam kernel (default there) vs triangular vs bucketed"
+for v in "" "JD_BWD_BUCKETED=1"; do env $v timeout 200 python bench.py --workload joint1024 --steps 20 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('joint1024 $v ms/step', d['ms_per_step'])"; done
 echo "== 4. split-FP16 prior kernel and the batched bootstrap runs"
 timeout 200 python bench.py --steps 50 --no-cpu-baseline --backend 2 > gpurun_out/next_bench_cfg2_fp16.json 2>/dev/null
 timeout 300 python bench.py --workload cfg5 --steps 20 > gpurun_out/next_bench_cfg5.json 2>/dev/null
