@@ -85,12 +85,16 @@ class MapEngine:
     def __init__(self, theta, datasets, prior=None, mask=None, use_log_flux=True, beta=1.0, lr=0.1, betas=(0.9, 0.999),
                  eps=1e-8, shift_table=None, datasets_validation=(), use_graph=True, process_group=None,
                  prior_weight=None, dataset_index=None, n_datasets_global=None, validation_index=None,
-                 n_validation_global=None, counts_shape=None, collective="nccl", stream_k=None):
+                 n_validation_global=None, counts_shape=None, collective="nccl", stream_k=None, overlap=None):
         """theta: 2-D CUDA fp32 tensor updated in place (the component's parameter storage).
         prior: None (uniform) or dict(packed=GMMPacked, stride, marginalize, backend).
         shift_table: (N, 2) int array of pre-drawn (row, col) cycle-spin shifts in consumption order.
         stream_k: stream-K decomposition of the tcgen05 prior forward (None = ops.use_stream_k: only when the
-        patch tiles do not fill the SMs; it buys latency of ONE run, not throughput of concurrent runs)."""
+        patch tiles do not fill the SMs; it buys latency of ONE run, not throughput of concurrent runs).
+        overlap: run the likelihood chain (convolutions, Poisson) and the prior chain (tensor-core forward, backward)
+        of a step on two streams - both only depend on the flux and meet at the Adam kernel; the prior kernels hold one
+        CTA per SM with ~27 KB of shared memory to spare, so the FP32 / FFT kernels co-reside.  None = JD_OVERLAP=1
+        (off by default: written at the end of round 1 without GPU minutes left to validate and time it)."""
         ops.require_device(theta.device)
         self.theta = ops._check(theta, "theta")
         assert theta.ndim == 2
@@ -192,6 +196,8 @@ class MapEngine:
         self._graphs = {}
         self._graph_nodes = {}
         self._capture_stream = None
+        self.overlap = (os.environ.get("JD_OVERLAP", "0") == "1") if overlap is None else bool(overlap)
+        self._side = torch.cuda.Stream(device=self.dev) if self.overlap else None  # created outside any capture
 
     # ------------------------------------------------------------------------------------------
     def _enable_peer(self):
@@ -338,12 +344,35 @@ class MapEngine:
               self.eps, self._s())
 
     # ------------------------------------------------------------------------------------------
+    def _fork(self):
+        """Side stream that has waited for everything enqueued so far on the current stream (event fork; inside a CUDA
+        graph capture this pulls the side stream into the capture)."""
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        self._side.wait_stream(torch.cuda.current_stream(self.dev))
+        return self._side
+
+    def _join(self, side):
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+
     def _step_body(self, i):
         """Reference step for dataset i: total = L_i - beta * prior / D  (core.py:214-229)."""
         d = self.datasets[i]
         self._begin_flux(advance_adam=1, zero_acc=self.acc)
+        has_prior = self.prior is not None and self.P > 0
+        if self.overlap and has_prior:
+            # likelihood chain on the side stream, prior chain on this one; they write disjoint buffers
+            # (conv, dpool, dflux_l, acc[0], acc[2:5] | value, argmax, logp, G, acc[1]) and meet at the Adam kernel
+            side = self._fork()
+            with torch.cuda.stream(side):
+                self._likelihood(d, self.acc.data_ptr(), want_grad=True)
+            self._prior_forward(self.acc.data_ptr() + 8)
+            self._prior_gradient(-self.c)
+            self._join(side)
+            self._adam_fold(-self.beta / self.prior_weight)
+            return
         self._likelihood(d, self.acc.data_ptr(), want_grad=True)
-        if self.prior is not None and self.P > 0:
+        if has_prior:
             self._prior_forward(self.acc.data_ptr() + 8)
             self._prior_gradient(-self.c)
             self._adam_fold(-self.beta / self.prior_weight)
@@ -356,12 +385,28 @@ class MapEngine:
         self._begin_flux(advance_adam=1, zero_acc=self.acc)
         if not self.datasets:
             self.dflux_l.zero_()
-        for j, d in enumerate(self.datasets):
-            if j > 0 and (d.train_bkg_norm or d.train_shift):
-                # the calibration-gradient accumulators acc[2:5] are per dataset: clear what the previous one left
-                _call("jd_step_begin", _p(self.counters), None, 0, None, 0, self.lr, self.b1, self.b2,
-                      _p(self.adam_scalars), self.acc.data_ptr() + 16, 3, self._s())
-            self._likelihood(d, self.acc.data_ptr(), want_grad=True, accumulate=j > 0)
+
+        def likelihoods():
+            for j, d in enumerate(self.datasets):
+                if j > 0 and (d.train_bkg_norm or d.train_shift):
+                    # the calibration-gradient accumulators acc[2:5] are per dataset: clear what the previous one left
+                    _call("jd_step_begin", _p(self.counters), None, 0, None, 0, self.lr, self.b1, self.b2,
+                          _p(self.adam_scalars), self.acc.data_ptr() + 16, 3, self._s())
+                self._likelihood(d, self.acc.data_ptr(), want_grad=True, accumulate=j > 0)
+
+        if self.overlap and self.prior is not None and self.P > 0 and self.datasets:
+            # the prior's forward and per-patch gradient rows G run beside the likelihoods; the fold accumulates into
+            # dflux_l and therefore waits for them
+            side = self._fork()
+            with torch.cuda.stream(side):
+                likelihoods()
+            self._prior_forward(self.acc.data_ptr() + 8)
+            self._prior_gradient(self.c * self.beta)
+            self._join(side)
+            _call("jd_patch_fold", _p(self.G), self.fH, self.fW, _p(self.cur_shift), self.stride, self.rows[0],
+                  self.rows[1], _p(self.dflux_l), 1, self._s())
+            return
+        likelihoods()
         if self.prior is not None:
             self._prior_forward(self.acc.data_ptr() + 8)
             self._prior_backward(self.c * self.beta, self.dflux_l, accumulate=True)
@@ -469,6 +514,20 @@ class MapEngine:
         if refresh_flux:
             self._flux()
         base = self.acc_trace.data_ptr()
+
+        def likelihoods():
+            for j, d in zip(self.dataset_index, self.datasets):
+                self._likelihood(d, base + 8 * j, want_grad=False)
+            for j, d in zip(self.validation_index, self.datasets_validation):
+                self._likelihood(d, base + 8 * (self.Dg + 1 + j), want_grad=False)
+
+        if self.overlap and self.prior is not None and self.P > 0:
+            side = self._fork()
+            with torch.cuda.stream(side):
+                likelihoods()
+            self._prior_forward(base + 8 * self.Dg)
+            self._join(side)
+            return
         for j, d in zip(self.dataset_index, self.datasets):
             self._likelihood(d, base + 8 * j, want_grad=False)
         if self.prior is not None:

@@ -185,3 +185,48 @@ def test_engine_support_matrix():
     # a trainable norm's parameters reach the optimiser through the component (models/core.py: components.parameters())
     with_norm = comps(J.GMMPatchPrior(gmm=gmm, norm=J.ASinhImageNorm(alpha=0.5)))
     assert len(list(with_norm.parameters())) == 3
+
+
+def test_overlap_forks_the_likelihood_chain_and_joins_before_the_update(recorder, monkeypatch):
+    """JD_OVERLAP / overlap=True: likelihood kernels are enqueued on the side stream between a fork and a join, the
+    prior chain on the main stream, and everything that reads both (Adam, fold into dflux_l) after the join."""
+    events = recorder  # same list: interleave stream events with the recorded C-ABI calls
+
+    class FakeStream:
+        def __init__(self, name="side", **kw):
+            self.name = name
+
+        def wait_stream(self, other):
+            events.append((f"{self.name}.wait({other.name})", ()))
+
+    main = FakeStream("main")
+
+    @contextlib.contextmanager
+    def fake_stream_ctx(stream):
+        events.append((f"enter({stream.name})", ()))
+        yield
+        events.append((f"exit({stream.name})", ()))
+
+    monkeypatch.setattr(torch.cuda, "Stream", FakeStream)
+    monkeypatch.setattr(torch.cuda, "stream", fake_stream_ctx)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: main)
+    prior = dict(packed=fake_packed(), stride=4, marginalize=False, backend=1)
+    eng = E.MapEngine(torch.zeros(32, 32), [dataset(), dataset()], prior=prior, use_graph=False, overlap=True)
+    eng.step(0)
+    assert names(events) == ["jd_step_begin_flux", "side.wait(main)", "enter(side)", "jd_conv_forward_direct",
+                             "jd_poisson_forward_backward", "jd_conv_backward_direct", "exit(side)",
+                             "jd_gmm_prior_forward_tc", "jd_gmm_prior_backward_max_tri", "main.wait(side)",
+                             "jd_adam_fold_step_dev"]
+    del events[:]
+    eng.joint_step()
+    seq = names(events)
+    assert seq[:3] == ["jd_step_begin_flux", "side.wait(main)", "enter(side)"]
+    assert seq.index("exit(side)") < seq.index("jd_gmm_prior_forward_tc") < seq.index("main.wait(side)")
+    assert seq[seq.index("main.wait(side)") + 1:] == ["jd_patch_fold", "jd_adam_step_dev"]  # fold accumulates into dflux_l
+    assert seq.count("jd_conv_backward_direct") == 2
+    del events[:]
+    eng.trace_enqueue(torch.zeros(eng.n_trace, dtype=torch.float64))
+    seq = names(events)
+    assert seq[0] == "jd_step_begin" and seq[-2:] == ["jd_gmm_prior_forward_tc", "main.wait(side)"]
+    # default: no side stream at all
+    assert E.MapEngine(torch.zeros(32, 32), [dataset()], prior=prior, use_graph=False)._side is None

@@ -4,6 +4,10 @@
 mkdir -p gpurun_out
 echo "== 1. full GPU suite with the pending tests enabled (shift kernels, fused shift engine path, shift runs)"
 JD_TEST_PENDING=1 timeout 400 python -m pytest tests -x -q -m gpu 2>&1 | tail -6
+echo "== 1b. the same e2e parity tests with the likelihood / prior chains on two streams (JD_OVERLAP=1), then its speed"
+JD_OVERLAP=1 timeout 300 python -m pytest tests/test_gpu_e2e.py tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -3
+for v in 0 1; do JD_OVERLAP=$v timeout 200 python bench.py --steps 100 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('cfg2 JD_OVERLAP=$v ms/step', d['ms_per_step'], 'e2e', d['e2e']['value'])"; done
+for v in 0 1; do JD_OVERLAP=$v timeout 200 python bench.py --workload joint1024 --steps 30 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('joint1024 JD_OVERLAP=$v ms/step', d['ms_per_step'])"; done
 echo "== 2. default bench (headline) with the per-entry breakdown"
 timeout 300 python bench.py --breakdown > gpurun_out/next_bench_cfg2.json 2> gpurun_out/next_bench_cfg2.err
 echo "== 3. BASELINE configs[2] and [3] (cfg3: 8 x 512^2, 64^2 PSFs; cfg4: 20 x 1024^2, 201^2 PSFs on 1280^2 FFTs), one GPU"
