@@ -20,6 +20,7 @@ from .norms import (  # noqa: F401
     FixedMaxImageNorm,
     IdentityImageNorm,
     ImageNorm,
+    InverseCDFImageNorm,
     LogImageNorm,
     MaxImageNorm,
     PowerImageNorm,

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 __all__ = ["ImageNorm", "IdentityImageNorm", "ASinhImageNorm", "MaxImageNorm", "FixedMaxImageNorm", "SigmoidImageNorm",
-           "ATanImageNorm", "LogImageNorm", "PowerImageNorm", "NORMS_REGISTRY"]
+           "ATanImageNorm", "LogImageNorm", "PowerImageNorm", "InverseCDFImageNorm", "NORMS_REGISTRY"]
 
 
 class ImageNorm(torch.nn.Module):
@@ -101,5 +101,36 @@ PowerImageNorm = _make("PowerImageNorm", "power", (("alpha", 1.0, True), ("beta"
                        lambda s, x: torch.pow(x / s.beta, s.alpha), lambda s, y: s.beta * torch.pow(y, 1 / s.alpha),
                        "y = (x / beta) ** alpha, beta a fixed buffer (norms.py:393-413)")
 
-NORMS_REGISTRY = {cls.registry_key: cls for cls in (MaxImageNorm, FixedMaxImageNorm, SigmoidImageNorm, ATanImageNorm,
+
+
+class InverseCDFImageNorm(ImageNorm):
+    """Histogram equalisation: y = cdf(x), piecewise linear between the tabulated points (norms.py:340-369; the
+    interpolation is `interp1d_torch`, utils/torch.py:146-169: segment index searchsorted(xp, x) clipped to
+    [0, len - 2], values taken at (index - 1, index), linear extrapolation outside)."""
+
+    registry_key = "inverse-cdf"
+
+    def __init__(self, x, cdf):
+        super().__init__()
+        if x.shape != cdf.shape:
+            raise ValueError(f"'x' and 'cdf' must have same shape, got {x.shape} and {cdf.shape}")
+        self.x, self.cdf = x, cdf
+
+    @classmethod
+    def from_image(cls, image, bins=1000):
+        weights, edges = torch.histogram(torch.from_numpy(image), bins=bins)
+        cdf = torch.cumsum(weights, 0)
+        cdf = (cdf - cdf.min()) / (cdf - cdf.min()).max()
+        return cls(x=(edges[1:] + edges[:-1]) / 2, cdf=cdf)
+
+    def forward(self, image):
+        hi = torch.clip(torch.searchsorted(self.x, image), 0, len(self.x) - 2)
+        x0, x1, y0, y1 = self.x[hi - 1], self.x[hi], self.cdf[hi - 1], self.cdf[hi]
+        return torch.lerp(y0, y1, (image - x0) / (x1 - x0))
+
+    def to_dict(self):
+        raise NotImplementedError
+
+
+NORMS_REGISTRY = {cls.registry_key: cls for cls in (InverseCDFImageNorm, MaxImageNorm, FixedMaxImageNorm, SigmoidImageNorm, ATanImageNorm,
                                                     ASinhImageNorm, IdentityImageNorm, LogImageNorm, PowerImageNorm)}

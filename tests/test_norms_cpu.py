@@ -54,3 +54,19 @@ def test_constructor_errors_and_positional_arguments():
     with pytest.raises(TypeError):
         N.FixedMaxImageNorm()
     assert "ASinhImageNorm" in str(N.ASinhImageNorm()) and N.PowerImageNorm().beta.requires_grad is False
+
+
+def test_inverse_cdf_norm():
+    """Histogram equalisation (norms.py:340-369 with interp1d_torch, utils/torch.py:146-169); bit-identical to the
+    imported reference when checked in the build container."""
+    img = np.random.default_rng(2).gamma(2.0, size=(40, 40)).astype(np.float32)
+    norm = N.InverseCDFImageNorm.from_image(img, bins=50)
+    assert norm.x.shape == norm.cdf.shape == (50,) and float(norm.cdf[0]) == 0.0 and float(norm.cdf[-1]) == 1.0
+    x = torch.tensor(img[None, None, :7, :7])
+    y = norm(x)
+    ref = np.interp(x.numpy(), norm.x.numpy(), norm.cdf.numpy())
+    inside = (x.numpy() >= float(norm.x[0])) & (x.numpy() <= float(norm.x[-2]))
+    np.testing.assert_allclose(y.numpy()[inside], ref[inside], rtol=1e-5, atol=1e-6)
+    assert N.NORMS_REGISTRY["inverse-cdf"] is N.InverseCDFImageNorm and list(norm.parameters()) == []
+    with pytest.raises(ValueError):
+        N.InverseCDFImageNorm(torch.zeros(3), torch.zeros(4))
