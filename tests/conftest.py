@@ -22,6 +22,22 @@ def pytest_configure(config):
         print(f"[conftest] could not (re)build libjolideco_b200.so: {exc}")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`-m gpu` tests need a CUDA device: skip them (instead of failing at import) on a CPU-only host."""
+    try:
+        import torch
+
+        has_cuda = torch.cuda.is_available()
+    except Exception:
+        has_cuda = False
+    if has_cuda:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (B200); jolideco_b200 has no CPU path")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 def load_golden(name):
     return dict(np.load(os.path.join(GOLDEN, name), allow_pickle=False))
 
