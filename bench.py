@@ -137,7 +137,7 @@ def config_of(workload, args, extra=None):
            "patches": ((fH - 8) // 4 + 1) ** 2 if cfg["K"] else 0, "marginalize": bool(args.marginalize),
            "l2_flush_between_iterations": not args.no_flush,
            "iteration_semantics": ("joint: all D datasets + one prior + one Adam step (TotalLoss.__call__)"
-                                   if workload["name"] in ("joint1024", "cfg3", "cfg4") else
+                                   if workload["name"] in JOINT_WORKLOADS else
                                    "reference step: one dataset + full prior + Adam (core.py:214-229)")}
     if extra:
         out.update(extra)
@@ -206,7 +206,7 @@ def build_run(J, workload, args, device, n_epochs, seed=0, mode="sequential"):
     return deco, comps
 
 
-JOINT_WORKLOADS = ("joint1024", "cfg3", "cfg4")
+JOINT_WORKLOADS = ("joint1024", "cfg3", "cfg4", "joint_tiny")
 
 
 def parallelism_of(joint, world, collective):

@@ -102,6 +102,46 @@ int jd_poisson_forward_backward(const float* conv, const float* background, cons
                                 double* dlogb, int H, int W, int f, int fW, float eps, float grad_scale,
                                 jd_stream_t stream);
 
+/* ---- a1..a7 batched: the likelihood of EVERY dataset of a joint iteration in one launch per direction ----
+ * (models/npred.py:160-191, 210-261; loss.py:35-37, 257-261).  One table entry per dataset, resident in device
+ * memory; all datasets of a call share the geometry (flux grid fH x fW, PSF kh x kw, f in {1, 2}).
+ * forward : conv = PSF (*) (flux . exposure) -> f x f sum-pool -> clip -> + B exp(*bkg_log_norm) -> Poisson cash
+ *           statistic and its gradient, all in the convolution epilogue (conv / npred never reach memory):
+ *             *loss_sum += sum_pix [npred - c log(npred + eps)] + loss_const
+ *             dpool      = grad_scale (1 - c / (npred + eps)) 1{pool >= 0}         (skipped when dpool == NULL)
+ *             *dlogb    += sum_pix grad_scale (1 - c / (npred + eps)) B exp(*bkg_log_norm)
+ *           loss_const = sum_pix 1{c > 1} (c log c - c + 1/2 log(2 pi c)), the counts-only Stirling term of
+ *           nn.PoissonNLLLoss(full=True), computed once per dataset by the caller.
+ * backward: dflux (+)= exposure . (PSF (*)^T up_f(dpool))   (+= when accumulate != 0).
+ * Same direct correlation as jd_conv_*_direct (asymmetric crop of even PSFs included). */
+typedef struct {
+  const float* flux;         /* NPred input: the flux, or this dataset's shifted flux; fH x fW */
+  const float* exposure;     /* fH x fW, may be NULL */
+  const float* psf;          /* kh x kw */
+  const float* background;   /* H x W */
+  const float* counts;       /* H x W */
+  const float* bkg_log_norm; /* 1 float or NULL (NPredCalibration._background_norm) */
+  float* dpool;              /* H x W: forward output / backward input; NULL = loss only */
+  double* loss_sum;          /* accumulator or NULL */
+  double* dlogb;             /* accumulator or NULL */
+  float* dflux;              /* fH x fW: backward output */
+  double loss_const;
+  int32_t accumulate;
+  int32_t reserved;
+} jd_lik_dataset;
+
+/* 1 if (kh, kw, f) is covered by the batched direct kernels (PSF rows of <= 29..32 taps, f in {1, 2}) */
+int jd_likelihood_supported(int kh, int kw, int f);
+int jd_likelihood_forward(const jd_lik_dataset* table_dev, int n_datasets, int fH, int fW, int kh, int kw, int f,
+                          int H, int W, float eps, float grad_scale, jd_stream_t stream);
+int jd_likelihood_backward(const jd_lik_dataset* table_dev, int n_datasets, int fH, int fW, int kh, int kw, int f,
+                           int H, int W, jd_stream_t stream);
+
+/* Measurement helper (bench.py): launches a pure FP32-FMA kernel (8 independent chains per thread, 8 x 256 threads
+ * per SM) and returns the number of floating-point operations it executes, or < 0 on a launch error.  Timed by the
+ * caller with CUDA events, it gives the FP32 pipe peak the direct convolution is compared with. */
+int64_t jd_probe_fp32_fma(int iters, float* out, jd_stream_t stream);
+
 /* ---- a9: GMM log-probabilities of explicit feature vectors (priors/patches/gmm.py:262-281) --
  * logp[p,k] = -0.5 * sum_j (x_p . Lw[k][:,j] - mw[k][j])^2 + ck[k]
  * with the packed constants  Lw[k] = L_k diag(sqrt(w)),  mw[k] = (mu_k L_k) sqrt(w),
@@ -253,6 +293,30 @@ int jd_adam_scalar_step_dev(float* param, float* m, float* v, const double* grad
 int jd_adam_allreduce_peer(const void* grad_ptrs_dev, const void* theta_ptrs_dev, int rank, int world, float* m,
                            float* v, const float* flux, const uint8_t* mask, int use_log_flux, int64_t n,
                            const float* adam_scalars, float beta1, float beta2, float eps, jd_stream_t stream);
+
+/* The same reduce + Adam + broadcast with both cross-rank barriers inside the kernel (flag words in symmetric
+ * memory, release/acquire at system scope), so that a multi-rank joint step is one CUDA graph per rank.
+ * sig_ptrs_dev: device array of `world` pointers to every rank's flag block (64 uint32, zero-initialised, symmetric
+ * memory); sync_state: 2 uint32 of THIS rank's device memory (epoch, finished-CTA count), zero-initialised and never
+ * reset by the caller.  Every rank must launch it the same number of times.  world <= 32. */
+int jd_adam_allreduce_peer_sync(const void* grad_ptrs_dev, const void* theta_ptrs_dev, const void* sig_ptrs_dev,
+                                uint32_t* sync_state, int rank, int world, float* m, float* v, const float* flux,
+                                const uint8_t* mask, int use_log_flux, int64_t n, const float* adam_scalars,
+                                float beta1, float beta2, float eps, jd_stream_t stream);
+
+/* Joint iteration (TotalLoss.__call__, loss.py:257-261), gradient assembly:
+ * jd_adam_joint_step_dev: g = sum_q parts[q] (n_parts images, part_stride floats apart) + scale_b * fold(G)
+ *   (G may be NULL), then chain rule + Adam as jd_adam_step_dev - the whole update of a one-GPU joint step;
+ * jd_grad_reduce_local : out = the same g, no update - this rank's partial gradient of a multi-GPU joint step
+ *   (out may alias parts[0]). */
+int jd_adam_joint_step_dev(float* theta, float* m, float* v, const float* flux, const uint8_t* mask,
+                           const float* parts, int n_parts, int64_t part_stride, const float* G, float scale_b,
+                           int use_log_flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
+                           int row_end, const float* adam_scalars, float beta1, float beta2, float eps,
+                           jd_stream_t stream);
+int jd_grad_reduce_local(const float* parts, int n_parts, int64_t part_stride, const float* G, float scale_b, int fH,
+                         int fW, const int32_t* shift_yx, int stride, int row_begin, int row_end, float* out,
+                         jd_stream_t stream);
 
 /* Fused variants used by the graph-captured step (one launch each instead of two):
  * jd_step_begin_flux = jd_step_begin + jd_flux_forward;

@@ -75,6 +75,18 @@ PROTOTYPES = {
     "jd_gmm_prior_backward_max_tri": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, c_f32p, c_f32p, c_int, c_i32p,
                                       c_float, c_f32p, c_stream],
     "jd_patch_fold": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, c_f32p, c_int, c_stream],
+    "jd_likelihood_supported": [c_int, c_int, c_int],
+    "jd_likelihood_forward": [ctypes.c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
+                              c_stream],
+    "jd_likelihood_backward": [ctypes.c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_stream],
+    "jd_probe_fp32_fma": [c_int, c_f32p, c_stream],
+    "jd_adam_joint_step_dev": [c_f32p, c_f32p, c_f32p, c_f32p, c_u8p, c_f32p, c_int, c_i64, c_f32p, c_float, c_int,
+                               c_int, c_int, c_i32p, c_int, c_int, c_int, c_f32p, c_float, c_float, c_float, c_stream],
+    "jd_grad_reduce_local": [c_f32p, c_int, c_i64, c_f32p, c_float, c_int, c_int, c_i32p, c_int, c_int, c_int, c_f32p,
+                             c_stream],
+    "jd_adam_allreduce_peer_sync": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_int, c_int,
+                                    c_f32p, c_f32p, c_f32p, c_u8p, c_int, c_i64, c_f32p, c_float, c_float, c_float,
+                                    c_stream],
     "jd_adam_step": [c_f32p, c_f32p, c_f32p, c_f32p, c_u8p, c_f32p, c_f32p, c_float, c_int, c_i64, c_int, c_float,
                      c_float, c_float, c_float, c_stream],
 }
@@ -104,7 +116,8 @@ def load():
         fn.restype = {"jd_last_error": ctypes.c_char_p, "jd_gmm_tc_packed_bytes": ctypes.c_size_t,
                       "jd_gmm_tc16_packed_bytes": ctypes.c_size_t,
                       "jd_gmm_backward_workspace_elems": ctypes.c_int64,
-                      "jd_gmm_tc_sk_workspace_bytes": ctypes.c_int64}.get(
+                      "jd_gmm_tc_sk_workspace_bytes": ctypes.c_int64,
+                      "jd_probe_fp32_fma": ctypes.c_int64}.get(
             name, ctypes.c_int)
     if lib.jd_abi_version() != 1:
         raise JolidecoB200Error(f"ABI version mismatch: library {lib.jd_abi_version()}, binding 1")

@@ -47,8 +47,8 @@ class BatchedRuns:
                     datasets=job["datasets"], datasets_validation=job.get("datasets_validation"),
                     components=components, beta=deco.beta, device=deco.device)
                 D = len(job["datasets"])
-                engine = deco._build_engine(total_loss, components, n_epochs * (D + 1),
-                                            stream_k=False)  # concurrent runs: throughput, not latency
+                # concurrent runs: throughput, not latency - no stream-K, no second stream per run
+                engine = deco._build_engine(total_loss, components, n_epochs * (D + 1), stream_k=False, overlap=False)
                 stream = self.streams[slot % len(self.streams)]
                 with torch.cuda.stream(stream):
                     engine.warmup()

@@ -95,9 +95,9 @@ class MAPDeconvolver:
     def _calibrations_fusable(cls, calibrations):
         """Calibrations the engine covers: background norm (trained or frozen); shifts at 0 never train in the
         reference (`shift_image_torch` returns early, utils/torch.py:211); psf_scale ~ 1 is the identity.  Non-zero
-        (trainable) shifts run in the engine through jd_shift_forward/backward when JD_FUSED_SHIFT=1 (written at the end
-        of round 1 without GPU minutes left: the autograd path stays the default until its GPU test has run)."""
-        fused_shift = os.environ.get("JD_FUSED_SHIFT", "0") == "1"
+        (trainable) shifts run in the engine through jd_shift_forward/backward (JD_FUSED_SHIFT=0 sends them to the
+        autograd path with grid_sample instead)."""
+        fused_shift = os.environ.get("JD_FUSED_SHIFT", "1") == "1"
         for cal in calibrations.values():
             if not cls._shift_is_zero(cal) and not fused_shift:
                 return False
@@ -130,7 +130,7 @@ class MAPDeconvolver:
             return None, 0, 1
         return pg, torch.distributed.get_rank(pg), world
 
-    def _build_engine(self, total_loss, components, n_draws, shard=None, stream_k=None):
+    def _build_engine(self, total_loss, components, n_draws, shard=None, stream_k=None, overlap=None):
         (name, comp), = components.items()
         theta = comp._flux_upsampled.data[0, 0]
         mask = comp.mask[0, 0].contiguous() if comp.mask is not None else None
@@ -173,7 +173,8 @@ class MAPDeconvolver:
                          use_log_flux=comp.use_log_flux, beta=self.beta, lr=self.optimizer_kwargs["lr"],
                          betas=self.optimizer_kwargs.get("betas", (0.9, 0.999)),
                          eps=self.optimizer_kwargs.get("eps", 1e-8), shift_table=table,
-                         datasets_validation=validation, use_graph=self.use_cuda_graph, stream_k=stream_k, **kwargs)
+                         datasets_validation=validation, use_graph=self.use_cuda_graph, stream_k=stream_k, overlap=overlap,
+                         **kwargs)
 
     def _early_stop(self, trace):
         if self.stop_early and len(trace) > self.stop_early_n_average:

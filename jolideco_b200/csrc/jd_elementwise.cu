@@ -18,10 +18,11 @@ void set_error(const char* fmt, ...) {
 }
 
 int num_sms() {
-  static int n = 0;
+  static int cache[64] = {};  // per device
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  int& n = cache[dev & 63];
   if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   }
   return n;
@@ -310,6 +311,56 @@ __global__ void adam_fold_kernel(float* __restrict__ theta, float* __restrict__ 
   }
 }
 
+// Joint step, one GPU: sum of the per-dataset likelihood gradients (`n_parts` images, `part_stride` floats apart,
+// fixed order) + fold of the prior's patch gradients (G may be NULL) + chain rule + Adam, one pass.
+__global__ void adam_joint_kernel(float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v,
+                                  const float* __restrict__ flux, const uint8_t* __restrict__ mask,
+                                  const float* __restrict__ parts, int n_parts, int64_t part_stride,
+                                  const float* __restrict__ G, float scale_b, int use_log, int fH, int fW,
+                                  const int32_t* __restrict__ shift_yx, int stride, int row_begin, int row_end,
+                                  const float* __restrict__ scalars, float b1, float b2, float eps) {
+  const float lr_over_bc1 = scalars[0], sqrt_bc2 = scalars[1];
+  const int sy = shift_yx ? shift_yx[0] : 0, sx = shift_yx ? shift_yx[1] : 0;
+  const int ny = (fH - PATCH) / stride + 1, nx = (fW - PATCH) / stride + 1;
+  const int64_t n = (int64_t)fH * fW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float g = 0.f;
+    for (int q = 0; q < n_parts; ++q) g += parts[q * part_stride + i];
+    if (G) {
+      int y = (int)(i / fW), x = (int)(i - (int64_t)y * fW);
+      g += scale_b * fold_gather(G, y, x, fH, fW, sy, sx, stride, ny, nx, row_begin, row_end);
+    }
+    g *= use_log ? flux[i] : (mask ? (float)mask[i] : 1.f);
+    float mi = m[i], vi = v[i];
+    mi = mi + (g - mi) * (1.f - b1);
+    vi = vi * b2 + (1.f - b2) * g * g;
+    float denom = sqrtf(vi) / sqrt_bc2 + eps;
+    theta[i] = theta[i] - lr_over_bc1 * (mi / denom);
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+
+// Joint step, several GPUs: this rank's partial flux gradient = its datasets' likelihood gradients + the fold of
+// its prior patch rows, written where the peers can read it (out may alias parts[0]).
+__global__ void grad_reduce_kernel(const float* __restrict__ parts, int n_parts, int64_t part_stride,
+                                   const float* __restrict__ G, float scale_b, int fH, int fW,
+                                   const int32_t* __restrict__ shift_yx, int stride, int row_begin, int row_end,
+                                   float* __restrict__ out) {
+  const int sy = shift_yx ? shift_yx[0] : 0, sx = shift_yx ? shift_yx[1] : 0;
+  const int ny = (fH - PATCH) / stride + 1, nx = (fW - PATCH) / stride + 1;
+  const int64_t n = (int64_t)fH * fW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float g = 0.f;
+    for (int q = 0; q < n_parts; ++q) g += parts[q * part_stride + i];
+    if (G && row_end > row_begin) {
+      int y = (int)(i / fW), x = (int)(i - (int64_t)y * fW);
+      g += scale_b * fold_gather(G, y, x, fH, fW, sy, sx, stride, ny, nx, row_begin, row_end);
+    }
+    out[i] = g;
+  }
+}
+
 // Adam on a handful of scalar calibration parameters (log background norm) whose gradients were accumulated in
 // double by the Poisson kernel.  torch.optim.Adam keeps one step counter per parameter and only advances it when
 // the parameter has a gradient (core.py:197-204, 229): `counter` is that per-parameter count.
@@ -482,6 +533,45 @@ int jd_adam_fold_step_dev(float* theta, float* m, float* v, const float* flux, c
       theta, m, v, flux, mask, dflux_a, G, scale_b, use_log_flux, fH, fW, shift_yx, stride, row_begin, row_end,
       adam_scalars, beta1, beta2, eps);
   JD_CHECK_LAUNCH("jd_adam_fold_step_dev");
+  return JD_OK;
+}
+
+int jd_adam_joint_step_dev(float* theta, float* m, float* v, const float* flux, const uint8_t* mask,
+                           const float* parts, int n_parts, int64_t part_stride, const float* G, float scale_b,
+                           int use_log_flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
+                           int row_end, const float* adam_scalars, float beta1, float beta2, float eps,
+                           jd_stream_t stream) {
+  JD_CHECK_ARG(theta && m && v && adam_scalars && fH > 0 && fW > 0, "jd_adam_joint_step_dev: null pointer");
+  JD_CHECK_ARG(n_parts >= 0 && (n_parts == 0 || parts), "jd_adam_joint_step_dev: bad gradient parts");
+  JD_CHECK_ARG(!use_log_flux || flux, "jd_adam_joint_step_dev: flux required for the log parameterisation");
+  if (G) {
+    JD_CHECK_ARG(fH >= PATCH && fW >= PATCH && stride >= 1 && stride <= PATCH, "jd_adam_joint_step_dev: bad geometry");
+    int ny = (fH - PATCH) / stride + 1;
+    JD_CHECK_ARG(row_begin >= 0 && row_end <= ny && row_begin <= row_end, "jd_adam_joint_step_dev: bad row block");
+  } else {
+    stride = 1;
+  }
+  adam_joint_kernel<<<grid_for((int64_t)fH * fW, 256), 256, 0, to_stream(stream)>>>(
+      theta, m, v, flux, mask, parts, n_parts, part_stride, G, scale_b, use_log_flux, fH, fW, shift_yx, stride, row_begin,
+      row_end, adam_scalars, beta1, beta2, eps);
+  JD_CHECK_LAUNCH("jd_adam_joint_step_dev");
+  return JD_OK;
+}
+
+int jd_grad_reduce_local(const float* parts, int n_parts, int64_t part_stride, const float* G, float scale_b, int fH,
+                         int fW, const int32_t* shift_yx, int stride, int row_begin, int row_end, float* out,
+                         jd_stream_t stream) {
+  JD_CHECK_ARG(out && fH > 0 && fW > 0 && n_parts >= 0 && (n_parts == 0 || parts), "jd_grad_reduce_local: bad arguments");
+  if (G) {
+    JD_CHECK_ARG(fH >= PATCH && fW >= PATCH && stride >= 1 && stride <= PATCH, "jd_grad_reduce_local: bad geometry");
+    int ny = (fH - PATCH) / stride + 1;
+    JD_CHECK_ARG(row_begin >= 0 && row_end <= ny && row_begin <= row_end, "jd_grad_reduce_local: bad row block");
+  } else {
+    stride = 1;
+  }
+  grad_reduce_kernel<<<grid_for((int64_t)fH * fW, 256), 256, 0, to_stream(stream)>>>(
+      parts, n_parts, part_stride, G, scale_b, fH, fW, shift_yx, stride, row_begin, row_end, out);
+  JD_CHECK_LAUNCH("jd_grad_reduce_local");
   return JD_OK;
 }
 

@@ -1,0 +1,33 @@
+// Instantiations of the batched likelihood kernel (jd_likelihood.cuh) for upsampling factor 2: tap rows padded to
+// whole groups of four (KT = 4), both directions.  key = 8 * mode + (KG - 1).
+#include "jd_likelihood.cuh"
+
+namespace jd {
+namespace lik {
+
+int dispatch_f2(int key, const jd_lik_dataset* table, int n_datasets, int fH, int fW, int kh, int kw, int H, int W,
+                float eps, float grad_scale, cudaStream_t st) {
+  switch (key) {
+    case 0: return launch<FWD, 2, 1, 4>(table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
+    case 1: return launch<FWD, 2, 2, 4>(table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
+    case 2: return launch<FWD, 2, 3, 4>(table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
+    case 3: return launch<FWD, 2, 4, 4>(table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
+    case 4: return launch<FWD, 2, 5, 4>(table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
+    case 5: return launch<FWD, 2, 6, 4>(table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
+    case 6: return launch<FWD, 2, 7, 4>(table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
+    case 7: return launch<FWD, 2, 8, 4>(table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
+    case 8: return launch<BWD, 2, 1, 4>(table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
+    case 9: return launch<BWD, 2, 2, 4>(table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
+    case 10: return launch<BWD, 2, 3, 4>(table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
+    case 11: return launch<BWD, 2, 4, 4>(table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
+    case 12: return launch<BWD, 2, 5, 4>(table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
+    case 13: return launch<BWD, 2, 6, 4>(table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
+    case 14: return launch<BWD, 2, 7, 4>(table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
+    case 15: return launch<BWD, 2, 8, 4>(table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
+  }
+  set_error("jd_likelihood: no f = 2 kernel for key %d", key);
+  return JD_ERR_UNSUPPORTED;
+}
+
+}  // namespace lik
+}  // namespace jd

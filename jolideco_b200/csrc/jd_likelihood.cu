@@ -1,0 +1,87 @@
+// C-ABI entry points of the batched likelihood kernels (jd_likelihood.cuh) and the FP32-FMA peak probe that
+// bench.py uses as the roofline denominator of the direct convolution.
+#include "jd_likelihood.cuh"
+
+namespace jd {
+namespace lik {
+
+int dispatch_f1_fwd_lo(int, const jd_lik_dataset*, int, int, int, int, int, int, int, float, float, cudaStream_t);
+int dispatch_f1_fwd_hi(int, const jd_lik_dataset*, int, int, int, int, int, int, int, float, float, cudaStream_t);
+int dispatch_f1_bwd_lo(int, const jd_lik_dataset*, int, int, int, int, int, int, int, float, float, cudaStream_t);
+int dispatch_f1_bwd_hi(int, const jd_lik_dataset*, int, int, int, int, int, int, int, float, float, cudaStream_t);
+int dispatch_f2(int, const jd_lik_dataset*, int, int, int, int, int, int, int, float, float, cudaStream_t);
+
+// taps per shared-memory row (zero lead taps for 16-byte alignment + the PSF row), or 0 if unsupported
+static int tap_count(int mode, int kw) {
+  const int sx = (kw - 1) / 2;
+  const int ox = mode == FWD ? sx - (kw - 1) : -sx;
+  const int lead = ((ox % 4) + 4) % 4;
+  return lead + kw;
+}
+
+static int run(int mode, const jd_lik_dataset* table, int n_datasets, int fH, int fW, int kh, int kw, int f, int H,
+               int W, float eps, float grad_scale, cudaStream_t st) {
+  JD_CHECK_ARG(table && n_datasets > 0 && n_datasets <= 65535, "jd_likelihood: bad dataset table");
+  JD_CHECK_ARG(fH > 0 && fW > 0 && kh > 0 && kw > 0, "jd_likelihood: bad geometry");
+  JD_CHECK_ARG(f == 1 || f == 2, "jd_likelihood: upsampling factor %d (supported: 1, 2)", f);
+  JD_CHECK_ARG(H * f == fH && W * f == fW, "jd_likelihood: counts grid %dx%d x f=%d != flux grid %dx%d", H, W, f, fH, fW);
+  const int nt = tap_count(mode, kw);
+  JD_CHECK_ARG(nt <= 32, "jd_likelihood: PSF rows of %d taps are too wide for the direct kernel (<= 32 incl. lead)", kw);
+  const int kg = (nt + 3) / 4, kt = nt - 4 * (kg - 1);
+  if (f == 2) return dispatch_f2(8 * mode + kg - 1, table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
+  const int key = (kg - 1) * 4 + kt - 1;
+  if (mode == FWD)
+    return kg <= 4 ? dispatch_f1_fwd_lo(key, table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st)
+                   : dispatch_f1_fwd_hi(key, table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
+  return kg <= 4 ? dispatch_f1_bwd_lo(key, table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st)
+                 : dispatch_f1_bwd_hi(key, table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
+}
+
+// FP32 FMA peak probe: 8 independent dependent-chains of FFMA per thread, 8 CTAs x 256 threads per SM
+__global__ void __launch_bounds__(256) fma_probe_kernel(int iters, float* out) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
+        a6 = a0 + 6.f, a7 = a0 + 7.f;
+  const float m = 0.999f + 1e-9f * blockIdx.x, b = 1e-3f;
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a0 = fmaf(a0, m, b), a1 = fmaf(a1, m, b), a2 = fmaf(a2, m, b), a3 = fmaf(a3, m, b);
+      a4 = fmaf(a4, m, b), a5 = fmaf(a5, m, b), a6 = fmaf(a6, m, b), a7 = fmaf(a7, m, b);
+    }
+  }
+  const float s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (s == 123.456f) out[0] = s;  // never true: keeps the chains alive
+}
+
+}  // namespace lik
+}  // namespace jd
+
+extern "C" {
+
+int jd_likelihood_supported(int kh, int kw, int f) {
+  if (f != 1 && f != 2) return 0;
+  if (kh <= 0 || kw <= 0) return 0;
+  if (jd::lik::tap_count(jd::lik::FWD, kw) > 32 || jd::lik::tap_count(jd::lik::BWD, kw) > 32) return 0;
+  return jd::lik::Tile<8>::smem_bytes(kh) <= 200 * 1024 ? 1 : 0;
+}
+
+int jd_likelihood_forward(const jd_lik_dataset* table_dev, int n_datasets, int fH, int fW, int kh, int kw, int f, int H,
+                          int W, float eps, float grad_scale, jd_stream_t stream) {
+  return jd::lik::run(jd::lik::FWD, table_dev, n_datasets, fH, fW, kh, kw, f, H, W, eps, grad_scale,
+                      jd::to_stream(stream));
+}
+
+int jd_likelihood_backward(const jd_lik_dataset* table_dev, int n_datasets, int fH, int fW, int kh, int kw, int f, int H,
+                           int W, jd_stream_t stream) {
+  return jd::lik::run(jd::lik::BWD, table_dev, n_datasets, fH, fW, kh, kw, f, H, W, 0.f, 0.f, jd::to_stream(stream));
+}
+
+int64_t jd_probe_fp32_fma(int iters, float* out, jd_stream_t stream) {
+  const int ctas = jd::num_sms() * 8;
+  jd::lik::fma_probe_kernel<<<ctas, 256, 0, jd::to_stream(stream)>>>(iters, out);
+  if (cudaGetLastError() != cudaSuccess) return -1;
+  return (int64_t)ctas * 256 * (int64_t)iters * 64 * 2;  // flops issued
+}
+
+}  // extern "C"

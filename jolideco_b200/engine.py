@@ -22,6 +22,8 @@ from . import _lib, dist, ops
 
 _p = ops._ptr
 
+LIK_DTYPE = ops.LIK_DTYPE
+
 # launch accounting / per-kernel timing hooks (bench.py): every C-ABI call below is exactly one
 # kernel launch on the current stream
 _STATS = {"launches": 0, "timed": None, "events": []}
@@ -79,6 +81,15 @@ class DatasetBuffers:
             ops._check(t, "dataset buffer")
         # large PSFs: cached PSF spectrum + scratch for the shared-memory FFT path
         self.fft = ops.FFTConvPlan(psf, self.fH, self.fW) if self.kh * self.kw >= ops.FFT_MIN_PSF_AREA else None
+        # small PSFs: the batched direct kernels with the Poisson statistic fused into the convolution epilogue
+        # (jd_likelihood_forward / _backward); JD_LIK_BATCHED=0 keeps the separate conv / Poisson / conv launches
+        self.lik_ok = (self.fft is None and os.environ.get("JD_LIK_BATCHED", "1") != "0"
+                       and self.H * self.f == self.fH and self.W * self.f == self.fW
+                       and _lib.load().jd_likelihood_supported(self.kh, self.kw, self.f) == 1)
+        # counts-only Stirling term of nn.PoissonNLLLoss(full=True) (loss.py:35-37): a constant of the dataset
+        self.loss_const = ops.stirling_constant(counts)
+        self.geom = (self.fH, self.fW, self.kh, self.kw, self.f, self.H, self.W)
+        self.flux_s = self.dflux_s = self.dpool = None  # per-dataset scratch, allocated by the engine
 
 
 class MapEngine:
@@ -93,8 +104,8 @@ class MapEngine:
         patch tiles do not fill the SMs; it buys latency of ONE run, not throughput of concurrent runs).
         overlap: run the likelihood chain (convolutions, Poisson) and the prior chain (tensor-core forward, backward)
         of a step on two streams - both only depend on the flux and meet at the Adam kernel; the prior kernels hold one
-        CTA per SM with ~27 KB of shared memory to spare, so the FP32 / FFT kernels co-reside.  None = JD_OVERLAP=1
-        (off by default: written at the end of round 1 without GPU minutes left to validate and time it)."""
+        CTA per SM with ~27 KB of shared memory to spare, so the FP32 / FFT kernels co-reside.  None = on unless
+        JD_OVERLAP=0 (parity suite green and cfg2 step 172 -> 153 us with it, profiles/r02_summary.md)."""
         ops.require_device(theta.device)
         self.theta = ops._check(theta, "theta")
         assert theta.ndim == 2
@@ -127,20 +138,24 @@ class MapEngine:
         self.v = torch.zeros_like(theta)
         self.flux = torch.empty_like(theta)
         self.conv = torch.empty_like(theta)
-        self.dflux_l = torch.zeros_like(theta)
-        Hmax = max([d.H for d in self.datasets + self.datasets_validation] + [1])
-        Wmax = max([d.W for d in self.datasets + self.datasets_validation] + [1])
-        self.dpool = torch.empty((Hmax, Wmax), **f32)
+        # per-dataset likelihood gradients d L_d / d flux of a (joint) step: summed, in a fixed order, by the Adam /
+        # local-reduce kernel instead of read-modify-write accumulation by every adjoint launch
+        self.parts = torch.zeros((max(self.D, 1), self.fH, self.fW), **f32)
+        self.dflux_l = self.parts[0]
         self.counters = torch.zeros(2, dtype=torch.int32, device=self.dev)
         self.cur_shift = torch.zeros(2, dtype=torch.int32, device=self.dev)
         self.adam_scalars = torch.zeros(2, **f32)
-        # acc[0] = Poisson loss sum of the last step, acc[1] = sum_p v_p of the last prior evaluation,
-        # acc[2] = d loss / d log(background norm) of the last step, acc[3:5] = d loss / d (shift_x, shift_y)
-        self.acc = torch.zeros(5, dtype=torch.float64, device=self.dev)
-        self.flux_s = self.dflux_s = None
-        if any(d.shift_xy is not None for d in self.datasets + self.datasets_validation):
-            self.flux_s = torch.empty_like(theta)   # shifted flux of the current dataset
-            self.dflux_s = torch.empty_like(theta)  # gradient w.r.t. the shifted flux
+        # acc[0] = Poisson loss sum of the last step, acc[1] = sum_p v_p of the last prior evaluation, then three slots
+        # per local dataset j: acc[2+3j] = d loss / d log(background norm), acc[3+3j : 5+3j] = d loss / d (shift_x, shift_y)
+        self.acc = torch.zeros(2 + 3 * max(self.D, 1), dtype=torch.float64, device=self.dev)
+        for d in self.datasets + self.datasets_validation:
+            if d.shift_xy is not None and d.flux_s is None:
+                d.flux_s = torch.empty_like(theta)   # this dataset's shifted flux
+                d.dflux_s = torch.empty_like(theta)  # gradient w.r.t. it
+        for d in self.datasets:
+            if d.dpool is None:
+                d.dpool = torch.empty((d.H, d.W), **f32)
+        self._tables = {}
         self.n_trace = self.Dg + 1 + self.Vg
         self.acc_trace = torch.zeros(self.n_trace, dtype=torch.float64, device=self.dev)
         self.shift_table = None
@@ -196,26 +211,36 @@ class MapEngine:
         self._graphs = {}
         self._graph_nodes = {}
         self._capture_stream = None
-        self.overlap = (os.environ.get("JD_OVERLAP", "0") == "1") if overlap is None else bool(overlap)
-        self._side = torch.cuda.Stream(device=self.dev) if self.overlap else None  # created outside any capture
+        self.overlap = (os.environ.get("JD_OVERLAP", "1") == "1") if overlap is None else bool(overlap)
+        # created outside any capture
+        self._side = torch.cuda.Stream(device=self.dev) if (self.overlap and self.dev.type == "cuda") else None
 
     # ------------------------------------------------------------------------------------------
     def _enable_peer(self):
-        """Move theta and the partial-gradient buffer into symmetric memory (peer-addressable over NVLink)."""
+        """Move theta and the partial-gradient buffer into symmetric memory (peer-addressable over NVLink), plus the
+        flag block of the in-kernel cross-rank barriers (jd_adam_allreduce_peer_sync)."""
         import torch.distributed._symmetric_memory as symm
 
         if self.n % 4:
             raise _lib.JolidecoB200Error("collective='peer' needs a flux pixel count divisible by 4")
+        if self.world > 32:
+            raise _lib.JolidecoB200Error("collective='peer' supports up to 32 ranks")
         with torch.cuda.device(self.dev):
             self.sym_grad = symm.empty(self.n, dtype=torch.float32, device=self.dev)
             self.sym_theta = symm.empty(self.n, dtype=torch.float32, device=self.dev)
+            self.sym_sig = symm.empty(64, dtype=torch.int32, device=self.dev)
             self.h_grad = symm.rendezvous(self.sym_grad, self.pg)
             self.h_theta = symm.rendezvous(self.sym_theta, self.pg)
+            self.h_sig = symm.rendezvous(self.sym_sig, self.pg)
             self.sym_grad.zero_()
+            self.sym_sig.zero_()
             self.sym_theta.copy_(self.theta.reshape(-1))
+            self.sync_state = torch.zeros(2, dtype=torch.int32, device=self.dev)  # epoch, finished CTAs: never restored
+            torch.cuda.synchronize(self.dev)
+        self.h_sig.barrier(channel=0)  # every flag block is zeroed before any rank can signal
         self._theta_param = self.theta  # the component's parameter storage: refreshed by sync_theta()
         self.theta = self.sym_theta.view(self.fH, self.fW)
-        self.dflux_l = self.sym_grad.view(self.fH, self.fW)
+        self.dflux_l = self.sym_grad.view(self.fH, self.fW)  # output of the local gradient reduce, read by the peers
 
     def sync_theta(self):
         """Copy the working theta back into the component's parameter storage (peer mode only)."""
@@ -240,21 +265,98 @@ class MapEngine:
               self.lr, self.b1, self.b2, _p(self.adam_scalars), _p(zero_acc), int(zero_acc.numel()), _p(self.theta),
               _p(self.mask), _p(self.flux), self.n, int(self.use_log_flux), self._s())
 
-    def _adam_fold(self, scale_b):
-        """col2im of the patch gradients + gradient sum + Adam in one launch"""
-        _call("jd_adam_fold_step_dev", _p(self.theta), _p(self.m), _p(self.v), _p(self.flux), _p(self.mask),
-              _p(self.dflux_l), _p(self.G), float(scale_b), int(self.use_log_flux), self.fH, self.fW, _p(self.cur_shift),
-              self.stride, self.rows[0], self.rows[1], _p(self.adam_scalars), self.b1, self.b2, self.eps, self._s())
+    def _adam_joint(self, n_parts, with_G, scale_b):
+        """sum of the likelihood gradient parts + fold of the patch gradients G + chain rule + Adam, one launch"""
+        G = self.G if with_G else None
+        rows = self.rows if self.prior is not None else (0, 0)
+        stride = self.stride if self.prior is not None else 1
+        _call("jd_adam_joint_step_dev", _p(self.theta), _p(self.m), _p(self.v), _p(self.flux), _p(self.mask),
+              _p(self.parts), int(n_parts), self.n, _p(G), float(scale_b), int(self.use_log_flux), self.fH, self.fW,
+              _p(self.cur_shift), stride, rows[0], rows[1], _p(self.adam_scalars), self.b1, self.b2, self.eps, self._s())
+
+    def _grad_reduce(self, n_parts, with_G, scale_b):
+        """this rank's partial gradient (likelihood parts + fold of its patch rows) -> dflux_l, no update"""
+        G = self.G if with_G else None
+        rows = self.rows if self.prior is not None else (0, 0)
+        stride = self.stride if self.prior is not None else 1
+        _call("jd_grad_reduce_local", _p(self.parts), int(n_parts), self.n, _p(G), float(scale_b), self.fH, self.fW,
+              _p(self.cur_shift), stride, rows[0], rows[1], _p(self.dflux_l), self._s())
 
     def _flux(self):
         _call("jd_flux_forward", _p(self.theta), _p(self.mask), _p(self.flux), self.n, int(self.use_log_flux), self._s())
 
-    def _likelihood(self, d, loss_acc, want_grad, accumulate=False):
+    def _slot(self, j):
+        """device address of the calibration-gradient accumulators (dlogb, dshift_x, dshift_y) of local dataset j"""
+        return self.acc.data_ptr() + 8 * (2 + 3 * j)
+
+    def _table(self, entries, want_grad):
+        """Device table of jd_lik_dataset records for one batched launch pair (cached: every pointer is static)."""
+        key = (tuple((id(d), j) for d, _, j in entries), bool(want_grad), tuple(lp for _, lp, _ in entries))
+        tab = self._tables.get(key)
+        if tab is None:
+            rec = np.zeros(len(entries), dtype=LIK_DTYPE)
+            for r, (d, loss_ptr, j) in zip(rec, entries):
+                shifted = d.shift_xy is not None
+                r["flux"] = _p(d.flux_s if shifted else self.flux)
+                r["exposure"], r["psf"] = _p(d.exposure), _p(d.psf)
+                r["background"], r["counts"] = _p(d.background), _p(d.counts)
+                r["bkg_log_norm"] = _p(d.bkg_log_norm) or 0
+                r["loss_sum"] = loss_ptr or 0
+                r["loss_const"] = d.loss_const
+                if want_grad:
+                    r["dpool"] = _p(d.dpool)
+                    r["dlogb"] = self._slot(j) if d.train_bkg_norm else 0
+                    r["dflux"] = _p(d.dflux_s) if shifted else self.parts.data_ptr() + 4 * self.n * j
+            host = torch.from_numpy(rec.view(np.uint8).reshape(-1).copy())
+            tab = host.to(self.dev) if self.dev.type == "cuda" else host
+            self._tables[key] = tab
+        return tab
+
+    def _likelihoods(self, entries, want_grad):
+        """Likelihood terms of `entries` = [(dataset, device address of its loss accumulator, gradient part index)]:
+        NPred forward + Poisson statistic (+ gradient into parts[j] when want_grad).  Datasets the batched direct
+        kernels cover go out in one launch per direction and geometry; the rest (FFT path) one by one."""
+        s = self._s()
+        batched = [e for e in entries if e[0].lik_ok]
+        groups = {}
+        for e in batched:
+            groups.setdefault(e[0].geom, []).append(e)
+        for d, _, _ in batched:
+            if d.shift_xy is not None:  # calibration shift: the NPred model sees the shifted flux (npred.py:226-230)
+                _call("jd_shift_forward", _p(self.flux), _p(d.shift_xy), d.f, d.fH, d.fW, _p(d.flux_s), s)
+        for (fH, fW, kh, kw, f, H, W), es in groups.items():
+            _call("jd_likelihood_forward", _p(self._table(es, want_grad)), len(es), fH, fW, kh, kw, f, H, W, 1e-25,
+                  1.0 / (H * W), s)
+        if want_grad:
+            for d, _, j in batched:
+                if d.train_bkg_norm:  # Adam on log(background norm) with the parameter's own step counter
+                    _call("jd_adam_scalar_step_dev", _p(d.bkg_log_norm), _p(d.cal_m), _p(d.cal_v), self._slot(j),
+                          _p(d.cal_t), 1, self.lr, self.b1, self.b2, self.eps, s)
+            for (fH, fW, kh, kw, f, H, W), es in groups.items():
+                _call("jd_likelihood_backward", _p(self._table(es, want_grad)), len(es), fH, fW, kh, kw, f, H, W, s)
+            for d, _, j in batched:
+                if d.shift_xy is not None:
+                    self._shift_backward(d, j)
+        for d, loss_ptr, j in entries:
+            if not d.lik_ok:
+                self._likelihood_single(d, loss_ptr, j, want_grad)
+
+    def _shift_backward(self, d, j):
+        s = self._s()
+        dshift = self._slot(j) + 8 if d.train_shift else None
+        _call("jd_shift_backward", _p(d.dflux_s), _p(self.flux), _p(d.shift_xy), d.f, d.fH, d.fW, _p(self.parts[j]), 0,
+              dshift, s)
+        if d.train_shift:  # Adam on (shift_x, shift_y): one parameter tensor, one step counter
+            _call("jd_adam_scalar_step_dev", _p(d.shift_xy), _p(d.shift_m), _p(d.shift_v), dshift, _p(d.shift_t), 2,
+                  self.lr, self.b1, self.b2, self.eps, s)
+
+    def _likelihood_single(self, d, loss_acc, j, want_grad):
+        """One dataset through the separate convolution (FFT or direct) / Poisson / adjoint launches."""
         s = self._s()
         src = self.flux
-        if d.shift_xy is not None:  # calibration shift: the NPred model sees the shifted flux (npred.py:226-230)
-            _call("jd_shift_forward", _p(self.flux), _p(d.shift_xy), d.f, d.fH, d.fW, _p(self.flux_s), s)
-            src = self.flux_s
+        if d.shift_xy is not None:
+            _call("jd_shift_forward", _p(self.flux), _p(d.shift_xy), d.f, d.fH, d.fW, _p(d.flux_s), s)
+            src = d.flux_s
         if d.fft is not None:
             _call("jd_conv_forward_fft", _p(src), _p(d.exposure), _p(d.fft.psf_hat), _p(d.fft.workspace),
                   _p(self.conv), d.fH, d.fW, d.kh, d.kw, s)
@@ -263,28 +365,22 @@ class MapEngine:
                   d.kw, s)
         train_cal = want_grad and d.train_bkg_norm
         _call("jd_poisson_forward_backward", _p(self.conv), _p(d.background), _p(d.bkg_log_norm), _p(d.counts), None,
-              _p(self.dpool) if want_grad else None, loss_acc, self.acc.data_ptr() + 16 if train_cal else None, d.H, d.W,
+              _p(d.dpool) if want_grad else None, loss_acc, self._slot(j) if train_cal else None, d.H, d.W,
               d.f, d.fW, 1e-25, 1.0 / (d.H * d.W), s)
-        if train_cal:  # Adam on log(background norm) with the parameter's own step counter
-            _call("jd_adam_scalar_step_dev", _p(d.bkg_log_norm), _p(d.cal_m), _p(d.cal_v), self.acc.data_ptr() + 16,
+        if train_cal:
+            _call("jd_adam_scalar_step_dev", _p(d.bkg_log_norm), _p(d.cal_m), _p(d.cal_v), self._slot(j),
                   _p(d.cal_t), 1, self.lr, self.b1, self.b2, self.eps, s)
         if not want_grad:
             return
-        # gradient w.r.t. the NPred model's input: straight into dflux_l, or via dflux_s when that input was shifted
-        out, acc_flag = (self.dflux_l, int(accumulate)) if d.shift_xy is None else (self.dflux_s, 0)
+        out = self.parts[j] if d.shift_xy is None else d.dflux_s
         if d.fft is not None:
-            _call("jd_conv_backward_fft", _p(self.dpool), _p(d.exposure), _p(d.fft.psf_hat), _p(d.fft.workspace),
-                  _p(out), acc_flag, d.fH, d.fW, d.kh, d.kw, d.f, d.H, d.W, s)
+            _call("jd_conv_backward_fft", _p(d.dpool), _p(d.exposure), _p(d.fft.psf_hat), _p(d.fft.workspace),
+                  _p(out), 0, d.fH, d.fW, d.kh, d.kw, d.f, d.H, d.W, s)
         else:
-            _call("jd_conv_backward_direct", _p(self.dpool), _p(d.exposure), _p(d.psf), _p(out),
-                  acc_flag, d.fH, d.fW, d.kh, d.kw, d.f, d.H, d.W, s)
+            _call("jd_conv_backward_direct", _p(d.dpool), _p(d.exposure), _p(d.psf), _p(out),
+                  0, d.fH, d.fW, d.kh, d.kw, d.f, d.H, d.W, s)
         if d.shift_xy is not None:
-            dshift = self.acc.data_ptr() + 24 if d.train_shift else None
-            _call("jd_shift_backward", _p(self.dflux_s), _p(self.flux), _p(d.shift_xy), d.f, d.fH, d.fW, _p(self.dflux_l),
-                  int(accumulate), dshift, s)
-            if d.train_shift:  # Adam on (shift_x, shift_y): one parameter tensor, one step counter
-                _call("jd_adam_scalar_step_dev", _p(d.shift_xy), _p(d.shift_m), _p(d.shift_v), dshift, _p(d.shift_t), 2,
-                      self.lr, self.b1, self.b2, self.eps, s)
+            self._shift_backward(d, j)
 
     def _prior_forward(self, sum_acc):
         if self.P <= 0:
@@ -328,21 +424,6 @@ class MapEngine:
               self.rows[1], _p(self.packed.Lam), _p(self.packed.bk), self.packed.K, int(self.marginalize),
               _p(self.argmax), _p(self.logp), _p(self.value), float(scale), _p(self.G), _p(self.bwd_ws), self._s())
 
-    def _prior_backward(self, scale, out, accumulate):
-        if self.P <= 0:
-            if not accumulate:
-                out.zero_()
-            return
-        s = self._s()
-        self._prior_gradient(scale)
-        _call("jd_patch_fold", _p(self.G), self.fH, self.fW, _p(self.cur_shift), self.stride, self.rows[0], self.rows[1],
-              _p(out), int(accumulate), s)
-
-    def _adam(self, dflux_b, scale_b):
-        _call("jd_adam_step_dev", _p(self.theta), _p(self.m), _p(self.v), _p(self.flux), _p(self.mask), _p(self.dflux_l),
-              _p(dflux_b), float(scale_b), int(self.use_log_flux), self.n, _p(self.adam_scalars), self.b1, self.b2,
-              self.eps, self._s())
-
     # ------------------------------------------------------------------------------------------
     def _fork(self):
         """Side stream that has waited for everything enqueued so far on the current stream (event fork; inside a CUDA
@@ -355,71 +436,67 @@ class MapEngine:
     def _join(self, side):
         torch.cuda.current_stream(self.dev).wait_stream(side)
 
-    def _step_body(self, i):
-        """Reference step for dataset i: total = L_i - beta * prior / D  (core.py:214-229)."""
-        d = self.datasets[i]
-        self._begin_flux(advance_adam=1, zero_acc=self.acc)
+    def _gradients(self, entries, prior_scale):
+        """Likelihood gradients of `entries` into their parts and the prior's per-patch gradient rows G.  The two
+        chains only depend on the flux and write disjoint buffers (dpool, parts, acc[0], acc[2:] | value, argmax, logp,
+        G, acc[1]): with `overlap` the likelihood chain runs on a side stream beside the tensor-core prior kernels
+        (which leave shared memory and registers for co-resident FP32 CTAs) and joins before the update."""
         has_prior = self.prior is not None and self.P > 0
-        if self.overlap and has_prior:
-            # likelihood chain on the side stream, prior chain on this one; they write disjoint buffers
-            # (conv, dpool, dflux_l, acc[0], acc[2:5] | value, argmax, logp, G, acc[1]) and meet at the Adam kernel
+        if self.overlap and has_prior and entries:
             side = self._fork()
             with torch.cuda.stream(side):
-                self._likelihood(d, self.acc.data_ptr(), want_grad=True)
+                self._likelihoods(entries, want_grad=True)
             self._prior_forward(self.acc.data_ptr() + 8)
-            self._prior_gradient(-self.c)
+            self._prior_gradient(prior_scale)
             self._join(side)
-            self._adam_fold(-self.beta / self.prior_weight)
-            return
-        self._likelihood(d, self.acc.data_ptr(), want_grad=True)
+            return has_prior
+        self._likelihoods(entries, want_grad=True)
         if has_prior:
             self._prior_forward(self.acc.data_ptr() + 8)
-            self._prior_gradient(-self.c)
-            self._adam_fold(-self.beta / self.prior_weight)
-        else:
-            self._adam(None, 0.0)
+            self._prior_gradient(prior_scale)
+        return has_prior
+
+    def _step_body(self, i):
+        """Reference step for dataset i: total = L_i - beta * prior / D  (core.py:214-229)."""
+        self._begin_flux(advance_adam=1, zero_acc=self.acc)
+        has_prior = self._gradients([(self.datasets[i], self.acc.data_ptr(), 0)], -self.c if self.prior else 0.0)
+        self._adam_joint(1, has_prior, -self.beta / self.prior_weight)
 
     def _joint_pre(self):
-        """Joint step up to the local gradient: sum_d dL_d/dflux (local datasets) - beta d prior/dflux (local
-        patch rows), folded into dflux_l (loss.py:257-261)."""
+        """Joint step up to the local gradient: d L_d / d flux of the local datasets in parts[j], the gradient rows G
+        of the local patch rows scaled by beta c (loss.py:257-261)."""
         self._begin_flux(advance_adam=1, zero_acc=self.acc)
-        if not self.datasets:
-            self.dflux_l.zero_()
-
-        def likelihoods():
-            for j, d in enumerate(self.datasets):
-                if j > 0 and (d.train_bkg_norm or d.train_shift):
-                    # the calibration-gradient accumulators acc[2:5] are per dataset: clear what the previous one left
-                    _call("jd_step_begin", _p(self.counters), None, 0, None, 0, self.lr, self.b1, self.b2,
-                          _p(self.adam_scalars), self.acc.data_ptr() + 16, 3, self._s())
-                self._likelihood(d, self.acc.data_ptr(), want_grad=True, accumulate=j > 0)
-
-        if self.overlap and self.prior is not None and self.P > 0 and self.datasets:
-            # the prior's forward and per-patch gradient rows G run beside the likelihoods; the fold accumulates into
-            # dflux_l and therefore waits for them
-            side = self._fork()
-            with torch.cuda.stream(side):
-                likelihoods()
-            self._prior_forward(self.acc.data_ptr() + 8)
-            self._prior_gradient(self.c * self.beta)
-            self._join(side)
-            _call("jd_patch_fold", _p(self.G), self.fH, self.fW, _p(self.cur_shift), self.stride, self.rows[0],
-                  self.rows[1], _p(self.dflux_l), 1, self._s())
-            return
-        likelihoods()
-        if self.prior is not None:
-            self._prior_forward(self.acc.data_ptr() + 8)
-            self._prior_backward(self.c * self.beta, self.dflux_l, accumulate=True)
-
-    def _joint_post(self):
-        self._adam(None, 0.0)
+        entries = [(d, self.acc.data_ptr(), j) for j, d in enumerate(self.datasets)]
+        return self._gradients(entries, self.c * self.beta if self.prior else 0.0)
 
     def _joint_body(self):
-        """Joint step on sum_d L_d - beta * prior; with ranks: one all-reduce of the flux gradient."""
-        self._joint_pre()
-        if self.world > 1:
+        """Joint step on sum_d L_d - beta * prior.  One GPU: a single update kernel.  Several ranks: local reduce into
+        the (symmetric) partial-gradient buffer, then the fused peer-memory reduce + Adam + theta broadcast with both
+        cross-rank barriers inside the kernel, or ncclAllReduce + replicated Adam."""
+        has_prior = self._joint_pre()
+        if self.world == 1:
+            self._adam_joint(self.D, has_prior, 1.0)
+            return
+        self._grad_reduce(self.D, has_prior, 1.0)
+        if self.collective == "peer":
+            self._peer_update()
+        else:
             torch.distributed.all_reduce(self.dflux_l, group=self.pg)
-        self._joint_post()
+            self._joint_post()
+
+    def _peer_update(self):
+        _call("jd_adam_allreduce_peer_sync", self.h_grad.buffer_ptrs_dev, self.h_theta.buffer_ptrs_dev,
+              self.h_sig.buffer_ptrs_dev, _p(self.sync_state), self.rank, self.world, _p(self.m), _p(self.v),
+              _p(self.flux), _p(self.mask), int(self.use_log_flux), self.n, _p(self.adam_scalars), self.b1, self.b2,
+              self.eps, self._s())
+
+    def _joint_local(self):
+        has_prior = self._joint_pre()
+        self._grad_reduce(self.D, has_prior, 1.0)
+
+    def _joint_post(self):
+        _call("jd_adam_step_dev", _p(self.theta), _p(self.m), _p(self.v), _p(self.flux), _p(self.mask), _p(self.dflux_l),
+              None, 0.0, int(self.use_log_flux), self.n, _p(self.adam_scalars), self.b1, self.b2, self.eps, self._s())
 
     def _run(self, key, body):
         if not self.use_graph:
@@ -461,36 +538,29 @@ class MapEngine:
         state = [t.clone() for t in tensors]
         graph = self.use_graph
         self.use_graph = False
-        if joint and self.collective == "peer":
-            self._joint_pre()
-            self.h_grad.barrier(channel=0)
-            self.h_grad.barrier(channel=1)  # communicator / signal pads warmed up; no update applied
-        elif joint:
+        if joint:
             self._joint_body()  # collective: every rank calls warmup(joint=True)
         else:
             for i in range(min(self.D, 1)):
                 self._step_body(i)
         self.use_graph = graph
         torch.cuda.synchronize(self.dev)
+        if joint and self.world > 1:
+            torch.distributed.barrier(group=self.pg)  # no peer is still writing theta slices into this replica
         for t, s in zip(tensors, state):
             t.copy_(s)
+        torch.cuda.synchronize(self.dev)
+        if joint and self.world > 1:
+            torch.distributed.barrier(group=self.pg)
 
     def step(self, i):
         self._run(("step", i), lambda: self._step_body(i))
 
     def joint_step(self):
-        if self.world == 1:
-            self._run(("joint",), self._joint_body)
+        if self.world == 1 or self.collective == "peer":
+            self._run(("joint",), self._joint_body)  # one graph: the peer kernel carries its own cross-rank barriers
             return
-        self._run(("joint-pre",), self._joint_pre)
-        if self.collective == "peer":
-            # barrier (all partial gradients written) -> fused reduce + Adam + theta broadcast -> barrier
-            self.h_grad.barrier(channel=0)
-            _call("jd_adam_allreduce_peer", self.h_grad.buffer_ptrs_dev, self.h_theta.buffer_ptrs_dev, self.rank,
-                  self.world, _p(self.m), _p(self.v), _p(self.flux), _p(self.mask), int(self.use_log_flux), self.n,
-                  _p(self.adam_scalars), self.b1, self.b2, self.eps, self._s())
-            self.h_grad.barrier(channel=1)
-            return
+        self._run(("joint-local",), self._joint_local)
         torch.distributed.all_reduce(self.dflux_l, group=self.pg)  # eager NCCL between the two graphs
         self._run(("joint-post",), self._joint_post)
 
@@ -514,26 +584,19 @@ class MapEngine:
         if refresh_flux:
             self._flux()
         base = self.acc_trace.data_ptr()
-
-        def likelihoods():
-            for j, d in zip(self.dataset_index, self.datasets):
-                self._likelihood(d, base + 8 * j, want_grad=False)
-            for j, d in zip(self.validation_index, self.datasets_validation):
-                self._likelihood(d, base + 8 * (self.Dg + 1 + j), want_grad=False)
-
-        if self.overlap and self.prior is not None and self.P > 0:
+        entries = [(d, base + 8 * j, None) for j, d in zip(self.dataset_index, self.datasets)]
+        entries += [(d, base + 8 * (self.Dg + 1 + j), None) for j, d in zip(self.validation_index, self.datasets_validation)]
+        has_prior = self.prior is not None and self.P > 0
+        if self.overlap and has_prior and entries:
             side = self._fork()
             with torch.cuda.stream(side):
-                likelihoods()
+                self._likelihoods(entries, want_grad=False)
             self._prior_forward(base + 8 * self.Dg)
             self._join(side)
             return
-        for j, d in zip(self.dataset_index, self.datasets):
-            self._likelihood(d, base + 8 * j, want_grad=False)
-        if self.prior is not None:
+        self._likelihoods(entries, want_grad=False)
+        if has_prior:
             self._prior_forward(base + 8 * self.Dg)  # this rank's patch-row block
-        for j, d in zip(self.validation_index, self.datasets_validation):
-            self._likelihood(d, base + 8 * (self.Dg + 1 + j), want_grad=False)
 
     def trace_losses(self, refresh_flux=False):
         """Per-epoch trace (loss.py:212-250): every dataset's Poisson loss and one more prior draw,

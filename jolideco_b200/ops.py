@@ -152,6 +152,53 @@ def poisson_forward_backward(conv, background, counts, f=1, bkg_log_norm=None, l
     return dict(loss_sum=loss_sum, npred=npred, dpool=dpool, dlogb=dlogb)
 
 
+# jd_lik_dataset of include/jolideco_b200.h (96 bytes): one record per dataset of a batched likelihood launch
+LIK_DTYPE = np.dtype([("flux", "u8"), ("exposure", "u8"), ("psf", "u8"), ("background", "u8"), ("counts", "u8"),
+                      ("bkg_log_norm", "u8"), ("dpool", "u8"), ("loss_sum", "u8"), ("dlogb", "u8"), ("dflux", "u8"),
+                      ("loss_const", "f8"), ("accumulate", "i4"), ("reserved", "i4")])
+
+
+def stirling_constant(counts):
+    """sum_pix 1{c > 1} (c log c - c + 1/2 log(2 pi c)): the counts-only term of nn.PoissonNLLLoss(full=True)
+    (loss.py:35-37), a constant of the dataset that the fused likelihood kernel adds once (setup-time, float64)."""
+    c = counts.double()
+    cc = c.clamp(min=1)
+    return float(torch.where(c > 1, c * torch.log(cc) - c + 0.5 * torch.log(2 * math.pi * cc), torch.zeros_like(c)).sum())
+
+
+def likelihood_batched(flux, datasets, f=1, want_grad=True, eps=1e-25):
+    """All datasets of a joint iteration through jd_likelihood_forward (+ _backward): list of dicts with CUDA tensors
+    exposure, psf, background, counts [, bkg_log_norm, flux (own NPred input)].  Returns dict(loss_sum (D,) double,
+    dlogb (D,) double, dpool [D x (H,W)], dflux (D,fH,fW))."""
+    _check(flux, "flux")
+    fH, fW = _hw(flux)
+    D = len(datasets)
+    kh, kw = _hw(datasets[0]["psf"])
+    H, W = _hw(datasets[0]["counts"])
+    dev = flux.device
+    loss = torch.zeros(D, dtype=torch.float64, device=dev)
+    dlogb = torch.zeros(D, dtype=torch.float64, device=dev)
+    dpool = torch.zeros((D, H, W), dtype=torch.float32, device=dev) if want_grad else None
+    dflux = torch.zeros((D, fH, fW), dtype=torch.float32, device=dev) if want_grad else None
+    rec = np.zeros(D, dtype=LIK_DTYPE)
+    for i, (r, d) in enumerate(zip(rec, datasets)):
+        for k in ("exposure", "psf", "background", "counts"):
+            r[k] = _ptr(_check(d[k], k))
+        r["flux"] = _ptr(_check(d.get("flux", flux), "flux"))
+        r["bkg_log_norm"] = _ptr(_check(d.get("bkg_log_norm"), "bkg_log_norm")) or 0
+        r["loss_sum"] = loss.data_ptr() + 8 * i
+        r["loss_const"] = stirling_constant(d["counts"])
+        if want_grad:
+            r["dpool"] = dpool.data_ptr() + 4 * H * W * i
+            r["dlogb"] = dlogb.data_ptr() + 8 * i
+            r["dflux"] = dflux.data_ptr() + 4 * fH * fW * i
+    table = torch.from_numpy(rec.view(np.uint8).reshape(-1).copy()).to(dev)
+    _lib.call("jd_likelihood_forward", _ptr(table), D, fH, fW, kh, kw, int(f), H, W, float(eps), 1.0 / (H * W), _stream())
+    if want_grad:
+        _lib.call("jd_likelihood_backward", _ptr(table), D, fH, fW, kh, kw, int(f), H, W, _stream())
+    return dict(loss_sum=loss, dlogb=dlogb, dpool=dpool, dflux=dflux)
+
+
 # ------------------------------------------------------------------------------------------------
 class GMMPacked:
     """Device constants of a Gaussian mixture in the layout the kernels consume.

@@ -13,6 +13,7 @@ WORKLOADS = {
     "cfg5": dict(H=256, f=1, psf=17, K=256, D=1, desc="one of 64 independent 256x256 GMM-prior runs"),
     "joint1024": dict(H=1024, f=1, psf=17, K=256, D=8,
                       desc="north-star: 1024x1024 8-dataset GMM-prior joint deconvolution, 17x17 PSFs, K=256"),
+    "joint_tiny": dict(H=64, f=1, psf=7, K=8, D=2, desc="joint-step smoke size: 2 datasets of 64x64, 7x7 PSFs, K=8"),
     "tiny": dict(H=48, f=1, psf=7, K=8, D=2, desc="smoke-test size"),
 }
 

@@ -319,6 +319,56 @@ def gmm_patch_prior(flux, gmm, shift_y, shift_x, stride=4, marginalize=False, re
     return prior, dflux, logp.argmax(axis=1)
 
 
+def gmm_patch_prior_lean(flux, gmm, shift_y, shift_x, stride=4, marginalize=False, row_begin=None, row_end=None):
+    """`gmm_patch_prior(..., return_grad=True)` for BASELINE-size inputs (P = 65 025, K = 256): the same arithmetic in
+    two passes over the components instead of keeping every whitened residual y_k (P x K x 64 values).  Pass 1 = the
+    log-probabilities (as `GMM.estimate_log_prob`, incl. its float32 `log_prob` buffer), pass 2 recomputes y_k only
+    for components that carry gradient.  Checked against `gmm_patch_prior` in tests/test_oracle_golden.py.
+
+    Returns dict(prior, dflux, value (P,), argmax (P,), gap (P,) = best minus second-best log-probability: patches
+    with a tiny gap are the ones whose argmax may legitimately differ between float32 implementations)."""
+    dt = flux.dtype
+    size = gmm.patch_size
+    r = cycle_spin_roll(flux, shift_y, shift_x)
+    X = view_as_overlapping_patches(r, size, stride)
+    fH, fW = flux.shape
+    ny, nx = (fH - size) // stride + 1, (fW - size) // stride + 1
+    sel = np.arange(ny * nx)
+    if row_begin is not None:
+        sel = sel[row_begin * nx : row_end * nx]
+        X = X[sel]
+    keep = np.all(X > -1e5, axis=1)
+    X, sel = X[keep], sel[keep]
+    Xc = X - X.mean(axis=1, keepdims=True)
+    logp = gmm.estimate_log_prob(Xc)
+    v = _logsumexp(logp, axis=1) if marginalize else logp.max(axis=1)
+    k_star = logp.argmax(axis=1)
+    top2 = np.partition(logp, -2, axis=1)[:, -2:] if gmm.K > 1 else np.stack([logp[:, 0] - np.inf, logp[:, 0]], axis=1)
+    gap = top2[:, 1] - top2[:, 0]
+    c = dt.type(stride**2 / (size * size)) / dt.type(flux.size)
+    G = np.zeros_like(Xc)
+    for k in range(gmm.K):
+        if marginalize:
+            rows = slice(None)
+            coef = (np.exp(logp[:, k] - v) * c).astype(np.float32).astype(dt)
+        else:
+            rows = np.nonzero(k_star == k)[0]
+            if rows.size == 0:
+                continue
+            coef = np.full(rows.size, np.float32(c), dtype=np.float32).astype(dt)
+        y = Xc[rows] @ gmm.precisions_cholesky[k] - gmm.means_precisions_cholesky[k]
+        G[rows] -= (coef[:, None] * (y * gmm.pixel_weights)) @ gmm.precisions_cholesky[k].T
+    G -= G.mean(axis=1, keepdims=True)
+    dr = np.zeros_like(flux)
+    Gim = G.reshape(-1, size, size)
+    iy, ix = np.divmod(sel, nx)
+    for u in range(size):  # scatter-add, one patch element at a time (each (u, v) hits distinct pixels)
+        for w_ in range(size):
+            np.add.at(dr, (stride * iy + u, stride * ix + w_), Gim[:, u, w_])
+    dflux = np.roll(dr, (-shift_y, -shift_x), axis=(0, 1))
+    return dict(prior=v.sum() * c, dflux=dflux, value=v, argmax=k_star, gap=gap, patch_index=sel)
+
+
 # --------------------------------------------------------------------------------------
 # a12 Adam                                          torch.optim.Adam defaults, core.py:39-42
 # --------------------------------------------------------------------------------------
@@ -523,7 +573,7 @@ def map_run(flux_init_up, datasets, n_epochs, lr=0.1, beta=1.0, gmm=None, shifts
 
 
 def joint_loss_and_grad(theta, datasets, beta, gmm=None, shifts=None, stride=4, marginalize=False,
-                        dataset_index=None, rows=None):
+                        dataset_index=None, rows=None, lean=False):
     """Value and gradient (w.r.t. theta) of the joint objective sum_d L_d - beta * prior
     (TotalLoss.__call__, loss.py:257-261).  `dataset_index` / `rows` restrict to a shard (subset of
     datasets, block of prior patch rows): shard values / gradients sum to the whole."""
@@ -537,7 +587,11 @@ def joint_loss_and_grad(theta, datasets, beta, gmm=None, shifts=None, stride=4, 
         dtheta += dth
     if gmm is not None:
         r0, r1 = (None, None) if rows is None else rows
-        if rows is None or r1 > r0:
+        if lean and (rows is None or r1 > r0):  # BASELINE-size inputs
+            res = gmm_patch_prior_lean(flux, gmm, shifts[0], shifts[1], stride, marginalize, r0, r1)
+            total -= beta * res["prior"]
+            dtheta -= theta.dtype.type(beta) * res["dflux"] * flux
+        elif rows is None or r1 > r0:
             prior, dflux_p, _ = gmm_patch_prior(flux, gmm, shifts[0], shifts[1], stride, marginalize, True, r0, r1)
             total -= beta * prior
             dtheta -= theta.dtype.type(beta) * dflux_p * flux

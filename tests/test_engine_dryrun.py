@@ -22,6 +22,7 @@ def recorder(monkeypatch):
         calls.append((name, args))
 
     monkeypatch.setattr(E._lib, "call", fake_call)
+    monkeypatch.setenv("JD_OVERLAP", "0")  # one stream unless a test asks for the fork / join structure
     monkeypatch.setattr(ops, "require_device", lambda *a, **k: None)
     monkeypatch.setattr(ops, "_check", lambda t, name, dtype=torch.float32: t)
     monkeypatch.setattr(ops, "use_stream_k", lambda P, device: False)
@@ -52,33 +53,44 @@ def test_reference_step_launch_sequence(recorder):
                                                                    backend=1), use_graph=False,
                       shift_table=np.zeros((4, 2), dtype=np.int32))
     eng.step(0)
-    assert names(recorder) == ["jd_step_begin_flux", "jd_conv_forward_direct", "jd_poisson_forward_backward",
-                               "jd_conv_backward_direct", "jd_gmm_prior_forward_tc", "jd_gmm_prior_backward_max_tri",
-                               "jd_adam_fold_step_dev"]
-    assert E._STATS["launches"] >= 7
+    assert names(recorder) == ["jd_step_begin_flux", "jd_likelihood_forward", "jd_likelihood_backward",
+                               "jd_gmm_prior_forward_tc", "jd_gmm_prior_backward_max_tri", "jd_adam_joint_step_dev"]
+    assert E._STATS["launches"] >= 6
+    fwd, bwd, adam = recorder[1][1], recorder[2][1], recorder[5][1]
+    assert fwd[1] == 1 and fwd[2:9] == (32, 32, 5, 5, 1, 32, 32) and bwd[0] == fwd[0]   # one dataset, same table
+    assert adam[5] == eng.parts.data_ptr() and adam[6] == 1 and adam[8] == eng.G.data_ptr()
     del recorder[:]
     eng.trace_enqueue(torch.zeros(eng.n_trace, dtype=torch.float64))
-    assert names(recorder) == ["jd_step_begin", "jd_conv_forward_direct", "jd_poisson_forward_backward",
-                               "jd_gmm_prior_forward_tc"]
+    assert names(recorder) == ["jd_step_begin", "jd_likelihood_forward", "jd_gmm_prior_forward_tc"]
+    assert recorder[1][1][0] != fwd[0]                                                  # loss-only table: no dpool
 
 
 def test_logsumexp_and_uniform_prior_sequences(recorder):
     eng = E.MapEngine(torch.zeros(32, 32), [dataset()], prior=dict(packed=fake_packed(), stride=4, marginalize=True,
                                                                    backend=1), use_graph=False)
     eng.step(0)
-    assert names(recorder)[-3:] == ["jd_gmm_prior_forward_tc", "jd_gmm_prior_backward_lse_tc", "jd_adam_fold_step_dev"]
+    assert names(recorder)[-3:] == ["jd_gmm_prior_forward_tc", "jd_gmm_prior_backward_lse_tc", "jd_adam_joint_step_dev"]
     del recorder[:]
     eng = E.MapEngine(torch.zeros(32, 32), [dataset()], prior=None, use_graph=False)
     eng.step(0)
+    assert names(recorder) == ["jd_step_begin_flux", "jd_likelihood_forward", "jd_likelihood_backward",
+                               "jd_adam_joint_step_dev"]
+    assert recorder[3][1][8] is None                                                    # uniform prior: no fold
+
+
+def test_separate_launches_when_the_batched_kernels_are_switched_off(recorder, monkeypatch):
+    monkeypatch.setenv("JD_LIK_BATCHED", "0")
+    eng = E.MapEngine(torch.zeros(32, 32), [dataset()], prior=None, use_graph=False)
+    eng.step(0)
     assert names(recorder) == ["jd_step_begin_flux", "jd_conv_forward_direct", "jd_poisson_forward_backward",
-                               "jd_conv_backward_direct", "jd_adam_step_dev"]
+                               "jd_conv_backward_direct", "jd_adam_joint_step_dev"]
 
 
 def test_fft_path_is_taken_for_large_psfs(recorder):
     eng = E.MapEngine(torch.zeros(64, 64), [dataset(n=64, k=31)], prior=None, use_graph=False)
     eng.step(0)
     assert "jd_conv_forward_fft" in names(recorder) and "jd_conv_backward_fft" in names(recorder)
-    assert "jd_conv_forward_direct" not in names(recorder)
+    assert "jd_conv_forward_direct" not in names(recorder) and "jd_likelihood_forward" not in names(recorder)
 
 
 def test_calibration_accumulators_and_shift_sequence(recorder):
@@ -87,29 +99,32 @@ def test_calibration_accumulators_and_shift_sequence(recorder):
     ds = [dataset(bkg_log_norm=logb, train_bkg_norm=True, shift_xy=shift, train_shift=True),
           dataset(bkg_log_norm=torch.zeros(1), train_bkg_norm=True)]
     eng = E.MapEngine(torch.zeros(32, 32), ds, prior=None, use_graph=False)
-    assert eng.flux_s is not None and eng.acc.numel() == 5
+    assert ds[0].flux_s is not None and ds[1].flux_s is None and eng.acc.numel() == 2 + 3 * 2
     eng.step(0)
     seq = names(recorder)
-    assert seq == ["jd_step_begin_flux", "jd_shift_forward", "jd_conv_forward_direct", "jd_poisson_forward_backward",
-                   "jd_adam_scalar_step_dev", "jd_conv_backward_direct", "jd_shift_backward", "jd_adam_scalar_step_dev",
-                   "jd_adam_step_dev"]
+    assert seq == ["jd_step_begin_flux", "jd_shift_forward", "jd_likelihood_forward", "jd_adam_scalar_step_dev",
+                   "jd_likelihood_backward", "jd_shift_backward", "jd_adam_scalar_step_dev", "jd_adam_joint_step_dev"]
     base = eng.acc.data_ptr()
-    poisson = recorder[3][1]
-    assert poisson[6] == base and poisson[7] == base + 16          # loss sum -> acc[0], dlogb -> acc[2]
-    conv_b, shift_b = recorder[5][1], recorder[6][1]
-    assert conv_b[3] == eng.dflux_s.data_ptr() and conv_b[4] == 0  # conv adjoint writes the gradient of the shifted flux
-    assert shift_b[6] == eng.dflux_l.data_ptr() and shift_b[8] == base + 24  # ... folded into dflux_l, dshift -> acc[3:5]
-    assert recorder[7][1][5] == 2                                 # Adam on the (shift_x, shift_y) pair
-    # joint step: the second dataset's calibration gradients start from cleared accumulators
+    rec = np.frombuffer(eng._tables[next(iter(eng._tables))].numpy().tobytes(), dtype=E.LIK_DTYPE)[0]
+    assert rec["loss_sum"] == base and rec["dlogb"] == base + 16       # loss sum -> acc[0], dlogb -> slot of dataset 0
+    assert rec["flux"] == ds[0].flux_s.data_ptr() and rec["dflux"] == ds[0].dflux_s.data_ptr()  # shifted in / out
+    assert recorder[3][1][3] == base + 16                               # Adam on log(background norm) reads the slot
+    shift_b = recorder[5][1]
+    assert shift_b[0] == ds[0].dflux_s.data_ptr() and shift_b[6] == eng.parts.data_ptr() and shift_b[7] == 0
+    assert shift_b[8] == base + 24                                      # dshift -> the two slots after dlogb
+    assert recorder[6][1][5] == 2                                       # Adam on the (shift_x, shift_y) pair
+    # joint step: both datasets in one launch per direction, each with its own accumulator slots and gradient part
     del recorder[:]
     eng.joint_step()
     seq = names(recorder)
-    i = seq.index("jd_step_begin")
-    assert seq[i - 1] == "jd_adam_scalar_step_dev" and recorder[i][1][9] == base + 16 and recorder[i][1][10] == 3
-    assert seq.count("jd_poisson_forward_backward") == 2 and seq[-1] == "jd_adam_step_dev"
-    # a dataset without shift keeps the direct route into dflux_l (accumulating for the second dataset)
-    conv_b2 = [c for c in recorder if c[0] == "jd_conv_backward_direct"][1][1]
-    assert conv_b2[3] == eng.dflux_l.data_ptr() and conv_b2[4] == 1
+    assert seq == ["jd_step_begin_flux", "jd_shift_forward", "jd_likelihood_forward", "jd_adam_scalar_step_dev",
+                   "jd_adam_scalar_step_dev", "jd_likelihood_backward", "jd_shift_backward", "jd_adam_scalar_step_dev",
+                   "jd_adam_joint_step_dev"]
+    assert recorder[2][1][1] == 2 and recorder[-1][1][6] == 2
+    key = [k for k in eng._tables if len(k[0]) == 2][0]
+    recs = np.frombuffer(eng._tables[key].numpy().tobytes(), dtype=E.LIK_DTYPE)
+    assert recs[1]["dlogb"] == base + 8 * (2 + 3) and recs[1]["dflux"] == eng.parts.data_ptr() + 4 * 32 * 32
+    assert recs[1]["flux"] == eng.flux.data_ptr() and recs[0]["loss_const"] == 0.0   # counts of 1: no Stirling term
 
 
 def test_calibration_routing(monkeypatch):
@@ -118,9 +133,10 @@ def test_calibration_routing(monkeypatch):
     assert MAPDeconvolver._calibrations_fusable(cals)            # shifts at 0: background norm only
     cals["b"] = J.NPredCalibration(shift_x=0.3, shift_y=0.0)
     monkeypatch.delenv("JD_FUSED_SHIFT", raising=False)
-    assert not MAPDeconvolver._calibrations_fusable(cals)        # non-zero shift: autograd path by default
-    monkeypatch.setenv("JD_FUSED_SHIFT", "1")
-    assert MAPDeconvolver._calibrations_fusable(cals)
+    assert MAPDeconvolver._calibrations_fusable(cals)            # non-zero shift: jd_shift_forward / backward
+    monkeypatch.setenv("JD_FUSED_SHIFT", "0")
+    assert not MAPDeconvolver._calibrations_fusable(cals)        # ... unless sent to the autograd path
+    monkeypatch.delenv("JD_FUSED_SHIFT")
     cals["c"] = J.NPredCalibration(psf_scale=1.1)
     assert not MAPDeconvolver._calibrations_fusable(cals)        # psf rescaling is not covered
     assert MAPDeconvolver._shift_is_zero(cals["a"]) and not MAPDeconvolver._shift_is_zero(cals["b"])
@@ -152,7 +168,7 @@ def test_deconvolver_run_builds_the_engine_with_calibrations(recorder, monkeypat
     assert b.shift_xy is None and not b.train_bkg_norm and b.bkg_log_norm is not None
     seq = names(recorder)
     assert seq.count("jd_shift_forward") == 2 * (1 + 1) + 1            # warm-up + 2 steps + 2 traces for dataset a
-    assert seq.count("jd_adam_fold_step_dev") == 2 * 2 + 1            # 2 epochs x 2 datasets + warm-up
+    assert seq.count("jd_adam_joint_step_dev") == 2 * 2 + 1           # 2 epochs x 2 datasets + warm-up
     assert len(res.trace_loss) == 2 and set(res.trace_loss.colnames) >= {"total", "dataset-a", "dataset-b"}
     assert res.flux_upsampled_total.shape == (48, 48)
     err = res.components["flux"].flux_upsampled_error_numpy   # compute_error: inf everywhere, as in the reference
@@ -213,20 +229,20 @@ def test_overlap_forks_the_likelihood_chain_and_joins_before_the_update(recorder
     prior = dict(packed=fake_packed(), stride=4, marginalize=False, backend=1)
     eng = E.MapEngine(torch.zeros(32, 32), [dataset(), dataset()], prior=prior, use_graph=False, overlap=True)
     eng.step(0)
-    assert names(events) == ["jd_step_begin_flux", "side.wait(main)", "enter(side)", "jd_conv_forward_direct",
-                             "jd_poisson_forward_backward", "jd_conv_backward_direct", "exit(side)",
+    assert names(events) == ["jd_step_begin_flux", "side.wait(main)", "enter(side)", "jd_likelihood_forward",
+                             "jd_likelihood_backward", "exit(side)",
                              "jd_gmm_prior_forward_tc", "jd_gmm_prior_backward_max_tri", "main.wait(side)",
-                             "jd_adam_fold_step_dev"]
+                             "jd_adam_joint_step_dev"]
     del events[:]
     eng.joint_step()
     seq = names(events)
     assert seq[:3] == ["jd_step_begin_flux", "side.wait(main)", "enter(side)"]
     assert seq.index("exit(side)") < seq.index("jd_gmm_prior_forward_tc") < seq.index("main.wait(side)")
-    assert seq[seq.index("main.wait(side)") + 1:] == ["jd_patch_fold", "jd_adam_step_dev"]  # fold accumulates into dflux_l
-    assert seq.count("jd_conv_backward_direct") == 2
+    assert seq[seq.index("main.wait(side)") + 1:] == ["jd_adam_joint_step_dev"]  # parts + fold + Adam in one launch
+    assert seq.count("jd_likelihood_backward") == 1
     del events[:]
     eng.trace_enqueue(torch.zeros(eng.n_trace, dtype=torch.float64))
     seq = names(events)
     assert seq[0] == "jd_step_begin" and seq[-2:] == ["jd_gmm_prior_forward_tc", "main.wait(side)"]
-    # default: no side stream at all
+    # JD_OVERLAP=0 (the fixture's setting): no side stream at all
     assert E.MapEngine(torch.zeros(32, 32), [dataset()], prior=prior, use_graph=False)._side is None

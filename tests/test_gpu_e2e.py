@@ -175,9 +175,6 @@ def test_background_norm_calibration_matches_imported_reference(fused):
     assert_allclose(norms, g["background_norm"], rtol=1e-4)
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("JD_TEST_PENDING"),
-                    reason="written at the end of round 1 without GPU minutes left; set JD_TEST_PENDING=1, and drop this "
-                           "mark after the first green run")
 @pytest.mark.parametrize("name,f", [("run_gmm_shift.npz", 1), ("run_gmm_shift_up2.npz", 2)])
 def test_shift_calibration_matches_imported_reference(name, f):
     """trainable non-zero sub-pixel shifts + background norms.  Not covered by the fused engine:
@@ -190,23 +187,20 @@ def test_shift_calibration_matches_imported_reference(name, f):
     cals = J.NPredCalibrations()
     for ds_name, b, (sx, sy) in zip(as_datasets(g), g["background_norm_init"], g["shift_xy_init"]):
         cals[ds_name] = J.NPredCalibration(shift_x=float(sx), shift_y=float(sy), background_norm=float(b))
-    deco = J.MAPDeconvolver(n_epochs=6, learning_rate=0.1, display_progress=False, device=DEV)
+    deco = J.MAPDeconvolver(n_epochs=6, learning_rate=0.1, display_progress=False, device=DEV, fused=False)
     res = deco.run(datasets=as_datasets(g), components=comps, calibrations=cals)
-    assert not hasattr(deco, "engine")  # the fused engine does not cover shifts
+    assert not hasattr(deco, "engine")  # autograd path: grid_sample + the CUDA kernels
     check(res, g, 6)
     assert_allclose([float(c.background_norm) for c in res.calibrations.values()], g["background_norm"], rtol=1e-4)
     shifts = np.stack([c.shift_xy.detach().cpu().numpy()[0] for c in res.calibrations.values()])
     assert_allclose(shifts, g["shift_xy"], rtol=1e-3, atol=1e-4)
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("JD_TEST_PENDING"),
-                    reason="written at the end of round 1 without GPU minutes left; set JD_TEST_PENDING=1, and drop this "
-                           "mark after the first green run")
 @pytest.mark.parametrize("name,f", [("run_gmm_shift.npz", 1), ("run_gmm_shift_up2.npz", 2)])
 def test_shift_calibration_fused_engine_matches_imported_reference(monkeypatch, name, f):
-    """The same runs through the fused engine (jd_shift_forward / jd_shift_backward + scalar Adam on the shift pair,
-    opt-in with JD_FUSED_SHIFT=1)."""
-    monkeypatch.setenv("JD_FUSED_SHIFT", "1")
+    """The same runs through the fused engine (jd_shift_forward / jd_shift_backward + scalar Adam on the shift pair),
+    the default route."""
+    monkeypatch.delenv("JD_FUSED_SHIFT", raising=False)
     g = load_golden(name)
     prior = make_prior(g, 8)
     comps = J.FluxComponents()
@@ -223,9 +217,6 @@ def test_shift_calibration_fused_engine_matches_imported_reference(monkeypatch, 
     assert_allclose(shifts, g["shift_xy"], rtol=1e-3, atol=1e-4)
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("JD_TEST_PENDING"),
-                    reason="written at the end of round 1 without GPU minutes left; set JD_TEST_PENDING=1, and drop this "
-                           "mark after the first green run")
 def test_shift_kernels_match_oracle():
     """jd_shift_forward / jd_shift_backward against the oracle's 4-tap restatement (pinned to shift_image_torch)."""
     from jolideco_b200 import _lib

@@ -286,3 +286,22 @@ def test_joint_objective_matches_imported_reference(tag, marginalize):
              for idx, rows in (([0, 2], (0, ny // 2)), ([1], (ny // 2, ny)))]
     assert_allclose(sum(p[0] for p in parts), total, rtol=1e-6)
     assert np.abs(sum(p[1] for p in parts) - dtheta).max() <= 1e-6 * np.abs(dtheta).max()
+
+
+@pytest.mark.parametrize("marginalize", [False, True])
+@pytest.mark.parametrize("rows", [None, (2, 7)])
+def test_lean_prior_oracle_equals_the_pinned_one(marginalize, rows):
+    """`gmm_patch_prior_lean` (two passes over the components; what the BASELINE-size GPU tests compare with) is the
+    same function as `gmm_patch_prior`, which the reference goldens pin."""
+    rng = np.random.default_rng(0)
+    K = 7
+    A = rng.normal(0, 0.05, size=(K, 64, 64))
+    gmm = O.GMM(rng.normal(0, 0.01, size=(K, 64)), A @ A.transpose(0, 2, 1) + 0.01 * np.eye(64), np.full(K, 1 / K),
+                dtype=np.float64)
+    flux = rng.gamma(2.0, size=(45, 52))
+    r0, r1 = (None, None) if rows is None else rows
+    prior, dflux, k = O.gmm_patch_prior(flux, gmm, 2, -1, 4, marginalize, True, r0, r1)
+    res = O.gmm_patch_prior_lean(flux, gmm, 2, -1, 4, marginalize, r0, r1)
+    assert abs(prior - res["prior"]) <= 1e-15 * abs(prior)
+    assert np.abs(dflux - res["dflux"]).max() <= 1e-14 * np.abs(dflux).max()
+    assert np.array_equal(k, res["argmax"]) and (res["gap"] >= 0).all()
