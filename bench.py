@@ -435,7 +435,7 @@ def parity_check(J, E, workload, args, device, rank, world, pg):
     # 1-rank engine over ALL datasets, eager, one joint gradient at the initial theta
     full = build_engine(J, E, workload, args, device, 0, 1, None, n_draws=4, shift_table=[shift], use_graph=False)
     full.overlap = False
-    full._joint_pre()
+    full._grad_reduce(full.D, full._joint_pre(), 1.0)  # sum_d dL_d/dflux - beta dprior/dflux -> dflux_l
     torch.cuda.synchronize()
     g_full = (full.dflux_l * full.flux).double()  # d total / d theta = d total / d flux * flux  (use_log_flux)
     acc = full.acc.cpu().numpy()
@@ -445,7 +445,7 @@ def parity_check(J, E, workload, args, device, rank, world, pg):
     if world > 1:
         part = build_engine(J, E, workload, args, device, rank, world, pg, n_draws=8, shift_table=[shift] * 8,
                             use_graph=False)
-        part._joint_pre()
+        part._grad_reduce(part.D, part._joint_pre(), 1.0)
         g = part.dflux_l.clone()
         dist.all_reduce(g, group=pg)
         g = (g * part.flux).double()
@@ -666,6 +666,8 @@ def measure_rooflines(E, eng, run_step, args, workload, flush):
         if name.startswith("jd_gmm_prior_forward") and eng.prior is not None:
             work = 2.0 * eng.P * 64 * 64 * eng.packed.K  # useful flops, counted once
             half = name != "jd_gmm_prior_forward_tc16"  # TF32 pipe = 1/2 bf16 rate; the split-FP16 kernel: bf16 rate
+            if name == "jd_gmm_prior_forward_tcm":  # tf32 main product + two fp16 corrections at twice the rate
+                eng.issued_over_useful = 2.0 * ((320.0 / 512.0) if eng.packed.upper_tri else 1.0)
             peak = bf16_burst / (2.0 if half else 1.0)
             ach = work / (avg_ms * 1e-3) / 1e12
             issued = getattr(eng, "issued_over_useful", None)

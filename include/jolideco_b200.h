@@ -216,6 +216,19 @@ int jd_gmm_prior_forward_tc16(const float* flux, int fH, int fW, const int32_t* 
                               const float* ck, int K, int upper_tri, int zero_mean, int marginalize,
                               float* value, int32_t* argmax, float* logp, double* sum, jd_stream_t stream);
 
+/* ---- a8..a10 forward, third tensor-core kernel (csrc/jd_gmm_tcm.cu): split-TF32 with the two correction products on
+ * the FP16 pipe (same 2^-21 accuracy as 3 x TF32, two thirds of the tensor work), persistent stream-K decomposition,
+ * gather of the next tile overlapped with the MMAs of the current one.  Same contract as jd_gmm_prior_forward_tc_sk;
+ * Bt / binv come from jd_gmm_tcm_pack (scaled operand image + 1 / component scale), `workspace` holds
+ * jd_gmm_tcm_workspace_bytes(n_patches, K) zero-initialised bytes (256-byte aligned; self-resetting counters). */
+size_t jd_gmm_tcm_packed_bytes(int K);
+int jd_gmm_tcm_pack(const float* Lw, int K, void* Bt, float* binv, jd_stream_t stream);
+int64_t jd_gmm_tcm_workspace_bytes(int64_t n_patches, int K);
+int jd_gmm_prior_forward_tcm(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
+                             int row_end, const void* Bt, const float* binv, const float* mw, const float* ck, int K,
+                             int upper_tri, int zero_mean, int marginalize, void* workspace, float* value,
+                             int32_t* argmax, float* logp, double* sum, jd_stream_t stream);
+
 /* Per-patch gradient  G[p',:] = scale * sum_k R[p',k] (xc_p Lam_k - bk_k),  minus its row mean,
  * R = one-hot(argmax) or softmax_k(logp) (marginalize=1; needs logp and value from the forward);
  * Lam_k = Lw_k Lw_k^T, bk_k = mw_k Lw_k^T.  (Autograd mirror of gmm.py:270-272 + norms.py:97-103.)

@@ -26,7 +26,7 @@ LIK_DTYPE = ops.LIK_DTYPE
 
 # launch accounting / per-kernel timing hooks (bench.py): every C-ABI call below is exactly one
 # kernel launch on the current stream
-_STATS = {"launches": 0, "timed": None, "events": []}
+_STATS = {"launches": 0, "timed": None, "events": [], "dry": False}
 
 
 # kernels launched by entry points that launch more than one
@@ -34,6 +34,8 @@ _KERNELS_PER_CALL = {"jd_conv_forward_fft": 3, "jd_conv_backward_fft": 3}
 
 
 def _call(name, *args):
+    if _STATS["dry"]:  # argument-building pass before a graph capture (lazy device tables are created here)
+        return
     n = _KERNELS_PER_CALL.get(name, 1)
     if name == "jd_gmm_prior_backward" and args[-2] is not None:
         n = 4  # histogram, scan, scatter, bucketed GEMV
@@ -170,6 +172,8 @@ class MapEngine:
                 self.packed.Bt  # pack the tensor-core operand before any graph capture
             elif self.backend == 2:
                 ops._bt16(self.packed)
+            elif self.backend == 3:
+                ops._btm(self.packed)
             self.ny, self.nx = ops.patch_grid(self.fH, self.fW, self.stride)
             self.c = self.stride**2 / ops.PD / self.n
             # row-block shard of the prior (whole grid on one GPU)
@@ -178,11 +182,13 @@ class MapEngine:
             self.P = P
             if self.backend == 1 and P > 0 and (ops.use_stream_k(P, self.dev) if stream_k is None else stream_k):
                 self.sk_ws = ops.tc_sk_workspace(P, self.packed.K, self.dev)
+            if self.backend == 3 and P > 0:
+                self.sk_ws = ops.tcm_workspace(P, self.packed.K, self.dev)
             self.value = torch.empty(max(P, 1), **f32)
             self.argmax = torch.empty(max(P, 1), dtype=torch.int32, device=self.dev)
             # logsumexp mode keeps logp for the backward; the tensor-core kernels use a component-major layout
             self.logp = torch.empty((max(P, 1), self.packed.K), **f32) if self.marginalize else None
-            if self.marginalize and self.backend in (1, 2):
+            if self.marginalize and self.backend in (1, 2, 3):
                 ops._bt_lam(self.packed)
             self.G = torch.empty((max(P, 1), ops.PD), **f32)
             # bucketed max-mode backward (patches grouped by winning component, Lam_k staged once per 32 patches):
@@ -385,6 +391,13 @@ class MapEngine:
     def _prior_forward(self, sum_acc):
         if self.P <= 0:
             return
+        if self.backend == 3:
+            bt, binv = ops._btm(self.packed)
+            _call("jd_gmm_prior_forward_tcm", _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride,
+                  self.rows[0], self.rows[1], _p(bt), _p(binv), _p(self.packed.mw), _p(self.packed.ck), self.packed.K,
+                  int(self.packed.upper_tri), int(self.packed.zero_mean), int(self.marginalize), _p(self.sk_ws),
+                  _p(self.value), _p(self.argmax), _p(self.logp), sum_acc, self._s())
+            return
         if self.backend == 2:
             bt, binv = ops._bt16(self.packed)
             _call("jd_gmm_prior_forward_tc16", _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride,
@@ -410,7 +423,7 @@ class MapEngine:
 
     def _prior_gradient(self, scale):
         """per-patch gradient rows G (consumed by _adam_fold)"""
-        if self.marginalize and self.backend in (1, 2):
+        if self.marginalize and self.backend in (1, 2, 3):
             _call("jd_gmm_prior_backward_lse_tc", _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride,
                   self.rows[0], self.rows[1], _p(ops._bt_lam(self.packed)), _p(self.packed.bk), self.packed.K,
                   _p(self.logp), _p(self.value), float(scale), _p(self.G), self._s())
@@ -508,6 +521,12 @@ class MapEngine:
         if g is None:
             # one eager pass would advance the state; capture directly instead (kernels are not
             # executed during capture) after making sure lazy one-time setup has happened
+            # dry pass: builds every lazily created device table (host -> device copies are illegal inside a capture)
+            _STATS["dry"] = True
+            try:
+                body()
+            finally:
+                _STATS["dry"] = False
             torch.cuda.synchronize(self.dev)
             g = torch.cuda.CUDAGraph()
             before = _STATS["launches"]

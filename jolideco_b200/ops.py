@@ -238,6 +238,7 @@ class GMMPacked:
         self.device = device
         self._Bt = None
         self._Bt16 = None
+        self._Btm = None
         self._Bt_lam = None
         self.upper_tri = bool(flags[0])
         self.zero_mean = bool(flags[1])
@@ -279,6 +280,26 @@ def _bt16(packed):
             _lib.call("jd_gmm_tc16_pack", _ptr(packed.Lw), packed.K, _ptr(bt), _ptr(binv), _stream())
         packed._Bt16 = (bt, binv)
     return packed._Bt16
+
+
+def _btm(packed):
+    """Operand image of the mixed TF32 / FP16 kernel (backend 3) + inverse component scales, packed once."""
+    if packed._Btm is None:
+        if packed.D != PD:
+            raise _lib.JolidecoB200Error("the tcgen05 prior kernels support 8x8 patches (D=64) only")
+        nbytes = _lib.load().jd_gmm_tcm_packed_bytes(packed.K)
+        with torch.cuda.device(packed.device):
+            bt = torch.empty(nbytes, dtype=torch.uint8, device=packed.device)
+            binv = torch.empty(packed.K, dtype=torch.float32, device=packed.device)
+            _lib.call("jd_gmm_tcm_pack", _ptr(packed.Lw), packed.K, _ptr(bt), _ptr(binv), _stream())
+        packed._Btm = (bt, binv)
+    return packed._Btm
+
+
+def tcm_workspace(P, K, device):
+    """Zero-initialised workspace of the backend-3 forward (arrival counters + per-segment partials)."""
+    n = int(_lib.load().jd_gmm_tcm_workspace_bytes(int(P), int(K)))
+    return torch.zeros(max(n, 256), dtype=torch.uint8, device=device)
 
 
 # tcgen05 prior forward: stream-K work decomposition (jd_gmm_prior_forward_tc_sk).  JD_TC_STREAMK = 0 | 1 forces it
@@ -350,13 +371,19 @@ def gmm_prior_forward(flux, shift_yx, packed, stride=4, marginalize=False, rows=
     if want_logp is None:
         want_logp = bool(marginalize)
     # the tensor-core forwards write logp component-major (K x P'): returned as the transposed (P', K) view
-    tc = int(backend) in (1, 2)
+    tc = int(backend) in (1, 2, 3)
     logp = None
     if want_logp:
         logp = torch.empty((packed.K, P) if tc else (P, packed.K), dtype=torch.float32, device=flux.device)
     if sum_out is None:
         sum_out = torch.zeros(1, dtype=torch.float64, device=flux.device)
-    if int(backend) == 2:
+    if int(backend) == 3:
+        bt, binv = _btm(packed)
+        ws = tcm_workspace(P, packed.K, flux.device)
+        _lib.call("jd_gmm_prior_forward_tcm", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(bt), _ptr(binv),
+                  _ptr(packed.mw), _ptr(packed.ck), packed.K, int(packed.upper_tri), int(packed.zero_mean),
+                  int(bool(marginalize)), _ptr(ws), _ptr(value), _ptr(argmax), _ptr(logp), _ptr(sum_out), _stream())
+    elif int(backend) == 2:
         bt, binv = _bt16(packed)
         _lib.call("jd_gmm_prior_forward_tc16", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(bt), _ptr(binv),
                   _ptr(packed.mw), _ptr(packed.ck), packed.K, int(packed.upper_tri), int(packed.zero_mean),

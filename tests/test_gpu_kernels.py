@@ -274,7 +274,7 @@ def prior_cuda(flux, gmm_packed, sy, sx, marginalize, rows=None, backend=0):
     return s.item() * c, dflux.cpu().numpy(), argmax.cpu().numpy()
 
 
-@pytest.mark.parametrize("backend", [0, 1, 2])
+@pytest.mark.parametrize("backend", [0, 1, 2, 3])
 @pytest.mark.parametrize("marginalize", [False, True])
 @pytest.mark.parametrize("shape,shift", [((38, 46), (0, 0)), ((38, 46), (-2, 1)), ((64, 80), (2, -2)), ((24, 24), (1, 2))])
 def test_gmm_prior_value_and_grad(marginalize, shape, shift, backend):
@@ -293,7 +293,7 @@ def test_gmm_prior_value_and_grad(marginalize, shape, shift, backend):
         assert rel_max(gr, ref_g) < 2e-5
 
 
-@pytest.mark.parametrize("backend", [0, 1, 2])
+@pytest.mark.parametrize("backend", [0, 1, 2, 3])
 @pytest.mark.parametrize("case", range(8))
 def test_gmm_prior_golden(case, backend):
     g = load_golden("prior_step.npz")
@@ -317,7 +317,7 @@ def test_gmm_prior_row_blocks_sum_to_whole():
     assert rel_max(sum(p[1] for p in parts), gr) < 1e-6
 
 
-@pytest.mark.parametrize("backend", [1, 2])
+@pytest.mark.parametrize("backend", [1, 2, 3])
 @pytest.mark.parametrize("mean_scale", [0.05, 0.0])
 @pytest.mark.parametrize("marginalize", [False, True])
 def test_gmm_prior_tensor_core_vs_cuda_core_full_size(marginalize, mean_scale, backend):
@@ -384,7 +384,7 @@ def test_gmm_prior_tensor_core_dense_precision_factors():
     assert not packed.upper_tri
     flux = t(rng.gamma(2.0, size=(100, 84)))
     v0, k0, lp0, s0 = ops.gmm_prior_forward(flux, (0, 1), packed, 4, False, want_logp=True, backend=0)
-    for backend in (1, 2):
+    for backend in (1, 2, 3):
         v1, k1, lp1, s1 = ops.gmm_prior_forward(flux, (0, 1), packed, 4, False, want_logp=True, backend=backend)
         lp1 = lp1.cpu().numpy().astype(np.float64)
         ref = lp0.cpu().numpy().astype(np.float64)
