@@ -182,11 +182,22 @@ class MAPDeconvolver:
             return trace[-1]["datasets-validation-total"] > np.mean(values[-self.stop_early_n_average:])
         return False
 
-    def _checkpoint(self, epoch, total_loss, components):
+    def _checkpoint(self, epoch, total_loss, components, calibrations=None, engine=None):
+        """Per-epoch checkpoint (core.py:234-243): a `MAPDeconvolverResult` with config, trace so far, components and
+        calibrations, written by rank 0 only (every rank holds the same replica).  The engine may train a working
+        copy of theta (symmetric memory of the peer collective): it is copied back into the component first."""
         if not self.checkpoint_path:
             return ""
         filename = self._default_checkpoint_filename.format(epoch=epoch)
-        np.savez(self.checkpoint_path / filename, **{f"flux_upsampled_{k}": v for k, v in components.to_numpy().items()})
+        rank = 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            rank = torch.distributed.get_rank()
+        if rank == 0:
+            if engine is not None:
+                engine.sync_theta()
+            checkpoint = MAPDeconvolverResult(config=self.to_dict(), trace_loss=total_loss.trace, components=components,
+                                              calibrations=calibrations)
+            checkpoint.write(self.checkpoint_path / filename, overwrite=True)
         return filename
 
     # ------------------------------------------------------------------------------------------
@@ -226,9 +237,9 @@ class MAPDeconvolver:
             if self.mode == "joint":
                 if not self._engine_supported(components, calibrations):
                     raise NotImplementedError("mode='joint' needs a configuration the fused engine supports")
-                self._run_joint(total_loss, components, shard)
+                self._run_joint(total_loss, components, shard, calibrations)
             elif self._engine_supported(components, calibrations):
-                self._run_fused(total_loss, components, len(datasets))
+                self._run_fused(total_loss, components, len(datasets), calibrations)
             else:
                 self._run_autograd(total_loss, components, calibrations)
 
@@ -246,20 +257,37 @@ class MAPDeconvolver:
                                     trace_loss=total_loss.trace, calibrations=calibrations,
                                     calibrations_init=calibrations_init, wcs=None)
 
-    def _run_fused(self, total_loss, components, n_datasets):
+    def _draw_state(self, components):
+        """Generator states of the priors' cycle-spin RNGs before the shift table is pre-drawn."""
+        return {name: prior.generator.get_state() for name, prior in components.priors.items()
+                if getattr(prior, "generator", None) is not None}
+
+    def _rewind_draws(self, components, states, n_consumed):
+        """The engine pre-draws n_epochs x (D + 1) shifts; an early stop consumes fewer.  Put the generators where the
+        reference's would be: initial state advanced by exactly the draws that were used (2 randint calls per draw,
+        utils/torch.py:108-116), so that a later run seeded from the same generator reproduces the reference."""
+        for name, prior in components.priors.items():
+            if name in states:
+                prior.generator.set_state(states[name])
+                for _ in range(n_consumed):
+                    prior.draw_shifts()
+
+    def _run_fused(self, total_loss, components, n_datasets, calibrations=None):
+        states = self._draw_state(components)
         engine = self._build_engine(total_loss, components, self.n_epochs * (n_datasets + 1))
         self.engine = engine
         engine.warmup()
         prior_names = list(total_loss.prior_loss.priors)
         # Without early stopping nothing on the host depends on the per-epoch trace: the accumulator rows stay
-        # on the device and are read back once at the end (the reference syncs with .item() every epoch).
-        deferred = not self.stop_early
+        # on the device and are read back once at the end (the reference syncs with .item() every epoch).  Checkpoints
+        # carry the trace so far (core.py:236-241), so they also need it on the host every epoch.
+        deferred = not self.stop_early and not self.checkpoint_path
         rows = torch.zeros((self.n_epochs, engine.n_trace), dtype=torch.float64, device=self.device) if deferred else None
         filenames = []
         for epoch in range(self.n_epochs):
             for i in range(n_datasets):
                 engine.step(i)
-            filename = self._checkpoint(epoch, total_loss, components)
+            filename = self._checkpoint(epoch, total_loss, components, calibrations, engine)
             if deferred:
                 engine.trace_enqueue(rows[epoch])
                 filenames.append(filename)
@@ -267,6 +295,7 @@ class MAPDeconvolver:
             ld, lp, lv = engine.trace_losses()
             total_loss.append_trace_values(ld, [lp] * len(prior_names), filename, lv if lv else None)
             if self._early_stop(total_loss.trace):
+                self._rewind_draws(components, states, (epoch + 1) * (n_datasets + 1))
                 break
         if deferred:
             host = rows.cpu().numpy()  # one synchronising read-back
@@ -275,18 +304,19 @@ class MAPDeconvolver:
                 total_loss.append_trace_values(ld, [lp] * len(prior_names), filename, lv if lv else None)
         torch.cuda.synchronize(self.device)
 
-    def _run_joint(self, total_loss, components, shard):
+    def _run_joint(self, total_loss, components, shard, calibrations=None):
         """One joint Adam step per epoch (+ trace); dataset- and prior-sharded when `shard` is given."""
+        states = self._draw_state(components)
         engine = self._build_engine(total_loss, components, self.n_epochs * 2, shard)
         self.engine = engine
         engine.warmup(joint=True)
         prior_names = list(total_loss.prior_loss.priors)
-        deferred = not self.stop_early
+        deferred = not self.stop_early and not self.checkpoint_path
         rows = torch.zeros((self.n_epochs, engine.n_trace), dtype=torch.float64, device=self.device) if deferred else None
         filenames = []
         for epoch in range(self.n_epochs):
             engine.joint_step()
-            filename = self._checkpoint(epoch, total_loss, components)
+            filename = self._checkpoint(epoch, total_loss, components, calibrations, engine)
             if deferred:
                 engine.trace_enqueue(rows[epoch])
                 filenames.append(filename)
@@ -294,6 +324,7 @@ class MAPDeconvolver:
             ld, lp, lv = engine.trace_losses()
             total_loss.append_trace_values(ld, [lp] * len(prior_names), filename, lv if lv else None)
             if self._early_stop(total_loss.trace):
+                self._rewind_draws(components, states, (epoch + 1) * 2)
                 break
         if deferred:
             if engine.world > 1:  # every slot is written by one rank (prior: partial sums): one all-reduce for all epochs
@@ -323,7 +354,7 @@ class MAPDeconvolver:
                 loss_total.backward()
                 self.optimizer.step()
             components.eval()
-            filename = self._checkpoint(epoch, total_loss, components)
+            filename = self._checkpoint(epoch, total_loss, components, calibrations)
             total_loss.append_trace(fluxes=fluxes, filename=filename)
             if self._early_stop(total_loss.trace):
                 break
@@ -369,3 +400,94 @@ class MAPDeconvolverResult:
     @property
     def config(self):
         return self._config
+
+    @property
+    def checkpoint_path(self):
+        return Path(self.config.get("checkpoint_path", None))
+
+    def read_checkpoint(self, epoch):
+        """Checkpoint of `epoch` as a `MAPDeconvolverResult` (core.py:329-343)."""
+        return self.__class__.read(self.checkpoint_path / self.trace_loss["filename"][epoch])
+
+    def write(self, filename, overwrite=False, format=None):
+        """Write the result (core.py:435-450).  The reference's FITS / ASDF writers are outside the hot path (no
+        astropy / asdf here): the container is an `.npz` with the config (JSON), the loss trace, every component's
+        upsampled flux (+ error, mask, parameterisation) and the calibration parameters - what `read` needs to hand
+        back an equivalent result and what a resumed run needs to start from."""
+        import json
+
+        filename = Path(filename)
+        if filename.exists() and not overwrite:
+            raise IOError(f"{filename} already exists and overwrite is False")
+        data = {"config": np.array(json.dumps({k: v for k, v in self.config.items() if _jsonable(v)}))}
+        trace = self.trace_loss
+        data["trace_colnames"] = np.array(list(trace.colnames))
+        for name in trace.colnames:
+            col = trace[name] if len(trace) else np.array([])
+            data[f"trace__{name}"] = np.asarray(col) if name != "filename" else np.array([str(v) for v in col])
+        data["component_names"] = np.array(list(self.components))
+        for name, comp in self.components.items():
+            data[f"flux_upsampled__{name}"] = comp.flux_upsampled_numpy
+            data[f"parameter__{name}"] = comp._flux_upsampled.detach().cpu().numpy()  # log flux when use_log_flux
+            data[f"component_meta__{name}"] = np.array([int(comp.upsampling_factor or 1), int(comp.use_log_flux),
+                                                        int(comp.frozen)])
+            if comp.flux_upsampled_error is not None:
+                data[f"flux_upsampled_error__{name}"] = comp.flux_upsampled_error_numpy
+            if comp.mask is not None:
+                data[f"mask__{name}"] = comp.mask.detach().cpu().numpy()[0, 0]
+        if self.calibrations:
+            data["calibration_names"] = np.array(list(self.calibrations))
+            for name, cal in self.calibrations.items():
+                d = cal.to_dict()
+                data[f"calibration__{name}"] = np.array([d["shift_x"], d["shift_y"], d["background_norm"], d["psf_scale"],
+                                                         float(d.get("frozen", False))], dtype=np.float64)
+        with open(filename, "wb") as fh:
+            np.savez(fh, **data)
+
+    @classmethod
+    def read(cls, filename, format=None):
+        """Read a result written by `write` (core.py:452-471).  Priors are not stored (the reference cannot serialise
+        a non-registry GMM either, gmm.py:458-471): components come back with a uniform prior."""
+        import json
+
+        from .loss import TotalLoss  # noqa: F401  (trace table type)
+        from .models import NPredCalibration, NPredCalibrations
+        from .table import TraceTable
+
+        with np.load(filename, allow_pickle=False) as f:
+            config = json.loads(str(f["config"]))
+            names = [str(n) for n in f["trace_colnames"]]
+            trace = TraceTable(names=names)
+            cols = {n: f[f"trace__{n}"] for n in names}
+            for i in range(len(cols[names[0]]) if names else 0):
+                trace.add_row({n: (str(cols[n][i]) if n == "filename" else float(cols[n][i])) for n in names})
+            components = FluxComponents()
+            for name in [str(n) for n in f["component_names"]]:
+                factor, use_log, frozen = (int(v) for v in f[f"component_meta__{name}"])
+                mask = f[f"mask__{name}"] if f"mask__{name}" in f else None
+                theta = torch.from_numpy(f[f"parameter__{name}"])
+                comp = SpatialFluxComponent(flux_upsampled=torch.ones_like(theta), use_log_flux=bool(use_log),
+                                            mask=None if mask is None else torch.from_numpy(mask[None, None]),
+                                            upsampling_factor=factor, frozen=bool(frozen), prior=UniformPrior())
+                comp._flux_upsampled.data.copy_(theta)  # the stored parameter itself: lossless under masks
+                if f"flux_upsampled_error__{name}" in f:
+                    comp._flux_upsampled_error = torch.from_numpy(f[f"flux_upsampled_error__{name}"])
+                components[name] = comp
+            calibrations = None
+            if "calibration_names" in f:
+                calibrations = NPredCalibrations()
+                for name in [str(n) for n in f["calibration_names"]]:
+                    sx, sy, b, ps, frozen = f[f"calibration__{name}"]
+                    calibrations[name] = NPredCalibration(shift_x=float(sx), shift_y=float(sy), background_norm=float(b),
+                                                          psf_scale=float(ps), frozen=bool(frozen))
+        return cls(config=config, components=components, trace_loss=trace, calibrations=calibrations)
+
+
+def _jsonable(v):
+    import json
+
+    try:
+        json.dumps(v)
+        return True
+    except TypeError:
+        return False

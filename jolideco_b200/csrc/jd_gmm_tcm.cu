@@ -148,6 +148,9 @@ gmm_fwd_tcm_kernel(const float* __restrict__ flux, Geom g, const int32_t* __rest
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rt_zero = (uint32_t)K >> 30;  // 0 at run time (K < 2^30), opaque to the compiler
+  // profiling knobs (JD_TC_DEBUG, results are wrong with any of them): 1 = no epilogue TMEM loads, 2 = no FP16
+  // correction products, 4 = no TF32 product, 8 = one MMA per component
+  const int dbg = marginalize >> 8;
   marginalize &= 1;
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -221,11 +224,20 @@ gmm_fwd_tcm_kernel(const float* __restrict__ flux, Geom g, const int32_t* __rest
         mbar_wait(empty_bar(s), ((pos / NSTAGE) & 1) ^ 1);
         if (!ZERO_MEAN) mbar_wait(tempty_bar(t), ((pos / NSLOT) & 1) ^ 1);
         if (elect_one()) {
-          // this CTA fetches half `crank` of the image (tf32 part | the two half parts) for both CTAs of the pair
-          mbar_arrive_expect_tx(full_bar(s), B_BYTES);
-          bulk_g2s_mc(smem_u32(sB + s * B_BYTES) + crank * (B_BYTES / CLUSTER),
-                      Bt + (size_t)kc * B_BYTES + crank * (B_BYTES / CLUSTER), B_BYTES / CLUSTER, full_bar(s),
-                      (uint16_t)((1u << CLUSTER) - 1));
+          // this CTA fetches half `crank` of the image (tf32 part | the two half parts) for both CTAs of the pair.
+          // Upper-triangular factors: whitened features 0..31 do not depend on input features 32..63, i.e. rows 0..31
+          // of the second tf32 k-block (4 KB) are zeros no MMA reads (k-steps 4..7 start at row 32): not copied.
+          mbar_arrive_expect_tx(full_bar(s), TRI ? B_BYTES - KBLOCK_BYTES / 2 : B_BYTES);
+          const uint32_t dst = smem_u32(sB + s * B_BYTES) + crank * (B_BYTES / CLUSTER);
+          const uint8_t* src = Bt + (size_t)kc * B_BYTES + crank * (B_BYTES / CLUSTER);
+          const uint16_t both = (uint16_t)((1u << CLUSTER) - 1);
+          if (TRI && crank == 0) {
+            bulk_g2s_mc(dst, src, KBLOCK_BYTES, full_bar(s), both);
+            bulk_g2s_mc(dst + KBLOCK_BYTES + KBLOCK_BYTES / 2, src + KBLOCK_BYTES + KBLOCK_BYTES / 2, KBLOCK_BYTES / 2,
+                        full_bar(s), both);
+          } else {
+            bulk_g2s_mc(dst, src, B_BYTES / CLUSTER, full_bar(s), both);
+          }
           if (!ZERO_MEAN) {
             mbar_arrive_expect_tx(mwfull_bar(t), MW_BYTES);
             bulk_g2s(smem_u32(sMW + t * 64), mw + (size_t)kc * 64, MW_BYTES, mwfull_bar(t));
@@ -264,6 +276,8 @@ gmm_fwd_tcm_kernel(const float* __restrict__ flux, Geom g, const int32_t* __rest
             const uint32_t b_base = pass == 0 ? b_h : b_r;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
+              if ((dbg & 2) && (kk > 0 || pass > 0 || !(dbg & 4))) continue;
+              if ((dbg & 8) && (kk > 0 || pass > 0)) continue;
               // upper-triangular Lw: input features [16kk, 16kk+16) only reach whitened features >= 16kk
               const uint32_t n0 = TRI ? 16u * kk : 0u;
               const uint32_t off16 = (kk * 32 + n0 * 128) >> 4;
@@ -273,9 +287,11 @@ gmm_fwd_tcm_kernel(const float* __restrict__ flux, Geom g, const int32_t* __rest
           }
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
+            if ((dbg & 12) != 0) continue;
             const uint32_t n0 = TRI ? 16u * (kk >> 1) : 0u;
             const uint32_t off16 = ((kk >> 2) * KBLOCK_BYTES + (kk & 3) * 32 + n0 * 128) >> 4;
-            umma_tf32_ts(d + n0, a_base + kk * 8, desc_from_lo(b_t + off16), idesc_tf32(64 - n0), 1);
+            umma_tf32_ts(d + n0, a_base + kk * 8, desc_from_lo(b_t + off16), idesc_tf32(64 - n0), acc);
+            acc = 1;
           }
           umma_commit_mc(empty_bar(s), (uint16_t)((1u << CLUSTER) - 1));  // stage free in both CTAs of the pair
           umma_commit(tfull_bar(t));                                       // accumulator slot complete
@@ -378,22 +394,41 @@ gmm_fwd_tcm_kernel(const float* __restrict__ flux, Geom g, const int32_t* __rest
       const int64_t p = (int64_t)tile * TM + row;
       float run_m = -CUDART_INF_F, run_s = 0.f;
       int run_k = 0x7fffffff;
-      for (int pos = pos_lo + ((pos_lo ^ grp) & 1); pos < pos_hi; pos += 2) {
-        int idx = pos - pos_lo + rot;  // same rotated component order as the producers
+      const int pos_first = pos_lo + ((pos_lo ^ grp) & 1);
+      // component of a position (same rotated order as the producers); its scalars are fetched one position ahead
+      auto comp_of = [&](int pos) {
+        int idx = pos - pos_lo + rot;
         idx = idx >= len ? idx - len : idx;
-        const int kc = ka + idx;
+        return ka + idx;
+      };
+      float c_next = 0.f, b_next = 0.f, row_inv = 0.f;
+      if (pos_first < pos_hi) {
+        c_next = __ldg(ck + comp_of(pos_first));
+        b_next = __ldg(binv + comp_of(pos_first));
+      }
+      for (int pos = pos_first; pos < pos_hi; pos += 2) {
+        const int kc = comp_of(pos);
         const int t = pos % NSLOT;
-        const float c_k = __ldg(ck + kc);
-        const float b_inv = __ldg(binv + kc);
+        const float c_k = c_next, b_inv = b_next;
+        if (pos + 2 < pos_hi) {
+          c_next = __ldg(ck + comp_of(pos + 2));
+          b_next = __ldg(binv + comp_of(pos + 2));
+        }
         if (!ZERO_MEAN) mbar_wait(mwfull_bar(t), (pos / NSLOT) & 1);
         mbar_wait(tfull_bar(t), (pos / NSLOT) & 1);
         tc_fence_after();
-        const float inv = s_rinv[buf * TM + row] * b_inv;  // undo the row and component scales
+        if (pos == pos_first) row_inv = s_rinv[buf * TM + row];  // written by the gather warps before the first MMA
+        const float inv = row_inv * b_inv;  // undo the row and component scales
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ACC0 + t * SLOT_COLS;
         float y0[32], y1[32];
-        tmem_ld32(taddr, y0);
-        tmem_ld32(taddr + 32, y1);
-        tmem_ld_wait();
+        if (dbg & 1) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) y0[i] = y1[i] = (float)lane;
+        } else {
+          tmem_ld32(taddr, y0);
+          tmem_ld32(taddr + 32, y1);
+          tmem_ld_wait();
+        }
         float qa = 0.f, qb = 0.f, qc = 0.f, qd = 0.f;
         if (ZERO_MEAN) {
 #pragma unroll
@@ -634,7 +669,13 @@ int jd_gmm_prior_forward_tcm(const float* flux, int fH, int fW, const int32_t* s
   float* ws_m = reinterpret_cast<float*>(ws + p.off_m);
   float* ws_s = reinterpret_cast<float*>(ws + p.off_s);
   int* ws_k = reinterpret_cast<int*>(ws + p.off_k);
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, flux, g, shift_yx, bt8, mw, ck, binv, K, marginalize ? 1 : 0, p.chunk,
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("JD_TC_DEBUG");
+    dbg = e ? atoi(e) : 0;
+  }
+  if (dbg & 16) kern = zero_mean ? tcm::gmm_fwd_tcm_kernel<false, true> : tcm::gmm_fwd_tcm_kernel<false, false>;  // dense
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, flux, g, shift_yx, bt8, mw, ck, binv, K, (marginalize ? 1 : 0) | (dbg << 8), p.chunk,
                                       p.smax, (unsigned)rot_env, counters, ws_m, ws_s, ws_k, value, argmax, logp, sum);
   if (le != cudaSuccess) {
     set_error("jd_gmm_prior_forward_tcm: launch failed: %s", cudaGetErrorString(le));

@@ -60,7 +60,10 @@ class PoissonLoss:
             npred_models = NPredModels.from_dataset_numpy(dataset=dataset, components=components,
                                                           calibration=calibration)
             npred_models_all.append(npred_models.to(device))
-            counts = torch.from_numpy(np.ascontiguousarray(dataset["counts"][np.newaxis, np.newaxis])).to(device)
+            # the engine and the kernels are float32 (the reference's data helpers default to it; integer counts and
+            # float64 arrays, which the reference promotes on the fly, are cast once here)
+            counts = torch.from_numpy(np.ascontiguousarray(np.asarray(dataset["counts"], dtype=np.float32)[
+                np.newaxis, np.newaxis])).to(device)
             counts_all.append(counts)
         return cls(counts_all=counts_all, npred_models_all=npred_models_all, names_all=list(datasets))
 

@@ -218,8 +218,8 @@ class NPredModel(nn.Module):
         dims = (np.newaxis, np.newaxis)
         kwargs = {
             "upsampling_factor": upsampling_factor,
-            "exposure": torch.from_numpy(exposure[dims]),
-            "psf": torch.from_numpy(psf[dims]),
+            "exposure": torch.from_numpy(np.ascontiguousarray(np.asarray(exposure, dtype=np.float32)[dims])),
+            "psf": torch.from_numpy(np.ascontiguousarray(np.asarray(psf, dtype=np.float32)[dims])),
         }
         for name in ["psf", "exposure"]:
             tensor = kwargs[name]
@@ -288,7 +288,8 @@ class NPredModels(nn.ModuleDict):
             npred_model = NPredModel.from_numpy(exposure=dataset["exposure"], psf=psf,
                                                 upsampling_factor=component.upsampling_factor)
             values.append((name, npred_model))
-        background = torch.from_numpy(dataset["background"][np.newaxis, np.newaxis])
+        background = torch.from_numpy(np.ascontiguousarray(np.asarray(dataset["background"], dtype=np.float32)[
+            np.newaxis, np.newaxis]))
         return cls(background, calibration, values)
 
 

@@ -311,7 +311,9 @@ class GMMPatchPrior(Prior):
                                       backend)
 
 
-_DEFAULT_BACKEND = 1  # tcgen05 split-TF32 forward; 0 = FP32 CUDA-core check path
+# 3 = tcgen05 split-TF32 forward with the correction products on the FP16 pipe, persistent stream-K (jd_gmm_tcm.cu);
+# 1 = tcgen05 3 x TF32 (jd_gmm_tc.cu), 2 = tcgen05 split-FP16 (jd_gmm_tc16.cu), 0 = FP32 CUDA-core check path
+_DEFAULT_BACKEND = 3
 
 
 def default_backend():
@@ -319,7 +321,7 @@ def default_backend():
 
 
 def set_default_backend(backend):
-    """0 = FP32 CUDA-core prior kernel, 1 = tcgen05 split-TF32 prior kernel."""
+    """0 = FP32 CUDA-core prior kernel, 1 / 2 / 3 = the tcgen05 kernels (see _DEFAULT_BACKEND)."""
     global _DEFAULT_BACKEND
     _DEFAULT_BACKEND = int(backend)
 

@@ -442,8 +442,89 @@ def golden_shift():
     print("shift_kat.npz", {k: v.shape for k, v in out.items() if k.startswith("c0")})
 
 
+def golden_validation_early_stop():
+    """`datasets_validation` + `stop_early` (core.py:251-261, loss.py:244-248), uniform prior.
+    Two runs on the reference's point-source test datasets: (a) 30 epochs, learning rate 0.1, with a validation
+    dataset, no early stop; (b) learning rate 0.3 and stop_early with a 5-epoch average: the validation loss starts to
+    oscillate (amplitude 1e-2) and the run ends after 16 of the 100 epochs, when it exceeds its running mean."""
+    rs = np.random.RandomState(642020)
+    all_ds = {str(i): gauss_and_point_sources_gauss_psf(random_state=rs) for i in range(3)}
+    rs = np.random.RandomState(642020)
+    flux_init = rs.gamma(20, size=(32, 32))
+    datasets = {n: all_ds[n] for n in ["0", "1"]}
+    validation = {n: all_ds[n] for n in ["2"]}
+    out = {}
+    pack_datasets(datasets, "ds", out)
+    pack_datasets(validation, "dv", out)
+    out["flux_init"] = flux_init
+    for tag, kwargs in [("a", dict(n_epochs=30, learning_rate=0.1)),
+                        ("b", dict(n_epochs=100, learning_rate=0.3, stop_early=True, stop_early_n_average=5))]:
+        comps = FluxComponents()
+        comps["flux-1"] = SpatialFluxComponent.from_numpy(flux=flux_init, upsampling_factor=1, prior=UniformPrior())
+        res = MAPDeconvolver(display_progress=False, **kwargs).run(
+            datasets=datasets, components=comps, datasets_validation=validation)
+        tr = res.trace_loss
+        out[f"{tag}_flux_up"] = res.flux_upsampled_total
+        out[f"{tag}_trace_total"] = np.asarray(tr["total"])
+        out[f"{tag}_trace_datasets"] = np.stack([np.asarray(tr[f"dataset-{n}"]) for n in datasets], axis=1)
+        out[f"{tag}_trace_validation"] = np.asarray(tr["datasets-validation-total"])
+        out[f"{tag}_n_epochs_run"] = len(tr)
+    np.savez_compressed(os.path.join(OUT, "run_validation.npz"), **out)
+    print("run_validation.npz epochs run:", out["a_n_epochs_run"], out["b_n_epochs_run"], "validation[-1]",
+          out["a_trace_validation"][-1], out["b_trace_validation"][-3:])
+
+
+def golden_gmm_asinh_norm():
+    """Analogue of the reference's only GMM e2e test (tests/test_core.py:191-220: GMMPatchPrior(norm=ASinhImageNorm()),
+    upsampling 2; its .mat GMM is not available offline): synthetic GMM, ASinhImageNorm with its two trainable
+    parameters in the optimiser (utils/norms.py:235-257), upsampling 2, 6 epochs."""
+    from jolideco.utils.norms import ASinhImageNorm
+
+    rs = np.random.RandomState(642020)
+    datasets = {str(i): disk_source_gauss_psf(random_state=rs) for i in range(3)}
+    rs = np.random.RandomState(642020)
+    flux_init = rs.gamma(20, size=(32, 32))
+    gmm_arrays = synthetic_gmm_arrays(8, seed=9)
+    gmm = GaussianMixtureModel.from_numpy(*gmm_arrays, meta=GaussianMixtureModelMeta(stride=4))
+    n_epochs, D = 6, len(datasets)
+    gen = torch.Generator().manual_seed(13)
+    g = torch.Generator()
+    g.set_state(gen.get_state())
+    shifts, trace_shifts = [], []
+    for _ in range(n_epochs):
+        for _ in range(D):
+            shifts.append(peek_and_advance(g))
+        trace_shifts.append(peek_and_advance(g))
+    norm = ASinhImageNorm()
+    prior = GMMPatchPrior(gmm=gmm, stride=4, generator=gen, norm=norm)
+    comps = FluxComponents()
+    comps["flux-1"] = SpatialFluxComponent.from_numpy(flux=flux_init, upsampling_factor=2, prior=prior)
+    out = {}
+    pack_datasets(datasets, "ds", out)
+    out["flux_init"] = flux_init
+    out["flux_init_up"] = comps["flux-1"].flux_upsampled.detach().numpy()[0, 0].copy()
+    out["gmm_means"], out["gmm_cov"], out["gmm_w"] = gmm_arrays
+    out["marginalize"] = False
+    out["norm_init"] = np.array([float(norm.alpha), float(norm.beta)])
+    res = MAPDeconvolver(n_epochs=n_epochs, learning_rate=0.1, display_progress=False).run(datasets=datasets, components=comps)
+    tr = res.trace_loss
+    out["flux_up"] = res.flux_upsampled_total
+    out["trace_total"] = np.asarray(tr["total"])
+    out["trace_datasets"] = np.stack([np.asarray(tr[f"dataset-{n}"]) for n in datasets], axis=1)
+    out["trace_prior"] = np.asarray(tr["priors-total"])
+    out["norm_final"] = np.array([float(norm.alpha), float(norm.beta)])
+    out["shifts"] = np.array(shifts).reshape(-1, 2)
+    out["trace_shifts"] = np.array(trace_shifts).reshape(-1, 2)
+    np.savez_compressed(os.path.join(OUT, "run_gmm_asinh.npz"), **out)
+    print("run_gmm_asinh.npz total", out["trace_total"][-1], "norm", out["norm_init"], "->", out["norm_final"])
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":
+        golden_validation_early_stop()
+        golden_gmm_asinh_norm()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "shift":
         golden_shift()
         golden_calibration_shift()
@@ -458,3 +539,5 @@ if __name__ == "__main__":
     golden_shift()
     golden_calibration_shift()
     golden_joint_objective()
+    golden_validation_early_stop()
+    golden_gmm_asinh_norm()

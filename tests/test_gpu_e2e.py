@@ -243,3 +243,109 @@ def test_shift_kernels_match_oracle():
         adj = O.shift_image_adjoint(cot.astype(np.float64), sy, sx, int(scale)) + 1
         assert np.abs(dflux.cpu().numpy() - adj).max() <= 3e-6 * np.abs(adj).max()
         assert_allclose(dshift.cpu().numpy(), [(cot * d_dx).sum(), (cot * d_dy).sum()], rtol=2e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# validation datasets + early stopping (core.py:251-261, loss.py:244-248); goldens from the imported
+# reference (oracle/make_golden.py::golden_validation_early_stop)
+# ---------------------------------------------------------------------------------------------------------------
+def _validation_run(g, fused, **kwargs):
+    comps = J.FluxComponents()
+    comps["flux-1"] = J.SpatialFluxComponent.from_numpy(flux=g["flux_init"], upsampling_factor=1, prior=J.UniformPrior())
+    datasets = {str(i): d for i, d in enumerate(unpack_datasets(g))}
+    validation = {"2": unpack_datasets(g, "dv")[0]}
+    deco = J.MAPDeconvolver(display_progress=False, device=DEV, fused=fused, **kwargs)
+    res = deco.run(datasets=datasets, components=comps, datasets_validation=validation)
+    assert hasattr(deco, "engine") == fused
+    return res
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_validation_datasets_trace_matches_imported_reference(fused):
+    g = load_golden("run_validation.npz")
+    res = _validation_run(g, fused, n_epochs=30, learning_rate=0.1)
+    tr = res.trace_loss
+    assert len(tr) == 30 == int(g["a_n_epochs_run"])
+    assert_allclose(tr["datasets-validation-total"], g["a_trace_validation"], rtol=2e-5)
+    assert_allclose(tr["total"], g["a_trace_total"], rtol=2e-5)
+    for i in range(2):
+        assert_allclose(tr[f"dataset-{i}"], g["a_trace_datasets"][:, i], rtol=2e-5)
+    rel = np.linalg.norm(res.flux_upsampled_total - g["a_flux_up"]) / np.linalg.norm(g["a_flux_up"])
+    assert rel < 1e-3
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_early_stopping_stops_where_the_reference_stops(fused):
+    """stop_early with a 5-epoch running mean: the reference ends after 16 of 100 epochs on this input."""
+    g = load_golden("run_validation.npz")
+    res = _validation_run(g, fused, n_epochs=100, learning_rate=0.3, stop_early=True, stop_early_n_average=5)
+    tr = res.trace_loss
+    assert len(tr) == int(g["b_n_epochs_run"]) == 16
+    assert_allclose(tr["datasets-validation-total"], g["b_trace_validation"], rtol=5e-5)
+    assert_allclose(tr["total"], g["b_trace_total"], rtol=5e-5)
+    rel = np.linalg.norm(res.flux_upsampled_total - g["b_flux_up"]) / np.linalg.norm(g["b_flux_up"])
+    assert rel < 1e-3
+
+
+def test_early_stop_leaves_the_prior_generator_where_the_reference_does():
+    """the engine pre-draws n_epochs x (D + 1) cycle-spin shifts; after an early stop the generator must
+    sit exactly behind the draws that were consumed (2 randint calls per evaluation of the prior)."""
+    g = load_golden("run_validation.npz")
+    gmm_g = load_golden("run_gmm_max.npz")
+    gmm = J.GaussianMixtureModel.from_numpy(gmm_g["gmm_means"], gmm_g["gmm_cov"], gmm_g["gmm_w"],
+                                            meta=J.GaussianMixtureModelMeta(stride=4))
+    gen = torch.Generator().manual_seed(21)
+    expect = torch.Generator().manual_seed(21)
+    prior = J.GMMPatchPrior(gmm=gmm, stride=4, generator=gen)
+    comps = J.FluxComponents()
+    comps["flux-1"] = J.SpatialFluxComponent.from_numpy(flux=g["flux_init"], upsampling_factor=1, prior=prior)
+    datasets = {str(i): d for i, d in enumerate(unpack_datasets(g))}
+    deco = J.MAPDeconvolver(n_epochs=60, learning_rate=0.3, stop_early=True, stop_early_n_average=3,
+                            display_progress=False, device=DEV)
+    res = deco.run(datasets=datasets, components=comps, datasets_validation={"2": unpack_datasets(g, "dv")[0]})
+    n = len(res.trace_loss)
+    assert n < 60
+    for _ in range(n * (len(datasets) + 1)):  # D training draws + 1 trace draw per completed epoch
+        torch.randint(-2, 3, (1,), generator=expect)
+        torch.randint(-2, 3, (1,), generator=expect)
+    assert torch.equal(gen.get_state(), expect.get_state())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SURVEY 8f row 4 / reference tests/test_core.py:191-220: GMM patch prior behind a non-identity, TRAINABLE image norm
+# (ASinhImageNorm) with upsampling 2 - the CUDA prior op inside torch autograd, norm parameters in the optimiser
+# ---------------------------------------------------------------------------------------------------------------
+def test_gmm_prior_with_asinh_norm_matches_imported_reference(tmp_path):
+    g = load_golden("run_gmm_asinh.npz")
+    gmm = J.GaussianMixtureModel.from_numpy(g["gmm_means"], g["gmm_cov"], g["gmm_w"],
+                                            meta=J.GaussianMixtureModelMeta(stride=4))
+    norm = J.ASinhImageNorm()
+    prior = J.GMMPatchPrior(gmm=gmm, stride=4, generator=torch.Generator().manual_seed(13), norm=norm)
+    comps = J.FluxComponents()
+    comps["flux-1"] = J.SpatialFluxComponent.from_numpy(flux=g["flux_init"], upsampling_factor=2, prior=prior)
+    deco = J.MAPDeconvolver(n_epochs=6, learning_rate=0.1, display_progress=False, device=DEV, checkpoint_path=tmp_path)
+    res = deco.run(datasets=as_datasets(g), components=comps)
+    assert not hasattr(deco, "engine")  # non-identity norm: the reference loop on the autograd bindings
+    assert res.flux_upsampled_total.shape == (64, 64)
+    check(res, g, 6, rtol_trace=5e-5)
+    final = [float(res.components["flux-1"].prior.norm.alpha), float(res.components["flux-1"].prior.norm.beta)]
+    assert_allclose(final, g["norm_final"], rtol=1e-3)
+    # per-epoch checkpoints (core.py:234-243) are results that read back
+    back = J.MAPDeconvolverResult.read(tmp_path / res.trace_loss["filename"][-1])
+    assert back.flux_upsampled_total.shape == (64, 64)
+    assert_allclose(back.flux_upsampled_total, res.flux_upsampled_total, rtol=1e-6)
+
+
+def test_fused_engine_checkpoints_hold_the_current_flux(tmp_path):
+    """checkpoints written by the fused engine carry the flux of THAT epoch (not the initial one) together
+    with the trace so far."""
+    g = load_golden("run_gmm_max.npz")
+    comps = J.FluxComponents()
+    comps["flux-1"] = J.SpatialFluxComponent.from_numpy(flux=g["flux_init"], upsampling_factor=1, prior=make_prior(g, 4))
+    deco = J.MAPDeconvolver(n_epochs=3, learning_rate=0.1, display_progress=False, device=DEV, checkpoint_path=tmp_path)
+    res = deco.run(datasets=as_datasets(g), components=comps)
+    assert hasattr(deco, "engine")
+    first = res.read_checkpoint(0).flux_upsampled_total
+    last = res.read_checkpoint(2).flux_upsampled_total
+    assert not np.allclose(first, g["flux_init_up"]) and not np.allclose(first, last)
+    assert_allclose(last, res.flux_upsampled_total, rtol=1e-6)

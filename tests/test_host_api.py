@@ -135,3 +135,50 @@ def test_gmm_numpy_accessors_and_host_log_prob():
     comps["a"] = J.SpatialFluxComponent.from_numpy(flux=np.full((8, 8), 2.0), prior=J.UniformPrior())
     comps["b"] = J.SpatialFluxComponent.from_numpy(flux=np.full((8, 8), 3.0), prior=J.UniformPrior())
     np.testing.assert_allclose(comps.flux_upsampled_total.detach().numpy()[0, 0], 5.0, rtol=1e-6)
+
+
+def test_result_write_read_roundtrip(tmp_path):
+    """MAPDeconvolverResult.write / read / read_checkpoint (core.py:329-343, 435-471): config, trace, the stored
+    parameter (lossless under a mask), errors and calibration parameters survive; an existing file is not overwritten."""
+    from jolideco_b200.core import MAPDeconvolverResult
+    from jolideco_b200.table import TraceTable
+
+    rng = np.random.default_rng(0)
+    mask = np.ones((8, 8), dtype=bool)
+    mask[0, 0] = False
+    comps = J.FluxComponents()
+    comps["flux"] = J.SpatialFluxComponent.from_numpy(flux=rng.gamma(2.0, size=(8, 8)), upsampling_factor=2, mask=mask)
+    cals = J.NPredCalibrations()
+    cals["obs"] = J.NPredCalibration(shift_x=0.3, shift_y=-0.1, background_norm=1.2)
+    trace = TraceTable(names=["total", "dataset-obs", "filename"])
+    trace.add_row({"total": 1.5, "dataset-obs": 1.25, "filename": "checkpoint-epoch-0.npz"})
+    res = MAPDeconvolverResult(config={"n_epochs": 3, "device": "cuda", "checkpoint_path": str(tmp_path)},
+                               components=comps, trace_loss=trace, calibrations=cals)
+    fn = tmp_path / "checkpoint-epoch-0.npz"
+    res.write(fn)
+    with pytest.raises(IOError):
+        res.write(fn)
+    res.write(fn, overwrite=True)
+    back = MAPDeconvolverResult.read(fn)
+    assert np.array_equal(back.flux_upsampled_total, res.flux_upsampled_total)
+    assert back.components["flux"].upsampling_factor == 2 and back.components["flux"].use_log_flux
+    assert back.trace_loss[-1]["total"] == 1.5 and back.trace_loss[-1]["filename"] == "checkpoint-epoch-0.npz"
+    assert back.calibrations["obs"].to_dict()["shift_x"] == pytest.approx(0.3)
+    assert back.config["n_epochs"] == 3
+    again = res.read_checkpoint(0)
+    assert np.array_equal(again.flux_upsampled_total, res.flux_upsampled_total)
+
+
+def test_datasets_are_cast_to_float32():
+    """Integer counts / float64 exposure, background and PSF (which the reference promotes on the fly) are cast at the
+    API boundary instead of failing inside the kernels' dtype checks."""
+    rng = np.random.default_rng(1)
+    ds = {"a": dict(counts=rng.poisson(2.0, size=(16, 16)), psf=np.full((3, 3), 1 / 9.0), exposure=np.ones((16, 16)),
+                    background=np.full((16, 16), 0.5))}
+    comps = J.FluxComponents()
+    comps["flux"] = J.SpatialFluxComponent.from_numpy(flux=np.ones((16, 16)))
+    loss = J.PoissonLoss.from_datasets(ds, comps, device="cpu")
+    assert loss.counts_all[0].dtype == torch.float32
+    model = loss.npred_models_all[0]
+    assert model.background.dtype == torch.float32 and model["flux"].psf.dtype == torch.float32
+    assert model["flux"].exposure.dtype == torch.float32
