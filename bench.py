@@ -271,6 +271,11 @@ def main():
     if not args.no_parity_check and joint:
         parity, ref_run = parity_check(J, E, workload, args, device, rank, world, pg)
 
+    if ref_run is not None:
+        # the reference's intra-op thread pool spins for a while after its last operator: keep it off the cores that
+        # enqueue the timed launches
+        torch.set_num_threads(1)
+        time.sleep(0.5)
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=device)
 
     def run_step(i):
@@ -349,6 +354,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
         cpu = reference_baseline(workload, args.steps, args.warmup, args.cpu_budget_s, args.marginalize, joint,
                                  run=ref_run)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -279,6 +279,19 @@ __global__ void step_begin_flux_kernel(int32_t* __restrict__ counters, const int
     for (int i = threadIdx.x; i < n_acc; i += blockDim.x) zero_acc[i] = 0.0;
   }
   if (!flux) return;
+  if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(theta) | reinterpret_cast<uintptr_t>(flux)) & 15) == 0) {
+    const int64_t n4 = n >> 2;  // four pixels per thread, 128-bit loads / stores
+    for (int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += (int64_t)gridDim.x * blockDim.x) {
+      const float4 t = *reinterpret_cast<const float4*>(theta + 4 * i4);
+      float4 f = use_log ? make_float4(expf(t.x), expf(t.y), expf(t.z), expf(t.w)) : t;
+      if (mask) {
+        const uchar4 mk = *reinterpret_cast<const uchar4*>(mask + 4 * i4);
+        f.x *= (float)mk.x, f.y *= (float)mk.y, f.z *= (float)mk.z, f.w *= (float)mk.w;
+      }
+      *reinterpret_cast<float4*>(flux + 4 * i4) = f;
+    }
+    return;
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float t = theta[i];
     float f = use_log ? expf(t) : t;
@@ -313,22 +326,68 @@ __global__ void adam_fold_kernel(float* __restrict__ theta, float* __restrict__ 
 
 // Joint step, one GPU: sum of the per-dataset likelihood gradients (`n_parts` images, `part_stride` floats apart,
 // fixed order) + fold of the prior's patch gradients (G may be NULL) + chain rule + Adam, one pass.
-__global__ void adam_joint_kernel(float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v,
-                                  const float* __restrict__ flux, const uint8_t* __restrict__ mask,
-                                  const float* __restrict__ parts, int n_parts, int64_t part_stride,
-                                  const float* __restrict__ G, float scale_b, int use_log, int fH, int fW,
-                                  const int32_t* __restrict__ shift_yx, int stride, int row_begin, int row_end,
-                                  const float* __restrict__ scalars, float b1, float b2, float eps) {
-  const float lr_over_bc1 = scalars[0], sqrt_bc2 = scalars[1];
+// Four consecutive pixels per thread with 128-bit loads / stores (fW % 4 == 0, 16-byte aligned images); UPDATE = false
+// only writes the gradient (this rank's partial gradient of a multi-GPU joint step).
+template <bool UPDATE>
+__global__ void __launch_bounds__(256)
+joint_grad_kernel(float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v,
+                  const float* __restrict__ flux, const uint8_t* __restrict__ mask, const float* __restrict__ parts,
+                  int n_parts, int64_t part_stride, const float* __restrict__ G, float scale_b, int use_log, int fH,
+                  int fW, const int32_t* __restrict__ shift_yx, int stride, int row_begin, int row_end,
+                  const float* __restrict__ scalars, float b1, float b2, float eps, float* __restrict__ out, int vec) {
+  const float lr_over_bc1 = UPDATE ? scalars[0] : 0.f, sqrt_bc2 = UPDATE ? scalars[1] : 1.f;
   const int sy = shift_yx ? shift_yx[0] : 0, sx = shift_yx ? shift_yx[1] : 0;
   const int ny = (fH - PATCH) / stride + 1, nx = (fW - PATCH) / stride + 1;
   const int64_t n = (int64_t)fH * fW;
+  const bool fold = G != nullptr && row_end > row_begin;
+  if (vec) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t i = i4 * 4;
+      float g[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int q = 0; q < n_parts; ++q) {
+        const float4 p4 = *reinterpret_cast<const float4*>(parts + q * part_stride + i);
+        g[0] += p4.x, g[1] += p4.y, g[2] += p4.z, g[3] += p4.w;
+      }
+      if (fold) {
+        const int y = (int)(i / fW), x = (int)(i - (int64_t)y * fW);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          g[c] += scale_b * fold_gather(G, y, x + c, fH, fW, sy, sx, stride, ny, nx, row_begin, row_end);
+      }
+      if (!UPDATE) {
+        *reinterpret_cast<float4*>(out + i) = make_float4(g[0], g[1], g[2], g[3]);
+        continue;
+      }
+      const float4 f4 = use_log ? *reinterpret_cast<const float4*>(flux + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+      const float ff[4] = {f4.x, f4.y, f4.z, f4.w};
+      const float4 t4 = *reinterpret_cast<const float4*>(theta + i);
+      const float4 m4 = *reinterpret_cast<const float4*>(m + i), v4 = *reinterpret_cast<const float4*>(v + i);
+      float th[4] = {t4.x, t4.y, t4.z, t4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float gc = g[c] * (use_log ? ff[c] : (mask ? (float)mask[i + c] : 1.f));
+        mm[c] = mm[c] + (gc - mm[c]) * (1.f - b1);
+        vv[c] = vv[c] * b2 + (1.f - b2) * gc * gc;
+        const float denom = sqrtf(vv[c]) / sqrt_bc2 + eps;
+        th[c] = th[c] - lr_over_bc1 * (mm[c] / denom);
+      }
+      *reinterpret_cast<float4*>(theta + i) = make_float4(th[0], th[1], th[2], th[3]);
+      *reinterpret_cast<float4*>(m + i) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+      *reinterpret_cast<float4*>(v + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    }
+    return;
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float g = 0.f;
     for (int q = 0; q < n_parts; ++q) g += parts[q * part_stride + i];
-    if (G) {
+    if (fold) {
       int y = (int)(i / fW), x = (int)(i - (int64_t)y * fW);
       g += scale_b * fold_gather(G, y, x, fH, fW, sy, sx, stride, ny, nx, row_begin, row_end);
+    }
+    if (!UPDATE) {
+      out[i] = g;
+      continue;
     }
     g *= use_log ? flux[i] : (mask ? (float)mask[i] : 1.f);
     float mi = m[i], vi = v[i];
@@ -338,26 +397,6 @@ __global__ void adam_joint_kernel(float* __restrict__ theta, float* __restrict__
     theta[i] = theta[i] - lr_over_bc1 * (mi / denom);
     m[i] = mi;
     v[i] = vi;
-  }
-}
-
-// Joint step, several GPUs: this rank's partial flux gradient = its datasets' likelihood gradients + the fold of
-// its prior patch rows, written where the peers can read it (out may alias parts[0]).
-__global__ void grad_reduce_kernel(const float* __restrict__ parts, int n_parts, int64_t part_stride,
-                                   const float* __restrict__ G, float scale_b, int fH, int fW,
-                                   const int32_t* __restrict__ shift_yx, int stride, int row_begin, int row_end,
-                                   float* __restrict__ out) {
-  const int sy = shift_yx ? shift_yx[0] : 0, sx = shift_yx ? shift_yx[1] : 0;
-  const int ny = (fH - PATCH) / stride + 1, nx = (fW - PATCH) / stride + 1;
-  const int64_t n = (int64_t)fH * fW;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float g = 0.f;
-    for (int q = 0; q < n_parts; ++q) g += parts[q * part_stride + i];
-    if (G && row_end > row_begin) {
-      int y = (int)(i / fW), x = (int)(i - (int64_t)y * fW);
-      g += scale_b * fold_gather(G, y, x, fH, fW, sy, sx, stride, ny, nx, row_begin, row_end);
-    }
-    out[i] = g;
   }
 }
 
@@ -437,6 +476,13 @@ static inline int grid_for(int64_t n, int block) {
 
 using namespace jd;
 
+static int joint_vec_ok(int fW, int64_t part_stride, const void* a, const void* b, const void* c, const void* d,
+                        const void* e, const void* f) {
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+                         reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(e) | reinterpret_cast<uintptr_t>(f);
+  return (fW & 3) == 0 && (part_stride & 3) == 0 && (bits & 15) == 0;
+}
+
 extern "C" {
 
 int jd_abi_version(void) { return JD_ABI_VERSION; }
@@ -512,7 +558,7 @@ int jd_step_begin_flux(int32_t* counters, const int32_t* shift_table, int n_shif
   JD_CHECK_ARG(!advance_adam || adam_scalars, "jd_step_begin_flux: adam_scalars required");
   JD_CHECK_ARG(!shift_table || n_shifts > 0, "jd_step_begin_flux: empty shift table");
   JD_CHECK_ARG(n_acc == 0 || zero_acc, "jd_step_begin_flux: null accumulator block");
-  step_begin_flux_kernel<<<grid_for(n, 256), 256, 0, to_stream(stream)>>>(counters, shift_table, n_shifts, shift_out,
+  step_begin_flux_kernel<<<grid_for((n & 3) ? n : n >> 2, 256), 256, 0, to_stream(stream)>>>(counters, shift_table, n_shifts, shift_out,
                                                                            advance_adam, lr, beta1, beta2, adam_scalars,
                                                                            zero_acc, n_acc, theta, mask, flux, n,
                                                                            use_log_flux);
@@ -551,9 +597,10 @@ int jd_adam_joint_step_dev(float* theta, float* m, float* v, const float* flux, 
   } else {
     stride = 1;
   }
-  adam_joint_kernel<<<grid_for((int64_t)fH * fW, 256), 256, 0, to_stream(stream)>>>(
+  const int vec = joint_vec_ok(fW, part_stride, theta, m, v, flux, parts, nullptr);
+  joint_grad_kernel<true><<<grid_for(((int64_t)fH * fW) >> (vec ? 2 : 0), 256), 256, 0, to_stream(stream)>>>(
       theta, m, v, flux, mask, parts, n_parts, part_stride, G, scale_b, use_log_flux, fH, fW, shift_yx, stride, row_begin,
-      row_end, adam_scalars, beta1, beta2, eps);
+      row_end, adam_scalars, beta1, beta2, eps, nullptr, vec);
   JD_CHECK_LAUNCH("jd_adam_joint_step_dev");
   return JD_OK;
 }
@@ -569,8 +616,10 @@ int jd_grad_reduce_local(const float* parts, int n_parts, int64_t part_stride, c
   } else {
     stride = 1;
   }
-  grad_reduce_kernel<<<grid_for((int64_t)fH * fW, 256), 256, 0, to_stream(stream)>>>(
-      parts, n_parts, part_stride, G, scale_b, fH, fW, shift_yx, stride, row_begin, row_end, out);
+  const int vec = joint_vec_ok(fW, part_stride, nullptr, nullptr, nullptr, nullptr, parts, out);
+  joint_grad_kernel<false><<<grid_for(((int64_t)fH * fW) >> (vec ? 2 : 0), 256), 256, 0, to_stream(stream)>>>(
+      nullptr, nullptr, nullptr, nullptr, nullptr, parts, n_parts, part_stride, G, scale_b, 0, fH, fW, shift_yx, stride,
+      row_begin, row_end, nullptr, 0.f, 0.f, 0.f, out, vec);
   JD_CHECK_LAUNCH("jd_grad_reduce_local");
   return JD_OK;
 }

@@ -123,65 +123,96 @@ lik_kernel(const jd_lik_dataset* __restrict__ table, int fH, int fW, int kh, int
     s_k[i] = v;
   }
 
-  // ---- input tile: rows [Y0, Y0 + TH + kh - 1), cols [X0, X0 + IW), zero outside the image
+  // ---- input tile: rows [Y0, Y0 + TH + kh - 1), cols [X0, X0 + IW), zero outside the image.  Register-staged in
+  // batches so that every thread keeps 16 independent 128-bit loads in flight (the tile load is pure latency).
   const int ih = TH + kh - 1;
+  constexpr int SB = 8;  // staging batch: SB (x2 in the forward) independent 128-bit loads in flight per thread
+  const int total = ih * T::NVEC;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (MODE == FWD) {
     const float* __restrict__ in = ds.flux;
     const float* __restrict__ sc = ds.exposure;
     const bool vec = (fW & 3) == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(sc)) & 15) == 0;
-#pragma unroll 4
-    for (int i = tid; i < ih * T::NVEC; i += NTHR) {
-      const int ry = i / T::NVEC, v = i - ry * T::NVEC;
-      const int y = Y0 + ry, x = X0 + 4 * v;
-      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (y >= 0 && y < fH) {
-        const int64_t o = (int64_t)y * fW + x;
-        if (vec) {
-          if (x >= 0 && x < fW) {
-            val = __ldg(reinterpret_cast<const float4*>(in + o));
-            if (sc) {
-              const float4 e = __ldg(reinterpret_cast<const float4*>(sc + o));
-              val.x *= e.x, val.y *= e.y, val.z *= e.z, val.w *= e.w;
-            }
+    if (vec) {
+      for (int base = tid; base < total; base += SB * NTHR) {
+        float4 fv[SB], ev[SB];
+#pragma unroll
+        for (int u = 0; u < SB; ++u) {
+          const int i = base + u * NTHR;
+          const int ry = i / T::NVEC, v = i - ry * T::NVEC;
+          const int y = Y0 + ry, x = X0 + 4 * v;
+          const bool ok = i < total && y >= 0 && y < fH && x >= 0 && x < fW;
+          const int64_t o = ok ? (int64_t)y * fW + x : 0;
+          fv[u] = ok ? __ldg(reinterpret_cast<const float4*>(in + o)) : zero4;
+          ev[u] = (ok && sc) ? __ldg(reinterpret_cast<const float4*>(sc + o)) : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+#pragma unroll
+        for (int u = 0; u < SB; ++u) {
+          const int i = base + u * NTHR;
+          if (i < total) {
+            const int ry = i / T::NVEC, v = i - ry * T::NVEC;
+            *reinterpret_cast<float4*>(s_in + ry * T::IWP + pcol(4 * v)) =
+                make_float4(fv[u].x * ev[u].x, fv[u].y * ev[u].y, fv[u].z * ev[u].z, fv[u].w * ev[u].w);
           }
-        } else {
-          float tmp[4];
+        }
+      }
+    } else {
+      for (int i = tid; i < total; i += NTHR) {
+        const int ry = i / T::NVEC, v = i - ry * T::NVEC;
+        const int y = Y0 + ry, x = X0 + 4 * v;
+        float tmp[4] = {0.f, 0.f, 0.f, 0.f};
+        if (y >= 0 && y < fH) {
+          const int64_t o = (int64_t)y * fW + x;
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int xx = x + e;
-            tmp[e] = (xx >= 0 && xx < fW) ? __ldg(in + o + e) * (sc ? __ldg(sc + o + e) : 1.f) : 0.f;
+            if (xx >= 0 && xx < fW) tmp[e] = __ldg(in + o + e) * (sc ? __ldg(sc + o + e) : 1.f);
           }
-          val = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
         }
+        *reinterpret_cast<float4*>(s_in + ry * T::IWP + pcol(4 * v)) = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
       }
-      *reinterpret_cast<float4*>(s_in + ry * T::IWP + pcol(4 * v)) = val;
     }
   } else {
     const float* __restrict__ in = ds.dpool;  // H x W, replicated f x f (adjoint of the sum-pool)
     const bool vec = F == 1 && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
-#pragma unroll 4
-    for (int i = tid; i < ih * T::NVEC; i += NTHR) {
-      const int ry = i / T::NVEC, v = i - ry * T::NVEC;
-      const int y = Y0 + ry, x = X0 + 4 * v;
-      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (y >= 0 && y < fH) {
-        const int py = y / F;
-        if (py < H) {
-          if (vec) {
-            if (x >= 0 && x < W) val = __ldg(reinterpret_cast<const float4*>(in + (int64_t)py * W + x));
-          } else {
-            float tmp[4];
+    if (vec) {
+      for (int base = tid; base < total; base += 2 * SB * NTHR) {
+        float4 dv[2 * SB];
+#pragma unroll
+        for (int u = 0; u < 2 * SB; ++u) {
+          const int i = base + u * NTHR;
+          const int ry = i / T::NVEC, v = i - ry * T::NVEC;
+          const int y = Y0 + ry, x = X0 + 4 * v;
+          const bool ok = i < total && y >= 0 && y < H && x >= 0 && x < W;
+          dv[u] = ok ? __ldg(reinterpret_cast<const float4*>(in + (int64_t)y * W + x)) : zero4;
+        }
+#pragma unroll
+        for (int u = 0; u < 2 * SB; ++u) {
+          const int i = base + u * NTHR;
+          if (i < total) {
+            const int ry = i / T::NVEC, v = i - ry * T::NVEC;
+            *reinterpret_cast<float4*>(s_in + ry * T::IWP + pcol(4 * v)) = dv[u];
+          }
+        }
+      }
+    } else {
+      for (int i = tid; i < total; i += NTHR) {
+        const int ry = i / T::NVEC, v = i - ry * T::NVEC;
+        const int y = Y0 + ry, x = X0 + 4 * v;
+        float tmp[4] = {0.f, 0.f, 0.f, 0.f};
+        if (y >= 0 && y < fH) {
+          const int py = y / F;
+          if (py < H) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int xx = x + e;
               const int px = xx / F;
-              tmp[e] = (xx >= 0 && xx < fW && px < W) ? __ldg(in + (int64_t)py * W + px) : 0.f;
+              if (xx >= 0 && xx < fW && px < W) tmp[e] = __ldg(in + (int64_t)py * W + px);
             }
-            val = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
           }
         }
+        *reinterpret_cast<float4*>(s_in + ry * T::IWP + pcol(4 * v)) = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
       }
-      *reinterpret_cast<float4*>(s_in + ry * T::IWP + pcol(4 * v)) = val;
     }
   }
   __syncthreads();

@@ -58,7 +58,7 @@ class PoissonLoss:
         for name, dataset in datasets.items():
             calibration = calibrations[name] if calibrations else None
             npred_models = NPredModels.from_dataset_numpy(dataset=dataset, components=components,
-                                                          calibration=calibration)
+                                                          calibration=calibration, device=device)
             npred_models_all.append(npred_models.to(device))
             # the engine and the kernels are float32 (the reference's data helpers default to it; integer counts and
             # float64 arrays, which the reference promotes on the fly, are cast once here)

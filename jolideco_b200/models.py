@@ -214,8 +214,13 @@ class NPredModel(nn.Module):
         return tuple(shape)
 
     @classmethod
-    def from_numpy(cls, exposure, psf, upsampling_factor, correct_exposure_edges=True):
+    def from_numpy(cls, exposure, psf, upsampling_factor, correct_exposure_edges=True, device=None):
+        """NPredModel.from_numpy (npred.py:66-115): bilinear upsampling of exposure and PSF, PSF / f^2, exposure edge
+        correction exposure /= PSF (*) 1.  With a CUDA `device` the arrays are uploaded first and the whole setup
+        runs there (the edge correction through the library's own convolution), which removes ~5 ms of host FFTs per
+        1024^2 dataset from `MAPDeconvolver.run`; without, on the host as the reference does."""
         dims = (np.newaxis, np.newaxis)
+        on_gpu = device is not None and torch.device(device).type == "cuda"
         kwargs = {
             "upsampling_factor": upsampling_factor,
             "exposure": torch.from_numpy(np.ascontiguousarray(np.asarray(exposure, dtype=np.float32)[dims])),
@@ -223,21 +228,35 @@ class NPredModel(nn.Module):
         }
         for name in ["psf", "exposure"]:
             tensor = kwargs[name]
-            if upsampling_factor:
+            if on_gpu:
+                tensor = tensor.to(device)
+            if upsampling_factor and upsampling_factor != 1:  # scale factor 1 is the identity (npred.py:96 still calls it)
                 tensor = F.interpolate(tensor, scale_factor=upsampling_factor, mode="bilinear")
             if name == "psf" and upsampling_factor:
                 tensor = tensor / upsampling_factor**2
             kwargs[name] = tensor
         if correct_exposure_edges:
             exposure_t = kwargs["exposure"]
-            weights = _convolve_fft_host(torch.ones_like(exposure_t), kwargs["psf"])
+            if on_gpu:
+                from . import ops
+
+                psf_t = kwargs["psf"][0, 0].contiguous()
+                ones = torch.ones_like(exposure_t[0, 0])
+                with torch.cuda.device(device):
+                    if psf_t.shape[0] * psf_t.shape[1] >= ops.FFT_MIN_PSF_AREA:
+                        weights = ops.conv_forward_fft(ones, ones, ops.FFTConvPlan(psf_t, *ones.shape))
+                    else:
+                        weights = ops.conv_forward(ones, ones, psf_t)
+                weights = weights[None, None]
+            else:
+                weights = _convolve_fft_host(torch.ones_like(exposure_t), kwargs["psf"])
             kwargs["exposure"] = exposure_t / weights
         return cls(**kwargs)
 
     @classmethod
-    def from_dataset_numpy(cls, dataset, upsampling_factor=None, correct_exposure_edges=True):
+    def from_dataset_numpy(cls, dataset, upsampling_factor=None, correct_exposure_edges=True, device=None):
         return cls.from_numpy(exposure=dataset["exposure"], psf=dataset["psf"], upsampling_factor=upsampling_factor,
-                              correct_exposure_edges=correct_exposure_edges)
+                              correct_exposure_edges=correct_exposure_edges, device=device)
 
     def forward(self, flux, psf_scale=None):
         if psf_scale is not None and not bool(torch.isclose(psf_scale.detach().cpu(), torch.tensor(1.0)).all()):
@@ -279,14 +298,14 @@ class NPredModels(nn.ModuleDict):
         return npred_total
 
     @classmethod
-    def from_dataset_numpy(cls, dataset, components, calibration=None):
+    def from_dataset_numpy(cls, dataset, components, calibration=None, device=None):
         values = []
         for name, component in components.items():
             psf = dataset["psf"]
             if isinstance(psf, dict):
                 psf = psf[name]
             npred_model = NPredModel.from_numpy(exposure=dataset["exposure"], psf=psf,
-                                                upsampling_factor=component.upsampling_factor)
+                                                upsampling_factor=component.upsampling_factor, device=device)
             values.append((name, npred_model))
         background = torch.from_numpy(np.ascontiguousarray(np.asarray(dataset["background"], dtype=np.float32)[
             np.newaxis, np.newaxis]))

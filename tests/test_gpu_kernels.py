@@ -476,3 +476,29 @@ def test_bad_arguments_raise():
         ops.extract_patches(t(np.zeros((4, 4))))  # smaller than a patch
     with pytest.raises(JolidecoB200Error):
         ops.flux_forward(torch.zeros(3, 3, device=DEV, dtype=torch.float64))
+
+
+@pytest.mark.parametrize("n,k", [(512, 64), (1024, 201)])
+def test_fft_convolution_at_baseline_shapes(n, k):
+    """BASELINE configs[2] and [3]: 512^2 flux with a 64 x 64 EVEN PSF (asymmetric crop, utils/torch.py:337-344) and
+    1024^2 with a 201 x 201 PSF on the radix-5 1280^2 plan; forward and adjoint, two datasets' worth of PSFs."""
+    rng = np.random.default_rng(100 + k)
+    flux = (rng.gamma(2.0, size=(n, n)) * np.exp(rng.normal(0, 1, size=(n, n)))).astype(np.float32)
+    E = rng.uniform(0.5, 1.5, size=(n, n)).astype(np.float32)
+    d = rng.normal(size=(n, n)).astype(np.float32)
+    for rep in range(2):
+        yy, xx = np.mgrid[:k, :k]
+        sig = k / (6.0 + rep)
+        psf = np.exp(-0.5 * (((yy - (k - 1) / 2 - 0.7 * rep) / sig) ** 2 + ((xx - (k - 1) / 2 + 1.3 * rep) / (1.2 * sig)) ** 2))
+        psf = (psf / psf.sum()).astype(np.float32)
+        plan = ops.FFTConvPlan(t(psf), n, n)
+        ref = O.convolve_fft(flux.astype(np.float64) * E, psf.astype(np.float64))
+        out = ops.conv_forward_fft(t(flux), t(E), plan).cpu().numpy()
+        assert rel_max(out, ref) < 5e-6
+        ref_b = O.correlate_adjoint(d.astype(np.float64), psf.astype(np.float64)) * E
+        out_b = ops.conv_backward_fft(t(d), t(E), plan, 1).cpu().numpy()
+        assert rel_max(out_b, ref_b) < 5e-6
+        # <conv(x), d> == <x, conv^T(d)> on the kernels themselves (adjoint consistency, float32 accumulation)
+        lhs = float((out.astype(np.float64) * d).sum())
+        rhs = float((flux.astype(np.float64) * out_b).sum())
+        assert abs(lhs - rhs) <= 2e-5 * max(abs(lhs), abs(rhs), np.abs(out).sum() * 1e-3)
