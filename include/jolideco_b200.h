@@ -130,7 +130,7 @@ typedef struct {
   int32_t reserved;
 } jd_lik_dataset;
 
-/* 1 if (kh, kw, f) is covered by the batched direct kernels (PSF rows of <= 29..32 taps, f in {1, 2}) */
+/* 1 if (kh, kw, f) is covered by the batched direct kernels (PSF rows of <= 37..40 taps, f in {1, 2}) */
 int jd_likelihood_supported(int kh, int kw, int f);
 int jd_likelihood_forward(const jd_lik_dataset* table_dev, int n_datasets, int fH, int fW, int kh, int kw, int f,
                           int H, int W, float eps, float grad_scale, jd_stream_t stream);

@@ -10,6 +10,8 @@ int dispatch_f1_fwd_hi(int, const jd_lik_dataset*, int, int, int, int, int, int,
 int dispatch_f1_bwd_lo(int, const jd_lik_dataset*, int, int, int, int, int, int, int, float, float, cudaStream_t);
 int dispatch_f1_bwd_hi(int, const jd_lik_dataset*, int, int, int, int, int, int, int, float, float, cudaStream_t);
 int dispatch_f2(int, const jd_lik_dataset*, int, int, int, int, int, int, int, float, float, cudaStream_t);
+int dispatch_f1_wide(int, const jd_lik_dataset*, int, int, int, int, int, int, int, float, float, cudaStream_t);
+constexpr int MAX_TAPS = 40;  // per shared-memory tap row, lead zeros included
 
 // taps per shared-memory row (zero lead taps for 16-byte alignment + the PSF row), or 0 if unsupported
 static int tap_count(int mode, int kw) {
@@ -26,9 +28,11 @@ static int run(int mode, const jd_lik_dataset* table, int n_datasets, int fH, in
   JD_CHECK_ARG(f == 1 || f == 2, "jd_likelihood: upsampling factor %d (supported: 1, 2)", f);
   JD_CHECK_ARG(H * f == fH && W * f == fW, "jd_likelihood: counts grid %dx%d x f=%d != flux grid %dx%d", H, W, f, fH, fW);
   const int nt = tap_count(mode, kw);
-  JD_CHECK_ARG(nt <= 32, "jd_likelihood: PSF rows of %d taps are too wide for the direct kernel (<= 32 incl. lead)", kw);
+  JD_CHECK_ARG(nt <= MAX_TAPS, "jd_likelihood: PSF rows of %d taps are too wide for the direct kernel (<= %d incl. lead)",
+               kw, MAX_TAPS);
   const int kg = (nt + 3) / 4, kt = nt - 4 * (kg - 1);
-  if (f == 2) return dispatch_f2(8 * mode + kg - 1, table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
+  if (f == 2) return dispatch_f2(16 * mode + kg - 1, table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
+  if (kg > 8) return dispatch_f1_wide(16 * mode + kg - 1, table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
   const int key = (kg - 1) * 4 + kt - 1;
   if (mode == FWD)
     return kg <= 4 ? dispatch_f1_fwd_lo(key, table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st)
@@ -62,8 +66,9 @@ extern "C" {
 int jd_likelihood_supported(int kh, int kw, int f) {
   if (f != 1 && f != 2) return 0;
   if (kh <= 0 || kw <= 0) return 0;
-  if (jd::lik::tap_count(jd::lik::FWD, kw) > 32 || jd::lik::tap_count(jd::lik::BWD, kw) > 32) return 0;
-  return jd::lik::Tile<8>::smem_bytes(kh) <= 200 * 1024 ? 1 : 0;
+  if (jd::lik::tap_count(jd::lik::FWD, kw) > jd::lik::MAX_TAPS || jd::lik::tap_count(jd::lik::BWD, kw) > jd::lik::MAX_TAPS)
+    return 0;
+  return jd::lik::Tile<10>::smem_bytes(kh) <= 200 * 1024 ? 1 : 0;
 }
 
 int jd_likelihood_forward(const jd_lik_dataset* table_dev, int n_datasets, int fH, int fW, int kh, int kw, int f, int H,

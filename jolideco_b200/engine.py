@@ -81,13 +81,15 @@ class DatasetBuffers:
         self.kh, self.kw = int(psf.shape[-2]), int(psf.shape[-1])
         for t in (counts, exposure, psf, background):
             ops._check(t, "dataset buffer")
-        # large PSFs: cached PSF spectrum + scratch for the shared-memory FFT path
-        self.fft = ops.FFTConvPlan(psf, self.fH, self.fW) if self.kh * self.kw >= ops.FFT_MIN_PSF_AREA else None
-        # small PSFs: the batched direct kernels with the Poisson statistic fused into the convolution epilogue
-        # (jd_likelihood_forward / _backward); JD_LIK_BATCHED=0 keeps the separate conv / Poisson / conv launches
-        self.lik_ok = (self.fft is None and os.environ.get("JD_LIK_BATCHED", "1") != "0"
+        # PSF rows of up to ~37 taps: the batched direct kernels with the Poisson statistic fused into the convolution
+        # epilogue (jd_likelihood_forward / _backward); JD_LIK_BATCHED=0 keeps the separate conv / Poisson / conv
+        # launches.  Larger PSFs: cached PSF spectrum + scratch for the shared-memory FFT path.
+        self.lik_ok = (os.environ.get("JD_LIK_BATCHED", "1") != "0"
                        and self.H * self.f == self.fH and self.W * self.f == self.fW
                        and _lib.load().jd_likelihood_supported(self.kh, self.kw, self.f) == 1)
+        self.fft = None
+        if not self.lik_ok and self.kh * self.kw >= ops.FFT_MIN_PSF_AREA:
+            self.fft = ops.FFTConvPlan(psf, self.fH, self.fW)
         # counts-only Stirling term of nn.PoissonNLLLoss(full=True) (loss.py:35-37): a constant of the dataset
         self.loss_const = ops.stirling_constant(counts)
         self.geom = (self.fH, self.fW, self.kh, self.kw, self.f, self.H, self.W)

@@ -87,7 +87,7 @@ def test_separate_launches_when_the_batched_kernels_are_switched_off(recorder, m
 
 
 def test_fft_path_is_taken_for_large_psfs(recorder):
-    eng = E.MapEngine(torch.zeros(64, 64), [dataset(n=64, k=31)], prior=None, use_graph=False)
+    eng = E.MapEngine(torch.zeros(64, 64), [dataset(n=64, k=41)], prior=None, use_graph=False)
     eng.step(0)
     assert "jd_conv_forward_fft" in names(recorder) and "jd_conv_backward_fft" in names(recorder)
     assert "jd_conv_forward_direct" not in names(recorder) and "jd_likelihood_forward" not in names(recorder)

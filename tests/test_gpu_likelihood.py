@@ -49,6 +49,8 @@ CASES = [  # (D, H, W, kh, kw, f)
     (1, 21, 17, 6, 6, 2),       # upsampling 2, ragged, even PSF
     (2, 96, 128, 1, 1, 1),      # 1 x 1 PSF
     (1, 128, 192, 23, 13, 1),   # non-square PSF
+    (1, 96, 80, 34, 34, 2),     # BASELINE configs[1]: 17 x 17 PSF upsampled by 2 (9 / 10 tap groups)
+    (2, 100, 120, 7, 37, 1),    # widest f = 1 row (lead 2 + 37 taps -> 10 groups, padded)
 ]
 
 
@@ -129,11 +131,11 @@ def test_batched_likelihood_equals_the_separate_kernels():
 
 def test_unsupported_geometries_are_refused():
     lib = _lib.load()
-    assert lib.jd_likelihood_supported(34, 34, 2) == 0 and lib.jd_likelihood_supported(17, 17, 3) == 0
+    assert lib.jd_likelihood_supported(34, 34, 2) == 1 and lib.jd_likelihood_supported(17, 17, 3) == 0
     assert lib.jd_likelihood_supported(64, 64, 1) == 0 and lib.jd_likelihood_supported(29, 29, 1) == 1
     with pytest.raises(_lib.JolidecoB200Error):
         ops.likelihood_batched(torch.ones(64, 64, device=DEV), [dict(
-            exposure=torch.ones(64, 64, device=DEV), psf=torch.ones(3, 40, device=DEV),
+            exposure=torch.ones(64, 64, device=DEV), psf=torch.ones(3, 44, device=DEV),
             background=torch.ones(64, 64, device=DEV), counts=torch.ones(64, 64, device=DEV))])
 
 
