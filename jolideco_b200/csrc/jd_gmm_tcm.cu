@@ -227,11 +227,11 @@ gmm_fwd_tcm_kernel(const float* __restrict__ flux, Geom g, const int32_t* __rest
           // this CTA fetches half `crank` of the image (tf32 part | the two half parts) for both CTAs of the pair.
           // Upper-triangular factors: whitened features 0..31 do not depend on input features 32..63, i.e. rows 0..31
           // of the second tf32 k-block (4 KB) are zeros no MMA reads (k-steps 4..7 start at row 32): not copied.
-          mbar_arrive_expect_tx(full_bar(s), TRI ? B_BYTES - KBLOCK_BYTES / 2 : B_BYTES);
+          mbar_arrive_expect_tx(full_bar(s), (TRI && !(dbg & 32)) ? B_BYTES - KBLOCK_BYTES / 2 : B_BYTES);
           const uint32_t dst = smem_u32(sB + s * B_BYTES) + crank * (B_BYTES / CLUSTER);
           const uint8_t* src = Bt + (size_t)kc * B_BYTES + crank * (B_BYTES / CLUSTER);
           const uint16_t both = (uint16_t)((1u << CLUSTER) - 1);
-          if (TRI && crank == 0) {
+          if (TRI && crank == 0 && !(dbg & 32)) {
             bulk_g2s_mc(dst, src, KBLOCK_BYTES, full_bar(s), both);
             bulk_g2s_mc(dst + KBLOCK_BYTES + KBLOCK_BYTES / 2, src + KBLOCK_BYTES + KBLOCK_BYTES / 2, KBLOCK_BYTES / 2,
                         full_bar(s), both);

@@ -81,19 +81,32 @@ class DatasetBuffers:
         self.kh, self.kw = int(psf.shape[-2]), int(psf.shape[-1])
         for t in (counts, exposure, psf, background):
             ops._check(t, "dataset buffer")
-        # PSF rows of up to ~37 taps: the batched direct kernels with the Poisson statistic fused into the convolution
-        # epilogue (jd_likelihood_forward / _backward); JD_LIK_BATCHED=0 keeps the separate conv / Poisson / conv
-        # launches.  Larger PSFs: cached PSF spectrum + scratch for the shared-memory FFT path.
+        # PSF rows of up to ~37 taps can go through the batched direct kernels with the Poisson statistic fused into the
+        # convolution epilogue (jd_likelihood_forward / _backward) - the engine takes them when a launch fills the SMs
+        # (MapEngine._use_batched); JD_LIK_BATCHED=0 keeps the separate conv / Poisson / conv launches.  Larger PSFs:
+        # cached PSF spectrum + scratch for the shared-memory FFT path (built on first use).
         self.lik_ok = (os.environ.get("JD_LIK_BATCHED", "1") != "0"
                        and self.H * self.f == self.fH and self.W * self.f == self.fW
                        and _lib.load().jd_likelihood_supported(self.kh, self.kw, self.f) == 1)
-        self.fft = None
-        if not self.lik_ok and self.kh * self.kw >= ops.FFT_MIN_PSF_AREA:
-            self.fft = ops.FFTConvPlan(psf, self.fH, self.fW)
+        self._fft = None
         # counts-only Stirling term of nn.PoissonNLLLoss(full=True) (loss.py:35-37): a constant of the dataset
         self.loss_const = ops.stirling_constant(counts)
         self.geom = (self.fH, self.fW, self.kh, self.kw, self.f, self.H, self.W)
+        self.n_tiles = ((self.fH + 63) // 64) * ((self.fW + 63) // 64)
         self.flux_s = self.dflux_s = self.dpool = None  # per-dataset scratch, allocated by the engine
+
+    @property
+    def fft(self):
+        """FFT plan (cached PSF spectrum + workspace) for PSFs of at least ops.FFT_MIN_PSF_AREA taps, else None."""
+        if self._fft is None and self.kh * self.kw >= ops.FFT_MIN_PSF_AREA:
+            self._fft = ops.FFTConvPlan(self.psf, self.fH, self.fW)
+        return self._fft
+
+
+# The batched likelihood kernels give every thread an 8 x 8 output block (64 x 64 outputs per 64-thread CTA): a launch
+# needs about a CTA per SM before they beat the FFT / split-row direct kernels, which spread a small image over more
+# threads (cfg2's single 512^2 dataset is 64 CTAs: 209 us against 29 us for the FFT path).  JD_LIK_MIN_CTAS overrides.
+LIK_MIN_CTAS = int(os.environ.get("JD_LIK_MIN_CTAS", "148"))
 
 
 class MapEngine:
@@ -325,10 +338,13 @@ class MapEngine:
         NPred forward + Poisson statistic (+ gradient into parts[j] when want_grad).  Datasets the batched direct
         kernels cover go out in one launch per direction and geometry; the rest (FFT path) one by one."""
         s = self._s()
-        batched = [e for e in entries if e[0].lik_ok]
         groups = {}
-        for e in batched:
-            groups.setdefault(e[0].geom, []).append(e)
+        for e in entries:
+            if e[0].lik_ok:
+                groups.setdefault(e[0].geom, []).append(e)
+        groups = {g: es for g, es in groups.items() if self._use_batched(es)}
+        batched = [e for es in groups.values() for e in es]
+        single = [e for e in entries if not any(e is b for b in batched)]
         for d, _, _ in batched:
             if d.shift_xy is not None:  # calibration shift: the NPred model sees the shifted flux (npred.py:226-230)
                 _call("jd_shift_forward", _p(self.flux), _p(d.shift_xy), d.f, d.fH, d.fW, _p(d.flux_s), s)
@@ -345,9 +361,13 @@ class MapEngine:
             for d, _, j in batched:
                 if d.shift_xy is not None:
                     self._shift_backward(d, j)
-        for d, loss_ptr, j in entries:
-            if not d.lik_ok:
-                self._likelihood_single(d, loss_ptr, j, want_grad)
+        for d, loss_ptr, j in single:
+            self._likelihood_single(d, loss_ptr, j, want_grad)
+
+    @staticmethod
+    def _use_batched(es):
+        """One launch over the datasets `es` (same geometry) fills the machine"""
+        return sum(d.n_tiles for d, _, _ in es) >= LIK_MIN_CTAS
 
     def _shift_backward(self, d, j):
         s = self._s()

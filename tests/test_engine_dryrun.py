@@ -23,6 +23,7 @@ def recorder(monkeypatch):
 
     monkeypatch.setattr(E._lib, "call", fake_call)
     monkeypatch.setenv("JD_OVERLAP", "0")  # one stream unless a test asks for the fork / join structure
+    monkeypatch.setattr(E, "LIK_MIN_CTAS", 0)  # batched likelihood kernels whatever the image size
     monkeypatch.setattr(ops, "require_device", lambda *a, **k: None)
     monkeypatch.setattr(ops, "_check", lambda t, name, dtype=torch.float32: t)
     monkeypatch.setattr(ops, "use_stream_k", lambda P, device: False)
@@ -84,6 +85,25 @@ def test_separate_launches_when_the_batched_kernels_are_switched_off(recorder, m
     eng.step(0)
     assert names(recorder) == ["jd_step_begin_flux", "jd_conv_forward_direct", "jd_poisson_forward_backward",
                                "jd_conv_backward_direct", "jd_adam_joint_step_dev"]
+
+
+def test_small_launches_keep_the_separate_kernels(recorder, monkeypatch):
+    """One 64 x 64 tile per dataset does not fill the SMs: conv / Poisson / conv per dataset; 2 x 80 tiles do."""
+    monkeypatch.setattr(E, "LIK_MIN_CTAS", 148)
+    eng = E.MapEngine(torch.zeros(32, 32), [dataset(), dataset()], prior=None, use_graph=False)
+    eng.joint_step()
+    assert names(recorder) == ["jd_step_begin_flux"] + ["jd_conv_forward_direct", "jd_poisson_forward_backward",
+                                                        "jd_conv_backward_direct"] * 2 + ["jd_adam_joint_step_dev"]
+    del recorder[:]
+    big = [dataset(n=576), dataset(n=576)]
+    assert big[0].n_tiles == 81
+    eng = E.MapEngine(torch.zeros(576, 576), big, prior=None, use_graph=False)
+    eng.joint_step()
+    assert names(recorder) == ["jd_step_begin_flux", "jd_likelihood_forward", "jd_likelihood_backward",
+                               "jd_adam_joint_step_dev"]
+    del recorder[:]
+    eng.step(0)  # the reference step handles one dataset: 81 CTAs, separate kernels
+    assert "jd_conv_forward_direct" in names(recorder)
 
 
 def test_fft_path_is_taken_for_large_psfs(recorder):

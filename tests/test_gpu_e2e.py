@@ -365,3 +365,47 @@ def test_npred_setup_on_the_gpu_equals_the_host_setup(f):
     assert_allclose(dev.exposure.cpu().numpy(), host.exposure.numpy(), rtol=2e-6)
     if f == 2:
         assert_allclose(dev.exposure.cpu().numpy()[0, 0], g["npred_exposure_up"], rtol=2e-6)
+
+
+@pytest.mark.parametrize("name,f,n,seed", [("run_gmm_max.npz", 1, 8, 4), ("run_gmm_lse.npz", 1, 8, 4),
+                                           ("run_gmm_up2.npz", 2, 6, 5)])
+def test_goldens_through_the_batched_likelihood_kernels(monkeypatch, name, f, n, seed):
+    """The golden images are a single 64 x 64 tile, which the engine would route to the separate conv / Poisson kernels
+    (engine.LIK_MIN_CTAS); forced through jd_likelihood_forward / _backward they reproduce the reference run too."""
+    from jolideco_b200 import engine as E
+
+    monkeypatch.setattr(E, "LIK_MIN_CTAS", 0)
+    seen = []
+    real = E._lib.call
+    monkeypatch.setattr(E._lib, "call", lambda name_, *a: (seen.append(name_), real(name_, *a))[1])
+    g = load_golden(name)
+    res = run(g, f, n, make_prior(g, seed), fused=True, graph=False)
+    check(res, g, n)
+    assert "jd_likelihood_forward" in seen and "jd_likelihood_backward" in seen and "jd_conv_forward_direct" not in seen
+
+
+def test_calibration_goldens_through_the_batched_likelihood_kernels(monkeypatch):
+    from jolideco_b200 import engine as E
+
+    monkeypatch.setattr(E, "LIK_MIN_CTAS", 0)
+    g = load_golden("run_gmm_calib.npz")
+    comps = J.FluxComponents()
+    comps["flux-1"] = J.SpatialFluxComponent.from_numpy(flux=g["flux_init"], upsampling_factor=1, prior=make_prior(g, 6))
+    cals = J.NPredCalibrations()
+    for name, b in zip(as_datasets(g), g["background_norm_init"]):
+        cals[name] = J.NPredCalibration(background_norm=float(b))
+    res = J.MAPDeconvolver(n_epochs=8, learning_rate=0.1, display_progress=False, device=DEV).run(
+        datasets=as_datasets(g), components=comps, calibrations=cals)
+    check(res, g, 8)
+    assert_allclose([float(c.background_norm) for c in res.calibrations.values()], g["background_norm"], rtol=1e-4)
+    g = load_golden("run_gmm_shift.npz")
+    comps = J.FluxComponents()
+    comps["flux-1"] = J.SpatialFluxComponent.from_numpy(flux=g["flux_init"], upsampling_factor=1, prior=make_prior(g, 8))
+    cals = J.NPredCalibrations()
+    for ds_name, b, (sx, sy) in zip(as_datasets(g), g["background_norm_init"], g["shift_xy_init"]):
+        cals[ds_name] = J.NPredCalibration(shift_x=float(sx), shift_y=float(sy), background_norm=float(b))
+    res = J.MAPDeconvolver(n_epochs=6, learning_rate=0.1, display_progress=False, device=DEV).run(
+        datasets=as_datasets(g), components=comps, calibrations=cals)
+    check(res, g, 6)
+    shifts = np.stack([c.shift_xy.detach().cpu().numpy()[0] for c in res.calibrations.values()])
+    assert_allclose(shifts, g["shift_xy"], rtol=1e-3, atol=1e-4)
