@@ -130,7 +130,7 @@ class MAPDeconvolver:
             return None, 0, 1
         return pg, torch.distributed.get_rank(pg), world
 
-    def _build_engine(self, total_loss, components, n_draws, shard=None, stream_k=None, overlap=None):
+    def _build_engine(self, total_loss, components, n_draws, shard=None, stream_k=None, overlap=None, backend=None):
         (name, comp), = components.items()
         theta = comp._flux_upsampled.data[0, 0]
         mask = comp.mask[0, 0].contiguous() if comp.mask is not None else None
@@ -153,7 +153,10 @@ class MAPDeconvolver:
         prior_cfg, table = None, None
         prior = comp.prior
         if isinstance(prior, GMMPatchPrior):
-            backend = default_backend() if prior.backend is None else prior.backend
+            if prior.backend is not None:
+                backend = prior.backend
+            elif backend is None:
+                backend = default_backend()
             prior_cfg = dict(packed=prior.gmm.packed(self.device), stride=prior.stride, marginalize=prior.marginalize,
                              backend=backend)
             table = np.array([prior.draw_shifts() for _ in range(n_draws)], dtype=np.int32).reshape(-1, 2)

@@ -395,25 +395,14 @@ gmm_fwd_tcm_kernel(const float* __restrict__ flux, Geom g, const int32_t* __rest
       float run_m = -CUDART_INF_F, run_s = 0.f;
       int run_k = 0x7fffffff;
       const int pos_first = pos_lo + ((pos_lo ^ grp) & 1);
-      // component of a position (same rotated order as the producers); its scalars are fetched one position ahead
-      auto comp_of = [&](int pos) {
-        int idx = pos - pos_lo + rot;
-        idx = idx >= len ? idx - len : idx;
-        return ka + idx;
-      };
-      float c_next = 0.f, b_next = 0.f, row_inv = 0.f;
-      if (pos_first < pos_hi) {
-        c_next = __ldg(ck + comp_of(pos_first));
-        b_next = __ldg(binv + comp_of(pos_first));
-      }
+      float row_inv = 0.f;
       for (int pos = pos_first; pos < pos_hi; pos += 2) {
-        const int kc = comp_of(pos);
+        int idx = pos - pos_lo + rot;  // same rotated component order as the producers
+        idx = idx >= len ? idx - len : idx;
+        const int kc = ka + idx;
         const int t = pos % NSLOT;
-        const float c_k = c_next, b_inv = b_next;
-        if (pos + 2 < pos_hi) {
-          c_next = __ldg(ck + comp_of(pos + 2));
-          b_next = __ldg(binv + comp_of(pos + 2));
-        }
+        const float c_k = __ldg(ck + kc);
+        const float b_inv = __ldg(binv + kc);
         if (!ZERO_MEAN) mbar_wait(mwfull_bar(t), (pos / NSLOT) & 1);
         mbar_wait(tfull_bar(t), (pos / NSLOT) & 1);
         tc_fence_after();

@@ -477,7 +477,8 @@ class MapEngine:
         G, acc[1]): with `overlap` the likelihood chain runs on a side stream beside the tensor-core prior kernels
         (which leave shared memory and registers for co-resident FP32 CTAs) and joins before the update."""
         has_prior = self.prior is not None and self.P > 0
-        if self.overlap and has_prior and entries:
+        # (one dataset: a handful of launches beside a prior kernel that owns every SM - measured slower than in order)
+        if self.overlap and has_prior and len(entries) > 1:
             side = self._fork()
             with torch.cuda.stream(side):
                 self._likelihoods(entries, want_grad=True)
@@ -628,7 +629,7 @@ class MapEngine:
         entries = [(d, base + 8 * j, None) for j, d in zip(self.dataset_index, self.datasets)]
         entries += [(d, base + 8 * (self.Dg + 1 + j), None) for j, d in zip(self.validation_index, self.datasets_validation)]
         has_prior = self.prior is not None and self.P > 0
-        if self.overlap and has_prior and entries:
+        if self.overlap and has_prior and len(entries) > 1:
             side = self._fork()
             with torch.cuda.stream(side):
                 self._likelihoods(entries, want_grad=False)
