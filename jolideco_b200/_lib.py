@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjolideco_b200.so")
+LIB_PATH = os.environ.get("JD_LIB_PATH") or os.path.join(_HERE, "libjolideco_b200.so")
 
 c_f32p = ctypes.c_void_p
 c_i32p = ctypes.c_void_p

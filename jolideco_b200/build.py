@@ -15,16 +15,19 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
-LIB = os.path.join(HERE, "libjolideco_b200.so")
-STAMP = os.path.join(HERE, ".build_stamp")
-OBJDIR = os.path.join(HERE, "build")
+# experiment builds (tools/): JD_NVCC_EXTRA="-DJD_X=1" JD_LIB_TAG=x python -m jolideco_b200.build writes
+# libjolideco_b200_x.so next to the product library; JD_LIB_PATH selects it at load time (_lib.py)
+TAG = os.environ.get("JD_LIB_TAG", "")
+LIB = os.path.join(HERE, f"libjolideco_b200{'_' + TAG if TAG else ''}.so")
+STAMP = os.path.join(HERE, f".build_stamp{'_' + TAG if TAG else ''}")
+OBJDIR = os.path.join(HERE, "build" + ("_" + TAG if TAG else ""))
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
-]
+] + os.environ.get("JD_NVCC_EXTRA", "").split()
 
 
 def sources():

@@ -43,7 +43,25 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
       : "memory");
   return done;
 }
+#if defined(JD_MBAR_SPIN)
+// experiment (tools/ubench.cu): non-suspending probe
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#if defined(JD_MBAR_SPIN)
+  for (int spin = 0; spin < (1 << 24); ++spin)
+    if (mbar_test(bar, parity)) return;
+#endif
   if (mbar_try(bar, parity)) return;  // fast path: no clock read
   const long long t0 = clock64();
   while (!mbar_try(bar, parity)) {

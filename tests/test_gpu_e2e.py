@@ -20,11 +20,11 @@ def as_datasets(g):
     return {str(i): d for i, d in enumerate(unpack_datasets(g))}
 
 
-def make_prior(g, seed):
+def make_prior(g, seed, backend=None):
     gmm = J.GaussianMixtureModel.from_numpy(g["gmm_means"], g["gmm_cov"], g["gmm_w"],
                                             meta=J.GaussianMixtureModelMeta(stride=4))
     gen = torch.Generator().manual_seed(seed)
-    return J.GMMPatchPrior(gmm=gmm, stride=4, generator=gen, marginalize=bool(g["marginalize"]))
+    return J.GMMPatchPrior(gmm=gmm, stride=4, generator=gen, marginalize=bool(g["marginalize"]), backend=backend)
 
 
 def run(g, f, n_epochs, prior, fused=True, graph=True):
@@ -137,14 +137,16 @@ def test_bad_arguments_match_reference_errors():
 
 
 def test_batched_independent_runs_equal_single_runs():
-    """run_many (runs interleaved on CUDA streams) gives exactly the result of running each job alone."""
+    """run_many (runs interleaved on CUDA streams) gives exactly the result of running each job alone (with the same
+    prior kernel: batched runs take the one-tile-per-CTA tcgen05 kernel, backend 1)."""
     g = load_golden("run_gmm_max.npz")
     jobs, singles = [], []
     for seed in (4, 5, 6):
         for store in (jobs, singles):
             comps = J.FluxComponents()
-            comps["flux-1"] = J.SpatialFluxComponent.from_numpy(flux=g["flux_init"] * (1 + 0.1 * seed),
-                                                                upsampling_factor=1, prior=make_prior(g, seed))
+            comps["flux-1"] = J.SpatialFluxComponent.from_numpy(
+                flux=g["flux_init"] * (1 + 0.1 * seed), upsampling_factor=1,
+                prior=make_prior(g, seed, backend=1 if store is singles else None))
             store.append(dict(datasets=as_datasets(g), components=comps))
     res = J.run_many(jobs, n_epochs=5, n_streams=2, device=DEV)
     assert sorted(res) == [0, 1, 2]

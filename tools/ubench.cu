@@ -91,11 +91,162 @@ __global__ void __launch_bounds__(512, 1) tmem_ld64_kernel(int iters, long long*
   }
 }
 
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+  uint32_t r[64];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31,%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,"
+      "%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
+        "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
+        "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]),
+        "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]),
+        "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// MODE 0: one 32x32b.x64 load + wait per accumulator;  MODE 1: software pipeline - the load of accumulator i+1 is in
+// flight while the squares of accumulator i are summed (two register buffers of 32 columns, x32 loads);
+// MODE 2: 16 columns per load (x16), four in flight before the wait
+template <int MODE>
+__global__ void __launch_bounds__(512, 1) tmem_ld_var_kernel(int iters, long long* cycles, float* sink) {
+  __shared__ uint32_t s_tmem;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t base = s_tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  float q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  __syncthreads();
+  const long long t0 = clock64();
+  if (MODE == 0) {
+    for (int it = 0; it < iters; ++it) {
+      float y[64];
+      tmem_ld64(base + (((it + (warp >> 2)) * 64) & 511), y);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 64; ++i) q[i & 7] = fmaf(y[i], y[i], q[i & 7]);
+    }
+  } else if (MODE == 1) {
+    float ya[32], yb[32];
+    tmem_ld32(base, ya);
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t col = ((it + (warp >> 2)) * 64) & 511;
+      tmem_ld_wait();
+      tmem_ld32(base + col + 32, yb);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) q[i & 7] = fmaf(ya[i], ya[i], q[i & 7]);
+      tmem_ld_wait();
+      tmem_ld32(base + ((col + 64) & 511), ya);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) q[i & 7] = fmaf(yb[i], yb[i], q[i & 7]);
+    }
+    tmem_ld_wait();
+  } else {
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t col = ((it + (warp >> 2)) * 64) & 511;
+      uint32_t r[64];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(r[16 * c]), "=r"(r[16 * c + 1]), "=r"(r[16 * c + 2]), "=r"(r[16 * c + 3]), "=r"(r[16 * c + 4]),
+              "=r"(r[16 * c + 5]), "=r"(r[16 * c + 6]), "=r"(r[16 * c + 7]), "=r"(r[16 * c + 8]), "=r"(r[16 * c + 9]),
+              "=r"(r[16 * c + 10]), "=r"(r[16 * c + 11]), "=r"(r[16 * c + 12]), "=r"(r[16 * c + 13]),
+              "=r"(r[16 * c + 14]), "=r"(r[16 * c + 15])
+            : "r"(base + col + 16 * c));
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const float a = __uint_as_float(r[i]);
+        q[i & 7] = fmaf(a, a, q[i & 7]);
+      }
+    }
+  }
+  __syncthreads();
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  if (q[0] + q[1] + q[2] + q[3] + q[4] + q[5] + q[6] + q[7] == 123.456f) sink[0] = q[0];
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(s_tmem, 512);
+  }
+}
+
+// ------------------------------------------------------------------ mbarrier wait flavours
+// WAIT 0: mbarrier.try_wait (may suspend the thread), 1: mbarrier.test_wait spin, 2: try_wait with a 32 ns suspend hint
+template <int WAIT>
+__device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity) {
+  if (WAIT == 0) {
+    while (!mbar_try(bar, parity)) {
+    }
+  } else if (WAIT == 1) {
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(bar), "r"(parity)
+          : "memory");
+    }
+  } else {
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(bar), "r"(parity), "r"(32)
+          : "memory");
+    }
+  }
+}
+
+// two warps hand a token back and forth through two mbarriers: cycles per one-way handoff
+template <int WAIT>
+__global__ void pingpong_kernel(int iters, long long* cycles) {
+  __shared__ uint64_t bars[2];
+  const uint32_t b0 = smem_u32(&bars[0]), b1 = smem_u32(&bars[1]);
+  if (threadIdx.x == 0) {
+    mbar_init(b0, 1);
+    mbar_init(b1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long t0 = clock64();
+  if (threadIdx.x == 0) {
+    for (int it = 0; it < iters; ++it) {
+      mbar_arrive(b0);
+      wait_bar<WAIT>(b1, it & 1);
+    }
+  } else if (threadIdx.x == 32) {
+    for (int it = 0; it < iters; ++it) {
+      wait_bar<WAIT>(b0, it & 1);
+      mbar_arrive(b1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = clock64() - t0;
+}
+
 // ------------------------------------------------------------------ bulk-TMA ingest per SM
 // Every CTA walks the `n_img` operand images of `img_bytes` (L2 resident) `rounds` times through an NST-stage ring.
 // mode 0: unicast, the CTA copies `bytes` of every image itself;  mode 1: 2-CTA cluster, each CTA copies one half of
 // `bytes` and multicasts it to both (the prior kernels' scheme).  One producer thread, one consumer thread that
 // frees the stage as soon as it is full.
+template <int WAIT>
 __global__ void __launch_bounds__(128, 1)
 tma_ingest_kernel(const uint8_t* __restrict__ img, int n_img, int img_bytes, int bytes, int rounds, int nst, int mode,
                   long long* cycles) {
@@ -121,7 +272,7 @@ tma_ingest_kernel(const uint8_t* __restrict__ img, int n_img, int img_bytes, int
   if (threadIdx.x == 0) {
     for (int pos = 0; pos < total; ++pos) {
       const int s = pos % nst;
-      mbar_wait(bar0 + 8 * (nst + s), ((pos / nst) & 1) ^ 1);
+      wait_bar<WAIT>(bar0 + 8 * (nst + s), ((pos / nst) & 1) ^ 1);
       const int k = (pos + rot) % n_img;
       mbar_arrive_expect_tx(bar0 + 8 * s, bytes);
       const uint32_t dst = smem_u32(ring + (size_t)s * bytes);
@@ -135,7 +286,7 @@ tma_ingest_kernel(const uint8_t* __restrict__ img, int n_img, int img_bytes, int
   } else if (threadIdx.x == 32) {
     for (int pos = 0; pos < total; ++pos) {
       const int s = pos % nst;
-      mbar_wait(bar0 + 8 * s, (pos / nst) & 1);
+      wait_bar<WAIT>(bar0 + 8 * s, (pos / nst) & 1);
       if (mode) {  // free the stage in both CTAs of the pair
         for (int c = 0; c < 2; ++c) {
           uint32_t remote;
@@ -187,19 +338,52 @@ int main() {
            c / iters, (double)nw * 32 * 64 * 4 * iters / c);
   }
 
+  for (int nw = 4; nw <= 16; nw *= 2) {
+    for (int mode = 0; mode < 3; ++mode) {
+      for (int rep = 0; rep < 2; ++rep) {
+        if (mode == 0) tmem_ld_var_kernel<0><<<sms, nw * 32>>>(iters, d_cyc, d_sink);
+        if (mode == 1) tmem_ld_var_kernel<1><<<sms, nw * 32>>>(iters, d_cyc, d_sink);
+        if (mode == 2) tmem_ld_var_kernel<2><<<sms, nw * 32>>>(iters, d_cyc, d_sink);
+      }
+      CK(cudaDeviceSynchronize());
+      const double c = mean_cycles(d_cyc, sms);
+      const char* names[3] = {"one 32x32b.x64 + wait + 64 FFMA", "pipelined x32 loads + 64 FFMA", "4 x (32x32b.x16) + wait + 64 FFMA"};
+      printf("tmem_ld %s, %2d warps: %.1f clk per 64-col accumulator per warp, %.1f B/clk/SM\n", names[mode], nw,
+             c / iters, (double)nw * 32 * 64 * 4 * iters / c);
+    }
+  }
+
+  // ---- mbarrier handoff latency
+  {
+    const int it2 = 20000;
+    pingpong_kernel<0><<<1, 64>>>(it2, d_cyc);
+    CK(cudaDeviceSynchronize());
+    printf("mbarrier ping-pong, try_wait          : %.1f clk per one-way handoff\n", mean_cycles(d_cyc, 1) / it2 / 2);
+    pingpong_kernel<1><<<1, 64>>>(it2, d_cyc);
+    CK(cudaDeviceSynchronize());
+    printf("mbarrier ping-pong, test_wait spin    : %.1f clk per one-way handoff\n", mean_cycles(d_cyc, 1) / it2 / 2);
+    pingpong_kernel<2><<<1, 64>>>(it2, d_cyc);
+    CK(cudaDeviceSynchronize());
+    printf("mbarrier ping-pong, try_wait hint 32ns: %.1f clk per one-way handoff\n", mean_cycles(d_cyc, 1) / it2 / 2);
+  }
+
   // ---- TMA ingest
   const int n_img = 256, img_bytes = 32768;
   uint8_t* d_img;
   CK(cudaMalloc(&d_img, (size_t)n_img * img_bytes));
   CK(cudaMemset(d_img, 1, (size_t)n_img * img_bytes));
-  CK(cudaFuncSetAttribute(tma_ingest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(tma_ingest_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(tma_ingest_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(tma_ingest_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   struct Case {
-    int mode, bytes, nst, grid;
+    int mode, bytes, nst, grid, wait;
   };
   const Case cases[] = {
-      {0, 32768, 6, sms},  {1, 32768, 6, sms},  {0, 16384, 6, sms},     {0, 16384, 12, sms}, {1, 16384, 12, sms},
-      {0, 8192, 12, sms},  {0, 8192, 24, sms},  {1, 32768, 6, sms / 2}, {0, 32768, 6, sms / 2},
-      {0, 28672, 6, sms},  {0, 10240, 16, sms}, {0, 4096, 24, sms},
+      {0, 32768, 6, sms, 0},  {0, 32768, 6, sms, 1},  {0, 32768, 6, sms, 2},  {1, 32768, 6, sms, 0},
+      {1, 32768, 6, sms, 1},  {0, 16384, 6, sms, 1},  {0, 16384, 12, sms, 1}, {1, 16384, 12, sms, 1},
+      {0, 8192, 12, sms, 1},  {0, 8192, 24, sms, 1},  {0, 28672, 6, sms, 1},  {0, 10240, 16, sms, 1},
+      {0, 4096, 24, sms, 1},  {0, 4096, 24, sms, 0},  {0, 32768, 6, sms / 2, 1}, {0, 32768, 3, sms, 1},
+      {0, 32768, 2, sms, 1},
   };
   for (const Case& c : cases) {
     const int rounds = 4;
@@ -220,8 +404,8 @@ int main() {
     CK(cudaEventCreate(&e1));
     for (int rep = 0; rep < 2; ++rep) {
       CK(cudaEventRecord(e0));
-      CK(cudaLaunchKernelEx(&cfg, tma_ingest_kernel, (const uint8_t*)d_img, n_img, img_bytes, c.bytes, rounds, c.nst,
-                            c.mode, d_cyc));
+      auto kern = c.wait == 0 ? tma_ingest_kernel<0> : (c.wait == 1 ? tma_ingest_kernel<1> : tma_ingest_kernel<2>);
+      CK(cudaLaunchKernelEx(&cfg, kern, (const uint8_t*)d_img, n_img, img_bytes, c.bytes, rounds, c.nst, c.mode, d_cyc));
       CK(cudaEventRecord(e1));
       CK(cudaDeviceSynchronize());
     }
@@ -229,9 +413,9 @@ int main() {
     CK(cudaEventElapsedTime(&ms, e0, e1));
     const double cyc = mean_cycles(d_cyc, cfg.gridDim.x);
     const double per_pos = cyc / (n_img * rounds);
-    printf("tma ingest %s, %5d B per position and SM, %2d stages, %3d CTAs: %.0f clk per position, %.1f B/clk/SM "
+    printf("tma ingest %s, wait %d, %5d B per position and SM, %2d stages, %3d CTAs: %.0f clk per position, %.1f B/clk/SM "
            "landed, L2 reads %.2f TB/s, %.1f us\n",
-           c.mode ? "pair-multicast" : "unicast       ", c.bytes, c.nst, cfg.gridDim.x, per_pos, c.bytes / per_pos,
+           c.mode ? "pair-multicast" : "unicast       ", c.wait, c.bytes, c.nst, cfg.gridDim.x, per_pos, c.bytes / per_pos,
            (double)cfg.gridDim.x * (c.mode ? c.bytes / 2 : c.bytes) * n_img * rounds / (ms * 1e-3) / 1e12, ms * 1e3);
   }
   return 0;
