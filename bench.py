@@ -672,7 +672,7 @@ def measure_rooflines(E, eng, run_step, args, workload, flush):
         if name.startswith("jd_gmm_prior_forward") and eng.prior is not None:
             work = 2.0 * eng.P * 64 * 64 * eng.packed.K  # useful flops, counted once
             half = name != "jd_gmm_prior_forward_tc16"  # TF32 pipe = 1/2 bf16 rate; the split-FP16 kernel: bf16 rate
-            if name == "jd_gmm_prior_forward_tcm":  # tf32 main product + two fp16 corrections at twice the rate
+            if name in ("jd_gmm_prior_forward_tcm", "jd_gmm_prior_forward_tcm2"):  # tf32 main product + two fp16 corrections at twice the rate
                 eng.issued_over_useful = 2.0 * ((320.0 / 512.0) if eng.packed.upper_tri else 1.0)
             peak = bf16_burst / (2.0 if half else 1.0)
             ach = work / (avg_ms * 1e-3) / 1e12

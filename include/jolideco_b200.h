@@ -229,6 +229,16 @@ int jd_gmm_prior_forward_tcm(const float* flux, int fH, int fW, const int32_t* s
                              int upper_tri, int zero_mean, int marginalize, void* workspace, float* value,
                              int32_t* argmax, float* logp, double* sum, jd_stream_t stream);
 
+/* ---- a8..a10 forward, fourth tensor-core kernel (csrc/jd_gmm_tcm2.cu): the mixed TF32 / FP16 split of
+ * jd_gmm_prior_forward_tcm with two patch tiles per CTA and staged operand image (half the bytes every SM takes in per
+ * unit of work - the limiter of the one-tile kernel).  Same contract and the same Bt / binv (jd_gmm_tcm_pack);
+ * `workspace`: jd_gmm_tcm2_workspace_bytes(n_patches, K) zero-initialised bytes, 256-byte aligned. */
+int64_t jd_gmm_tcm2_workspace_bytes(int64_t n_patches, int K);
+int jd_gmm_prior_forward_tcm2(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
+                              int row_end, const void* Bt, const float* binv, const float* mw, const float* ck, int K,
+                              int upper_tri, int zero_mean, int marginalize, void* workspace, float* value,
+                              int32_t* argmax, float* logp, double* sum, jd_stream_t stream);
+
 /* Per-patch gradient  G[p',:] = scale * sum_k R[p',k] (xc_p Lam_k - bk_k),  minus its row mean,
  * R = one-hot(argmax) or softmax_k(logp) (marginalize=1; needs logp and value from the forward);
  * Lam_k = Lw_k Lw_k^T, bk_k = mw_k Lw_k^T.  (Autograd mirror of gmm.py:270-272 + norms.py:97-103.)

@@ -75,6 +75,10 @@ PROTOTYPES = {
     "jd_gmm_prior_forward_tcm": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, ctypes.c_void_p, c_f32p, c_f32p,
                                  c_f32p, c_int, c_int, c_int, c_int, ctypes.c_void_p, c_f32p, c_i32p, c_f32p, c_f64p,
                                  c_stream],
+    "jd_gmm_tcm2_workspace_bytes": [c_i64, c_int],
+    "jd_gmm_prior_forward_tcm2": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, ctypes.c_void_p, c_f32p, c_f32p,
+                                 c_f32p, c_int, c_int, c_int, c_int, ctypes.c_void_p, c_f32p, c_i32p, c_f32p, c_f64p,
+                                 c_stream],
     "jd_gmm_backward_workspace_elems": [c_i64, c_int],
     "jd_gmm_prior_backward": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, c_f32p, c_f32p, c_int, c_int,
                               c_i32p, c_f32p, c_f32p, c_float, c_f32p, c_i32p, c_stream],
@@ -123,6 +127,7 @@ def load():
                       "jd_gmm_tc16_packed_bytes": ctypes.c_size_t,
                       "jd_gmm_tcm_packed_bytes": ctypes.c_size_t,
                       "jd_gmm_tcm_workspace_bytes": ctypes.c_int64,
+                      "jd_gmm_tcm2_workspace_bytes": ctypes.c_int64,
                       "jd_gmm_backward_workspace_elems": ctypes.c_int64,
                       "jd_gmm_tc_sk_workspace_bytes": ctypes.c_int64,
                       "jd_probe_fp32_fma": ctypes.c_int64}.get(

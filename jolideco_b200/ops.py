@@ -296,9 +296,10 @@ def _btm(packed):
     return packed._Btm
 
 
-def tcm_workspace(P, K, device):
-    """Zero-initialised workspace of the backend-3 forward (arrival counters + per-segment partials)."""
-    n = int(_lib.load().jd_gmm_tcm_workspace_bytes(int(P), int(K)))
+def tcm_workspace(P, K, device, backend=3):
+    """Zero-initialised workspace of the backend-3 / 4 forwards (arrival counters + per-segment partials)."""
+    fn = _lib.load().jd_gmm_tcm2_workspace_bytes if int(backend) == 4 else _lib.load().jd_gmm_tcm_workspace_bytes
+    n = int(fn(int(P), int(K)))
     return torch.zeros(max(n, 256), dtype=torch.uint8, device=device)
 
 
@@ -371,16 +372,16 @@ def gmm_prior_forward(flux, shift_yx, packed, stride=4, marginalize=False, rows=
     if want_logp is None:
         want_logp = bool(marginalize)
     # the tensor-core forwards write logp component-major (K x P'): returned as the transposed (P', K) view
-    tc = int(backend) in (1, 2, 3)
+    tc = int(backend) in (1, 2, 3, 4)
     logp = None
     if want_logp:
         logp = torch.empty((packed.K, P) if tc else (P, packed.K), dtype=torch.float32, device=flux.device)
     if sum_out is None:
         sum_out = torch.zeros(1, dtype=torch.float64, device=flux.device)
-    if int(backend) == 3:
+    if int(backend) in (3, 4):
         bt, binv = _btm(packed)
-        ws = tcm_workspace(P, packed.K, flux.device)
-        _lib.call("jd_gmm_prior_forward_tcm", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(bt), _ptr(binv),
+        ws = tcm_workspace(P, packed.K, flux.device, backend)
+        _lib.call("jd_gmm_prior_forward_tcm2" if int(backend) == 4 else "jd_gmm_prior_forward_tcm", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(bt), _ptr(binv),
                   _ptr(packed.mw), _ptr(packed.ck), packed.K, int(packed.upper_tri), int(packed.zero_mean),
                   int(bool(marginalize)), _ptr(ws), _ptr(value), _ptr(argmax), _ptr(logp), _ptr(sum_out), _stream())
     elif int(backend) == 2:

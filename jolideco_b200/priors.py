@@ -5,6 +5,7 @@ Mirrors `jolideco/priors/core.py` (Prior, Priors, UniformPrior), `jolideco/prior
 (GMMPatchPrior); arithmetic runs in the CUDA kernels of `libjolideco_b200.so`.
 """
 import math
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -312,8 +313,10 @@ class GMMPatchPrior(Prior):
 
 
 # 3 = tcgen05 split-TF32 forward with the correction products on the FP16 pipe, persistent stream-K (jd_gmm_tcm.cu);
-# 1 = tcgen05 3 x TF32 (jd_gmm_tc.cu), 2 = tcgen05 split-FP16 (jd_gmm_tc16.cu), 0 = FP32 CUDA-core check path
-_DEFAULT_BACKEND = 3
+# 4 = the same with two patch tiles per CTA and staged operand image (jd_gmm_tcm2.cu);
+# 1 = tcgen05 3 x TF32 (jd_gmm_tc.cu), 2 = tcgen05 split-FP16 (jd_gmm_tc16.cu), 0 = FP32 CUDA-core check path.
+# JD_PRIOR_BACKEND overrides the default (A/B runs).
+_DEFAULT_BACKEND = int(os.environ.get("JD_PRIOR_BACKEND", "3"))
 
 
 def default_backend():
