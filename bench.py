@@ -318,6 +318,19 @@ def main():
     total_iters = args.steps * (1 if joint else world)
     value = total_iters / (dev_ms / 1e3)
 
+    # where the time of the fused peer kernel goes (its own %globaltimer stamps of the last timed step, per rank):
+    # waiting for the slowest rank's gradient, reduce + Adam + theta broadcast over NVLink, waiting for every slice
+    peer_us = None
+    if joint and world > 1 and eng.collective == "peer":
+        st = eng.sync_state[4:12].view(torch.int64).to(torch.float64)
+        mine = torch.stack([st[1] - st[0], st[2] - st[1], st[3] - st[2]]) / 1e3
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        allr = torch.stack(allr).cpu().numpy()
+        peer_us = {"entry_wait": [round(float(x), 1) for x in allr[:, 0]],
+                   "reduce_adam_broadcast": [round(float(x), 1) for x in allr[:, 1]],
+                   "exit_wait": [round(float(x), 1) for x in allr[:, 2]]}
+
     if parity is not None and joint and world > 1:  # replicas after warm-up + K timed steps: still bit-identical?
         parity["theta_replicas_bit_identical_after_timed_steps"] = replicas_identical(eng, pg)
         if not parity["theta_replicas_bit_identical_after_timed_steps"]:
@@ -372,6 +385,8 @@ def main():
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "parity_check": parity}
         if breakdown:
             line["breakdown_us_per_step"] = breakdown
+        if peer_us:
+            line["peer_kernel_us_per_rank_last_step"] = peer_us
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -671,7 +686,8 @@ def measure_rooflines(E, eng, run_step, args, workload, flush):
         o = {"kernel": name, "avg_launch_ms": avg_ms, "launches_per_step": calls, "launches_timed": len(durs)}
         if name.startswith("jd_gmm_prior_forward") and eng.prior is not None:
             work = 2.0 * eng.P * 64 * 64 * eng.packed.K  # useful flops, counted once
-            half = name != "jd_gmm_prior_forward_tc16"  # TF32 pipe = 1/2 bf16 rate; the split-FP16 kernel: bf16 rate
+            # TF32 pipe = 1/2 bf16 rate; the split-FP16 kernels run (and are measured against) the full bf16 / fp16 rate
+            half = name not in ("jd_gmm_prior_forward_tc16", "jd_gmm_prior_forward_tc16x2")
             if name in ("jd_gmm_prior_forward_tcm", "jd_gmm_prior_forward_tcm2"):  # tf32 main product + two fp16 corrections at twice the rate
                 eng.issued_over_useful = 2.0 * ((320.0 / 512.0) if eng.packed.upper_tri else 1.0)
             peak = bf16_burst / (2.0 if half else 1.0)

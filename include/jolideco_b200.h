@@ -229,15 +229,22 @@ int jd_gmm_prior_forward_tcm(const float* flux, int fH, int fW, const int32_t* s
                              int upper_tri, int zero_mean, int marginalize, void* workspace, float* value,
                              int32_t* argmax, float* logp, double* sum, jd_stream_t stream);
 
-/* ---- a8..a10 forward, fourth tensor-core kernel (csrc/jd_gmm_tcm2.cu): the mixed TF32 / FP16 split of
- * jd_gmm_prior_forward_tcm with two patch tiles per CTA and staged operand image (half the bytes every SM takes in per
- * unit of work - the limiter of the one-tile kernel).  Same contract and the same Bt / binv (jd_gmm_tcm_pack);
- * `workspace`: jd_gmm_tcm2_workspace_bytes(n_patches, K) zero-initialised bytes, 256-byte aligned. */
+/* ---- a8..a10 forward, fourth tensor-core kernel (csrc/jd_gmm_tcm2.cu): two patch tiles per CTA against every staged
+ * operand image, one issuer warp + epilogue group + private accumulator slots per tile, a stripped issue loop.  Same
+ * contract as jd_gmm_prior_forward_tcm, in two precision recipes of equal accuracy (22 significand bits per operand):
+ *   jd_gmm_prior_forward_tcm2   - mixed TF32 / FP16 split, Bt / binv from jd_gmm_tcm_pack;
+ *   jd_gmm_prior_forward_tc16x2 - split FP16, Bt / binv from jd_gmm_tc16_pack (12 instead of 16 MMAs per tile and
+ *                                 component, three accumulator slots per tile, half the operand bytes).
+ * `workspace`: jd_gmm_tcm2_workspace_bytes(n_patches, K) zero-initialised bytes, 256-byte aligned (both recipes). */
 int64_t jd_gmm_tcm2_workspace_bytes(int64_t n_patches, int K);
 int jd_gmm_prior_forward_tcm2(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
                               int row_end, const void* Bt, const float* binv, const float* mw, const float* ck, int K,
                               int upper_tri, int zero_mean, int marginalize, void* workspace, float* value,
                               int32_t* argmax, float* logp, double* sum, jd_stream_t stream);
+int jd_gmm_prior_forward_tc16x2(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
+                                int row_end, const void* Bt16, const float* binv, const float* mw, const float* ck,
+                                int K, int upper_tri, int zero_mean, int marginalize, void* workspace, float* value,
+                                int32_t* argmax, float* logp, double* sum, jd_stream_t stream);
 
 /* Per-patch gradient  G[p',:] = scale * sum_k R[p',k] (xc_p Lam_k - bk_k),  minus its row mean,
  * R = one-hot(argmax) or softmax_k(logp) (marginalize=1; needs logp and value from the forward);
@@ -320,8 +327,10 @@ int jd_adam_allreduce_peer(const void* grad_ptrs_dev, const void* theta_ptrs_dev
 /* The same reduce + Adam + broadcast with both cross-rank barriers inside the kernel (flag words in symmetric
  * memory, release/acquire at system scope), so that a multi-rank joint step is one CUDA graph per rank.
  * sig_ptrs_dev: device array of `world` pointers to every rank's flag block (64 uint32, zero-initialised, symmetric
- * memory); sync_state: 2 uint32 of THIS rank's device memory (epoch, finished-CTA count), zero-initialised and never
- * reset by the caller.  Every rank must launch it the same number of times.  world <= 32. */
+ * memory); sync_state: 12 uint32 of THIS rank's device memory, 8-byte aligned, zero-initialised and never reset by the
+ * caller: [0] epoch, [1] finished-CTA count, [4..11] four int64 %globaltimer stamps of the last launch (entry, entry
+ * barrier passed, theta stores fenced, exit barrier passed).  Every rank must launch it the same number of times.
+ * world <= 32; the peer loads are unrolled for world = 2, 4, 8. */
 int jd_adam_allreduce_peer_sync(const void* grad_ptrs_dev, const void* theta_ptrs_dev, const void* sig_ptrs_dev,
                                 uint32_t* sync_state, int rank, int world, float* m, float* v, const float* flux,
                                 const uint8_t* mask, int use_log_flux, int64_t n, const float* adam_scalars,

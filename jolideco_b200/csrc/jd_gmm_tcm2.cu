@@ -1,25 +1,36 @@
-// GMM patch prior forward on tcgen05, fourth generation: the mixed TF32 / FP16 split of jd_gmm_tcm.cu with TWO patch
-// tiles per CTA and B stage.
+// GMM patch prior forward on tcgen05, fourth generation: TWO patch tiles per CTA against every staged operand image,
+// one issuer warp + one epilogue group + private accumulator slots per tile, in two precision recipes:
+//   R = 0  mixed TF32 / FP16 split of jd_gmm_tcm.cu (operand image of jd_gmm_tcm_pack, 32 KB per component)
+//   R = 1  split FP16 of jd_gmm_tc16.cu          (operand image of jd_gmm_tc16_pack, 16 KB per component)
+// Both carry 22 significand bits per operand (2^-21..2^-22 relative accuracy of every log-probability, FP32
+// accumulation in TMEM); R = 1 issues 12 instead of 16 MMAs per tile and component, needs half the TMEM columns for the A
+// operand (64 instead of 128 per tile) - which buys a third accumulator slot per tile - and half the operand bytes.
 //
-// Why.  ncu on the one-tile kernel at 1024^2 / K = 256 (profiles/r02_ncu_joint1024_step.csv): 3.75 GB cross the
-// crossbar into the SMs per launch (l1tex__m_xbar2l1tex_read_bytes) = 41 B/clk/SM for 314 us, the tensor pipe is 65 %
-// busy, and switching the epilogue's TMEM loads or all but one MMA off (JD_TC_DEBUG) barely moves the time: every SM has
-// to take in the whole 28 KB operand image of a component for 128 patches of work, and a CTA-pair multicast does not
-// change what ONE SM must receive.  tools/ubench.cu: TMEM reads sustain > 400 B/clk/SM (not the limiter).  Processing
-// two tiles (256 patches) against each staged image halves the bytes per unit of work and the number of
-// producer / issuer / epilogue hand-overs.
+// Why (measurements on B200, 1024^2 image, K = 256; profiles/r02_summary.md):
+//   * ncu on the one-tile kernel jd_gmm_tcm.cu: tensor pipe 65 % busy, 3.75 GB of operand images cross into the SMs
+//     per launch (41 B/clk/SM); switching its epilogue TMEM loads off, or all MMAs but one, barely changes the time;
+//   * tools/ubench.cu: TMEM reads sustain > 400 B/clk/SM with 16 warps, an mbarrier hand-over costs ~140 clk, bulk-TMA
+//     delivers > 90 B/clk/SM - none of these is the limiter;
+//   * clock64 stamps of every hand-over (JD_TCM_TRACE build, tools/tcm_trace.py) on the first two-tile version: ONE
+//     elected lane needs ~36 clk per tcgen05.mma (R2UR + descriptor arithmetic + the debug-knob branches around each
+//     instruction): 1141 clk to issue the 32 MMAs of a position whose tensor work is 640 clk; and an accumulator slot
+//     turns around in issue + ~150 (commit -> epilogue) + ~700 (TMEM loads 460, squares 230) + ~300 (release -> issuer)
+//     clk, so with two slots the issuer and the epilogue of a slot simply alternate.
+// Hence: the issue loop is stripped to descriptor adds + UTCHMMA (no run-time knobs, warp index made uniform with a
+// shuffle so that operands live in uniform registers), the two tiles of a CTA are issued by two warps in parallel (each
+// with its own `tfull` / `tempty` barriers, so a tile's epilogue starts as soon as ITS accumulator is complete), and
+// recipe 1 runs three slots per tile.
 //
-// What changes against jd_gmm_tcm.cu:
-//   * work unit = tile group of CLUSTER x TPC = 4 tiles; the stream-K space is (tile group, component);
-//   * TMEM (512 columns): [0,128) A of tile 0 | [128,256) A of tile 1 | two accumulator slots of 2 x 64 columns.  The A
-//     operand is single-buffered: at a segment boundary the gather warps (which prefetch tile 0 into registers while
-//     the last MMAs of the previous segment run) store once the issuers' last commit has fired;
-//   * epilogue group A (warps 8-11) owns tile 0, group B (12-15) tile 1, both take every position: no merge between the
-//     groups, each finishes (or stream-K-merges) its own tile.
-// Precision recipe, operand image (jd_gmm_tcm_pack), barriers-on-position-counter scheme: unchanged.
+// Work decomposition (as jd_gmm_tcm.cu): the (tile group, component) space is linearised and cut into equal chunks, one
+// per CTA pair (2-CTA cluster, each CTA fetches half of every operand image and multicasts it to both); tile group =
+// CLUSTER x TPC = 4 tiles; a chunk is a sequence of segments (component range of one tile group); partial (max, sum-exp,
+// argmax) rows of split tiles go through a workspace, the last segment of a tile to arrive merges them in component order.
+// The A operand is single-buffered: at a segment boundary the gather warps (tile 0's patch already in registers) store
+// once the issuers' last commits of the previous segment have fired.
 //
-// Warps (512 threads, one CTA per SM): 0-1 bulk-TMA producers | 2-3 MMA issuers | 4-7 gather | 8-11 epilogue of tile 0
-// | 12-15 epilogue of tile 1.
+// Warps (512 threads, one CTA per SM): 0-1 bulk-TMA producers | 2, 3 MMA issuers of tile 0, 1 | 4-7 gather | 8-11
+// epilogue of tile 0 | 12-15 epilogue of tile 1.
+// TMEM (512 columns): [0, TPC A_COLS) A operands | then NSLOT x TPC accumulators of 64 columns, slot-major.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -29,35 +40,49 @@
 #include "jd_tc_ptx.cuh"
 
 namespace jd {
-namespace tcm2 {
+namespace tcx2 {
 
 using namespace tcx;
 
 constexpr int TM = 128;
-constexpr int TPC = 2;                       // patch tiles per CTA and B stage
-constexpr int NSTAGE = 6;
-constexpr int NSLOT = 2;                     // accumulator slots (positions in flight between issuers and epilogue)
+constexpr int TPC = 2;  // patch tiles per CTA and staged operand image
 constexpr int ACC_COLS = 64;
-constexpr int SLOT_COLS = TPC * ACC_COLS;    // both tiles' accumulators of one position
-constexpr int A_COLS = 128;                  // per tile
-constexpr int ACC0 = TPC * A_COLS;
 constexpr int TMEM_COLS = 512;
-constexpr int KBLOCK_BYTES = 64 * 128;           // 8 KB: 64 rows x 128 B
-constexpr int B_TF32_BYTES = 2 * KBLOCK_BYTES;   // 64 x 64 tf32
-constexpr int B_F16_BYTES = KBLOCK_BYTES;        // 64 x 64 half
-constexpr int B_BYTES = B_TF32_BYTES + 2 * B_F16_BYTES;
+constexpr int KBLOCK_BYTES = 64 * 128;  // 8 KB: 64 rows x 128 B (one swizzle atom wide)
 constexpr int CLUSTER = 2;
 constexpr int NPROD = 2;
-constexpr int NMMA = 2;
-static_assert(NSTAGE % NPROD == 0 && NSLOT % NMMA == 0, "fixed barrier ownership (jd_gmm_tc.cu)");
-static_assert(ACC0 + NSLOT * SLOT_COLS <= 512, "TMEM budget");
-constexpr int M0 = NPROD;      // first MMA warp (owns the TMEM allocation)
-constexpr int G0 = 4;          // first gather warp
-constexpr int E0 = 8;          // first epilogue warp
+constexpr int M0 = NPROD;  // first MMA warp (owns the TMEM allocation); warp M0 + h issues tile h
+constexpr int G0 = 4;      // first gather warp
+constexpr int E0 = 8;      // first epilogue warp
 constexpr int NTHREADS = 512;
-constexpr int MW_BYTES = 64 * 4;
-constexpr int NBAR = 2 * NSTAGE + 3 * NSLOT + TPC + 1;
-constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + NSTAGE * B_BYTES + NSLOT * MW_BYTES + 6144 /*barriers, flags*/;
+static_assert(M0 + TPC == G0, "warp roles");
+
+template <int R>
+struct Recipe;
+template <>
+struct Recipe<0> {  // tf32(x') tf32(L') + half(xr) half(L') + half(x') half(Lr)
+  static constexpr int A_COLS = 128;  // [0,64) tf32(x') | [64,96) half2(xr) | [96,128) half2(x')
+  static constexpr int NSLOT = 2;
+  static constexpr int NSTAGE = 6;
+  static constexpr int B_BYTES = 4 * KBLOCK_BYTES;  // [0,16K) tf32(L') | [16K,24K) half(L') | [24K,32K) half(Lr)
+};
+template <>
+struct Recipe<1> {  // lo.hi + hi.lo + hi.hi in FP16
+  static constexpr int A_COLS = 64;  // [0,32) half2(hi) | [32,64) half2(lo)
+  static constexpr int NSLOT = 3;
+  static constexpr int NSTAGE = 10;
+  static constexpr int B_BYTES = 2 * KBLOCK_BYTES;  // hi | lo
+};
+
+template <int R>
+struct Layout {
+  using Rc = Recipe<R>;
+  static constexpr int ACC0 = TPC * Rc::A_COLS;
+  static constexpr int NBAR = 2 * Rc::NSTAGE + 2 * Rc::NSLOT * TPC + TPC + 1;
+  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)Rc::NSTAGE * Rc::B_BYTES + 6144 /*barriers, flags*/;
+  static_assert(ACC0 + Rc::NSLOT * TPC * ACC_COLS <= TMEM_COLS, "TMEM budget");
+  static_assert(Rc::NSTAGE % NPROD == 0, "a smem stage must always be refilled by the same producer warp");
+};
 
 __device__ __host__ constexpr uint32_t idesc_tf32(uint32_t n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
@@ -65,15 +90,42 @@ __device__ __host__ constexpr uint32_t idesc_tf32(uint32_t n) {
 __device__ __host__ constexpr uint32_t idesc_f16(uint32_t n) {
   return (1u << 4) | (0u << 7) | (0u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
-__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+// D[tmem] (+)= A[tmem] . B[smem]; ACC is a compile-time constant (no predicate arithmetic in the issue loop)
+template <bool F16, bool ACC>
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc) {
+  if (F16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "n"(ACC ? 1 : 0)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "n"(ACC ? 1 : 0)
+        : "memory");
+  }
 }
+
+// Experiment build (JD_NVCC_EXTRA=-DJD_TCM_TRACE, tools/tcm_trace.py): clock64 stamps of the hand-overs of CTA 0, per
+// position: 0 producer past `empty` | 1 issuer 0 past `tempty` | 2 issuer 0 past `full` | 3 issuer 0 done | 4 epilogue 0
+// past `tfull` | 5 epilogue 0 loads landed | 6 epilogue 0 released the slot | 7 epilogue 1 past `tfull` | 8 issuer 1 past
+// `tempty` | 9 issuer 1 past `full` | 10 issuer 1 done | 11 epilogue 1 released the slot
+#if defined(JD_TCM_TRACE)
+constexpr int TRACE_POS = 2048;
+__device__ long long g_trace[TRACE_POS * 16];
+#define JD_TRACE(ev, pos)                                                                   \
+  do {                                                                                      \
+    if (blockIdx.x == 0 && (pos) < TRACE_POS) g_trace[(pos)*16 + (ev)] = clock64();         \
+  } while (0)
+#else
+#define JD_TRACE(ev, pos) \
+  do {                    \
+  } while (0)
+#endif
 
 __device__ __forceinline__ int seg_rotation(int cl, int len, unsigned mul) {
   return (int)(((unsigned)cl * mul) % (unsigned)len);
@@ -83,40 +135,100 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return (uint32_t)__half_as_ushort(__float2half_rn(a)) | ((uint32_t)__half_as_ushort(__float2half_rn(b)) << 16);
 }
 
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+      "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+      : "memory");
+}
+
+// ---------------------------------------------------------------- the MMAs of one tile and component
+// a: TMEM address of the tile's A operand, d: its accumulator, b: low descriptor word of the staged operand image.
+template <int R, bool TRI>
+__device__ __forceinline__ void issue_tile(uint32_t d, uint32_t a, uint32_t b) {
+  if (R == 0) {
+    const uint32_t b_h = b + (2 * KBLOCK_BYTES >> 4), b_r = b_h + (KBLOCK_BYTES >> 4);
+    // small terms first: xr . half(L'), half(x') . half(Lr), then tf32(x') . tf32(L').  Upper-triangular Lw: input
+    // features [16kk, 16kk+16) only reach whitened features >= 16kk, the MMA's N extent shrinks accordingly
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const uint32_t n0 = TRI ? 16u * kk : 0u;
+      const uint32_t off16 = (kk * 32 + n0 * 128) >> 4;
+      if (kk == 0)
+        umma_ts<true, false>(d + n0, a + 64 + kk * 8, desc_from_lo(b_h + off16), idesc_f16(64 - n0));
+      else
+        umma_ts<true, true>(d + n0, a + 64 + kk * 8, desc_from_lo(b_h + off16), idesc_f16(64 - n0));
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const uint32_t n0 = TRI ? 16u * kk : 0u;
+      const uint32_t off16 = (kk * 32 + n0 * 128) >> 4;
+      umma_ts<true, true>(d + n0, a + 96 + kk * 8, desc_from_lo(b_r + off16), idesc_f16(64 - n0));
+    }
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const uint32_t n0 = TRI ? 16u * (kk >> 1) : 0u;
+      const uint32_t off16 = ((kk >> 2) * KBLOCK_BYTES + (kk & 3) * 32 + n0 * 128) >> 4;
+      umma_ts<false, true>(d + n0, a + kk * 8, desc_from_lo(b + off16), idesc_tf32(64 - n0));
+    }
+  } else {
+    const uint32_t b_hi = b, b_lo = b + (KBLOCK_BYTES >> 4);
+    // small terms first: lo . hi, hi . lo, then hi . hi
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+      const uint32_t a_col = pass == 0 ? 32u : 0u;
+      const uint32_t b_base = pass == 1 ? b_lo : b_hi;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const uint32_t n0 = TRI ? 16u * kk : 0u;
+        const uint32_t off16 = (kk * 32 + n0 * 128) >> 4;
+        if (pass == 0 && kk == 0)
+          umma_ts<true, false>(d + n0, a + a_col + kk * 8, desc_from_lo(b_base + off16), idesc_f16(64 - n0));
+        else
+          umma_ts<true, true>(d + n0, a + a_col + kk * 8, desc_from_lo(b_base + off16), idesc_f16(64 - n0));
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- the forward kernel
-template <bool TRI, bool ZERO_MEAN>
+template <int R, bool TRI, bool ZERO_MEAN>
 __global__ void __launch_bounds__(NTHREADS, 1)
-gmm_fwd_tcm2_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restrict__ shift_yx,
-                   const uint8_t* __restrict__ Bt, const float* __restrict__ mw, const float* __restrict__ ck,
-                   const float* __restrict__ binv, int K, int marginalize, int chunk, int smax, unsigned rot_mul,
-                   unsigned* __restrict__ counters, float* __restrict__ ws_m, float* __restrict__ ws_s,
-                   int* __restrict__ ws_k, float* __restrict__ value, int32_t* __restrict__ argmax,
-                   float* __restrict__ logp, double* __restrict__ sum) {
+gmm_fwd_tcx2_kernel(const float* __restrict__ flux, Geom g, const int32_t* __restrict__ shift_yx,
+                    const uint8_t* __restrict__ Bt, const float* __restrict__ mw, const float* __restrict__ ck,
+                    const float* __restrict__ binv, int K, int marginalize, int chunk, int smax, unsigned rot_mul,
+                    unsigned* __restrict__ counters, float* __restrict__ ws_m, float* __restrict__ ws_s,
+                    int* __restrict__ ws_k, float* __restrict__ value, int32_t* __restrict__ argmax,
+                    float* __restrict__ logp, double* __restrict__ sum) {
+  using Rc = Recipe<R>;
+  using L = Layout<R>;
+  constexpr int NSTAGE = Rc::NSTAGE, NSLOT = Rc::NSLOT, A_COLS = Rc::A_COLS, B_BYTES = Rc::B_BYTES, ACC0 = L::ACC0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sB = smem;                                            // NSTAGE x 32 KB
-  float* sMW = reinterpret_cast<float*>(sB + NSTAGE * B_BYTES);  // NSLOT x 64 floats
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + NSTAGE * B_BYTES + NSLOT * MW_BYTES);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + NBAR);
-  int* s_flag = reinterpret_cast<int*>(s_tmem + 2);           // one per epilogue group
+  uint8_t* sB = smem;  // NSTAGE operand images
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + NSTAGE * B_BYTES);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + L::NBAR);
+  int* s_flag = reinterpret_cast<int*>(s_tmem + 2);  // one per epilogue group
   // per-row flags of the gather warps, double-buffered on the segment parity: [parity][tile][row]
   int* s_valid = reinterpret_cast<int*>(s_tmem + 4);
   float* s_rinv = reinterpret_cast<float*>(s_valid + 2 * TPC * TM);  // 1 / (row scale)
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform (role dispatch, positions, stage / slot
+  // indices and with them every MMA operand stay in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
   const uint32_t rt_zero = (uint32_t)K >> 30;  // 0 at run time (K < 2^30), opaque to the compiler
-  // profiling knobs (JD_TC_DEBUG, results are wrong with any of them): 1 = no epilogue TMEM loads, 2 = no FP16
-  // correction products, 4 = no TF32 product, 8 = one MMA per component
-  const int dbg = marginalize >> 8;
+  const int dbg = marginalize >> 8;             // JD_TC_DEBUG & 1 (timing only, wrong results): no epilogue TMEM loads
   marginalize &= 1;
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
-  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + s); };
-  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + NSLOT + s); };
-  auto mwfull_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 * NSLOT + s); };
-  auto afull_bar = [&](int h) { return bar0 + 8u * (2 * NSTAGE + 3 * NSLOT + h); };  // A operand of tile h stored
-  const uint32_t aempty_bar = bar0 + 8u * (2 * NSTAGE + 3 * NSLOT + TPC);             // last MMAs of the segment done
+  auto tfull_bar = [&](int t, int h) { return bar0 + 8u * (2 * NSTAGE + t * TPC + h); };
+  auto tempty_bar = [&](int t, int h) { return bar0 + 8u * (2 * NSTAGE + NSLOT * TPC + t * TPC + h); };
+  auto afull_bar = [&](int h) { return bar0 + 8u * (2 * NSTAGE + 2 * NSLOT * TPC + h); };  // A operand of tile h stored
+  const uint32_t aempty_bar = bar0 + 8u * (2 * NSTAGE + 2 * NSLOT * TPC + TPC);             // last MMAs of the segment done
   const uint32_t crank = cluster_ctarank();
 
   // this CTA pair's chunk of the linearised (tile group, component) space; tile group tp = tiles [4 tp, 4 tp + 4):
@@ -136,15 +248,15 @@ gmm_fwd_tcm2_kernel(const float* __restrict__ flux, Geom g, const int32_t* __res
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), CLUSTER);  // released by the MMA commits of both CTAs of the pair
+      mbar_init(empty_bar(s), CLUSTER * TPC);  // released by the MMA commits of both issuers of both CTAs of the pair
     }
-    for (int s = 0; s < NSLOT; ++s) {
-      mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4 * TPC);  // one arrive per epilogue warp (both tiles' accumulators share the slot)
-      mbar_init(mwfull_bar(s), 1);
-    }
+    for (int t = 0; t < NSLOT; ++t)
+      for (int h = 0; h < TPC; ++h) {
+        mbar_init(tfull_bar(t, h), 1);
+        mbar_init(tempty_bar(t, h), 4);  // one arrive per warp of the tile's epilogue group
+      }
     for (int h = 0; h < TPC; ++h) mbar_init(afull_bar(h), 4);  // one arrive per gather warp
-    mbar_init(aempty_bar, NMMA);                                // last MMAs of the segment, both issuers
+    mbar_init(aempty_bar, TPC);                                 // last MMAs of the segment, both issuers
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == M0) tmem_alloc(smem_u32(s_tmem), TMEM_COLS);
@@ -168,7 +280,7 @@ gmm_fwd_tcm2_kernel(const float* __restrict__ flux, Geom g, const int32_t* __res
   (void)ka; (void)rot; (void)par;
 
   if (warp < NPROD) {
-    // ===================== bulk-TMA producers ======================================================
+    // ===================== bulk-TMA producers: position pos is loaded by warp pos % NPROD ==========
     for (int tp = tp_first; tp <= tp_last; ++tp) {
       JD_SEGMENT(tp)
       int pos = pos_lo + ((pos_lo % NPROD) == warp ? 0 : (warp - (pos_lo % NPROD) + NPROD) % NPROD);
@@ -176,92 +288,54 @@ gmm_fwd_tcm2_kernel(const float* __restrict__ flux, Geom g, const int32_t* __res
         int idx = pos - pos_lo + rot;
         idx = idx >= len ? idx - len : idx;
         const int kc = ka + idx;
-        const int s = pos % NSTAGE, t = pos % NSLOT;
+        const int s = pos % NSTAGE;
         mbar_wait(empty_bar(s), ((pos / NSTAGE) & 1) ^ 1);
-        if (!ZERO_MEAN) mbar_wait(tempty_bar(t), ((pos / NSLOT) & 1) ^ 1);
         if (elect_one()) {
-          // this CTA fetches half `crank` of the image (tf32 part | the two half parts) for both CTAs of the pair.
-          // Upper-triangular factors: whitened features 0..31 do not depend on input features 32..63, i.e. rows 0..31
-          // of the second tf32 k-block (4 KB) are zeros no MMA reads (k-steps 4..7 start at row 32): not copied.
-          mbar_arrive_expect_tx(full_bar(s), (TRI && !(dbg & 32)) ? B_BYTES - KBLOCK_BYTES / 2 : B_BYTES);
+          JD_TRACE(0, pos);
+          // this CTA fetches half `crank` of the image for both CTAs of the pair.  Recipe 0, upper-triangular factors:
+          // whitened features 0..31 do not depend on input features 32..63, i.e. rows 0..31 of the second tf32 k-block
+          // (4 KB) are zeros no MMA reads (k-steps 4..7 start at row 32): not copied.
+          const bool trim = R == 0 && TRI;
+          mbar_arrive_expect_tx(full_bar(s), trim ? B_BYTES - KBLOCK_BYTES / 2 : B_BYTES);
           const uint32_t dst = smem_u32(sB + s * B_BYTES) + crank * (B_BYTES / CLUSTER);
           const uint8_t* src = Bt + (size_t)kc * B_BYTES + crank * (B_BYTES / CLUSTER);
           const uint16_t both = (uint16_t)((1u << CLUSTER) - 1);
-          if (TRI && crank == 0 && !(dbg & 32)) {
+          if (trim && crank == 0) {
             bulk_g2s_mc(dst, src, KBLOCK_BYTES, full_bar(s), both);
             bulk_g2s_mc(dst + KBLOCK_BYTES + KBLOCK_BYTES / 2, src + KBLOCK_BYTES + KBLOCK_BYTES / 2, KBLOCK_BYTES / 2,
                         full_bar(s), both);
           } else {
             bulk_g2s_mc(dst, src, B_BYTES / CLUSTER, full_bar(s), both);
           }
-          if (!ZERO_MEAN) {
-            mbar_arrive_expect_tx(mwfull_bar(t), MW_BYTES);
-            bulk_g2s(smem_u32(sMW + t * 64), mw + (size_t)kc * 64, MW_BYTES, mwfull_bar(t));
-          }
         }
         __syncwarp();
       }
     }
-  } else if (warp < M0 + NMMA) {
-    // ===================== MMA issuers (warp-uniform control flow, one elected lane issues) =========
-    const int w = warp - M0;
+  } else if (warp < M0 + TPC) {
+    // ===================== MMA issuers: warp M0 + h issues tile h, every position (warp-uniform control flow, one
+    // elected lane issues) =======================================================================
+    const int h = warp - M0;
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t sB_lo0 = desc_lo(smem_u32(sB));
+    const uint32_t a_base = tmem_u + h * A_COLS;
     for (int tp = tp_first; tp <= tp_last; ++tp) {
       JD_SEGMENT(tp)
-#pragma unroll
-      for (int h = 0; h < TPC; ++h) mbar_wait(afull_bar(h), par);  // the gather warps have stored this segment's A operands
+      mbar_wait(afull_bar(h), par);  // the gather warps have stored this segment's A operand of tile h
       tc_fence_after();
-      int pos = pos_lo + ((pos_lo % NMMA) == w ? 0 : (w - (pos_lo % NMMA) + NMMA) % NMMA);
-      bool released = false;
-      for (; pos < pos_hi; pos += NMMA) {
+      for (int pos = pos_lo; pos < pos_hi; ++pos) {
         const int s = pos % NSTAGE, t = pos % NSLOT;
-        const bool last = pos + NMMA >= pos_hi;
-        mbar_wait(tempty_bar(t), ((pos / NSLOT) & 1) ^ 1);
+        mbar_wait(tempty_bar(t, h), ((pos / NSLOT) & 1) ^ 1);
+        if (lane == 0) JD_TRACE(h == 0 ? 1 : 8, pos);
         mbar_wait(full_bar(s), (pos / NSTAGE) & 1);
+        if (lane == 0) JD_TRACE(h == 0 ? 2 : 9, pos);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t b_t = sB_lo0 + s * (B_BYTES >> 4);
-          const uint32_t b_h = b_t + (B_TF32_BYTES >> 4), b_r = b_h + (B_F16_BYTES >> 4);
-#pragma unroll
-          for (int h = 0; h < TPC; ++h) {  // both tiles against the same staged image
-            const uint32_t a_base = tmem_u + h * A_COLS;
-            const uint32_t d = tmem_u + ACC0 + t * SLOT_COLS + h * ACC_COLS;
-            uint32_t acc = 0;
-            // small terms first: xr . half(L'), half(x') . half(Lr), then tf32(x') . tf32(L')
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-              const uint32_t a_col = pass == 0 ? 64u : 96u;
-              const uint32_t b_base = pass == 0 ? b_h : b_r;
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                if ((dbg & 2) && (kk > 0 || pass > 0 || !(dbg & 4))) continue;
-                if ((dbg & 8) && (kk > 0 || pass > 0)) continue;
-                // upper-triangular Lw: input features [16kk, 16kk+16) only reach whitened features >= 16kk
-                const uint32_t n0 = TRI ? 16u * kk : 0u;
-                const uint32_t off16 = (kk * 32 + n0 * 128) >> 4;
-                umma_f16_ts(d + n0, a_base + a_col + kk * 8, desc_from_lo(b_base + off16), idesc_f16(64 - n0), acc);
-                acc = 1;
-              }
-            }
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-              if ((dbg & 12) != 0) continue;
-              const uint32_t n0 = TRI ? 16u * (kk >> 1) : 0u;
-              const uint32_t off16 = ((kk >> 2) * KBLOCK_BYTES + (kk & 3) * 32 + n0 * 128) >> 4;
-              umma_tf32_ts(d + n0, a_base + kk * 8, desc_from_lo(b_t + off16), idesc_tf32(64 - n0), acc);
-              acc = 1;
-            }
-          }
+          issue_tile<R, TRI>(tmem_u + ACC0 + (t * TPC + h) * ACC_COLS, a_base, sB_lo0 + s * (B_BYTES >> 4));
           umma_commit_mc(empty_bar(s), (uint16_t)((1u << CLUSTER) - 1));  // stage free in both CTAs of the pair
-          umma_commit(tfull_bar(t));                                       // both accumulators of the slot complete
-          if (last) umma_commit(aempty_bar);  // this warp's last read of the A operands (same thread as its MMAs)
+          umma_commit(tfull_bar(t, h));                                    // this tile's accumulator complete
+          if (pos == pos_hi - 1) umma_commit(aempty_bar);  // last read of the tile's A operand (same thread as its MMAs)
+          JD_TRACE(h == 0 ? 3 : 10, pos);
         }
-        released = released || last;
-        __syncwarp();
-      }
-      if (!released) {  // no position of this segment fell to this warp
-        if (elect_one()) mbar_arrive(aempty_bar);
         __syncwarp();
       }
     }
@@ -271,88 +345,87 @@ gmm_fwd_tcm2_kernel(const float* __restrict__ flux, Geom g, const int32_t* __res
       JD_SEGMENT(tp)
 #pragma unroll 1
       for (int h = 0; h < TPC; ++h) {
-      const int tile = (tp * CLUSTER + (int)crank) * TPC + h;
-      const int64_t p = (int64_t)tile * TM + row;
-      float vals[64];
-      float sm = 0.f;
-      bool ok = p < g.P;
-      if (ok) {
-        int iy = (int)(p / g.nx) + g.row_begin, ix = (int)(p % g.nx);
-        int cols[8];
+        const int tile = (tp * CLUSTER + (int)crank) * TPC + h;
+        const int64_t p = (int64_t)tile * TM + row;
+        float vals[64];
+        float sm = 0.f;
+        bool ok = p < g.P;
+        if (ok) {
+          int iy = (int)(p / g.nx) + g.row_begin, ix = (int)(p % g.nx);
+          int cols[8];
 #pragma unroll
-        for (int v = 0; v < 8; ++v) cols[v] = src_col(g, ix, v);
+          for (int v = 0; v < 8; ++v) cols[v] = src_col(g, ix, v);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float* src = flux + (int64_t)src_row(g, iy, u) * g.fW;
+          for (int u = 0; u < 8; ++u) {
+            const float* src = flux + (int64_t)src_row(g, iy, u) * g.fW;
 #pragma unroll
-          for (int v = 0; v < 8; ++v) {
-            float x = __ldg(src + cols[v]);
-            vals[u * 8 + v] = x;
-            sm += x;
-            ok = ok && (x > -1e5f);
+            for (int v = 0; v < 8; ++v) {
+              float x = __ldg(src + cols[v]);
+              vals[u * 8 + v] = x;
+              sm += x;
+              ok = ok && (x > -1e5f);
+            }
           }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) vals[i] = 0.f;
         }
-      } else {
+        const float mean = sm * (1.f / 64.f);
+        float amax = 0.f;
 #pragma unroll
-        for (int i = 0; i < 64; ++i) vals[i] = 0.f;
-      }
-      const float mean = sm * (1.f / 64.f);
-      float amax = 0.f;
-#pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        vals[i] = ok ? vals[i] - mean : 0.f;
-        amax = fmaxf(amax, fabsf(vals[i]));
-      }
-      int e = amax > 0.f ? ilogbf(amax) : 13;
-      e = max(-100, min(100, e));
-      const float sA = ldexpf(1.f, 13 - e);
-      // the A operands are free once the last MMAs of the previous segment have completed (tile 0's patch is already in
-      // registers by then)
-      if (h == 0) {
-        mbar_wait(aempty_bar, par ^ 1);
-        tc_fence_after();
-      }
-      const uint32_t a_lane = tmem_base + ((uint32_t)(q * 32) << 16) + h * A_COLS;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float xt[32], xr[16], xh[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float a0 = vals[h * 32 + 2 * i] * sA, a1 = vals[h * 32 + 2 * i + 1] * sA;
-          const float t0 = tf32_rna(a0), t1 = tf32_rna(a1);
-          xt[2 * i] = t0, xt[2 * i + 1] = t1;
-          xr[i] = __uint_as_float(pack_half2(a0 - t0, a1 - t1));
-          xh[i] = __uint_as_float(pack_half2(a0, a1));
+        for (int i = 0; i < 64; ++i) {
+          vals[i] = ok ? vals[i] - mean : 0.f;
+          amax = fmaxf(amax, fabsf(vals[i]));
         }
-        tmem_st32(a_lane + h * 32, xt);
-        // 16 packed words each: features [32h, 32h+32) land in columns [64 + 16h, +16) and [96 + 16h, +16)
-        float pk[32];
+        int e = amax > 0.f ? ilogbf(amax) : 13;
+        e = max(-100, min(100, e));
+        const float sA = ldexpf(1.f, 13 - e);
+        // the A operands are free once the last MMAs of the previous segment have completed (tile 0's patch is already in
+        // registers by then)
+        if (h == 0) {
+          mbar_wait(aempty_bar, par ^ 1);
+          tc_fence_after();
+        }
+        const uint32_t a_lane = tmem_base + ((uint32_t)(q * 32) << 16) + h * A_COLS;
+        if (R == 0) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = xr[i], pk[16 + i] = xh[i];
-        // two 16-column stores through one 32-wide helper would overlap: store xr and xh halves separately below
-        asm volatile(
-            "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-            "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(a_lane + 64 + h * 16),
-            "f"(pk[0]), "f"(pk[1]), "f"(pk[2]), "f"(pk[3]), "f"(pk[4]), "f"(pk[5]), "f"(pk[6]), "f"(pk[7]), "f"(pk[8]),
-            "f"(pk[9]), "f"(pk[10]), "f"(pk[11]), "f"(pk[12]), "f"(pk[13]), "f"(pk[14]), "f"(pk[15])
-            : "memory");
-        asm volatile(
-            "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-            "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(a_lane + 96 + h * 16),
-            "f"(pk[16]), "f"(pk[17]), "f"(pk[18]), "f"(pk[19]), "f"(pk[20]), "f"(pk[21]), "f"(pk[22]), "f"(pk[23]),
-            "f"(pk[24]), "f"(pk[25]), "f"(pk[26]), "f"(pk[27]), "f"(pk[28]), "f"(pk[29]), "f"(pk[30]), "f"(pk[31])
-            : "memory");
-      }
-      tmem_st_wait();
-      s_valid[(par * TPC + h) * TM + row] = ok ? 1 : 0;
-      s_rinv[(par * TPC + h) * TM + row] = ldexpf(1.f, e - 13);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(afull_bar(h));
+          for (int hh = 0; hh < 2; ++hh) {
+            float xt[32], pk[32];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float a0 = vals[hh * 32 + 2 * i] * sA, a1 = vals[hh * 32 + 2 * i + 1] * sA;
+              const float t0 = tf32_rna(a0), t1 = tf32_rna(a1);
+              xt[2 * i] = t0, xt[2 * i + 1] = t1;
+              pk[i] = __uint_as_float(pack_half2(a0 - t0, a1 - t1));
+              pk[16 + i] = __uint_as_float(pack_half2(a0, a1));
+            }
+            tmem_st32(a_lane + hh * 32, xt);
+            // 16 packed words each: features [32hh, 32hh+32) land in columns [64 + 16hh, +16) and [96 + 16hh, +16)
+            tmem_st16(a_lane + 64 + hh * 16, pk);
+            tmem_st16(a_lane + 96 + hh * 16, pk + 16);
+          }
+        } else {
+          float hi[32], lo[32];  // 32 packed half2 words each (64 features)
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float x0 = vals[2 * c] * sA, x1 = vals[2 * c + 1] * sA;
+            const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+            hi[c] = __uint_as_float((uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16));
+            lo[c] = __uint_as_float(pack_half2(x0 - __half2float(h0), x1 - __half2float(h1)));
+          }
+          tmem_st32(a_lane, hi);
+          tmem_st32(a_lane + 32, lo);
+        }
+        tmem_st_wait();
+        s_valid[(par * TPC + h) * TM + row] = ok ? 1 : 0;
+        s_rinv[(par * TPC + h) * TM + row] = ldexpf(1.f, e - 13);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(afull_bar(h));
       }
     }
   } else {
-    // ===================== epilogue: group A (warps 8-11) tile 0, group B (12-15) tile 1, every position ========
+    // ===================== epilogue: group 0 (warps 8-11) tile 0, group 1 (12-15) tile 1, every position ========
     const int grp = warp >= E0 + 4 ? 1 : 0;
     const int bar_id = 2 + grp;  // named barrier of this group's 128 threads
     for (int tp = tp_first; tp <= tp_last; ++tp) {
@@ -370,15 +443,15 @@ gmm_fwd_tcm2_kernel(const float* __restrict__ flux, Geom g, const int32_t* __res
         const int t = pos % NSLOT;
         const float c_k = __ldg(ck + kc);
         const float b_inv = __ldg(binv + kc);
-        if (!ZERO_MEAN) mbar_wait(mwfull_bar(t), (pos / NSLOT) & 1);
-        mbar_wait(tfull_bar(t), (pos / NSLOT) & 1);
+        mbar_wait(tfull_bar(t, grp), (pos / NSLOT) & 1);
+        if (lane == 0 && (warp == E0 || warp == E0 + 4)) JD_TRACE(warp == E0 ? 4 : 7, pos);
         tc_fence_after();
         if (pos == pos_lo) {  // written by the gather warps before the first MMA of the segment
           row_inv = s_rinv[(par * TPC + grp) * TM + row];
           ok = s_valid[(par * TPC + grp) * TM + row] != 0;
         }
         const float inv = row_inv * b_inv;  // undo the row and component scales
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ACC0 + t * SLOT_COLS + grp * ACC_COLS;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ACC0 + (t * TPC + grp) * ACC_COLS;
         float y0[32], y1[32];
         if (dbg & 1) {
 #pragma unroll
@@ -388,6 +461,7 @@ gmm_fwd_tcm2_kernel(const float* __restrict__ flux, Geom g, const int32_t* __res
           tmem_ld32(taddr + 32, y1);
           tmem_ld_wait();
         }
+        if (lane == 0 && warp == E0) JD_TRACE(5, pos);
         float qa = 0.f, qb = 0.f, qc = 0.f, qd = 0.f;
         if (ZERO_MEAN) {
 #pragma unroll
@@ -400,10 +474,11 @@ gmm_fwd_tcm2_kernel(const float* __restrict__ flux, Geom g, const int32_t* __res
           const float i2 = inv * inv;
           qa *= i2, qb *= i2, qc *= i2, qd *= i2;
         } else {
-          const float4* mwk = reinterpret_cast<const float4*>(sMW + t * 64);
+          // (mw_k through the read-only path: every lane reads the same 16 x 16 B, an L1 broadcast)
+          const float4* mwk = reinterpret_cast<const float4*>(mw + (size_t)kc * 64);
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
-            float4 b0 = mwk[c4], b1 = mwk[8 + c4];
+            const float4 b0 = __ldg(mwk + c4), b1 = __ldg(mwk + 8 + c4);
             float d0 = fmaf(y0[4 * c4], inv, -b0.x), d1 = fmaf(y0[4 * c4 + 1], inv, -b0.y);
             float d2 = fmaf(y0[4 * c4 + 2], inv, -b0.z), d3 = fmaf(y0[4 * c4 + 3], inv, -b0.w);
             float e0 = fmaf(y1[4 * c4], inv, -b1.x), e1 = fmaf(y1[4 * c4 + 1], inv, -b1.y);
@@ -419,9 +494,10 @@ gmm_fwd_tcm2_kernel(const float* __restrict__ flux, Geom g, const int32_t* __res
           }
         }
         const float lp = fmaf(-0.5f, (qa + qb) + (qc + qd), c_k);
-        tc_fence_before();  // slot and mw row are free once consumed (lp depends on every load, see mbar_arrive_after)
+        tc_fence_before();  // the slot is free once consumed (lp depends on every load, see mbar_arrive_after)
         __syncwarp();
-        if (lane == 0) mbar_arrive_after(tempty_bar(t), lp, rt_zero);
+        if (lane == 0) mbar_arrive_after(tempty_bar(t, grp), lp, rt_zero);
+        if (lane == 0 && (warp == E0 || warp == E0 + 4)) JD_TRACE(warp == E0 ? 6 : 11, pos);
         if (logp && p < g.P) logp[(size_t)kc * g.P + p] = lp;
         if (marginalize) {
           if (lp > run_m) {
@@ -525,63 +601,53 @@ static Plan plan(int64_t P, int K) {
   return p;
 }
 
-}  // namespace tcm2
-}  // namespace jd
-
-using namespace jd;
-
-extern "C" {
-
-int64_t jd_gmm_tcm2_workspace_bytes(int64_t P, int K) {
-  if (P <= 0 || K <= 0) return 0;
-  return (int64_t)tcm2::plan(P, K).bytes;
-}
-
-int jd_gmm_prior_forward_tcm2(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
-                             int row_end, const void* Bt, const float* binv, const float* mw, const float* ck, int K,
-                             int upper_tri, int zero_mean, int marginalize, void* workspace, float* value,
-                             int32_t* argmax, float* logp, double* sum, jd_stream_t stream) {
-  JD_CHECK_ARG(flux && Bt && binv && mw && ck && workspace && K > 0, "jd_gmm_prior_forward_tcm2: null pointer");
-  JD_CHECK_ARG(fH >= PATCH && fW >= PATCH && stride >= 1 && stride <= PATCH, "jd_gmm_prior_forward_tcm2: bad geometry");
+template <int R>
+static int launch(const char* who, const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
+                  int row_end, const void* Bt, const float* binv, const float* mw, const float* ck, int K, int upper_tri,
+                  int zero_mean, int marginalize, void* workspace, float* value, int32_t* argmax, float* logp,
+                  double* sum, jd_stream_t stream) {
+  JD_CHECK_ARG(flux && Bt && binv && mw && ck && workspace && K > 0, "%s: null pointer", who);
+  JD_CHECK_ARG(fH >= PATCH && fW >= PATCH && stride >= 1 && stride <= PATCH, "%s: bad geometry", who);
   int ny = (fH - PATCH) / stride + 1, nx = (fW - PATCH) / stride + 1;
-  JD_CHECK_ARG(row_begin >= 0 && row_end <= ny && row_begin < row_end,
-               "jd_gmm_prior_forward_tcm2: bad patch-row block [%d,%d) of %d", row_begin, row_end, ny);
+  JD_CHECK_ARG(row_begin >= 0 && row_end <= ny && row_begin < row_end, "%s: bad patch-row block [%d,%d) of %d", who,
+               row_begin, row_end, ny);
   JD_CHECK_ARG((reinterpret_cast<uintptr_t>(Bt) & 15) == 0 && (reinterpret_cast<uintptr_t>(mw) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
-               "jd_gmm_prior_forward_tcm2: Bt and mw must be 16-byte aligned, the workspace 256-byte aligned");
+               "%s: Bt and mw must be 16-byte aligned, the workspace 256-byte aligned", who);
   tcx::Geom g{fH, fW, 0, 0, stride, nx, row_begin, (row_end - row_begin) * nx};
-  static bool attr_set[64] = {};  // per device
+  const void* kerns[4] = {(const void*)gmm_fwd_tcx2_kernel<R, false, false>, (const void*)gmm_fwd_tcx2_kernel<R, false, true>,
+                          (const void*)gmm_fwd_tcx2_kernel<R, true, false>, (const void*)gmm_fwd_tcx2_kernel<R, true, true>};
+  static bool attr_set[64] = {};  // per device (and per recipe: the static lives in the template instance)
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
     cudaError_t e = cudaSuccess;
-    const void* kerns[4] = {(const void*)tcm2::gmm_fwd_tcm2_kernel<false, false>, (const void*)tcm2::gmm_fwd_tcm2_kernel<false, true>,
-                            (const void*)tcm2::gmm_fwd_tcm2_kernel<true, false>, (const void*)tcm2::gmm_fwd_tcm2_kernel<true, true>};
     for (int i = 0; i < 4 && e == cudaSuccess; ++i)
-      e = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcm2::SMEM_BYTES);
+      e = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Layout<R>::SMEM_BYTES);
     if (e != cudaSuccess) {
-      set_error("jd_gmm_prior_forward_tcm2: cannot reserve %zu B of shared memory: %s", tcm2::SMEM_BYTES,
-                cudaGetErrorString(e));
+      set_error("%s: cannot reserve %zu B of shared memory: %s", who, Layout<R>::SMEM_BYTES, cudaGetErrorString(e));
       return JD_ERR_CUDA;
     }
     attr_set[dev & 63] = true;
   }
-  const tcm2::Plan p = tcm2::plan(g.P, K);
-  static int rot_env = -1;
+  const Plan p = plan(g.P, K);
+  static int rot_env = -1, dbg = -1;
   if (rot_env < 0) {
     const char* e = getenv("JD_TC_SK_ROT");  // 0: visit the components of a segment in ascending order
     rot_env = e ? atoi(e) : 40503;
   }
-  auto kern = upper_tri ? (zero_mean ? tcm2::gmm_fwd_tcm2_kernel<true, true> : tcm2::gmm_fwd_tcm2_kernel<true, false>)
-                        : (zero_mean ? tcm2::gmm_fwd_tcm2_kernel<false, true> : tcm2::gmm_fwd_tcm2_kernel<false, false>);
+  if (dbg < 0) {
+    const char* e = getenv("JD_TC_DEBUG");
+    dbg = e ? atoi(e) : 0;
+  }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(p.n_clusters * tcm2::CLUSTER);
-  cfg.blockDim = dim3(tcm2::NTHREADS);
-  cfg.dynamicSmemBytes = tcm2::SMEM_BYTES;
+  cfg.gridDim = dim3(p.n_clusters * CLUSTER);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = Layout<R>::SMEM_BYTES;
   cfg.stream = to_stream(stream);
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = tcm2::CLUSTER;
+  attr[0].val.clusterDim.x = CLUSTER;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -592,21 +658,63 @@ int jd_gmm_prior_forward_tcm2(const float* flux, int fH, int fW, const int32_t* 
   float* ws_m = reinterpret_cast<float*>(ws + p.off_m);
   float* ws_s = reinterpret_cast<float*>(ws + p.off_s);
   int* ws_k = reinterpret_cast<int*>(ws + p.off_k);
-  static int dbg = -1;
-  if (dbg < 0) {
-    const char* e = getenv("JD_TC_DEBUG");
-    dbg = e ? atoi(e) : 0;
-  }
-  if (dbg & 16) kern = zero_mean ? tcm2::gmm_fwd_tcm2_kernel<false, true> : tcm2::gmm_fwd_tcm2_kernel<false, false>;  // dense
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, flux, g, shift_yx, bt8, mw, ck, binv, K, (marginalize ? 1 : 0) | (dbg << 8), p.chunk,
-                                      p.smax, (unsigned)rot_env, counters, ws_m, ws_s, ws_k, value, argmax, logp, sum);
+  const int marg = (marginalize ? 1 : 0) | ((dbg & 1) << 8);
+  cudaError_t le;
+  if (upper_tri && zero_mean)
+    le = cudaLaunchKernelEx(&cfg, gmm_fwd_tcx2_kernel<R, true, true>, flux, g, shift_yx, bt8, mw, ck, binv, K, marg,
+                            p.chunk, p.smax, (unsigned)rot_env, counters, ws_m, ws_s, ws_k, value, argmax, logp, sum);
+  else if (upper_tri)
+    le = cudaLaunchKernelEx(&cfg, gmm_fwd_tcx2_kernel<R, true, false>, flux, g, shift_yx, bt8, mw, ck, binv, K, marg,
+                            p.chunk, p.smax, (unsigned)rot_env, counters, ws_m, ws_s, ws_k, value, argmax, logp, sum);
+  else if (zero_mean)
+    le = cudaLaunchKernelEx(&cfg, gmm_fwd_tcx2_kernel<R, false, true>, flux, g, shift_yx, bt8, mw, ck, binv, K, marg,
+                            p.chunk, p.smax, (unsigned)rot_env, counters, ws_m, ws_s, ws_k, value, argmax, logp, sum);
+  else
+    le = cudaLaunchKernelEx(&cfg, gmm_fwd_tcx2_kernel<R, false, false>, flux, g, shift_yx, bt8, mw, ck, binv, K, marg,
+                            p.chunk, p.smax, (unsigned)rot_env, counters, ws_m, ws_s, ws_k, value, argmax, logp, sum);
   if (le != cudaSuccess) {
-    set_error("jd_gmm_prior_forward_tcm2: launch failed: %s", cudaGetErrorString(le));
+    set_error("%s: launch failed: %s", who, cudaGetErrorString(le));
     cudaGetLastError();
     return JD_ERR_CUDA;
   }
-  JD_CHECK_LAUNCH("jd_gmm_prior_forward_tcm2");
+  JD_CHECK_LAUNCH(who);
   return JD_OK;
+}
+
+}  // namespace tcx2
+}  // namespace jd
+
+using namespace jd;
+
+extern "C" {
+
+#if defined(JD_TCM_TRACE)
+int jd_debug_tcm2_trace(long long* host_dst, int n_positions) {
+  if (n_positions > tcx2::TRACE_POS) n_positions = tcx2::TRACE_POS;
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(host_dst, tcx2::g_trace, (size_t)n_positions * 16 * sizeof(long long)) == cudaSuccess ? 0 : 1;
+}
+#endif
+
+int64_t jd_gmm_tcm2_workspace_bytes(int64_t P, int K) {
+  if (P <= 0 || K <= 0) return 0;
+  return (int64_t)tcx2::plan(P, K).bytes;
+}
+
+int jd_gmm_prior_forward_tcm2(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
+                              int row_end, const void* Bt, const float* binv, const float* mw, const float* ck, int K,
+                              int upper_tri, int zero_mean, int marginalize, void* workspace, float* value,
+                              int32_t* argmax, float* logp, double* sum, jd_stream_t stream) {
+  return tcx2::launch<0>("jd_gmm_prior_forward_tcm2", flux, fH, fW, shift_yx, stride, row_begin, row_end, Bt, binv, mw,
+                         ck, K, upper_tri, zero_mean, marginalize, workspace, value, argmax, logp, sum, stream);
+}
+
+int jd_gmm_prior_forward_tc16x2(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
+                                int row_end, const void* Bt16, const float* binv, const float* mw, const float* ck,
+                                int K, int upper_tri, int zero_mean, int marginalize, void* workspace, float* value,
+                                int32_t* argmax, float* logp, double* sum, jd_stream_t stream) {
+  return tcx2::launch<1>("jd_gmm_prior_forward_tc16x2", flux, fH, fW, shift_yx, stride, row_begin, row_end, Bt16, binv,
+                         mw, ck, K, upper_tri, zero_mean, marginalize, workspace, value, argmax, logp, sum, stream);
 }
 
 }  // extern "C"

@@ -61,21 +61,32 @@ adam_allreduce_peer_kernel(const float* const* __restrict__ grad_ptrs, float* co
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ long long global_timer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 
+// WORLD > 0: compile-time rank count - the WORLD peer loads of a pixel group are all in flight before the first add
+// (a run-time loop issues them one NVLink round trip after the other); WORLD = 0: any rank count.
+// `stamps` (optional, 4 x int64 of %globaltimer ns): kernel entry, entry barrier passed, last CTA's theta stores
+// fenced, exit barrier passed - bench.py --breakdown turns them into wait / transfer shares.
+template <int WORLD>
 __global__ void __launch_bounds__(256)
 adam_allreduce_peer_sync_kernel(const float* const* __restrict__ grad_ptrs, float* const* __restrict__ theta_ptrs,
                                 uint32_t* const* __restrict__ sig_ptrs, uint32_t* __restrict__ epoch_ctr,
                                 unsigned* __restrict__ done_ctr, int rank, int world, float* __restrict__ m,
                                 float* __restrict__ v, const float* __restrict__ flux, const uint8_t* __restrict__ mask,
                                 int use_log, int64_t lo4, int64_t hi4, const float* __restrict__ scalars, float b1,
-                                float b2, float eps) {
+                                float b2, float eps, long long* __restrict__ stamps) {
   const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(epoch_ctr) + 1u;
   uint32_t* my_sig = sig_ptrs[rank];
+  if (stamps && blockIdx.x == 0 && threadIdx.x == 0) stamps[0] = global_timer_ns();
   if (blockIdx.x == 0 && threadIdx.x < world) {
     __threadfence_system();
     st_release_sys(sig_ptrs[threadIdx.x] + rank, epoch);
@@ -84,15 +95,30 @@ adam_allreduce_peer_sync_kernel(const float* const* __restrict__ grad_ptrs, floa
     while ((int32_t)(ld_acquire_sys(my_sig + threadIdx.x) - epoch) < 0) __nanosleep(20);
   }
   __syncthreads();
+  if (stamps && blockIdx.x == 0 && threadIdx.x == 0) stamps[1] = global_timer_ns();
 
   const float lr_over_bc1 = scalars[0], sqrt_bc2 = scalars[1];
   float* theta_own = theta_ptrs[rank];
+  const float* gp[WORLD > 0 ? WORLD : 1];
+  float* tp[WORLD > 0 ? WORLD : 1];
+  if (WORLD > 0) {
+#pragma unroll
+    for (int q = 0; q < WORLD; ++q) gp[q] = grad_ptrs[q], tp[q] = theta_ptrs[q];
+  }
   for (int64_t i4 = lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < hi4; i4 += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = i4 * 4;
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int q = 0; q < world; ++q) {  // fixed order: bit-reproducible
-      const float4 gq = __ldcg(reinterpret_cast<const float4*>(grad_ptrs[q] + i));
-      g.x += gq.x, g.y += gq.y, g.z += gq.z, g.w += gq.w;
+    if (WORLD > 0) {
+      float4 gq[WORLD > 0 ? WORLD : 1];
+#pragma unroll
+      for (int q = 0; q < WORLD; ++q) gq[q] = __ldcg(reinterpret_cast<const float4*>(gp[q] + i));
+#pragma unroll
+      for (int q = 0; q < WORLD; ++q) g.x += gq[q].x, g.y += gq[q].y, g.z += gq[q].z, g.w += gq[q].w;  // fixed order
+    } else {
+      for (int q = 0; q < world; ++q) {  // fixed order: bit-reproducible
+        const float4 gq = __ldcg(reinterpret_cast<const float4*>(grad_ptrs[q] + i));
+        g.x += gq.x, g.y += gq.y, g.z += gq.z, g.w += gq.w;
+      }
     }
     float gg[4] = {g.x, g.y, g.z, g.w};
     const float4 t4 = *reinterpret_cast<const float4*>(theta_own + i);
@@ -112,7 +138,12 @@ adam_allreduce_peer_sync_kernel(const float* const* __restrict__ grad_ptrs, floa
     *reinterpret_cast<float4*>(m + i) = make_float4(mm[0], mm[1], mm[2], mm[3]);
     *reinterpret_cast<float4*>(v + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
     const float4 tn = make_float4(th[0], th[1], th[2], th[3]);
-    for (int q = 0; q < world; ++q) *reinterpret_cast<float4*>(theta_ptrs[q] + i) = tn;
+    if (WORLD > 0) {
+#pragma unroll
+      for (int q = 0; q < WORLD; ++q) *reinterpret_cast<float4*>(tp[q] + i) = tn;
+    } else {
+      for (int q = 0; q < world; ++q) *reinterpret_cast<float4*>(theta_ptrs[q] + i) = tn;
+    }
   }
 
   // ---- exit barrier
@@ -122,6 +153,7 @@ adam_allreduce_peer_sync_kernel(const float* const* __restrict__ grad_ptrs, floa
   if (threadIdx.x == 0) s_last = (atomicAdd(done_ctr, 1u) + 1u == gridDim.x) ? 1 : 0;
   __syncthreads();
   if (!s_last) return;
+  if (stamps && threadIdx.x == 0) stamps[2] = global_timer_ns();
   if (threadIdx.x < world) {
     __threadfence_system();
     st_release_sys(sig_ptrs[threadIdx.x] + 32 + rank, epoch);
@@ -129,6 +161,7 @@ adam_allreduce_peer_sync_kernel(const float* const* __restrict__ grad_ptrs, floa
   }
   __syncthreads();
   if (threadIdx.x == 0) {
+    if (stamps) stamps[3] = global_timer_ns();
     *done_ctr = 0;
     *epoch_ctr = epoch;
     __threadfence();
@@ -175,10 +208,16 @@ extern "C" int jd_adam_allreduce_peer_sync(const void* grad_ptrs_dev, const void
   // every CTA spins at the entry barrier: the grid must be co-resident (<= 2 CTAs of 256 threads per SM here)
   int64_t cap = (int64_t)num_sms() * 2;
   if (blocks < 1) blocks = 1;
-  adam_allreduce_peer_sync_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, to_stream(stream)>>>(
+  auto kern = world == 8   ? adam_allreduce_peer_sync_kernel<8>
+              : world == 4 ? adam_allreduce_peer_sync_kernel<4>
+              : world == 2 ? adam_allreduce_peer_sync_kernel<2>
+                           : adam_allreduce_peer_sync_kernel<0>;
+  // sync_state: [0] epoch, [1] finished CTAs, [2..3] unused, [4..11] four int64 time stamps of the last launch
+  long long* stamps = reinterpret_cast<long long*>(sync_state + 4);
+  kern<<<(int)(blocks > cap ? cap : blocks), 256, 0, to_stream(stream)>>>(
       reinterpret_cast<const float* const*>(grad_ptrs_dev), reinterpret_cast<float* const*>(theta_ptrs_dev),
       reinterpret_cast<uint32_t* const*>(sig_ptrs_dev), sync_state, sync_state + 1, rank, world, m, v, flux, mask,
-      use_log_flux, lo4, hi4, adam_scalars, beta1, beta2, eps);
+      use_log_flux, lo4, hi4, adam_scalars, beta1, beta2, eps, stamps);
   JD_CHECK_LAUNCH("jd_adam_allreduce_peer_sync");
   return JD_OK;
 }

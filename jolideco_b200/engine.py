@@ -189,6 +189,8 @@ class MapEngine:
                 ops._bt16(self.packed)
             elif self.backend in (3, 4):
                 ops._btm(self.packed)
+            elif self.backend == 5:
+                ops._bt16(self.packed)
             self.ny, self.nx = ops.patch_grid(self.fH, self.fW, self.stride)
             self.c = self.stride**2 / ops.PD / self.n
             # row-block shard of the prior (whole grid on one GPU)
@@ -197,13 +199,13 @@ class MapEngine:
             self.P = P
             if self.backend == 1 and P > 0 and (ops.use_stream_k(P, self.dev) if stream_k is None else stream_k):
                 self.sk_ws = ops.tc_sk_workspace(P, self.packed.K, self.dev)
-            if self.backend in (3, 4) and P > 0:
+            if self.backend in (3, 4, 5) and P > 0:
                 self.sk_ws = ops.tcm_workspace(P, self.packed.K, self.dev, self.backend)
             self.value = torch.empty(max(P, 1), **f32)
             self.argmax = torch.empty(max(P, 1), dtype=torch.int32, device=self.dev)
             # logsumexp mode keeps logp for the backward; the tensor-core kernels use a component-major layout
             self.logp = torch.empty((max(P, 1), self.packed.K), **f32) if self.marginalize else None
-            if self.marginalize and self.backend in (1, 2, 3, 4):
+            if self.marginalize and self.backend in (1, 2, 3, 4, 5):
                 ops._bt_lam(self.packed)
             self.G = torch.empty((max(P, 1), ops.PD), **f32)
             # bucketed max-mode backward (patches grouped by winning component, Lam_k staged once per 32 patches):
@@ -256,7 +258,8 @@ class MapEngine:
             self.sym_grad.zero_()
             self.sym_sig.zero_()
             self.sym_theta.copy_(self.theta.reshape(-1))
-            self.sync_state = torch.zeros(2, dtype=torch.int32, device=self.dev)  # epoch, finished CTAs: never restored
+            # epoch, finished CTAs (never restored), 2 pad, 4 x int64 time stamps of the last launch (jd_peer.cu)
+            self.sync_state = torch.zeros(12, dtype=torch.int32, device=self.dev)
             torch.cuda.synchronize(self.dev)
         self.h_sig.barrier(channel=0)  # every flag block is zeroed before any rank can signal
         self._theta_param = self.theta  # the component's parameter storage: refreshed by sync_theta()
@@ -413,9 +416,9 @@ class MapEngine:
     def _prior_forward(self, sum_acc):
         if self.P <= 0:
             return
-        if self.backend in (3, 4):
-            bt, binv = ops._btm(self.packed)
-            _call("jd_gmm_prior_forward_tcm2" if self.backend == 4 else "jd_gmm_prior_forward_tcm", _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride,
+        if self.backend in (3, 4, 5):
+            bt, binv = ops._bt16(self.packed) if self.backend == 5 else ops._btm(self.packed)
+            _call(ops.TCM_ENTRY[self.backend], _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride,
                   self.rows[0], self.rows[1], _p(bt), _p(binv), _p(self.packed.mw), _p(self.packed.ck), self.packed.K,
                   int(self.packed.upper_tri), int(self.packed.zero_mean), int(self.marginalize), _p(self.sk_ws),
                   _p(self.value), _p(self.argmax), _p(self.logp), sum_acc, self._s())
@@ -445,7 +448,7 @@ class MapEngine:
 
     def _prior_gradient(self, scale):
         """per-patch gradient rows G (consumed by _adam_fold)"""
-        if self.marginalize and self.backend in (1, 2, 3, 4):
+        if self.marginalize and self.backend in (1, 2, 3, 4, 5):
             _call("jd_gmm_prior_backward_lse_tc", _p(self.flux), self.fH, self.fW, _p(self.cur_shift), self.stride,
                   self.rows[0], self.rows[1], _p(ops._bt_lam(self.packed)), _p(self.packed.bk), self.packed.K,
                   _p(self.logp), _p(self.value), float(scale), _p(self.G), self._s())

@@ -296,9 +296,13 @@ def _btm(packed):
     return packed._Btm
 
 
+# persistent stream-K forwards: backend -> C entry point
+TCM_ENTRY = {3: "jd_gmm_prior_forward_tcm", 4: "jd_gmm_prior_forward_tcm2", 5: "jd_gmm_prior_forward_tc16x2"}
+
+
 def tcm_workspace(P, K, device, backend=3):
     """Zero-initialised workspace of the backend-3 / 4 forwards (arrival counters + per-segment partials)."""
-    fn = _lib.load().jd_gmm_tcm2_workspace_bytes if int(backend) == 4 else _lib.load().jd_gmm_tcm_workspace_bytes
+    fn = _lib.load().jd_gmm_tcm2_workspace_bytes if int(backend) in (4, 5) else _lib.load().jd_gmm_tcm_workspace_bytes
     n = int(fn(int(P), int(K)))
     return torch.zeros(max(n, 256), dtype=torch.uint8, device=device)
 
@@ -372,16 +376,16 @@ def gmm_prior_forward(flux, shift_yx, packed, stride=4, marginalize=False, rows=
     if want_logp is None:
         want_logp = bool(marginalize)
     # the tensor-core forwards write logp component-major (K x P'): returned as the transposed (P', K) view
-    tc = int(backend) in (1, 2, 3, 4)
+    tc = int(backend) in (1, 2, 3, 4, 5)
     logp = None
     if want_logp:
         logp = torch.empty((packed.K, P) if tc else (P, packed.K), dtype=torch.float32, device=flux.device)
     if sum_out is None:
         sum_out = torch.zeros(1, dtype=torch.float64, device=flux.device)
-    if int(backend) in (3, 4):
-        bt, binv = _btm(packed)
+    if int(backend) in (3, 4, 5):
+        bt, binv = _bt16(packed) if int(backend) == 5 else _btm(packed)
         ws = tcm_workspace(P, packed.K, flux.device, backend)
-        _lib.call("jd_gmm_prior_forward_tcm2" if int(backend) == 4 else "jd_gmm_prior_forward_tcm", _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(bt), _ptr(binv),
+        _lib.call(TCM_ENTRY[int(backend)], _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(bt), _ptr(binv),
                   _ptr(packed.mw), _ptr(packed.ck), packed.K, int(packed.upper_tri), int(packed.zero_mean),
                   int(bool(marginalize)), _ptr(ws), _ptr(value), _ptr(argmax), _ptr(logp), _ptr(sum_out), _stream())
     elif int(backend) == 2:

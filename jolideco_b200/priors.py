@@ -313,7 +313,8 @@ class GMMPatchPrior(Prior):
 
 
 # 3 = tcgen05 split-TF32 forward with the correction products on the FP16 pipe, persistent stream-K (jd_gmm_tcm.cu);
-# 4 = the same with two patch tiles per CTA and staged operand image (jd_gmm_tcm2.cu);
+# 4 = the same split, two patch tiles per CTA and staged operand image, per-tile issuer / epilogue / slots (jd_gmm_tcm2.cu);
+# 5 = that kernel with the split-FP16 recipe (12 MMAs, 3 accumulator slots per tile, half the operand bytes);
 # 1 = tcgen05 3 x TF32 (jd_gmm_tc.cu), 2 = tcgen05 split-FP16 (jd_gmm_tc16.cu), 0 = FP32 CUDA-core check path.
 # JD_PRIOR_BACKEND overrides the default (A/B runs).
 _DEFAULT_BACKEND = int(os.environ.get("JD_PRIOR_BACKEND", "3"))

@@ -59,19 +59,19 @@ def footprint_mask(shape, patch_index, nx, shift, stride=4):
 
 
 @pytest.mark.parametrize("size", [512, 1024])
-@pytest.mark.parametrize("variant", ["tcm2", "tcm", "tc", "tc_stream_k", "tc16", "simt"])
+@pytest.mark.parametrize("variant", ["tc16x2", "tcm2", "tcm", "tc", "tc_stream_k", "tc16", "simt"])
 def test_prior_forward_backward_at_benchmark_size(size, variant, monkeypatch):
     flux, gmm, ref = prior_case(size)
     if variant == "simt" and size == 1024:
         pytest.skip("CUDA-core check path: covered at 512^2")
     packed = ops.GMMPacked(gmm.means, gmm.precisions_cholesky, gmm.weights, gmm.pixel_weights, DEV)
     assert not packed.zero_mean and packed.upper_tri
-    backend = {"tcm2": 4, "tcm": 3, "tc": 1, "tc_stream_k": 1, "tc16": 2, "simt": 0}[variant]
+    backend = {"tc16x2": 5, "tcm2": 4, "tcm": 3, "tc": 1, "tc_stream_k": 1, "tc16": 2, "simt": 0}[variant]
     monkeypatch.setattr(ops, "TC_STREAMK", variant == "tc_stream_k")
     fl = t(flux)
     ny, nx = ops.patch_grid(size, size, 4)
     P = ny * nx
-    for rep in range(8 if variant in ("tcm", "tcm2") else 3):  # the slot-release race of round 1 showed up in ~1 launch of 20
+    for rep in range(8 if variant in ("tcm", "tcm2", "tc16x2") else 3):  # the slot-release race of round 1 showed up in ~1 launch of 20
         value, argmax, _, total = ops.gmm_prior_forward(fl, SHIFT, packed, 4, False, backend=backend)
         if rep == 0:
             first = (value.clone(), argmax.clone())

@@ -274,7 +274,7 @@ def prior_cuda(flux, gmm_packed, sy, sx, marginalize, rows=None, backend=0):
     return s.item() * c, dflux.cpu().numpy(), argmax.cpu().numpy()
 
 
-@pytest.mark.parametrize("backend", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("backend", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("marginalize", [False, True])
 @pytest.mark.parametrize("shape,shift", [((38, 46), (0, 0)), ((38, 46), (-2, 1)), ((64, 80), (2, -2)), ((24, 24), (1, 2))])
 def test_gmm_prior_value_and_grad(marginalize, shape, shift, backend):
@@ -293,7 +293,7 @@ def test_gmm_prior_value_and_grad(marginalize, shape, shift, backend):
         assert rel_max(gr, ref_g) < 2e-5
 
 
-@pytest.mark.parametrize("backend", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("backend", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("case", range(8))
 def test_gmm_prior_golden(case, backend):
     g = load_golden("prior_step.npz")
@@ -317,7 +317,7 @@ def test_gmm_prior_row_blocks_sum_to_whole():
     assert rel_max(sum(p[1] for p in parts), gr) < 1e-6
 
 
-@pytest.mark.parametrize("backend", [1, 2, 3, 4])
+@pytest.mark.parametrize("backend", [1, 2, 3, 4, 5])
 @pytest.mark.parametrize("mean_scale", [0.05, 0.0])
 @pytest.mark.parametrize("marginalize", [False, True])
 def test_gmm_prior_tensor_core_vs_cuda_core_full_size(marginalize, mean_scale, backend):
@@ -378,22 +378,25 @@ def test_gmm_prior_stream_k_equals_tile_per_cta(monkeypatch, shape, rows, K, mar
 @pytest.mark.parametrize("shape,rows,K,mean_scale", [((512, 512), None, 256, 0.0), ((1024, 1024), (31, 63), 256, 0.02),
                                                      ((200, 328), None, 40, 0.02), ((64, 80), None, 3, 0.0),
                                                      ((1024, 1024), None, 64, 0.02), ((96, 2048), None, 16, 0.02)])
-def test_gmm_prior_two_tiles_per_cta_equals_one_tile(shape, rows, K, mean_scale, marginalize):
-    """Backend 4 (two patch tiles per CTA and staged operand image, jd_gmm_tcm2.cu) issues the same MMAs into the same
-    kind of accumulator as backend 3: bit-identical per-component log-probabilities, max and argmax; the workspace's
-    arrival counters are back at zero after every launch (two launches on the same workspace)."""
+@pytest.mark.parametrize("new,old", [(4, 3), (5, 2)])
+def test_gmm_prior_two_tiles_per_cta_equals_one_tile(shape, rows, K, mean_scale, marginalize, new, old):
+    """Backends 4 / 5 (two patch tiles per CTA and staged operand image, jd_gmm_tcm2.cu; mixed TF32 / FP16 and split-FP16
+    recipes) issue the same MMAs in the same order as the one-tile kernels of their recipe (backends 3 / 2): bit-identical
+    per-component log-probabilities, max and argmax; the workspace's arrival counters are back at zero after every
+    launch (two launches on the same workspace)."""
     rng = np.random.default_rng(16)
     flux = t(rng.gamma(2.0, size=shape) * np.exp(rng.normal(0, 0.7, size=shape)))
     packed = pack(O.GMM(*synthetic_gmm(K, seed=9, mean_scale=mean_scale)))
-    v0, k0, lp0, s0 = ops.gmm_prior_forward(flux, (2, -1), packed, 4, marginalize, rows=rows, want_logp=True, backend=3)
+    v0, k0, lp0, s0 = ops.gmm_prior_forward(flux, (2, -1), packed, 4, marginalize, rows=rows, want_logp=True,
+                                            backend=old)
     P = v0.numel()
-    ws = ops.tcm_workspace(P, packed.K, flux.device, 4)
+    ws = ops.tcm_workspace(P, packed.K, flux.device, new)
     orig = ops.tcm_workspace
     ops.tcm_workspace = lambda *a: ws
     try:
         for _ in range(2):
             v1, k1, lp1, s1 = ops.gmm_prior_forward(flux, (2, -1), packed, 4, marginalize, rows=rows, want_logp=True,
-                                                    backend=4)
+                                                    backend=new)
             diff = lp0 != lp1
             if bool(diff.any()):
                 idx = diff.nonzero().cpu().numpy()
@@ -423,7 +426,7 @@ def test_gmm_prior_tensor_core_dense_precision_factors():
     assert not packed.upper_tri
     flux = t(rng.gamma(2.0, size=(100, 84)))
     v0, k0, lp0, s0 = ops.gmm_prior_forward(flux, (0, 1), packed, 4, False, want_logp=True, backend=0)
-    for backend in (1, 2, 3, 4):
+    for backend in (1, 2, 3, 4, 5):
         v1, k1, lp1, s1 = ops.gmm_prior_forward(flux, (0, 1), packed, 4, False, want_logp=True, backend=backend)
         lp1 = lp1.cpu().numpy().astype(np.float64)
         ref = lp0.cpu().numpy().astype(np.float64)

@@ -20,7 +20,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for n in sizes:
     flux = torch.from_numpy(np.random.default_rng(0).gamma(2.0, size=(n, n)).astype(np.float32)).to(dev)
     P = ((n - 8) // 4 + 1) ** 2
-    for backend in [int(b) for b in os.environ.get("JD_EXP_BACKENDS", "3,4").split(",")]:
+    for backend in [int(b) for b in os.environ.get("JD_EXP_BACKENDS", "3,4,5").split(",")]:
         for _ in range(3):
             ops.gmm_prior_forward(flux, (1, -2), packed, 4, False, backend=backend)
         ts = []
