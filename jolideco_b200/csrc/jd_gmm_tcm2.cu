@@ -1,10 +1,10 @@
 // GMM patch prior forward on tcgen05, fourth generation: TWO patch tiles per CTA against every staged operand image,
-// one issuer warp + one epilogue group + private accumulator slots per tile, in two precision recipes:
+// round-robin issuer warps with a stripped issue loop, one epilogue group per tile, in two precision recipes:
 //   R = 0  mixed TF32 / FP16 split of jd_gmm_tcm.cu (operand image of jd_gmm_tcm_pack, 32 KB per component)
 //   R = 1  split FP16 of jd_gmm_tc16.cu          (operand image of jd_gmm_tc16_pack, 16 KB per component)
 // Both carry 22 significand bits per operand (2^-21..2^-22 relative accuracy of every log-probability, FP32
 // accumulation in TMEM); R = 1 issues 12 instead of 16 MMAs per tile and component, needs half the TMEM columns for the A
-// operand (64 instead of 128 per tile) - which buys a third accumulator slot per tile - and half the operand bytes.
+// operand (64 instead of 128 per tile) - which buys a third accumulator slot - and half the operand bytes.
 //
 // Why (measurements on B200, 1024^2 image, K = 256; profiles/r02_summary.md):
 //   * ncu on the one-tile kernel jd_gmm_tcm.cu: tensor pipe 65 % busy, 3.75 GB of operand images cross into the SMs
@@ -16,10 +16,14 @@
 //     instruction): 1141 clk to issue the 32 MMAs of a position whose tensor work is 640 clk; and an accumulator slot
 //     turns around in issue + ~150 (commit -> epilogue) + ~700 (TMEM loads 460, squares 230) + ~300 (release -> issuer)
 //     clk, so with two slots the issuer and the epilogue of a slot simply alternate.
+//   * second version (one issuer warp per tile, stripped issue loop: UTCHMMAs back to back): issuing 12 MMAs takes 340
+//     clk, but the issuer's loop still needs ~1100 clk per position - every mbarrier wait costs ~100 clk even when the
+//     phase is already complete, and the wait that follows the commits stalls another ~300 clk: ~450 clk of fixed
+//     overhead per issuer iteration against 240 clk of tensor work.
 // Hence: the issue loop is stripped to descriptor adds + UTCHMMA (no run-time knobs, warp index made uniform with a
-// shuffle so that operands live in uniform registers), the two tiles of a CTA are issued by two warps in parallel (each
-// with its own `tfull` / `tempty` barriers, so a tile's epilogue starts as soon as ITS accumulator is complete), and
-// recipe 1 runs three slots per tile.
+// shuffle so that operands live in uniform registers); an issuer iteration covers BOTH tiles of a position (24 / 32 MMAs
+// per pair of waits and commits), NMMA = NSLOT issuer warps take the positions round-robin so that their fixed
+// overheads overlap, and recipe 1 runs three accumulator slots.
 //
 // Work decomposition (as jd_gmm_tcm.cu): the (tile group, component) space is linearised and cut into equal chunks, one
 // per CTA pair (2-CTA cluster, each CTA fetches half of every operand image and multicasts it to both); tile group =
@@ -28,9 +32,9 @@
 // The A operand is single-buffered: at a segment boundary the gather warps (tile 0's patch already in registers) store
 // once the issuers' last commits of the previous segment have fired.
 //
-// Warps (512 threads, one CTA per SM): 0-1 bulk-TMA producers | 2, 3 MMA issuers of tile 0, 1 | 4-7 gather | 8-11
-// epilogue of tile 0 | 12-15 epilogue of tile 1.
-// TMEM (512 columns): [0, TPC A_COLS) A operands | then NSLOT x TPC accumulators of 64 columns, slot-major.
+// Warps (512 threads, one CTA per SM): 0 bulk-TMA producer | 1..NMMA MMA issuers | 4-7 gather | 8-11 epilogue of tile
+// 0 | 12-15 epilogue of tile 1.
+// TMEM (512 columns): [0, TPC A_COLS) A operands | then NSLOT slots of TPC x 64 accumulator columns.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -50,19 +54,17 @@ constexpr int ACC_COLS = 64;
 constexpr int TMEM_COLS = 512;
 constexpr int KBLOCK_BYTES = 64 * 128;  // 8 KB: 64 rows x 128 B (one swizzle atom wide)
 constexpr int CLUSTER = 2;
-constexpr int NPROD = 2;
-constexpr int M0 = NPROD;  // first MMA warp (owns the TMEM allocation); warp M0 + h issues tile h
-constexpr int G0 = 4;      // first gather warp
-constexpr int E0 = 8;      // first epilogue warp
+constexpr int M0 = 1;  // first MMA-issuer warp (owns the TMEM allocation); position pos is issued by warp M0 + pos % NMMA
+constexpr int G0 = 4;  // first gather warp
+constexpr int E0 = 8;  // first epilogue warp
 constexpr int NTHREADS = 512;
-static_assert(M0 + TPC == G0, "warp roles");
 
 template <int R>
 struct Recipe;
 template <>
 struct Recipe<0> {  // tf32(x') tf32(L') + half(xr) half(L') + half(x') half(Lr)
   static constexpr int A_COLS = 128;  // [0,64) tf32(x') | [64,96) half2(xr) | [96,128) half2(x')
-  static constexpr int NSLOT = 2;
+  static constexpr int NSLOT = 2;   // accumulator slots (both tiles of a position) = issuer warps
   static constexpr int NSTAGE = 6;
   static constexpr int B_BYTES = 4 * KBLOCK_BYTES;  // [0,16K) tf32(L') | [16K,24K) half(L') | [24K,32K) half(Lr)
 };
@@ -77,11 +79,13 @@ struct Recipe<1> {  // lo.hi + hi.lo + hi.hi in FP16
 template <int R>
 struct Layout {
   using Rc = Recipe<R>;
+  static constexpr int NMMA = Rc::NSLOT;  // a slot always belongs to the same issuer warp (fixed barrier ownership)
   static constexpr int ACC0 = TPC * Rc::A_COLS;
-  static constexpr int NBAR = 2 * Rc::NSTAGE + 2 * Rc::NSLOT * TPC + TPC + 1;
+  static constexpr int SLOT_COLS = TPC * ACC_COLS;
+  static constexpr int NBAR = 2 * Rc::NSTAGE + 2 * Rc::NSLOT + TPC + 1;
   static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)Rc::NSTAGE * Rc::B_BYTES + 6144 /*barriers, flags*/;
-  static_assert(ACC0 + Rc::NSLOT * TPC * ACC_COLS <= TMEM_COLS, "TMEM budget");
-  static_assert(Rc::NSTAGE % NPROD == 0, "a smem stage must always be refilled by the same producer warp");
+  static_assert(ACC0 + Rc::NSLOT * SLOT_COLS <= TMEM_COLS, "TMEM budget");
+  static_assert(M0 + NMMA <= G0, "warp roles");
 };
 
 __device__ __host__ constexpr uint32_t idesc_tf32(uint32_t n) {
@@ -111,9 +115,9 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
 }
 
 // Experiment build (JD_NVCC_EXTRA=-DJD_TCM_TRACE, tools/tcm_trace.py): clock64 stamps of the hand-overs of CTA 0, per
-// position: 0 producer past `empty` | 1 issuer 0 past `tempty` | 2 issuer 0 past `full` | 3 issuer 0 done | 4 epilogue 0
-// past `tfull` | 5 epilogue 0 loads landed | 6 epilogue 0 released the slot | 7 epilogue 1 past `tfull` | 8 issuer 1 past
-// `tempty` | 9 issuer 1 past `full` | 10 issuer 1 done | 11 epilogue 1 released the slot
+// position: 0 producer past `empty` | 1 issuer past `tempty` | 2 issuer past `full` | 3 issuer done | 4 epilogue 0 past
+// `tfull` | 5 epilogue 0 loads landed | 6 epilogue 0 released the slot | 7 epilogue 1 past `tfull` | 8 MMAs issued |
+// 9 stage commit issued | 10 issuer warp reconverged | 11 epilogue 1 released the slot
 #if defined(JD_TCM_TRACE)
 constexpr int TRACE_POS = 2048;
 __device__ long long g_trace[TRACE_POS * 16];
@@ -126,6 +130,29 @@ __device__ long long g_trace[TRACE_POS * 16];
   do {                    \
   } while (0)
 #endif
+
+// Packed FP32 pairs (fma.rn.f32x2, sm_100): the epilogue is bound by the instructions its warps can issue, the squares
+// of an accumulator row take 32 instead of 64 FMAs.
+__device__ __forceinline__ void fma2_sq(float2& acc, float a0, float a1) {  // acc += (a0^2, a1^2)
+  asm("{\n\t.reg .b64 va, vc;\n\t"
+      "mov.b64 va, {%2, %3};\n\t"
+      "mov.b64 vc, {%0, %1};\n\t"
+      "fma.rn.f32x2 vc, va, va, vc;\n\t"
+      "mov.b64 {%0, %1}, vc;\n\t}"
+      : "+f"(acc.x), "+f"(acc.y)
+      : "f"(a0), "f"(a1));
+}
+// (d0, d1) = (a0, a1) * s - (b0, b1)
+__device__ __forceinline__ void fma2_sub(float& d0, float& d1, float a0, float a1, float s, float b0, float b1) {
+  asm("{\n\t.reg .b64 va, vs, vb, vd;\n\t"
+      "mov.b64 va, {%2, %3};\n\t"
+      "mov.b64 vs, {%4, %4};\n\t"
+      "mov.b64 vb, {%5, %6};\n\t"
+      "fma.rn.f32x2 vd, va, vs, vb;\n\t"
+      "mov.b64 {%0, %1}, vd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(s), "f"(-b0), "f"(-b1));
+}
 
 __device__ __forceinline__ int seg_rotation(int cl, int len, unsigned mul) {
   return (int)(((unsigned)cl * mul) % (unsigned)len);
@@ -205,6 +232,7 @@ gmm_fwd_tcx2_kernel(const float* __restrict__ flux, Geom g, const int32_t* __res
   using Rc = Recipe<R>;
   using L = Layout<R>;
   constexpr int NSTAGE = Rc::NSTAGE, NSLOT = Rc::NSLOT, A_COLS = Rc::A_COLS, B_BYTES = Rc::B_BYTES, ACC0 = L::ACC0;
+  constexpr int NMMA = L::NMMA, SLOT_COLS = L::SLOT_COLS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sB = smem;  // NSTAGE operand images
@@ -220,15 +248,17 @@ gmm_fwd_tcx2_kernel(const float* __restrict__ flux, Geom g, const int32_t* __res
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t rt_zero = (uint32_t)K >> 30;  // 0 at run time (K < 2^30), opaque to the compiler
-  const int dbg = marginalize >> 8;             // JD_TC_DEBUG & 1 (timing only, wrong results): no epilogue TMEM loads
+#if defined(JD_TCM_TRACE)
+  const int dbg = marginalize >> 8;  // trace build, JD_TC_DEBUG & 1 (timing only, wrong results): no epilogue TMEM loads
+#endif
   marginalize &= 1;
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
-  auto tfull_bar = [&](int t, int h) { return bar0 + 8u * (2 * NSTAGE + t * TPC + h); };
-  auto tempty_bar = [&](int t, int h) { return bar0 + 8u * (2 * NSTAGE + NSLOT * TPC + t * TPC + h); };
-  auto afull_bar = [&](int h) { return bar0 + 8u * (2 * NSTAGE + 2 * NSLOT * TPC + h); };  // A operand of tile h stored
-  const uint32_t aempty_bar = bar0 + 8u * (2 * NSTAGE + 2 * NSLOT * TPC + TPC);             // last MMAs of the segment done
+  auto tfull_bar = [&](int t) { return bar0 + 8u * (2 * NSTAGE + t); };
+  auto tempty_bar = [&](int t) { return bar0 + 8u * (2 * NSTAGE + NSLOT + t); };
+  auto afull_bar = [&](int h) { return bar0 + 8u * (2 * NSTAGE + 2 * NSLOT + h); };  // A operand of tile h stored
+  const uint32_t aempty_bar = bar0 + 8u * (2 * NSTAGE + 2 * NSLOT + TPC);             // last MMAs of the segment done
   const uint32_t crank = cluster_ctarank();
 
   // this CTA pair's chunk of the linearised (tile group, component) space; tile group tp = tiles [4 tp, 4 tp + 4):
@@ -248,15 +278,14 @@ gmm_fwd_tcx2_kernel(const float* __restrict__ flux, Geom g, const int32_t* __res
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), CLUSTER * TPC);  // released by the MMA commits of both issuers of both CTAs of the pair
+      mbar_init(empty_bar(s), CLUSTER);  // released by the MMA commits of both CTAs of the pair
     }
-    for (int t = 0; t < NSLOT; ++t)
-      for (int h = 0; h < TPC; ++h) {
-        mbar_init(tfull_bar(t, h), 1);
-        mbar_init(tempty_bar(t, h), 4);  // one arrive per warp of the tile's epilogue group
-      }
+    for (int t = 0; t < NSLOT; ++t) {
+      mbar_init(tfull_bar(t), 1);
+      mbar_init(tempty_bar(t), 4 * TPC);  // one arrive per epilogue warp (both tiles' accumulators share the slot)
+    }
     for (int h = 0; h < TPC; ++h) mbar_init(afull_bar(h), 4);  // one arrive per gather warp
-    mbar_init(aempty_bar, TPC);                                 // last MMAs of the segment, both issuers
+    mbar_init(aempty_bar, NMMA);                                // last MMAs of the segment, every issuer
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == M0) tmem_alloc(smem_u32(s_tmem), TMEM_COLS);
@@ -279,12 +308,11 @@ gmm_fwd_tcx2_kernel(const float* __restrict__ flux, Geom g, const int32_t* __res
   const int sidx = (tp)-tp_first, par = sidx & 1;                                                    \
   (void)ka; (void)rot; (void)par;
 
-  if (warp < NPROD) {
-    // ===================== bulk-TMA producers: position pos is loaded by warp pos % NPROD ==========
+  if (warp == 0) {
+    // ===================== bulk-TMA producer (one warp, every position) ============================
     for (int tp = tp_first; tp <= tp_last; ++tp) {
       JD_SEGMENT(tp)
-      int pos = pos_lo + ((pos_lo % NPROD) == warp ? 0 : (warp - (pos_lo % NPROD) + NPROD) % NPROD);
-      for (; pos < pos_hi; pos += NPROD) {
+      for (int pos = pos_lo; pos < pos_hi; ++pos) {
         int idx = pos - pos_lo + rot;
         idx = idx >= len ? idx - len : idx;
         const int kc = ka + idx;
@@ -311,35 +339,49 @@ gmm_fwd_tcx2_kernel(const float* __restrict__ flux, Geom g, const int32_t* __res
         __syncwarp();
       }
     }
-  } else if (warp < M0 + TPC) {
-    // ===================== MMA issuers: warp M0 + h issues tile h, every position (warp-uniform control flow, one
-    // elected lane issues) =======================================================================
-    const int h = warp - M0;
+  } else if (warp >= M0 && warp < M0 + NMMA) {
+    // ===================== MMA issuers: position pos (both tiles) is issued by warp M0 + pos % NMMA into slot
+    // pos % NSLOT (warp-uniform control flow, one elected lane issues) =================================
+    const int w = warp - M0;
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t sB_lo0 = desc_lo(smem_u32(sB));
-    const uint32_t a_base = tmem_u + h * A_COLS;
     for (int tp = tp_first; tp <= tp_last; ++tp) {
       JD_SEGMENT(tp)
-      mbar_wait(afull_bar(h), par);  // the gather warps have stored this segment's A operand of tile h
+#pragma unroll
+      for (int h = 0; h < TPC; ++h) mbar_wait(afull_bar(h), par);  // the gather warps have stored this segment's A operands
       tc_fence_after();
-      for (int pos = pos_lo; pos < pos_hi; ++pos) {
+      int pos = pos_lo + ((pos_lo % NMMA) == w ? 0 : (w - (pos_lo % NMMA) + NMMA) % NMMA);
+      bool released = false;
+      for (; pos < pos_hi; pos += NMMA) {
         const int s = pos % NSTAGE, t = pos % NSLOT;
-        mbar_wait(tempty_bar(t, h), ((pos / NSLOT) & 1) ^ 1);
-        if (lane == 0) JD_TRACE(h == 0 ? 1 : 8, pos);
+        const bool last = pos + NMMA >= pos_hi;
+        mbar_wait(tempty_bar(t), ((pos / NSLOT) & 1) ^ 1);
+        if (lane == 0) JD_TRACE(1, pos);
         mbar_wait(full_bar(s), (pos / NSTAGE) & 1);
-        if (lane == 0) JD_TRACE(h == 0 ? 2 : 9, pos);
+        if (lane == 0) JD_TRACE(2, pos);
         tc_fence_after();
         if (elect_one()) {
-          issue_tile<R, TRI>(tmem_u + ACC0 + (t * TPC + h) * ACC_COLS, a_base, sB_lo0 + s * (B_BYTES >> 4));
+          const uint32_t b = sB_lo0 + s * (B_BYTES >> 4), d = tmem_u + ACC0 + t * SLOT_COLS;
+#pragma unroll
+          for (int h = 0; h < TPC; ++h)  // both tiles against the same staged image
+            issue_tile<R, TRI>(d + h * ACC_COLS, tmem_u + h * A_COLS, b);
+          JD_TRACE(8, pos);
           umma_commit_mc(empty_bar(s), (uint16_t)((1u << CLUSTER) - 1));  // stage free in both CTAs of the pair
-          umma_commit(tfull_bar(t, h));                                    // this tile's accumulator complete
-          if (pos == pos_hi - 1) umma_commit(aempty_bar);  // last read of the tile's A operand (same thread as its MMAs)
-          JD_TRACE(h == 0 ? 3 : 10, pos);
+          JD_TRACE(9, pos);
+          umma_commit(tfull_bar(t));                                       // both accumulators of the slot complete
+          if (last) umma_commit(aempty_bar);  // this warp's last read of the A operands (same thread as its MMAs)
+          JD_TRACE(3, pos);
         }
+        released = released || last;
+        __syncwarp();
+        if (lane == 0) JD_TRACE(10, pos);
+      }
+      if (!released) {  // no position of this segment fell to this warp
+        if (elect_one()) mbar_arrive(aempty_bar);
         __syncwarp();
       }
     }
-  } else if (warp < E0) {
+  } else if (warp >= G0 && warp < E0) {
     // ===================== gather: thread = patch row; 64 loads, mean, scale, split, tcgen05.st ==============
     for (int tp = tp_first; tp <= tp_last; ++tp) {
       JD_SEGMENT(tp)
@@ -424,7 +466,7 @@ gmm_fwd_tcx2_kernel(const float* __restrict__ flux, Geom g, const int32_t* __res
         if (lane == 0) mbar_arrive(afull_bar(h));
       }
     }
-  } else {
+  } else if (warp >= E0) {
     // ===================== epilogue: group 0 (warps 8-11) tile 0, group 1 (12-15) tile 1, every position ========
     const int grp = warp >= E0 + 4 ? 1 : 0;
     const int bar_id = 2 + grp;  // named barrier of this group's 128 threads
@@ -443,7 +485,7 @@ gmm_fwd_tcx2_kernel(const float* __restrict__ flux, Geom g, const int32_t* __res
         const int t = pos % NSLOT;
         const float c_k = __ldg(ck + kc);
         const float b_inv = __ldg(binv + kc);
-        mbar_wait(tfull_bar(t, grp), (pos / NSLOT) & 1);
+        mbar_wait(tfull_bar(t), (pos / NSLOT) & 1);
         if (lane == 0 && (warp == E0 || warp == E0 + 4)) JD_TRACE(warp == E0 ? 4 : 7, pos);
         tc_fence_after();
         if (pos == pos_lo) {  // written by the gather warps before the first MMA of the segment
@@ -451,52 +493,53 @@ gmm_fwd_tcx2_kernel(const float* __restrict__ flux, Geom g, const int32_t* __res
           ok = s_valid[(par * TPC + grp) * TM + row] != 0;
         }
         const float inv = row_inv * b_inv;  // undo the row and component scales
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ACC0 + (t * TPC + grp) * ACC_COLS;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ACC0 + t * SLOT_COLS + grp * ACC_COLS;
         float y0[32], y1[32];
+#if defined(JD_TCM_TRACE)
         if (dbg & 1) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) y0[i] = y1[i] = (float)lane;
-        } else {
+        } else
+#endif
+        {
           tmem_ld32(taddr, y0);
           tmem_ld32(taddr + 32, y1);
           tmem_ld_wait();
         }
         if (lane == 0 && warp == E0) JD_TRACE(5, pos);
-        float qa = 0.f, qb = 0.f, qc = 0.f, qd = 0.f;
+        float2 qa = make_float2(0.f, 0.f), qb = qa, qc = qa, qd = qa;  // eight independent chains of packed squares
+        float lp;
         if (ZERO_MEAN) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            qa = fmaf(y0[i], y0[i], qa);
-            qb = fmaf(y1[i], y1[i], qb);
-            qc = fmaf(y0[i + 1], y0[i + 1], qc);
-            qd = fmaf(y1[i + 1], y1[i + 1], qd);
+          for (int i = 0; i < 32; i += 4) {
+            fma2_sq(qa, y0[i], y0[i + 1]);
+            fma2_sq(qb, y1[i], y1[i + 1]);
+            fma2_sq(qc, y0[i + 2], y0[i + 3]);
+            fma2_sq(qd, y1[i + 2], y1[i + 3]);
           }
-          const float i2 = inv * inv;
-          qa *= i2, qb *= i2, qc *= i2, qd *= i2;
+          // the scales are powers of two: applying them to the sum is exact
+          lp = fmaf(-0.5f * (inv * inv), ((qa.x + qa.y) + (qb.x + qb.y)) + ((qc.x + qc.y) + (qd.x + qd.y)), c_k);
         } else {
           // (mw_k through the read-only path: every lane reads the same 16 x 16 B, an L1 broadcast)
           const float4* mwk = reinterpret_cast<const float4*>(mw + (size_t)kc * 64);
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
             const float4 b0 = __ldg(mwk + c4), b1 = __ldg(mwk + 8 + c4);
-            float d0 = fmaf(y0[4 * c4], inv, -b0.x), d1 = fmaf(y0[4 * c4 + 1], inv, -b0.y);
-            float d2 = fmaf(y0[4 * c4 + 2], inv, -b0.z), d3 = fmaf(y0[4 * c4 + 3], inv, -b0.w);
-            float e0 = fmaf(y1[4 * c4], inv, -b1.x), e1 = fmaf(y1[4 * c4 + 1], inv, -b1.y);
-            float e2 = fmaf(y1[4 * c4 + 2], inv, -b1.z), e3 = fmaf(y1[4 * c4 + 3], inv, -b1.w);
-            qa = fmaf(d0, d0, qa);
-            qb = fmaf(e0, e0, qb);
-            qc = fmaf(d1, d1, qc);
-            qd = fmaf(e1, e1, qd);
-            qa = fmaf(d2, d2, qa);
-            qb = fmaf(e2, e2, qb);
-            qc = fmaf(d3, d3, qc);
-            qd = fmaf(e3, e3, qd);
+            float d0, d1, d2, d3, e0, e1, e2, e3;
+            fma2_sub(d0, d1, y0[4 * c4], y0[4 * c4 + 1], inv, b0.x, b0.y);
+            fma2_sub(d2, d3, y0[4 * c4 + 2], y0[4 * c4 + 3], inv, b0.z, b0.w);
+            fma2_sub(e0, e1, y1[4 * c4], y1[4 * c4 + 1], inv, b1.x, b1.y);
+            fma2_sub(e2, e3, y1[4 * c4 + 2], y1[4 * c4 + 3], inv, b1.z, b1.w);
+            fma2_sq(qa, d0, d1);
+            fma2_sq(qb, e0, e1);
+            fma2_sq(qc, d2, d3);
+            fma2_sq(qd, e2, e3);
           }
+          lp = fmaf(-0.5f, ((qa.x + qa.y) + (qb.x + qb.y)) + ((qc.x + qc.y) + (qd.x + qd.y)), c_k);
         }
-        const float lp = fmaf(-0.5f, (qa + qb) + (qc + qd), c_k);
         tc_fence_before();  // the slot is free once consumed (lp depends on every load, see mbar_arrive_after)
         __syncwarp();
-        if (lane == 0) mbar_arrive_after(tempty_bar(t, grp), lp, rt_zero);
+        if (lane == 0) mbar_arrive_after(tempty_bar(t), lp, rt_zero);
         if (lane == 0 && (warp == E0 || warp == E0 + 4)) JD_TRACE(warp == E0 ? 6 : 11, pos);
         if (logp && p < g.P) logp[(size_t)kc * g.P + p] = lp;
         if (marginalize) {
@@ -658,7 +701,7 @@ static int launch(const char* who, const float* flux, int fH, int fW, const int3
   float* ws_m = reinterpret_cast<float*>(ws + p.off_m);
   float* ws_s = reinterpret_cast<float*>(ws + p.off_s);
   int* ws_k = reinterpret_cast<int*>(ws + p.off_k);
-  const int marg = (marginalize ? 1 : 0) | ((dbg & 1) << 8);
+  const int marg = (marginalize ? 1 : 0) | ((dbg & 1) << 8);  // (the knob only exists in the JD_TCM_TRACE build)
   cudaError_t le;
   if (upper_tri && zero_mean)
     le = cudaLaunchKernelEx(&cfg, gmm_fwd_tcx2_kernel<R, true, true>, flux, g, shift_yx, bt8, mw, ck, binv, K, marg,

@@ -381,9 +381,11 @@ def test_gmm_prior_stream_k_equals_tile_per_cta(monkeypatch, shape, rows, K, mar
 @pytest.mark.parametrize("new,old", [(4, 3), (5, 2)])
 def test_gmm_prior_two_tiles_per_cta_equals_one_tile(shape, rows, K, mean_scale, marginalize, new, old):
     """Backends 4 / 5 (two patch tiles per CTA and staged operand image, jd_gmm_tcm2.cu; mixed TF32 / FP16 and split-FP16
-    recipes) issue the same MMAs in the same order as the one-tile kernels of their recipe (backends 3 / 2): bit-identical
-    per-component log-probabilities, max and argmax; the workspace's arrival counters are back at zero after every
-    launch (two launches on the same workspace)."""
+    recipes) issue the same MMAs in the same order as the one-tile kernels of their recipe (backends 3 / 2) - the
+    accumulators are identical, the epilogue sums the 64 squares in packed pairs (another order): per-component
+    log-probabilities agree to FP32 rounding of that sum, the argmax except on ties within that rounding.  The
+    workspace's arrival counters are back at zero after every launch (two launches on the same workspace) and the two
+    launches are bit-identical."""
     rng = np.random.default_rng(16)
     flux = t(rng.gamma(2.0, size=shape) * np.exp(rng.normal(0, 0.7, size=shape)))
     packed = pack(O.GMM(*synthetic_gmm(K, seed=9, mean_scale=mean_scale)))
@@ -394,22 +396,29 @@ def test_gmm_prior_two_tiles_per_cta_equals_one_tile(shape, rows, K, mean_scale,
     orig = ops.tcm_workspace
     ops.tcm_workspace = lambda *a: ws
     try:
+        runs = []
         for _ in range(2):
             v1, k1, lp1, s1 = ops.gmm_prior_forward(flux, (2, -1), packed, 4, marginalize, rows=rows, want_logp=True,
                                                     backend=new)
-            diff = lp0 != lp1
-            if bool(diff.any()):
-                idx = diff.nonzero().cpu().numpy()
-                a, b = lp0[diff].cpu().numpy(), lp1[diff].cpu().numpy()
+            runs.append((v1.clone(), k1.clone(), lp1.clone()))
+            a, b = lp0.cpu().numpy().astype(np.float64), lp1.cpu().numpy().astype(np.float64)
+            # -0.5 * sum of squares + c_k: rounding of the sum relative to the larger of the two terms
+            err = np.abs(a - b)
+            tol = 2e-6 * (np.abs(a) + np.abs(packed.ck.cpu().numpy().astype(np.float64))[None, :])
+            if (err > tol).any():
+                idx = np.argwhere(err > tol)
                 raise AssertionError(f"logp differs in {idx.shape[0]} entries: tiles {np.unique(idx[:, 0] // 128)[:16]}, "
                                      f"rows {np.unique(idx[:, 0] % 128)[:16]}, components {np.unique(idx[:, 1])[:32]}, "
-                                     f"max |diff| {np.abs(a - b).max()}, samples {a[:4]} vs {b[:4]}")
-            assert torch.equal(k0, k1)
-            if marginalize:
-                assert_allclose(v1.cpu().numpy(), v0.cpu().numpy(), rtol=2e-6)
-            else:
-                assert torch.equal(v0, v1)
-            assert_allclose(s1.item(), s0.item(), rtol=1e-9 if not marginalize else 1e-6)
+                                     f"max |diff| {err.max()}, samples {a[err > tol][:4]} vs {b[err > tol][:4]}")
+            flipped = (k0 != k1).cpu().numpy()
+            if flipped.any():  # only where the two best components tie within the rounding above
+                top2 = np.sort(a[flipped], axis=1)[:, -2:]
+                assert (top2[:, 1] - top2[:, 0] <= 1e-6 * np.abs(top2[:, 1])).all()
+                assert flipped.sum() <= max(2, P // 2000)
+            assert_allclose(v1.cpu().numpy(), v0.cpu().numpy(), rtol=2e-6)
+            assert_allclose(s1.item(), s0.item(), rtol=1e-6)
+        for x, y in zip(*runs):
+            assert torch.equal(x, y)  # run-to-run bit-identical
     finally:
         ops.tcm_workspace = orig
     n_tiles4 = ((P + 127) // 128 + 3) // 4 * 4  # arrival counters: one per tile, whole tile groups

@@ -34,22 +34,24 @@ assert rc == 0
 t = buf.astype(np.float64)
 t0 = t[0, 0]
 sel = slice(40, 200)  # steady state inside the first segment
-names = ["prod>empty", "is0>tempty", "is0>full", "is0 done", "ep0>tfull", "ep0 ld", "ep0 rel", "ep1>tfull",
-         "is1>tempty", "is1>full", "is1 done", "ep1 rel"]
+names = ["prod>empty", "iss>tempty", "iss>full", "iss done", "ep0>tfull", "ep0 ld", "ep0 rel", "ep1>tfull",
+         "mma issued", "stage commit", "reconverged", "ep1 rel"]
 print(f"backend {backend}; first positions (clk since the producer's first issue):")
-for p in range(0, 10):
+for p in list(range(0, 6)) + list(range(100, 112)):
     print(p, " ".join(f"{names[e]}={t[p, e] - t0:7.0f}" for e in range(12)))
 per = np.diff(t[sel, 3]).mean()
 print(f"\nsteady state (positions {sel.start}..{sel.stop}): period {per:.0f} clk per position "
       f"({per / 2:.0f} per tile-position)")
 d = lambda a, b: (t[sel, a] - t[sel, b]).mean()
-print(f"  issuer 0: past tempty -> past full {d(2, 1):6.0f} | issue + commits {d(3, 2):6.0f}    issuer 1: {d(9, 8):6.0f} | {d(10, 9):6.0f}")
-print(f"  TMA:      producer issue -> issuer 0 sees full {d(2, 0):6.0f}")
-print(f"  tensor:   issuer 0 done -> epilogue 0 sees tfull {d(4, 3):6.0f} | issuer 1 done -> epilogue 1 {d(7, 10):6.0f}")
+print(f"  issuer:   past tempty -> past full {d(2, 1):6.0f} | MMAs issued {d(8, 2):6.0f} | stage commit {d(9, 8):6.0f} | "
+      f"slot commit {d(3, 9):6.0f} | reconverged {d(10, 3):6.0f}")
+nxt_own = t[sel.start + nslot:sel.stop + nslot, 1]
+print(f"            reconverged (pos p) -> same warp past tempty (pos p+{nslot}) {(nxt_own - t[sel, 10]).mean():6.0f}")
+print(f"  TMA:      producer issue -> issuer sees full {d(2, 0):6.0f}")
+print(f"  tensor:   issuer done -> epilogue 0 sees tfull {d(4, 3):6.0f} | epilogue 1 {d(7, 3):6.0f}")
 print(f"  epilogue: tfull -> loads landed {d(5, 4):6.0f} | loads -> slot released {d(6, 5):6.0f} | epilogue 1 total {d(11, 7):6.0f}")
-rel = t[sel.start:sel.stop, 6]
-nxt = t[sel.start + nslot:sel.stop + nslot, 1]
-print(f"  slot:     epilogue 0 release (pos p) -> issuer 0 past tempty (pos p+{nslot}) {(nxt - rel).mean():6.0f}")
+rel = np.maximum(t[sel.start:sel.stop, 6], t[sel.start:sel.stop, 11])
+print(f"  slot:     both epilogues released (pos p) -> issuer past tempty (pos p+{nslot}) {(nxt_own - rel).mean():6.0f}")
 nst = 10 if backend == 5 else 6
 prv = t[sel.start + nst:sel.stop + nst, 0]
-print(f"  stage:    issuer 0 done (pos p) -> producer past empty (pos p+{nst}) {(prv - t[sel, 3]).mean():6.0f}")
+print(f"  stage:    issuer done (pos p) -> producer past empty (pos p+{nst}) {(prv - t[sel, 3]).mean():6.0f}")

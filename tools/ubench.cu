@@ -182,6 +182,170 @@ __global__ void __launch_bounds__(512, 1) tmem_ld_var_kernel(int iters, long lon
   }
 }
 
+
+// ------------------------------------------------------------------ tcgen05.mma rate vs N (A operand in TMEM)
+// one elected lane issues `iters` MMAs  D[128 x N] += A[128 x 32 B] . B[N x 32 B]^T  back to back into the same
+// accumulator, then commits and waits: clk per MMA as a function of N, for kind::f16 (K = 16) and kind::tf32 (K = 8)
+template <bool F16>
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, int n, long long* cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint32_t s_tmem;
+  __shared__ uint64_t bar;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 32768 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 512);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint32_t idesc = (1u << 4) | ((F16 ? 0u : 2u) << 7) | ((F16 ? 0u : 2u) << 10) | (((uint32_t)n >> 3) << 17) |
+                         ((128u >> 4) << 24);
+  if (warp == 1) {
+    const uint64_t desc = make_desc(smem_u32(smem));
+    const long long t0 = clock64();
+    if (elect_one()) {
+      for (int i = 0; i < iters; ++i) {
+        if (F16)
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem + 256),
+                       "r"(tmem + (uint32_t)((i & 7) * 8)), "l"(desc), "r"(idesc)
+                       : "memory");
+        else
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem + 256),
+                       "r"(tmem + (uint32_t)((i & 7) * 8)), "l"(desc), "r"(idesc)
+                       : "memory");
+      }
+      umma_commit(smem_u32(&bar));
+    }
+    __syncwarp();
+    while (!mbar_try(smem_u32(&bar), 0)) {
+    }
+    const long long t1 = clock64();
+    if ((threadIdx.x & 31) == 0) cycles[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+
+// the prior kernels' real MMA sequence (recipe 1: three passes of N = 64, 48, 32, 16 at row offsets 0, 16, 32, 48 into
+// one 64-column accumulator, first MMA overwrites) issued by `nw` warps concurrently, each warp into its own accumulator
+// slot(s), optionally with `nld` more warps streaming accumulators out of TMEM (tcgen05.ld) at the same time
+__global__ void __launch_bounds__(512, 1) mma_pattern_kernel(int iters, int nw, int nld, int dense, int ncommit, long long* cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint32_t s_tmem;
+  __shared__ uint64_t bar[4];
+  __shared__ uint64_t sink_bar[4];  // arrival count never reached: per-position commits land here
+  __shared__ volatile int s_stop;
+  const int warp = threadIdx.x >> 5;
+  const bool rnd = (dense & 2) != 0;  // random FP16 operands (|x| < 2) instead of zeros: data-dependent power
+  dense &= 1;
+  for (int i = threadIdx.x; i < 65536 / 4; i += blockDim.x) {
+    uint32_t r = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+    r ^= r >> 13, r *= 2246822519u, r ^= r >> 16;
+    reinterpret_cast<uint32_t*>(smem)[i] = rnd ? (r & 0xBFFFBFFFu) : 0u;
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bar[i]), 1);
+    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&sink_bar[i]), (1u << 20) - 1);
+    s_stop = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 512);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint32_t sb = desc_lo(smem_u32(smem));
+  if (rnd && warp < 4) {  // random A operand in TMEM columns [0, 64)
+    float v[32];
+    for (int c = 0; c < 64; c += 32) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        uint32_t r = (uint32_t)(threadIdx.x * 64 + c + i) * 2654435761u;
+        r ^= r >> 13, r *= 2246822519u, r ^= r >> 16;
+        v[i] = __uint_as_float(r & 0xBFFFBFFFu);
+      }
+      tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp < nw) {
+    const long long t0 = clock64();
+    if (elect_one()) {
+      for (int it = 0; it < iters; ++it) {
+        const uint32_t d = tmem + 128 + ((uint32_t)(warp * 2 + (it & 1)) * 64) % 384;
+        const uint32_t b = sb + (uint32_t)((it % 4) * (16384 >> 4));
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t n0 = dense ? 0u : 16u * kk;
+            const uint32_t idesc = (1u << 4) | (((64u - n0) >> 3) << 17) | ((128u >> 4) << 24);
+            const uint64_t desc = desc_from_lo(b + ((pass == 1 ? 8192u : 0u) >> 4) + ((kk * 32 + n0 * 128) >> 4));
+            const uint32_t a = tmem + (pass == 0 ? 32u : 0u) + kk * 8;
+            if (pass == 0 && kk == 0)
+              asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\t"
+                           "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d + n0),
+                           "r"(a), "l"(desc), "r"(idesc)
+                           : "memory");
+            else
+              asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                           "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d + n0),
+                           "r"(a), "l"(desc), "r"(idesc)
+                           : "memory");
+          }
+        for (int c = 0; c < ncommit; ++c) umma_commit(smem_u32(&sink_bar[(warp + c) & 3]));
+      }
+      umma_commit(smem_u32(&bar[warp]));
+    }
+    __syncwarp();
+    while (!mbar_try(smem_u32(&bar[warp]), 0)) {
+    }
+    const long long t1 = clock64();
+    if ((threadIdx.x & 31) == 0) cycles[blockIdx.x * 4 + warp] = t1 - t0;
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) atomicAdd((int*)&s_stop, 1);
+  } else if (warp >= 4 && warp < 4 + nld) {
+    const uint32_t base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 128;
+    float q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int it = 0;
+    while (s_stop < nw) {
+      float y0[32], y1[32];
+      tmem_ld32(base + ((it * 64) % 384), y0);
+      tmem_ld32(base + ((it * 64) % 384) + 32, y1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) q[i & 7] = fmaf(y0[i], y0[i], fmaf(y1[i], y1[i], q[i & 7]));
+      ++it;
+    }
+    if (q[0] + q[1] + q[2] + q[3] + q[4] + q[5] + q[6] + q[7] == 123.456f) cycles[1022] = it;
+    if (blockIdx.x == 0 && threadIdx.x == 128) cycles[1023] = it;  // accumulators streamed by one reader warp
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 // ------------------------------------------------------------------ mbarrier wait flavours
 // WAIT 0: mbarrier.try_wait (may suspend the thread), 1: mbarrier.test_wait spin, 2: try_wait with a 32 ns suspend hint
 template <int WAIT>
@@ -350,6 +514,49 @@ int main() {
       const char* names[3] = {"one 32x32b.x64 + wait + 64 FFMA", "pipelined x32 loads + 64 FFMA", "4 x (32x32b.x16) + wait + 64 FFMA"};
       printf("tmem_ld %s, %2d warps: %.1f clk per 64-col accumulator per warp, %.1f B/clk/SM\n", names[mode], nw,
              c / iters, (double)nw * 32 * 64 * 4 * iters / c);
+    }
+  }
+
+
+  // ---- MMA rate vs N
+  {
+    CK(cudaFuncSetAttribute(mma_rate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 40 * 1024));
+    CK(cudaFuncSetAttribute(mma_rate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 40 * 1024));
+    const int ns[] = {16, 32, 48, 64, 96, 128, 192, 256};
+    const int it3 = 2048;
+    for (int f16 = 1; f16 >= 0; --f16)
+      for (int n : ns) {
+        for (int rep = 0; rep < 2; ++rep) {
+          if (f16) mma_rate_kernel<true><<<sms, 128, 34 * 1024>>>(it3, n, d_cyc);
+          else mma_rate_kernel<false><<<sms, 128, 34 * 1024>>>(it3, n, d_cyc);
+        }
+        CK(cudaDeviceSynchronize());
+        const double c = mean_cycles(d_cyc, sms);
+        printf("tcgen05.mma kind::%s M=128 N=%3d K=%2d, A in TMEM: %.1f clk per MMA (N/2 = %d)\n", f16 ? "f16 " : "tf32", n,
+               f16 ? 16 : 8, c / it3, n / 2);
+      }
+  }
+
+
+  // ---- the kernels' MMA pattern: issuing warps x concurrent TMEM readers
+  {
+    CK(cudaFuncSetAttribute(mma_pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 70 * 1024));
+    const int it4 = 512;
+    const int cfgs[][4] = {{1, 0, 0, 0}, {1, 0, 1, 0}, {3, 0, 0, 0}, {3, 8, 0, 0}, {1, 0, 0, 1}, {1, 0, 0, 2}, {1, 0, 0, 3},
+                            {3, 0, 0, 1}, {3, 0, 0, 3}, {3, 8, 0, 3}, {3, 8, 2, 3}, {1, 0, 2, 0}, {3, 8, 3, 3}};
+    for (auto& c : cfgs) {
+      for (int rep = 0; rep < 2; ++rep) mma_pattern_kernel<<<sms, 512, 66 * 1024>>>(it4, c[0], c[1], c[2], c[3], d_cyc);
+      CK(cudaDeviceSynchronize());
+      long long h[1024];
+      CK(cudaMemcpy(h, d_cyc, sizeof(h), cudaMemcpyDeviceToHost));
+      double mx = 0;
+      for (int b = 0; b < 8; ++b)
+        for (int w = 0; w < c[0]; ++w) mx = h[b * 4 + w] > mx ? (double)h[b * 4 + w] : mx;
+      printf("mma pattern (12 MMAs per tile-position, %s), %d issuing warps, %d tcgen05.ld warps, %d commits per "
+             "tile-position: %.0f clk per tile-position per SM (%.1f clk per MMA)\n",
+             (c[2] & 1) ? ((c[2] & 2) ? "dense N=64, random operands" : "dense N=64") : ((c[2] & 2) ? "trimmed, random operands" : "trimmed N=64,48,32,16"), c[0], c[1], c[3], mx / (it4 * c[0]),
+             mx / (it4 * c[0] * 12.0));
+      if (c[1]) printf("    a reader warp took %.0f clk per 64-column accumulator (2 x tcgen05.ld.x32 + wait + 64 FFMA)\n", mx / (double)h[1023]);
     }
   }
 
