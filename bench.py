@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--no-gpu-baseline", action="store_true",
                     help="skip timing the unmodified reference with device='cuda' on the same B200")
     ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--datasets", type=int, default=None,
+                    help="experiments only: override the workload's number of datasets (the line's config says so)")
     ap.add_argument("--collective", default="peer", choices=["nccl", "peer"],
                     help="joint multi-GPU step: NCCL all-reduce + Adam, or the fused peer-memory reduce+Adam kernel")
     return ap.parse_args()
@@ -230,7 +232,9 @@ def main():
     if args.workload == "cfg5":
         return bench_batched(args, rank, local_rank, world)
     joint = args.workload in JOINT_WORKLOADS
-    workload = synthetic.make_workload(args.workload, seed=0 if joint else rank)
+    workload = synthetic.make_workload(args.workload, seed=0 if joint else rank, n_datasets=args.datasets)
+    if args.datasets is not None:
+        workload["name"] = f"{workload['name']}-with-{args.datasets}-datasets"
 
     # ------------------------------------------------------------------ reference arm (host CPU)
     if args.impl == "reference":

@@ -250,9 +250,10 @@ int jd_gmm_prior_forward_tc16x2(const float* flux, int fH, int fW, const int32_t
  * R = one-hot(argmax) or softmax_k(logp) (marginalize=1; needs logp and value from the forward);
  * Lam_k = Lw_k Lw_k^T, bk_k = mw_k Lw_k^T.  (Autograd mirror of gmm.py:270-272 + norms.py:97-103.)
  * For d prior/d flux pass scale = -stride^2/64/(fH fW).
- * workspace (optional, marginalize=0): jd_gmm_backward_workspace_elems(P', K) int32; when given, patches are
- * bucketed by winning component so that each Lam_k is staged in shared memory once per <= 32 patches instead of
- * being re-read from L2 for every patch. */
+ * workspace (optional, marginalize=0): jd_gmm_backward_workspace_elems(P', K) int32, ZERO-INITIALISED before the first
+ * use (the kernels leave it ready for the next launch); when given, patches are bucketed by winning component and
+ * each Lam_k is staged in shared memory once per <= 64 patches (a register-tiled 64x64x64 product) instead of being
+ * re-read from L2 for every patch - the faster path from a few ten thousand patches on.  K <= 4096. */
 int64_t jd_gmm_backward_workspace_elems(int64_t P, int K);
 int jd_gmm_prior_backward(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride,
                           int row_begin, int row_end, const float* Lam, const float* bk, int K,

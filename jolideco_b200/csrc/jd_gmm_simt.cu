@@ -7,6 +7,7 @@
 // double-buffered cp.async stage and a 128x64x64 register-tiled product (8x4 per thread) is formed.
 // The epilogue never writes Y: it subtracts mw_k, squares, reduces over the 64 whitened features
 // with half-warp shuffles and folds the component into a running max/argmax or online logsumexp.
+#include <algorithm>
 #include <cuda_pipeline.h>
 #include <math_constants.h>
 
@@ -370,99 +371,191 @@ gmm_bwd_max_tri_kernel(const float* __restrict__ flux, PatchGeom g, const int32_
 }
 
 // ---- max-mode backward, bucketed by winning component ------------------------------------------------
-// Patches are grouped by argmax (histogram -> scan -> scatter), then one CTA per (component, chunk of <= CH
-// patches) stages Lam_k once in shared memory and runs the 64x64 GEMVs of its patches from there: the
-// per-patch 16 KB reads of Lam_k* from L2 (P x 16 KB per launch) become one read per work item.
-constexpr int CH = 32;  // patches per work item
+// The warp-per-patch kernels read one 12-16 KB matrix per patch from L2 / L1: 1 GB per launch at 65 025 patches, which is
+// what they cost.  Here the patches are grouped by argmax (shared-memory histogram -> one-warp scan -> scatter), then one
+// CTA per (component, chunk of <= BCH patches) stages Lam_k once and runs a 64 x 64 x 64 register-tiled product:
+//     G[p, :] = scale * ((x_p - mean) Lam_k - bk_k), minus its row mean.
+// Work items are not materialised: item i belongs to the component k with item_base[k] <= i < item_base[k + 1]
+// (binary search in shared memory), its patches are perm[cursor0[k] + BCH (i - item_base[k]) ...].
+constexpr int BCH = 64;   // patches per work item
+constexpr int BXS = 68;   // padded row length of the staged patches
 
-__global__ void bwd_hist_kernel(const int32_t* __restrict__ argmax, int P, int K, int32_t* __restrict__ counts,
-                                float* __restrict__ G) {
+__global__ void __launch_bounds__(256)
+bwd_hist_kernel(const int32_t* __restrict__ argmax, int P, int K, int32_t* __restrict__ counts, float* __restrict__ G) {
+  extern __shared__ int32_t s_cnt[];
+  for (int k = threadIdx.x; k < K; k += blockDim.x) s_cnt[k] = 0;
+  __syncthreads();
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
     int k = argmax[p];
     if (k >= 0 && k < K) {
-      atomicAdd(counts + k, 1);
+      atomicAdd(s_cnt + k, 1);
     } else {  // filtered patch: zero gradient row
       float4* row = reinterpret_cast<float4*>(G + (int64_t)p * PD);
 #pragma unroll
       for (int i = 0; i < 16; ++i) row[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x)
+    if (s_cnt[k]) atomicAdd(counts + k, s_cnt[k]);
 }
 
-// one block: exclusive scan of the K counts -> offsets / cursors, and the work-item list (k, start, count)
-__global__ void bwd_scan_kernel(int K, const int32_t* __restrict__ counts, int32_t* __restrict__ cursor,
-                                int32_t* __restrict__ items, int32_t* __restrict__ n_items) {
-  // K is small (<= a few hundred): a serial scan by one thread is cheaper than a parallel one + syncs
-  if (threadIdx.x == 0) {
-    int off = 0, ni = 0;
-    for (int k = 0; k < K; ++k) {
-      int c = counts[k];
-      cursor[k] = off;
-      for (int s0 = 0; s0 < c; s0 += CH) {
-        items[3 * ni + 0] = k;
-        items[3 * ni + 1] = off + s0;
-        items[3 * ni + 2] = min(CH, c - s0);
-        ++ni;
-      }
-      off += c;
+// one warp: exclusive scans of the K counts (patch offsets) and of the per-component item counts
+__global__ void bwd_scan_kernel(int K, int32_t* __restrict__ counts, int32_t* __restrict__ cursor0,
+                                int32_t* __restrict__ cursor, int32_t* __restrict__ item_base) {
+  const int lane = threadIdx.x;
+  int off = 0, ioff = 0;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    const int k = k0 + lane;
+    const int c = k < K ? counts[k] : 0;
+    const int ni = (c + BCH - 1) / BCH;
+    int sc = c, si = ni;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, sc, o), b2 = __shfl_up_sync(0xffffffffu, si, o);
+      if (lane >= o) sc += a, si += b2;
     }
-    n_items[0] = ni;
+    if (k < K) {
+      cursor0[k] = off + sc - c;
+      cursor[k] = off + sc - c;
+      item_base[k] = ioff + si - ni;
+      counts[k] = 0;  // ready for the next launch
+    }
+    off += __shfl_sync(0xffffffffu, sc, 31);
+    ioff += __shfl_sync(0xffffffffu, si, 31);
   }
+  if (lane == 0) item_base[K] = ioff;
 }
 
-__global__ void bwd_scatter_kernel(const int32_t* __restrict__ argmax, int P, int K, int32_t* __restrict__ cursor,
-                                   int32_t* __restrict__ perm) {
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
-    int k = argmax[p];
-    if (k >= 0 && k < K) perm[atomicAdd(cursor + k, 1)] = p;
+__global__ void __launch_bounds__(256)
+bwd_scatter_kernel(const int32_t* __restrict__ argmax, int P, int K, int32_t* __restrict__ cursor,
+                   int32_t* __restrict__ perm) {
+  // block-local ranks first (shared-memory atomics), one global reservation per (block, component)
+  extern __shared__ int32_t s_buf[];
+  int32_t* s_cnt = s_buf;
+  int32_t* s_base = s_buf + K;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) s_cnt[k] = 0;
+  __syncthreads();
+  constexpr int PER = 4;
+  const int p0 = blockIdx.x * blockDim.x * PER;
+  int kk[PER], rk[PER];
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    const int p = p0 + u * blockDim.x + threadIdx.x;
+    kk[u] = p < P ? argmax[p] : -1;
+    rk[u] = (kk[u] >= 0 && kk[u] < K) ? atomicAdd(s_cnt + kk[u], 1) : 0;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) s_base[k] = s_cnt[k] ? atomicAdd(cursor + k, s_cnt[k]) : 0;
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    const int p = p0 + u * blockDim.x + threadIdx.x;
+    if (kk[u] >= 0 && kk[u] < K) perm[s_base[kk[u]] + rk[u]] = p;
   }
 }
 
 __global__ void __launch_bounds__(256)
 gmm_bwd_bucket_kernel(const float* __restrict__ flux, PatchGeom g, const int32_t* __restrict__ shift_yx,
-                      const float* __restrict__ Lam, const float* __restrict__ bk, const int32_t* __restrict__ perm,
-                      const int32_t* __restrict__ items, const int32_t* __restrict__ n_items, float scale,
+                      const float* __restrict__ Lam, const float* __restrict__ bk, int K,
+                      const int32_t* __restrict__ perm, const int32_t* __restrict__ cursor0,
+                      const int32_t* __restrict__ cursor_end, const int32_t* __restrict__ item_base, float scale,
                       float* __restrict__ G) {
-  __shared__ __align__(16) float Ls[PD * PD];
+  __shared__ __align__(16) float Ls[PD * PD];   // Lam_k, row i = input feature
+  __shared__ __align__(16) float Xs[BCH * BXS];  // centred patches of the item, row = patch
   __shared__ float bs[PD];
-  __shared__ float xs[4][PD];
-  __shared__ float red[4][2];
-  if ((int)blockIdx.x >= n_items[0]) return;
+  __shared__ int s_p[BCH];
+  __shared__ int s_k, s_start, s_cnt;
+  if ((int)blockIdx.x >= item_base[K]) return;
   if (shift_yx) {
     g.sy = shift_yx[0];
     g.sx = shift_yx[1];
   }
-  const int k = items[3 * blockIdx.x], start = items[3 * blockIdx.x + 1], cnt = items[3 * blockIdx.x + 2];
+  if (threadIdx.x == 0) {  // component of this item: last k with item_base[k] <= item
+    int lo = 0, hi = K;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (item_base[mid] <= (int)blockIdx.x) lo = mid; else hi = mid;
+    }
+    const int first = cursor0[lo] + BCH * ((int)blockIdx.x - item_base[lo]);
+    s_k = lo;
+    s_start = first;
+    s_cnt = min(BCH, cursor_end[lo] - first);  // after the scatter the running cursor of k is the end of its bucket
+  }
+  __syncthreads();
+  const int k = s_k, start = s_start, cnt = s_cnt;
   const float4* Lsrc = reinterpret_cast<const float4*>(Lam + (int64_t)k * PD * PD);
 #pragma unroll
   for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(Ls)[threadIdx.x + i * 256] = __ldg(Lsrc + threadIdx.x + i * 256);
   if (threadIdx.x < PD) bs[threadIdx.x] = bk[(int64_t)k * PD + threadIdx.x];
-  const int grp = threadIdx.x >> 6, j = threadIdx.x & 63, half = (threadIdx.x >> 5) & 1, lane = threadIdx.x & 31;
-  for (int it = 0; it < cnt; it += 4) {
-    const bool act = it + grp < cnt;
-    int64_t p = 0;
-    float x = 0.f;
-    if (act) {
-      p = perm[start + it + grp];
-      int iy = (int)(p / g.nx) + g.row_begin, ix = (int)(p % g.nx);
-      x = __ldg(flux + (int64_t)patch_src_row(g, iy, j >> 3) * g.fW + patch_src_col(g, ix, j & 7));
+  if (threadIdx.x < BCH) s_p[threadIdx.x] = threadIdx.x < cnt ? perm[start + threadIdx.x] : -1;
+  __syncthreads();
+  {  // gather: 4 threads per patch, 2 patch rows (16 values) each; mean over the quad
+    const int pi = threadIdx.x >> 2, qd = threadIdx.x & 3;
+    const int p = s_p[pi];
+    float v[16];
+    float sm = 0.f;
+    if (p >= 0) {
+      const int iy = p / g.nx + g.row_begin, ix = p % g.nx;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float* src = flux + (int64_t)patch_src_row(g, iy, 2 * qd + u) * g.fW;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          v[8 * u + c] = __ldg(src + patch_src_col(g, ix, c));
+          sm += v[8 * u + c];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0.f;
     }
-    float sx_ = warp_sum(x);
-    if (lane == 0) red[grp][half] = sx_;
-    __syncthreads();  // also orders the Ls / bs staging before the first use
-    x -= (red[grp][0] + red[grp][1]) * (1.f / 64.f);
-    xs[grp][j] = x;
-    __syncthreads();
-    float acc = -bs[j];
-#pragma unroll 16
-    for (int i = 0; i < PD; ++i) acc = fmaf(xs[grp][i], Ls[i * PD + j], acc);
-    float sg = warp_sum(acc);
-    __syncthreads();  // red / xs reuse
-    if (lane == 0) red[grp][half] = sg;
-    __syncthreads();
-    const float gm = (red[grp][0] + red[grp][1]) * (1.f / 64.f);
-    if (act) G[p * PD + j] = scale * (acc - gm);
-    __syncthreads();
+    sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+    sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+    const float mean = sm * (1.f / 64.f);
+#pragma unroll
+    for (int i = 0; i < 16; i += 4)
+      *reinterpret_cast<float4*>(Xs + pi * BXS + 16 * qd + i) =
+          make_float4(v[i] - mean, v[i + 1] - mean, v[i + 2] - mean, v[i + 3] - mean);
+  }
+  __syncthreads();
+  // product: thread (ty, tx) = 4 patches (ty + 16 r) x 4 outputs (4 tx + c)
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+#pragma unroll 4
+  for (int i = 0; i < PD; i += 4) {
+    float4 xr[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) xr[r] = *reinterpret_cast<const float4*>(Xs + (ty + 16 * r) * BXS + i);
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+      const float4 l = *reinterpret_cast<const float4*>(Ls + (i + ii) * PD + 4 * tx);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float x = ii == 0 ? xr[r].x : ii == 1 ? xr[r].y : ii == 2 ? xr[r].z : xr[r].w;
+        acc[r][0] = fmaf(x, l.x, acc[r][0]);
+        acc[r][1] = fmaf(x, l.y, acc[r][1]);
+        acc[r][2] = fmaf(x, l.z, acc[r][2]);
+        acc[r][3] = fmaf(x, l.w, acc[r][3]);
+      }
+    }
+  }
+  const float4 b4 = *reinterpret_cast<const float4*>(bs + 4 * tx);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    acc[r][0] -= b4.x, acc[r][1] -= b4.y, acc[r][2] -= b4.z, acc[r][3] -= b4.w;
+    float sg = (acc[r][0] + acc[r][1]) + (acc[r][2] + acc[r][3]);  // row sum over the 16 threads tx of a half warp
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) sg += __shfl_xor_sync(0xffffffffu, sg, o);
+    const float gm = sg * (1.f / 64.f);
+    const int p = s_p[ty + 16 * r];
+    if (p >= 0)
+      *reinterpret_cast<float4*>(G + (int64_t)p * PD + 4 * tx) =
+          make_float4(scale * (acc[r][0] - gm), scale * (acc[r][1] - gm), scale * (acc[r][2] - gm), scale * (acc[r][3] - gm));
   }
 }
 
@@ -575,8 +668,8 @@ int jd_extract_patches(const float* flux, int fH, int fW, const int32_t* shift_y
 }
 
 int64_t jd_gmm_backward_workspace_elems(int64_t P, int K) {
-  // counts[K] cursor[K] n_items[1] items[3 (K + P/CH + 1)] perm[P]
-  return 2 * (int64_t)K + 1 + 3 * ((int64_t)K + P / CH + 1) + P;
+  // counts[K] (zero at entry, left at zero) cursor0[K] cursor[K] item_base[K + 1] perm[P]
+  return 4 * (int64_t)K + 1 + P;
 }
 
 int jd_gmm_prior_backward(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
@@ -602,18 +695,19 @@ int jd_gmm_prior_backward(const float* flux, int fH, int fW, const int32_t* shif
   } else {
     JD_CHECK_ARG(argmax, "jd_gmm_prior_backward: marginalize=0 needs argmax from the forward");
     if (workspace) {
+      JD_CHECK_ARG(K <= 4096, "jd_gmm_prior_backward: the bucketed backward supports up to 4096 components");
       int32_t* counts = workspace;
-      int32_t* cursor = counts + K;
-      int32_t* n_items = cursor + K;
-      int32_t* items = n_items + 1;
-      const int max_items = K + g.P / CH + 1;
-      int32_t* perm = items + 3 * (int64_t)max_items;
-      cudaMemsetAsync(counts, 0, sizeof(int32_t) * K, st);
-      int blocks = (g.P + 255) / 256;
-      bwd_hist_kernel<<<blocks, 256, 0, st>>>(argmax, g.P, K, counts, G);
-      bwd_scan_kernel<<<1, 32, 0, st>>>(K, counts, cursor, items, n_items);
-      bwd_scatter_kernel<<<blocks, 256, 0, st>>>(argmax, g.P, K, cursor, perm);
-      gmm_bwd_bucket_kernel<<<max_items, 256, 0, st>>>(flux, g, shift_yx, Lam, bk, perm, items, n_items, scale, G);
+      int32_t* cursor0 = counts + K;
+      int32_t* cursor = cursor0 + K;
+      int32_t* item_base = cursor + K;
+      int32_t* perm = item_base + K + 1;
+      const int max_items = K + g.P / BCH + 1;
+      const int hb = (int)std::min<int64_t>(((int64_t)g.P + 1023) / 1024, (int64_t)num_sms() * 4);
+      bwd_hist_kernel<<<hb, 256, sizeof(int32_t) * K, st>>>(argmax, g.P, K, counts, G);
+      bwd_scan_kernel<<<1, 32, 0, st>>>(K, counts, cursor0, cursor, item_base);
+      bwd_scatter_kernel<<<(g.P + 1023) / 1024, 256, 2 * sizeof(int32_t) * K, st>>>(argmax, g.P, K, cursor, perm);
+      gmm_bwd_bucket_kernel<<<max_items, 256, 0, st>>>(flux, g, shift_yx, Lam, bk, K, perm, cursor0, cursor, item_base,
+                                                       scale, G);
     } else {
       int64_t blocks = ((int64_t)g.P + 7) / 8;
       int64_t cap = (int64_t)num_sms() * 16;

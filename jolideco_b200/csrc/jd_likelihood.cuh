@@ -28,16 +28,18 @@
 namespace jd {
 namespace lik {
 
-constexpr int RT = 8, CT = 8;        // outputs per thread
+constexpr int CT = 8;                // output columns per thread; rows per thread: template parameter RT (8, or 4 for
+                                     // launches that would leave the SMs with a couple of warps each)
 constexpr int TYN = 8, TXN = 8;      // threads per CTA
 constexpr int NTHR = TYN * TXN;      // 64
-constexpr int TH = RT * TYN, TW = CT * TXN;  // 64 x 64 output tile
+constexpr int TW = CT * TXN;         // 64 output columns per CTA, RT * TYN = 64 or 32 rows
 enum { FWD = 0, BWD = 1 };
 
 __host__ __device__ __forceinline__ int pcol(int c) { return c + ((c >> 5) << 2); }
 
-template <int KG>
+template <int KG, int RT = 8>
 struct Tile {
+  static constexpr int TH = RT * TYN;
   static constexpr int KWP = 4 * KG;                                // tap row length in shared memory
   static constexpr int IW = TW + KWP;                               // staged input row, logical floats
   static constexpr int IWP = IW + (((IW - 1) >> 5) << 2);           // physical (skewed) row length, multiple of 4
@@ -46,10 +48,10 @@ struct Tile {
 };
 
 // acc[r][c] += sum_{a,b} tap[a][b] * tile[ty*8 + r + a][tx*8 + c + b]
-template <int KG, int KT>
+template <int KG, int KT, int RT>
 __device__ __forceinline__ void conv_core(const float* __restrict__ s_in, const float* __restrict__ s_k, int kh,
                                           int ty, int tx, float (&acc)[RT][CT]) {
-  using T = Tile<KG>;
+  using T = Tile<KG, RT>;
   constexpr int NWF = CT + 4 * (KG - 1) + KT - 1;  // window floats a thread needs per input row
   constexpr int NW = (NWF + 3) / 4;
   int off[NW];
@@ -96,11 +98,12 @@ __device__ __forceinline__ float poisson_px(float pool, float bkg, float c, floa
   return pool >= 0.f ? d : 0.f;
 }
 
-template <int MODE, int F, int KG, int KT>
+template <int MODE, int F, int KG, int KT, int RT = 8>
 __global__ void __launch_bounds__(NTHR)
 lik_kernel(const jd_lik_dataset* __restrict__ table, int fH, int fW, int kh, int kw, int H, int W, float eps,
            float grad_scale) {
-  using T = Tile<KG>;
+  using T = Tile<KG, RT>;
+  constexpr int TH = T::TH;
   extern __shared__ __align__(16) float smem[];
   float* s_in = smem;
   float* s_k = smem + (TH + kh - 1) * T::IWP;
@@ -222,7 +225,7 @@ lik_kernel(const jd_lik_dataset* __restrict__ table, int fH, int fW, int kh, int
   for (int r = 0; r < RT; ++r)
 #pragma unroll
     for (int c = 0; c < CT; ++c) acc[r][c] = 0.f;
-  conv_core<KG, KT>(s_in, s_k, kh, ty, tx, acc);
+  conv_core<KG, KT, RT>(s_in, s_k, kh, ty, tx, acc);
 
   const int y0 = tile_y + ty * RT, x0 = tile_x + tx * CT;
   if (MODE == BWD) {
@@ -322,13 +325,14 @@ lik_kernel(const jd_lik_dataset* __restrict__ table, int fH, int fW, int kh, int
 }
 
 // host side: launch one instantiation
-template <int MODE, int F, int KG, int KT>
+template <int MODE, int F, int KG, int KT, int RT = 8>
 int launch(const jd_lik_dataset* table, int n_datasets, int fH, int fW, int kh, int kw, int H, int W, float eps,
            float grad_scale, cudaStream_t st) {
-  using T = Tile<KG>;
+  using T = Tile<KG, RT>;
+  constexpr int TH = T::TH;
   const size_t sm = T::smem_bytes(kh);
   JD_CHECK_ARG(sm <= 200 * 1024, "jd_likelihood: PSF too tall for the direct kernel (kh=%d)", kh);
-  auto kern = lik_kernel<MODE, F, KG, KT>;
+  auto kern = lik_kernel<MODE, F, KG, KT, RT>;
   static bool attr_set[64] = {};  // per device: opt in to > 48 KB of dynamic shared memory
   int dev = 0;
   cudaGetDevice(&dev);

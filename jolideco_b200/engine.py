@@ -208,11 +208,10 @@ class MapEngine:
             if self.marginalize and self.backend in (1, 2, 3, 4, 5):
                 ops._bt_lam(self.packed)
             self.G = torch.empty((max(P, 1), ops.PD), **f32)
-            # bucketed max-mode backward (patches grouped by winning component, Lam_k staged once per 32 patches):
-            # measured slower than the warp-per-patch kernels at 16 129 patches / K = 256 (profiles/r01_summary.md);
-            # JD_BWD_BUCKETED=1 enables it for comparison at larger patch counts
+            # bucketed max-mode backward (patches grouped by winning component, Lam_k staged once per 64 patches): the
+            # faster path at large patch counts (ops.use_bwd_bucketed; JD_BWD_BUCKETED = 0 | 1 forces it)
             self.bwd_ws = None
-            if os.environ.get("JD_BWD_BUCKETED", "0") == "1" and not self.marginalize and P > 0:
+            if P > 0 and ops.use_bwd_bucketed(P, self.marginalize):
                 self.bwd_ws = ops.gmm_backward_workspace(P, self.packed.K, self.dev)
             self.dflux_p = torch.zeros_like(theta)
             if shift_table is None:

@@ -412,8 +412,21 @@ def gmm_prior_forward(flux, shift_yx, packed, stride=4, marginalize=False, rows=
 
 
 def gmm_backward_workspace(P, K, device):
+    """Zero-initialised workspace of the bucketed max-mode backward (the kernels leave it ready for the next launch)."""
     n = _lib.load().jd_gmm_backward_workspace_elems(int(P), int(K))
-    return torch.empty(n, dtype=torch.int32, device=device)
+    return torch.zeros(n, dtype=torch.int32, device=device)
+
+
+# max-mode backward bucketed by winning component (Lam_k staged once per 64 patches): from this many patches on
+# (profiles/r02_summary.md); JD_BWD_BUCKETED = 0 | 1 forces it off / on
+BWD_BUCKETED = {"0": False, "1": True}.get(os.environ.get("JD_BWD_BUCKETED", "auto"), None)
+BWD_BUCKETED_MIN_PATCHES = 32768
+
+
+def use_bwd_bucketed(P, marginalize=False):
+    if marginalize:
+        return False
+    return (P >= BWD_BUCKETED_MIN_PATCHES) if BWD_BUCKETED is None else BWD_BUCKETED
 
 
 # max-mode backward from the triangular factor Lw (12 KB of L2 reads per patch) instead of Lam = Lw Lw^T (16 KB);

@@ -89,7 +89,8 @@ def test_prior_forward_backward_at_benchmark_size(size, variant, monkeypatch):
     assert flipped.size <= ambiguous.size <= max(8, P // 500)
     # gradient: the kernels the engine would pick at this size, then the deterministic fold
     c = 16.0 / 64.0 / flux.size
-    G = ops.gmm_prior_backward(fl, SHIFT, packed, c, 4, False, None, t(argmax, torch.int32), None, t(value))
+    G = ops.gmm_prior_backward(fl, SHIFT, packed, c, 4, False, None, t(argmax, torch.int32), None, t(value),
+                               bucketed=ops.use_bwd_bucketed(P))
     dflux = ops.patch_fold(G, size, size, SHIFT, 4).cpu().numpy().astype(np.float64)
     ok = ~footprint_mask(flux.shape, ambiguous, nx, SHIFT)
     scale = np.abs(ref["dflux"]).max()
