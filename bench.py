@@ -141,6 +141,8 @@ def config_of(workload, args, extra=None):
            "iteration_semantics": ("joint: all D datasets + one prior + one Adam step (TotalLoss.__call__)"
                                    if workload["name"] in JOINT_WORKLOADS else
                                    "reference step: one dataset + full prior + Adam (core.py:214-229)")}
+    if workload.get("variant"):
+        out["variant"] = workload["variant"]
     if extra:
         out.update(extra)
     return out
@@ -234,7 +236,7 @@ def main():
     joint = args.workload in JOINT_WORKLOADS
     workload = synthetic.make_workload(args.workload, seed=0 if joint else rank, n_datasets=args.datasets)
     if args.datasets is not None:
-        workload["name"] = f"{workload['name']}-with-{args.datasets}-datasets"
+        workload["variant"] = f"{args.datasets} datasets instead of the workload's own number (experiment)"
 
     # ------------------------------------------------------------------ reference arm (host CPU)
     if args.impl == "reference":

@@ -345,9 +345,16 @@ joint_grad_kernel(float* __restrict__ theta, float* __restrict__ m, float* __res
     for (int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += (int64_t)gridDim.x * blockDim.x) {
       const int64_t i = i4 * 4;
       float g[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int q = 0; q < n_parts; ++q) {
-        const float4 p4 = *reinterpret_cast<const float4*>(parts + q * part_stride + i);
-        g[0] += p4.x, g[1] += p4.y, g[2] += p4.z, g[3] += p4.w;
+      // (groups of up to eight independent loads in flight, summed in the fixed order q = 0, 1, ...)
+      for (int q0 = 0; q0 < n_parts; q0 += 8) {
+        float4 p4[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          p4[u] = q0 + u < n_parts ? __ldcs(reinterpret_cast<const float4*>(parts + (q0 + u) * part_stride + i))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (q0 + u < n_parts) g[0] += p4[u].x, g[1] += p4[u].y, g[2] += p4[u].z, g[3] += p4[u].w;
       }
       if (fold) {
         const int y = (int)(i / fW), x = (int)(i - (int64_t)y * fW);

@@ -13,7 +13,7 @@ int dispatch_f1_bwd_lo(int, const jd_lik_dataset*, int, int, int, int, int, int,
 int dispatch_f1_bwd_hi(int, const jd_lik_dataset*, int, int, int, int, int, int, int, float, float, cudaStream_t);
 int dispatch_f2(int, const jd_lik_dataset*, int, int, int, int, int, int, int, float, float, cudaStream_t);
 int dispatch_f1_wide(int, const jd_lik_dataset*, int, int, int, int, int, int, int, float, float, cudaStream_t);
-int dispatch_f1_rt4(int, const jd_lik_dataset*, int, int, int, int, int, int, int, float, float, cudaStream_t);
+int dispatch_f1_rt8(int, const jd_lik_dataset*, int, int, int, int, int, int, int, float, float, cudaStream_t);
 constexpr int MAX_TAPS = 40;  // per shared-memory tap row, lead zeros included
 
 // taps per shared-memory row (zero lead taps for 16-byte alignment + the PSF row), or 0 if unsupported
@@ -35,16 +35,15 @@ static int run(int mode, const jd_lik_dataset* table, int n_datasets, int fH, in
                kw, MAX_TAPS);
   const int kg = (nt + 3) / 4, kt = nt - 4 * (kg - 1);
   if (f == 2) return dispatch_f2(16 * mode + kg - 1, table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
-  // 4 x 8 outputs per thread (32-row tiles) when the 8 x 8 launch would have fewer than ~3 CTAs per SM; JD_LIK_RT = 4 | 8
-  // forces either
+  // f = 1 kernels give every thread 4 x 8 outputs (32 x 64 tiles); JD_LIK_RT=8 selects the 8 x 8 variant where one is
+  // instantiated (tap rows of 17..20 taps), for A/B runs
   static int rt_env = -1;
   if (rt_env < 0) {
     const char* e = getenv("JD_LIK_RT");
     rt_env = e ? atoi(e) : 0;
   }
-  const long long ctas8 = (long long)((fW + TW - 1) / TW) * ((fH + 63) / 64) * n_datasets;
-  const bool rt4 = rt_env == 4 || (rt_env != 8 && ctas8 < 3LL * num_sms());
-  if (rt4 && kg == 5) return dispatch_f1_rt4(4 * mode + kt - 1, table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
+  if (rt_env == 8 && kg == 5)
+    return dispatch_f1_rt8(4 * mode + kt - 1, table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
   if (kg > 8) return dispatch_f1_wide(16 * mode + kg - 1, table, n_datasets, fH, fW, kh, kw, H, W, eps, grad_scale, st);
   const int key = (kg - 1) * 4 + kt - 1;
   if (mode == FWD)

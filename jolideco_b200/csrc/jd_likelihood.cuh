@@ -14,7 +14,8 @@
 // (forward: Kc = flip(psf), (oy,ox) = (s-(k-1)); adjoint: Kc = psf, (oy,ox) = -s; s = (k-1)/2), which keeps the
 // asymmetric crop of even PSFs.
 //
-// Thread = 8 x 8 outputs (64 FP32 accumulators), CTA = 8 x 8 threads = 64 x 64 outputs.  The input tile
+// Thread = RT x 8 outputs (RT = 4 for f = 1: 32 accumulators, 32 x 64 tiles; RT = 8 for f = 2 and rows of more than 32
+// taps), CTA = 8 x 8 threads.  The input tile
 // (64+kh-1) x (64+4 KG) and the taps live in shared memory; per staged input row t a thread loads its sliding
 // window once (<= 10 LDS.128) and feeds the up to 8 output rows r with tap row a = t - r: 32 FFMA per broadcast
 // LDS.128 of four taps -> the FMA pipe, not the LSU, is the limiter (the 4 x 4 tile of jd_conv.cu's conv3 kernel
