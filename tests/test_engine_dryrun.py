@@ -223,6 +223,47 @@ def test_engine_support_matrix():
     assert len(list(with_norm.parameters())) == 3
 
 
+@pytest.mark.parametrize("backend,entry", [(4, "jd_gmm_prior_forward_tcm2"), (5, "jd_gmm_prior_forward_tc16x2"),
+                                           (3, "jd_gmm_prior_forward_tcm")])
+def test_two_tile_prior_kernels_and_bucketed_backward_are_wired(recorder, monkeypatch, backend, entry):
+    """Backends 4 / 5 (jd_gmm_tcm2.cu) take the operand image of their recipe and a workspace of their own size; from
+    ops.BWD_BUCKETED_MIN_PATCHES patches on the max-mode backward goes through the bucketed kernel (workspace given)."""
+    sizes = []
+    lib = types.SimpleNamespace(
+        jd_gmm_tcm_workspace_bytes=lambda P, K: sizes.append(("tcm", P, K)) or 512,
+        jd_gmm_tcm2_workspace_bytes=lambda P, K: sizes.append(("tcm2", P, K)) or 1024,
+        jd_gmm_backward_workspace_elems=lambda P, K: sizes.append(("bwd", P, K)) or 4 * K + 1 + P,
+        jd_likelihood_supported=lambda kh, kw, f: 1)
+    monkeypatch.setattr(E._lib, "load", lambda: lib)
+    monkeypatch.setattr(ops._lib, "load", lambda: lib)
+    packed = fake_packed()
+    images = {"tcm": (torch.zeros(8, dtype=torch.uint8), torch.zeros(4)), "tc16": (torch.zeros(4, dtype=torch.uint8), torch.zeros(4))}
+    monkeypatch.setattr(ops, "_btm", lambda p: images["tcm"])
+    monkeypatch.setattr(ops, "_bt16", lambda p: images["tc16"])
+    prior = dict(packed=packed, stride=4, marginalize=False, backend=backend)
+    monkeypatch.setattr(ops, "BWD_BUCKETED_MIN_PATCHES", 10)
+    eng = E.MapEngine(torch.zeros(32, 32), [dataset()], prior=prior, use_graph=False)
+    assert eng.P == 49 and eng.bwd_ws is not None and eng.bwd_ws.numel() == 4 * 4 + 1 + 49 and not eng.bwd_ws.any()
+    assert sizes[0] == (("tcm2" if backend in (4, 5) else "tcm"), 49, 4)
+    assert eng.sk_ws.numel() == (1024 if backend in (4, 5) else 512) and not eng.sk_ws.any()
+    eng.step(0)
+    assert names(recorder) == ["jd_step_begin_flux", "jd_likelihood_forward", "jd_likelihood_backward", entry,
+                               "jd_gmm_prior_backward", "jd_adam_joint_step_dev"]
+    fwd, bwd = recorder[3][1], recorder[4][1]
+    want = images["tc16"] if backend == 5 else images["tcm"]
+    assert fwd[7] == want[0].data_ptr() and fwd[8] == want[1].data_ptr()   # operand image, inverse component scales
+    assert fwd[15] == eng.sk_ws.data_ptr() and bwd[-2] == eng.bwd_ws.data_ptr()
+    # fewer patches than the threshold: the triangular warp-per-patch kernel, no workspace
+    monkeypatch.setattr(ops, "BWD_BUCKETED_MIN_PATCHES", 1000)
+    eng = E.MapEngine(torch.zeros(32, 32), [dataset()], prior=prior, use_graph=False)
+    assert eng.bwd_ws is None
+    del recorder[:]
+    eng.step(0)
+    assert names(recorder)[4] == "jd_gmm_prior_backward_max_tri"
+    # logsumexp mode never buckets
+    assert not ops.use_bwd_bucketed(10 ** 6, marginalize=True)
+
+
 def test_overlap_forks_the_likelihood_chain_and_joins_before_the_update(recorder, monkeypatch):
     """JD_OVERLAP / overlap=True: likelihood kernels are enqueued on the side stream between a fork and a join, the
     prior chain on the main stream, and everything that reads both (Adam, fold into dflux_l) after the join."""
