@@ -158,6 +158,39 @@ __device__ __forceinline__ float fold_gather(const float* __restrict__ G, int y,
   return acc;
 }
 
+// The same sum for four consecutive pixels of one image row at stride 4 (8 x 8 patches every 4 pixels: a pixel lies in
+// at most 2 x 2 patches).  Same summation order per pixel as fold_gather (patch rows high -> low, patch columns high ->
+// low), so the results are bit-identical; the row part (rolled row, covering patch rows) is computed once and the
+// divisions by the stride are shifts.
+__device__ __forceinline__ void fold_gather4_s4(const float* __restrict__ G, int y, int x, int fH, int fW, int sy, int sx,
+                                                int ny, int nx, int row_begin, int row_end, float (&out)[4]) {
+  const int ry = wrap(y + sy, fH);
+  const int iy_hi = min(ry >> 2, min(ny, row_end) - 1);
+  // up to two covering patch rows: (iy_hi, u0) and (iy_hi - 1, u0 + 4)
+  const int u0 = ry - 4 * iy_hi;
+  const bool r0 = iy_hi >= row_begin && u0 < PATCH, r1 = r0 && iy_hi - 1 >= row_begin && u0 + 4 < PATCH;
+  const float* g0 = G + ((int64_t)(iy_hi - row_begin) * nx) * PD + u0 * PATCH;  // row iy_hi, patch column 0
+  const float* g1 = g0 - (int64_t)nx * PD + 4 * PATCH;                          // row iy_hi - 1
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int rx = wrap(x + c + sx, fW);
+    const int ix_hi = min(rx >> 2, nx - 1);
+    const int v0 = rx - 4 * ix_hi;
+    const bool c0 = v0 < PATCH, c1 = c0 && ix_hi >= 1 && v0 + 4 < PATCH;
+    const int o0 = ix_hi * PD + v0, o1 = o0 - PD + 4;
+    float acc = 0.f;
+    if (r0) {
+      if (c0) acc += g0[o0];
+      if (c1) acc += g0[o1];
+    }
+    if (r1) {
+      if (c0) acc += g1[o0];
+      if (c1) acc += g1[o1];
+    }
+    out[c] = acc;
+  }
+}
+
 __global__ void fold_kernel(const float* __restrict__ G, int fH, int fW, const int32_t* __restrict__ shift_yx,
                             int stride, int row_begin, int row_end, float* __restrict__ dflux, int accumulate) {
   const int sy = shift_yx ? shift_yx[0] : 0, sx = shift_yx ? shift_yx[1] : 0;
@@ -358,9 +391,16 @@ joint_grad_kernel(float* __restrict__ theta, float* __restrict__ m, float* __res
       }
       if (fold) {
         const int y = (int)(i / fW), x = (int)(i - (int64_t)y * fW);
+        if (stride == 4) {
+          float fg[4];
+          fold_gather4_s4(G, y, x, fH, fW, sy, sx, ny, nx, row_begin, row_end, fg);
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          g[c] += scale_b * fold_gather(G, y, x + c, fH, fW, sy, sx, stride, ny, nx, row_begin, row_end);
+          for (int c = 0; c < 4; ++c) g[c] += scale_b * fg[c];
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            g[c] += scale_b * fold_gather(G, y, x + c, fH, fW, sy, sx, stride, ny, nx, row_begin, row_end);
+        }
       }
       if (!UPDATE) {
         *reinterpret_cast<float4*>(out + i) = make_float4(g[0], g[1], g[2], g[3]);

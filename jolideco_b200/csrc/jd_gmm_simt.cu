@@ -400,29 +400,39 @@ bwd_hist_kernel(const int32_t* __restrict__ argmax, int P, int K, int32_t* __res
     if (s_cnt[k]) atomicAdd(counts + k, s_cnt[k]);
 }
 
-// one warp: exclusive scans of the K counts (patch offsets) and of the per-component item counts
+// one warp: exclusive scans of the K counts (patch offsets) and of the per-component item counts.  The counts of eight
+// 32-component chunks are loaded together (one L2 round trip per 256 components instead of one per 32).
 __global__ void bwd_scan_kernel(int K, int32_t* __restrict__ counts, int32_t* __restrict__ cursor0,
                                 int32_t* __restrict__ cursor, int32_t* __restrict__ item_base) {
   const int lane = threadIdx.x;
   int off = 0, ioff = 0;
-  for (int k0 = 0; k0 < K; k0 += 32) {
-    const int k = k0 + lane;
-    const int c = k < K ? counts[k] : 0;
-    const int ni = (c + BCH - 1) / BCH;
-    int sc = c, si = ni;
+  for (int kb = 0; kb < K; kb += 256) {
+    int cnt[8];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int a = __shfl_up_sync(0xffffffffu, sc, o), b2 = __shfl_up_sync(0xffffffffu, si, o);
-      if (lane >= o) sc += a, si += b2;
+    for (int j = 0; j < 8; ++j) {
+      const int k = kb + 32 * j + lane;
+      cnt[j] = k < K ? counts[k] : 0;
     }
-    if (k < K) {
-      cursor0[k] = off + sc - c;
-      cursor[k] = off + sc - c;
-      item_base[k] = ioff + si - ni;
-      counts[k] = 0;  // ready for the next launch
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kb + 32 * j + lane;
+      const int c = cnt[j];
+      const int ni = (c + BCH - 1) / BCH;
+      int sc = c, si = ni;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, sc, o), b2 = __shfl_up_sync(0xffffffffu, si, o);
+        if (lane >= o) sc += a, si += b2;
+      }
+      if (k < K) {
+        cursor0[k] = off + sc - c;
+        cursor[k] = off + sc - c;
+        item_base[k] = ioff + si - ni;
+        counts[k] = 0;  // ready for the next launch
+      }
+      off += __shfl_sync(0xffffffffu, sc, 31);
+      ioff += __shfl_sync(0xffffffffu, si, 31);
     }
-    off += __shfl_sync(0xffffffffu, sc, 31);
-    ioff += __shfl_sync(0xffffffffu, si, 31);
   }
   if (lane == 0) item_base[K] = ioff;
 }
