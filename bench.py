@@ -714,11 +714,14 @@ def measure_rooflines(E, eng, run_step, args, workload, flush):
             ach = work / (avg_ms * 1e-3) / 1e12
             o.update(bound="fp32", achieved=ach, peak=fp32_peak, unit="TFLOP/s", frac=ach / fp32_peak,
                      algorithmic_work=work, peak_source="FP32 FMA peak measured live (jd_probe_fp32_fma)")
-        elif name in ("jd_conv_forward_fft", "jd_conv_backward_fft"):
+        elif name in ("jd_conv_forward_fft", "jd_conv_backward_fft", "jd_likelihood_forward_fft",
+                      "jd_likelihood_backward_fft"):
             d0 = eng.datasets[0] if eng.datasets else None
             S2 = float(d0.fft.Sy * d0.fft.Sx) if (d0 is not None and d0.fft is not None and hasattr(d0.fft, "Sy")) else \
                 float((fH + k - 1) ** 2)
             work = 8.0 * n + 20.0 * S2
+            if name.startswith("jd_likelihood"):  # every local dataset per launch (+ the fused Poisson pass's 12 B/px)
+                work = (work + (12.0 * npool if name.endswith("forward_fft") else 0.0)) * len(eng.datasets)
             ach = work / (avg_ms * 1e-3) / 1e9
             o.update(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, algorithmic_work=work,
                      peak_source=hbm_src)

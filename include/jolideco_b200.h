@@ -137,6 +137,21 @@ int jd_likelihood_forward(const jd_lik_dataset* table_dev, int n_datasets, int f
 int jd_likelihood_backward(const jd_lik_dataset* table_dev, int n_datasets, int fH, int fW, int kh, int kw, int f,
                            int H, int W, jd_stream_t stream);
 
+/* The same two entry points for large PSFs, on the shared-memory FFT path (csrc/jd_fft.cu) - every dataset of the step
+ * per launch (grid.y): row FFTs -> column FFT . PSF^ . inverse column FFT -> inverse row FFTs with the sum-pool (f = 1, 2)
+ * and the Poisson statistic + gradient fused into the last pass (the convolution is never written); the adjoint the same
+ * three passes with conj(PSF^).  Record = jd_lik_dataset (its `psf` field is not read) + the dataset's cached PSF spectrum
+ * (jd_fftconv_prepare_psf) and its own spectrum workspace (jd_fftconv_sizes). */
+typedef struct {
+  jd_lik_dataset lik;
+  float* workspace;     /* jd_fftconv_sizes(...).workspace_elems floats, private to the dataset */
+  const float* psf_hat; /* jd_fftconv_prepare_psf */
+} jd_fftlik_dataset;
+int jd_likelihood_forward_fft(const jd_fftlik_dataset* table_dev, int n_datasets, int fH, int fW, int kh, int kw, int f,
+                              int H, int W, float eps, float grad_scale, jd_stream_t stream);
+int jd_likelihood_backward_fft(const jd_fftlik_dataset* table_dev, int n_datasets, int fH, int fW, int kh, int kw, int f,
+                               int H, int W, jd_stream_t stream);
+
 /* Measurement helper (bench.py): launches a pure FP32-FMA kernel (8 independent chains per thread, 8 x 256 threads
  * per SM) and returns the number of floating-point operations it executes, or < 0 on a launch error.  Timed by the
  * caller with CUDA events, it gives the FP32 pipe peak the direct convolution is compared with. */

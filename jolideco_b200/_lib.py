@@ -69,6 +69,9 @@ PROTOTYPES = {
     "jd_gmm_tc16_pack": [c_f32p, c_int, ctypes.c_void_p, c_f32p, c_stream],
     "jd_gmm_prior_forward_tc16": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, ctypes.c_void_p, c_f32p, c_f32p,
                                   c_f32p, c_int, c_int, c_int, c_int, c_f32p, c_i32p, c_f32p, c_f64p, c_stream],
+    "jd_likelihood_forward_fft": [ctypes.c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                  c_float, c_stream],
+    "jd_likelihood_backward_fft": [ctypes.c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_stream],
     "jd_gmm_tcm_packed_bytes": [c_int],
     "jd_gmm_tcm_pack": [c_f32p, c_int, ctypes.c_void_p, c_f32p, c_stream],
     "jd_gmm_tcm_workspace_bytes": [c_i64, c_int],

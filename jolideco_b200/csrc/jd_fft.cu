@@ -22,6 +22,7 @@
 
 #include "jd_common.cuh"
 #include "jd_fft_stages.cuh"
+#include "jd_likelihood.cuh"  // lik::poisson_px: the fused forward epilogue evaluates the same statistic
 
 namespace jd {
 namespace fft {
@@ -55,9 +56,18 @@ __device__ __forceinline__ int wrap_index(int i, int S) { return i >= S ? i - S 
 enum { IN_FLUX = 0, IN_DPOOL = 1, IN_PSF = 2 };
 
 // ---- pass 1: row FFTs.  CTA handles row pair (2 rows) per iteration, `pairs` pairs per CTA.
+// Batched launches (jd_likelihood_*_fft): `table` != NULL, blockIdx.y = dataset, the per-dataset pointers come from its
+// record.
 template <int MODE>
 __global__ void rows_fwd_kernel(const float* __restrict__ in, const float* __restrict__ scale, Plan pl, int nrows,
-                                int ncols, int f, int H, int W, float2* __restrict__ specT, int pairs) {
+                                int ncols, int f, int H, int W, float2* __restrict__ specT, int pairs,
+                                const jd_fftlik_dataset* __restrict__ table) {
+  if (table) {
+    const jd_fftlik_dataset& ds = table[blockIdx.y];
+    in = MODE == IN_FLUX ? ds.lik.flux : ds.lik.dpool;
+    scale = MODE == IN_FLUX ? ds.lik.exposure : nullptr;
+    specT = reinterpret_cast<float2*>(ds.workspace);
+  }
   extern __shared__ __align__(16) float2 sm[];
   float2* bx = sm;
   float2* by = sm + pl.Sx;
@@ -104,7 +114,13 @@ __global__ void rows_fwd_kernel(const float* __restrict__ in, const float* __res
 // PSF_MODE: 0 = multiply by psf_hat, 1 = multiply by conj(psf_hat), 2 = no product (PSF spectrum setup: forward only)
 template <int PSF_MODE>
 __global__ void cols_kernel(float2* __restrict__ specT, const float2* __restrict__ psf_hat, Plan pl, int nrows_in,
-                            int nrows_out, int off, float norm, float2* __restrict__ psf_out) {
+                            int nrows_out, int off, float norm, float2* __restrict__ psf_out,
+                            const jd_fftlik_dataset* __restrict__ table) {
+  if (table) {
+    const jd_fftlik_dataset& ds = table[blockIdx.y];
+    specT = reinterpret_cast<float2*>(ds.workspace);
+    psf_hat = reinterpret_cast<const float2*>(ds.psf_hat);
+  }
   extern __shared__ __align__(16) float2 sm[];
   float2* bx = sm;
   float2* by = sm + pl.Sy;
@@ -134,10 +150,24 @@ __global__ void cols_kernel(float2* __restrict__ specT, const float2* __restrict
 }
 
 // ---- pass 3: inverse row FFTs of row pairs, column crop, output transform.
-// OUT_MODE 0: out = value;  1: out (+)= value * scale
+// OUT_MODE 0: out = value;  1: out (+)= value * scale;  2 (batched forward only): sum-pool f x f (f = 1, 2: the two
+// rows of a pair are one pooling pair), Poisson statistic + gradient of the pooled pixel (lik::poisson_px, as the
+// direct kernels' epilogue) - the convolution itself is never written
 template <int OUT_MODE>
 __global__ void rows_inv_kernel(const float2* __restrict__ specT, Plan pl, int nrows, int ncols, int off,
-                                const float* __restrict__ scale, float* __restrict__ out, int accumulate, int pairs) {
+                                const float* __restrict__ scale, float* __restrict__ out, int accumulate, int pairs,
+                                const jd_fftlik_dataset* __restrict__ table, int f, int H, int W, float eps,
+                                float grad_scale) {
+  const jd_fftlik_dataset* ds = table ? table + blockIdx.y : nullptr;
+  if (ds) {
+    specT = reinterpret_cast<const float2*>(ds->workspace);
+    if (OUT_MODE == 1) {
+      out = ds->lik.dflux;
+      scale = ds->lik.exposure;
+      accumulate = ds->lik.accumulate;
+    }
+  }
+  float lacc = 0.f, bacc = 0.f;
   extern __shared__ __align__(16) float2 sm[];
   float2* bx = sm;
   float2* by = sm + pl.Sx;
@@ -160,7 +190,26 @@ __global__ void rows_inv_kernel(const float2* __restrict__ specT, Plan pl, int n
     for (int j = threadIdx.x; j < ncols; j += blockDim.x) {
       const float2 v = z[wrap_index(j + off, pl.Sx)];
       int64_t oa = (int64_t)ra * ncols + j, ob = (int64_t)rb * ncols + j;
-      if (OUT_MODE == 0) {
+      if (OUT_MODE == 2) {
+        const float bnorm = ds->lik.bkg_log_norm ? expf(__ldg(ds->lik.bkg_log_norm)) : 1.f;
+        if (f == 1) {
+          const float da = lik::poisson_px(v.x, __ldg(ds->lik.background + oa) * bnorm, __ldg(ds->lik.counts + oa), eps,
+                                           grad_scale, lacc, bacc);
+          if (ds->lik.dpool) ds->lik.dpool[oa] = da;
+          if (rb < nrows) {
+            const float db = lik::poisson_px(v.y, __ldg(ds->lik.background + ob) * bnorm, __ldg(ds->lik.counts + ob), eps,
+                                             grad_scale, lacc, bacc);
+            if (ds->lik.dpool) ds->lik.dpool[ob] = db;
+          }
+        } else if ((j & 1) == 0 && (j >> 1) < W && (ra >> 1) < H) {  // f = 2: rows (ra, rb) x columns (j, j + 1)
+          const float2 v1 = z[wrap_index(j + 1 + off, pl.Sx)];
+          const float pool = ((v.x + v1.x) + v.y) + v1.y;
+          const int64_t o = (int64_t)(ra >> 1) * W + (j >> 1);
+          const float d = lik::poisson_px(pool, __ldg(ds->lik.background + o) * bnorm, __ldg(ds->lik.counts + o), eps,
+                                          grad_scale, lacc, bacc);
+          if (ds->lik.dpool) ds->lik.dpool[o] = d;
+        }
+      } else if (OUT_MODE == 0) {
         out[oa] = v.x;
         if (rb < nrows) out[ob] = v.y;
       } else {
@@ -173,6 +222,21 @@ __global__ void rows_inv_kernel(const float2* __restrict__ specT, Plan pl, int n
       }
     }
     // bx/by are rewritten at the top of the next iteration after a barrier
+  }
+  if (OUT_MODE == 2) {  // loss (+ d loss / d log background norm) of this CTA's rows
+    __shared__ float s_red[2][32];
+    lacc = warp_sum(lacc);
+    bacc = warp_sum(bacc);
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) s_red[0][w] = lacc, s_red[1][w] = bacc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double l = 0.0, b = 0.0;
+      for (int i = 0; i < (int)((blockDim.x + 31) >> 5); ++i) l += (double)s_red[0][i], b += (double)s_red[1][i];
+      if (blockIdx.x == 0) l += ds->lik.loss_const;
+      if (ds->lik.loss_sum) atomicAdd(ds->lik.loss_sum, l);
+      if (ds->lik.dlogb) atomicAdd(ds->lik.dlogb, b);
+    }
   }
 }
 
@@ -239,17 +303,20 @@ int jd_fftconv_prepare_psf(const float* psf, int kh, int kw, int fH, int fW, flo
   opt_in_smem(rows_fwd_kernel<IN_PSF>, smx);
   opt_in_smem(cols_kernel<2>, smy);
   rows_fwd_kernel<IN_PSF><<<(kh + 2 * pairs - 1) / (2 * pairs), threads_for(pl.Sx), smx, st>>>(
-      psf, nullptr, pl, kh, kw, 1, kh, kw, reinterpret_cast<float2*>(workspace), pairs);
+      psf, nullptr, pl, kh, kw, 1, kh, kw, reinterpret_cast<float2*>(workspace), pairs, nullptr);
   JD_CHECK_LAUNCH("jd_fftconv_prepare_psf(rows)");
   cols_kernel<2><<<pl.Sx / 2 + 1, threads_for(pl.Sy), smy, st>>>(reinterpret_cast<float2*>(workspace), nullptr, pl, kh, 0,
-                                                                 0, 1.f, reinterpret_cast<float2*>(psf_hat));
+                                                                 0, 1.f, reinterpret_cast<float2*>(psf_hat), nullptr);
   JD_CHECK_LAUNCH("jd_fftconv_prepare_psf(cols)");
   return JD_OK;
 }
 
+// mode 0: forward model, 1: adjoint.  table == NULL: one dataset through the pointer arguments; else `n` datasets per
+// launch (grid.y), forward with the fused Poisson epilogue (lik_f / H / W / eps / grad_scale).
 static int run_fftconv(const char* name, int mode, const float* in, const float* exposure, const float* psf_hat,
                        float* workspace, float* out, int accumulate, int fH, int fW, int kh, int kw, int f, int H, int W,
-                       cudaStream_t st) {
+                       cudaStream_t st, const jd_fftlik_dataset* table = nullptr, int n = 1, float eps = 0.f,
+                       float grad_scale = 0.f) {
   Plan pl;
   int rc = make_plan(name, fH, fW, kh, kw, &pl);
   if (rc) return rc;
@@ -258,29 +325,38 @@ static int run_fftconv(const char* name, int mode, const float* in, const float*
   size_t smx = smem_for(pl.Sx), smy = smem_for(pl.Sy);
   JD_CHECK_ARG(smx <= 200 * 1024 && smy <= 200 * 1024, "%s: FFT size too large for shared memory", name);
   const int pairs = 1;  // one row pair per CTA: >= 2 CTAs per SM already at 512 rows, phases of different CTAs overlap
-  const int grid_rows = (fH + 2 * pairs - 1) / (2 * pairs);
+  const dim3 grid_rows((fH + 2 * pairs - 1) / (2 * pairs), n), grid_cols(pl.Sx / 2 + 1, n);
   float2* spec = reinterpret_cast<float2*>(workspace);
   const float2* ph = reinterpret_cast<const float2*>(psf_hat);
   if (mode == 0) {
     opt_in_smem(rows_fwd_kernel<IN_FLUX>, smx);
     opt_in_smem(cols_kernel<0>, smy);
-    opt_in_smem(rows_inv_kernel<0>, smx);
-    rows_fwd_kernel<IN_FLUX><<<grid_rows, threads_for(pl.Sx), smx, st>>>(in, exposure, pl, fH, fW, 1, fH, fW, spec, pairs);
+    rows_fwd_kernel<IN_FLUX><<<grid_rows, threads_for(pl.Sx), smx, st>>>(in, exposure, pl, fH, fW, 1, fH, fW, spec, pairs,
+                                                                          table);
     JD_CHECK_LAUNCH(name);
-    cols_kernel<0><<<pl.Sx / 2 + 1, threads_for(pl.Sy), smy, st>>>(spec, ph, pl, fH, fH, sy, norm, nullptr);
+    cols_kernel<0><<<grid_cols, threads_for(pl.Sy), smy, st>>>(spec, ph, pl, fH, fH, sy, norm, nullptr, table);
     JD_CHECK_LAUNCH(name);
-    rows_inv_kernel<0><<<grid_rows, threads_for(pl.Sx), smx, st>>>(spec, pl, fH, fW, sx, nullptr, out, 0, pairs);
+    if (table) {
+      opt_in_smem(rows_inv_kernel<2>, smx);
+      rows_inv_kernel<2><<<grid_rows, threads_for(pl.Sx), smx, st>>>(spec, pl, fH, fW, sx, nullptr, nullptr, 0, pairs,
+                                                                      table, f, H, W, eps, grad_scale);
+    } else {
+      opt_in_smem(rows_inv_kernel<0>, smx);
+      rows_inv_kernel<0><<<grid_rows, threads_for(pl.Sx), smx, st>>>(spec, pl, fH, fW, sx, nullptr, out, 0, pairs, nullptr,
+                                                                      1, fH, fW, 0.f, 0.f);
+    }
     JD_CHECK_LAUNCH(name);
   } else {
     opt_in_smem(rows_fwd_kernel<IN_DPOOL>, smx);
     opt_in_smem(cols_kernel<1>, smy);
     opt_in_smem(rows_inv_kernel<1>, smx);
-    rows_fwd_kernel<IN_DPOOL><<<grid_rows, threads_for(pl.Sx), smx, st>>>(in, nullptr, pl, fH, fW, f, H, W, spec, pairs);
+    rows_fwd_kernel<IN_DPOOL><<<grid_rows, threads_for(pl.Sx), smx, st>>>(in, nullptr, pl, fH, fW, f, H, W, spec, pairs,
+                                                                           table);
     JD_CHECK_LAUNCH(name);
-    cols_kernel<1><<<pl.Sx / 2 + 1, threads_for(pl.Sy), smy, st>>>(spec, ph, pl, fH, fH, pl.Sy - sy, norm, nullptr);
+    cols_kernel<1><<<grid_cols, threads_for(pl.Sy), smy, st>>>(spec, ph, pl, fH, fH, pl.Sy - sy, norm, nullptr, table);
     JD_CHECK_LAUNCH(name);
-    rows_inv_kernel<1><<<grid_rows, threads_for(pl.Sx), smx, st>>>(spec, pl, fH, fW, pl.Sx - sx, exposure, out,
-                                                                    accumulate, pairs);
+    rows_inv_kernel<1><<<grid_rows, threads_for(pl.Sx), smx, st>>>(spec, pl, fH, fW, pl.Sx - sx, exposure, out, accumulate,
+                                                                    pairs, table, f, H, W, 0.f, 0.f);
     JD_CHECK_LAUNCH(name);
   }
   return JD_OK;
@@ -300,6 +376,24 @@ int jd_conv_backward_fft(const float* dpool, const float* exposure, const float*
   JD_CHECK_ARG(f >= 1 && H * f <= fH && W * f <= fW, "jd_conv_backward_fft: bad shape");
   return run_fftconv("jd_conv_backward_fft", 1, dpool, exposure, psf_hat, workspace, dflux, accumulate, fH, fW, kh, kw, f,
                      H, W, to_stream(stream));
+}
+
+int jd_likelihood_forward_fft(const jd_fftlik_dataset* table_dev, int n_datasets, int fH, int fW, int kh, int kw, int f,
+                              int H, int W, float eps, float grad_scale, jd_stream_t stream) {
+  JD_CHECK_ARG(table_dev && n_datasets > 0 && n_datasets <= 65535, "jd_likelihood_forward_fft: bad dataset table");
+  JD_CHECK_ARG((f == 1 || f == 2) && H * f == fH && W * f == fW,
+               "jd_likelihood_forward_fft: upsampling factor %d (supported: 1, 2) or counts grid %dx%d != flux grid / f", f,
+               H, W);
+  return run_fftconv("jd_likelihood_forward_fft", 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0, fH, fW, kh, kw, f, H,
+                     W, to_stream(stream), table_dev, n_datasets, eps, grad_scale);
+}
+
+int jd_likelihood_backward_fft(const jd_fftlik_dataset* table_dev, int n_datasets, int fH, int fW, int kh, int kw, int f,
+                               int H, int W, jd_stream_t stream) {
+  JD_CHECK_ARG(table_dev && n_datasets > 0 && n_datasets <= 65535, "jd_likelihood_backward_fft: bad dataset table");
+  JD_CHECK_ARG(f >= 1 && H * f <= fH && W * f <= fW, "jd_likelihood_backward_fft: bad shape");
+  return run_fftconv("jd_likelihood_backward_fft", 1, nullptr, nullptr, nullptr, nullptr, nullptr, 0, fH, fW, kh, kw, f, H,
+                     W, to_stream(stream), table_dev, n_datasets);
 }
 
 }  // extern "C"

@@ -23,6 +23,9 @@ from . import _lib, dist, ops
 _p = ops._ptr
 
 LIK_DTYPE = ops.LIK_DTYPE
+# datasets on the FFT path go out together (grid.y = dataset, Poisson statistic fused into the inverse row pass);
+# JD_FFT_BATCHED=0 keeps the per-dataset convolution / Poisson / adjoint launches
+FFT_BATCHED = os.environ.get("JD_FFT_BATCHED", "1") != "0"
 
 # launch accounting / per-kernel timing hooks (bench.py): every C-ABI call below is exactly one
 # kernel launch on the current stream
@@ -30,7 +33,8 @@ _STATS = {"launches": 0, "timed": None, "events": [], "dry": False}
 
 
 # kernels launched by entry points that launch more than one
-_KERNELS_PER_CALL = {"jd_conv_forward_fft": 3, "jd_conv_backward_fft": 3}
+_KERNELS_PER_CALL = {"jd_conv_forward_fft": 3, "jd_conv_backward_fft": 3, "jd_likelihood_forward_fft": 3,
+                     "jd_likelihood_backward_fft": 3}
 
 
 def _call(name, *args):
@@ -312,13 +316,16 @@ class MapEngine:
         """device address of the calibration-gradient accumulators (dlogb, dshift_x, dshift_y) of local dataset j"""
         return self.acc.data_ptr() + 8 * (2 + 3 * j)
 
-    def _table(self, entries, want_grad):
-        """Device table of jd_lik_dataset records for one batched launch pair (cached: every pointer is static)."""
-        key = (tuple((id(d), j) for d, _, j in entries), bool(want_grad), tuple(lp for _, lp, _ in entries))
+    def _table(self, entries, want_grad, fft=False):
+        """Device table of jd_lik_dataset (fft: jd_fftlik_dataset) records for one batched launch pair (cached: every
+        pointer is static)."""
+        key = (tuple((id(d), j) for d, _, j in entries), bool(want_grad), tuple(lp for _, lp, _ in entries), bool(fft))
         tab = self._tables.get(key)
         if tab is None:
-            rec = np.zeros(len(entries), dtype=LIK_DTYPE)
+            rec = np.zeros(len(entries), dtype=ops.FFTLIK_DTYPE if fft else LIK_DTYPE)
             for r, (d, loss_ptr, j) in zip(rec, entries):
+                if fft:
+                    r["workspace"], r["psf_hat"] = _p(d.fft.workspace), _p(d.fft.psf_hat)
                 shifted = d.shift_xy is not None
                 r["flux"] = _p(d.flux_s if shifted else self.flux)
                 r["exposure"], r["psf"] = _p(d.exposure), _p(d.psf)
@@ -346,13 +353,26 @@ class MapEngine:
                 groups.setdefault(e[0].geom, []).append(e)
         groups = {g: es for g, es in groups.items() if self._use_batched(es)}
         batched = [e for es in groups.values() for e in es]
-        single = [e for e in entries if not any(e is b for b in batched)]
+        rest = [e for e in entries if not any(e is b for b in batched)]
+        # large PSFs: the FFT path, all datasets of a geometry per launch
+        fft_groups = {}
+        if FFT_BATCHED:
+            for e in rest:
+                d = e[0]
+                if d.fft is not None and d.f in (1, 2) and d.H * d.f == d.fH and d.W * d.f == d.fW:
+                    fft_groups.setdefault(d.geom, []).append(e)
+        fft_batched = [e for es in fft_groups.values() for e in es]
+        single = [e for e in rest if not any(e is b for b in fft_batched)]
+        batched = batched + fft_batched
         for d, _, _ in batched:
             if d.shift_xy is not None:  # calibration shift: the NPred model sees the shifted flux (npred.py:226-230)
                 _call("jd_shift_forward", _p(self.flux), _p(d.shift_xy), d.f, d.fH, d.fW, _p(d.flux_s), s)
         for (fH, fW, kh, kw, f, H, W), es in groups.items():
             _call("jd_likelihood_forward", _p(self._table(es, want_grad)), len(es), fH, fW, kh, kw, f, H, W, 1e-25,
                   1.0 / (H * W), s)
+        for (fH, fW, kh, kw, f, H, W), es in fft_groups.items():
+            _call("jd_likelihood_forward_fft", _p(self._table(es, want_grad, fft=True)), len(es), fH, fW, kh, kw, f, H, W,
+                  1e-25, 1.0 / (H * W), s)
         if want_grad:
             for d, _, j in batched:
                 if d.train_bkg_norm:  # Adam on log(background norm) with the parameter's own step counter
@@ -360,6 +380,9 @@ class MapEngine:
                           _p(d.cal_t), 1, self.lr, self.b1, self.b2, self.eps, s)
             for (fH, fW, kh, kw, f, H, W), es in groups.items():
                 _call("jd_likelihood_backward", _p(self._table(es, want_grad)), len(es), fH, fW, kh, kw, f, H, W, s)
+            for (fH, fW, kh, kw, f, H, W), es in fft_groups.items():
+                _call("jd_likelihood_backward_fft", _p(self._table(es, want_grad, fft=True)), len(es), fH, fW, kh, kw, f,
+                      H, W, s)
             for d, _, j in batched:
                 if d.shift_xy is not None:
                     self._shift_backward(d, j)

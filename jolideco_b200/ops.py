@@ -158,6 +158,10 @@ LIK_DTYPE = np.dtype([("flux", "u8"), ("exposure", "u8"), ("psf", "u8"), ("backg
                       ("loss_const", "f8"), ("accumulate", "i4"), ("reserved", "i4")])
 
 
+# jd_fftlik_dataset: the same record + the dataset's spectrum workspace and cached PSF spectrum (FFT path)
+FFTLIK_DTYPE = np.dtype(LIK_DTYPE.descr + [("workspace", "u8"), ("psf_hat", "u8")])
+
+
 def stirling_constant(counts):
     """sum_pix 1{c > 1} (c log c - c + 1/2 log(2 pi c)): the counts-only term of nn.PoissonNLLLoss(full=True)
     (loss.py:35-37), a constant of the dataset that the fused likelihood kernel adds once (setup-time, float64)."""
@@ -166,10 +170,11 @@ def stirling_constant(counts):
     return float(torch.where(c > 1, c * torch.log(cc) - c + 0.5 * torch.log(2 * math.pi * cc), torch.zeros_like(c)).sum())
 
 
-def likelihood_batched(flux, datasets, f=1, want_grad=True, eps=1e-25):
-    """All datasets of a joint iteration through jd_likelihood_forward (+ _backward): list of dicts with CUDA tensors
-    exposure, psf, background, counts [, bkg_log_norm, flux (own NPred input)].  Returns dict(loss_sum (D,) double,
-    dlogb (D,) double, dpool [D x (H,W)], dflux (D,fH,fW))."""
+def likelihood_batched(flux, datasets, f=1, want_grad=True, eps=1e-25, fft=False):
+    """All datasets of a joint iteration through jd_likelihood_forward (+ _backward), or with fft=True through the
+    shared-memory FFT path jd_likelihood_forward_fft (+ _backward_fft): list of dicts with CUDA tensors exposure, psf,
+    background, counts [, bkg_log_norm, flux (own NPred input)].  Returns dict(loss_sum (D,) double, dlogb (D,) double,
+    dpool [D x (H,W)], dflux (D,fH,fW))."""
     _check(flux, "flux")
     fH, fW = _hw(flux)
     D = len(datasets)
@@ -180,10 +185,13 @@ def likelihood_batched(flux, datasets, f=1, want_grad=True, eps=1e-25):
     dlogb = torch.zeros(D, dtype=torch.float64, device=dev)
     dpool = torch.zeros((D, H, W), dtype=torch.float32, device=dev) if want_grad else None
     dflux = torch.zeros((D, fH, fW), dtype=torch.float32, device=dev) if want_grad else None
-    rec = np.zeros(D, dtype=LIK_DTYPE)
+    rec = np.zeros(D, dtype=FFTLIK_DTYPE if fft else LIK_DTYPE)
+    plans = [FFTConvPlan(d["psf"], fH, fW) for d in datasets] if fft else []
     for i, (r, d) in enumerate(zip(rec, datasets)):
         for k in ("exposure", "psf", "background", "counts"):
             r[k] = _ptr(_check(d[k], k))
+        if fft:
+            r["workspace"], r["psf_hat"] = _ptr(plans[i].workspace), _ptr(plans[i].psf_hat)
         r["flux"] = _ptr(_check(d.get("flux", flux), "flux"))
         r["bkg_log_norm"] = _ptr(_check(d.get("bkg_log_norm"), "bkg_log_norm")) or 0
         r["loss_sum"] = loss.data_ptr() + 8 * i
@@ -193,9 +201,11 @@ def likelihood_batched(flux, datasets, f=1, want_grad=True, eps=1e-25):
             r["dlogb"] = dlogb.data_ptr() + 8 * i
             r["dflux"] = dflux.data_ptr() + 4 * fH * fW * i
     table = torch.from_numpy(rec.view(np.uint8).reshape(-1).copy()).to(dev)
-    _lib.call("jd_likelihood_forward", _ptr(table), D, fH, fW, kh, kw, int(f), H, W, float(eps), 1.0 / (H * W), _stream())
+    sfx = "_fft" if fft else ""
+    _lib.call("jd_likelihood_forward" + sfx, _ptr(table), D, fH, fW, kh, kw, int(f), H, W, float(eps), 1.0 / (H * W),
+              _stream())
     if want_grad:
-        _lib.call("jd_likelihood_backward", _ptr(table), D, fH, fW, kh, kw, int(f), H, W, _stream())
+        _lib.call("jd_likelihood_backward" + sfx, _ptr(table), D, fH, fW, kh, kw, int(f), H, W, _stream())
     return dict(loss_sum=loss, dlogb=dlogb, dpool=dpool, dflux=dflux)
 
 

@@ -106,11 +106,31 @@ def test_small_launches_keep_the_separate_kernels(recorder, monkeypatch):
     assert "jd_conv_forward_direct" in names(recorder)
 
 
-def test_fft_path_is_taken_for_large_psfs(recorder):
-    eng = E.MapEngine(torch.zeros(64, 64), [dataset(n=64, k=41)], prior=None, use_graph=False)
+def test_fft_path_is_taken_for_large_psfs(recorder, monkeypatch):
+    """PSFs of >= ops.FFT_MIN_PSF_AREA taps: the shared-memory FFT path, all datasets of a geometry per launch with the
+    Poisson statistic fused into the last pass (jd_likelihood_*_fft); JD_FFT_BATCHED=0: one dataset at a time."""
+    plan = types.SimpleNamespace(psf_hat=torch.zeros(4), workspace=torch.zeros(4))
+    monkeypatch.setattr(ops, "FFTConvPlan", lambda psf, fH, fW: types.SimpleNamespace(psf_hat=torch.zeros(4),
+                                                                                       workspace=torch.zeros(4)))
+    ds = [dataset(n=64, k=41), dataset(n=64, k=41)]
+    eng = E.MapEngine(torch.zeros(64, 64), ds, prior=None, use_graph=False)
+    eng.joint_step()
+    assert names(recorder) == ["jd_step_begin_flux", "jd_likelihood_forward_fft", "jd_likelihood_backward_fft",
+                               "jd_adam_joint_step_dev"]
+    fwd, bwd = recorder[1][1], recorder[2][1]
+    assert fwd[1] == 2 and fwd[2:9] == (64, 64, 41, 41, 1, 64, 64) and bwd[0] == fwd[0]
+    table = eng._table([(d, eng.acc.data_ptr(), j) for j, d in enumerate(ds)], True, fft=True)
+    rec = table.numpy().view(ops.FFTLIK_DTYPE)
+    assert rec.shape == (2,) and rec.itemsize == 112
+    assert [int(r["workspace"]) for r in rec] == [d.fft.workspace.data_ptr() for d in ds]
+    assert [int(r["psf_hat"]) for r in rec] == [d.fft.psf_hat.data_ptr() for d in ds]
+    assert int(rec[1]["dflux"]) == eng.parts.data_ptr() + 4 * eng.n
+    del recorder[:]
+    monkeypatch.setattr(E, "FFT_BATCHED", False)
     eng.step(0)
     assert "jd_conv_forward_fft" in names(recorder) and "jd_conv_backward_fft" in names(recorder)
     assert "jd_conv_forward_direct" not in names(recorder) and "jd_likelihood_forward" not in names(recorder)
+    assert plan is not None
 
 
 def test_calibration_accumulators_and_shift_sequence(recorder):
