@@ -373,6 +373,9 @@ joint_grad_kernel(float* __restrict__ theta, float* __restrict__ m, float* __res
   const int ny = (fH - PATCH) / stride + 1, nx = (fW - PATCH) / stride + 1;
   const int64_t n = (int64_t)fH * fW;
   const bool fold = G != nullptr && row_end > row_begin;
+  __shared__ __align__(16) float s_fold[4 * 256];
+  // one image row per CTA pass: fW = 4 x blockDim (every thread then runs the same number of passes)
+  const bool row_fold = fold && vec && stride == 4 && fW == 4 * (int)blockDim.x && blockDim.x == 256;
   if (vec) {
     const int64_t n4 = n >> 2;
     for (int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += (int64_t)gridDim.x * blockDim.x) {
@@ -391,7 +394,36 @@ joint_grad_kernel(float* __restrict__ theta, float* __restrict__ m, float* __res
       }
       if (fold) {
         const int y = (int)(i / fW), x = (int)(i - (int64_t)y * fW);
-        if (stride == 4) {
+        if (row_fold) {
+          // The CTA's 256 threads cover exactly one image row: fold the ROLLED row into shared memory with threads on
+          // the patch grid (rolled columns 4t .. 4t+3 = one 16-byte piece of at most 2 x 2 patch rows: four 128-bit
+          // loads instead of sixteen scattered 32-bit ones, same summation order per pixel), then read it back at the
+          // pixel's rolled position.
+          const int t = threadIdx.x;
+          const int ry = wrap(y + sy, fH);
+          const int iy_hi = min(ry >> 2, min(ny, row_end) - 1);
+          const int u0 = ry - 4 * iy_hi;
+          const bool r0 = iy_hi >= row_begin && u0 < PATCH, r1 = r0 && iy_hi - 1 >= row_begin && u0 + 4 < PATCH;
+          const int ix_hi = min(t, nx - 1), v0 = 4 * (t - ix_hi);
+          const bool c0 = v0 < PATCH, c1 = c0 && ix_hi >= 1 && v0 + 4 < PATCH;
+          const float* g0 = G + ((int64_t)(iy_hi - row_begin) * nx + ix_hi) * PD + u0 * PATCH + v0;
+          const float* g1 = g0 - (int64_t)nx * PD + 4 * PATCH;
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 a00 = (r0 && c0) ? __ldg(reinterpret_cast<const float4*>(g0)) : z4;
+          const float4 a01 = (r0 && c1) ? __ldg(reinterpret_cast<const float4*>(g0 - PD + 4)) : z4;
+          const float4 a10 = (r1 && c0) ? __ldg(reinterpret_cast<const float4*>(g1)) : z4;
+          const float4 a11 = (r1 && c1) ? __ldg(reinterpret_cast<const float4*>(g1 - PD + 4)) : z4;
+          float4 acc = z4;  // skipped terms add +0.0f to a sum that starts at +0.0f: the same value as not adding them
+          acc.x += a00.x, acc.y += a00.y, acc.z += a00.z, acc.w += a00.w;
+          acc.x += a01.x, acc.y += a01.y, acc.z += a01.z, acc.w += a01.w;
+          acc.x += a10.x, acc.y += a10.y, acc.z += a10.z, acc.w += a10.w;
+          acc.x += a11.x, acc.y += a11.y, acc.z += a11.z, acc.w += a11.w;
+          __syncthreads();  // the previous row has been read
+          *reinterpret_cast<float4*>(s_fold + 4 * t) = acc;
+          __syncthreads();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) g[c] += scale_b * s_fold[wrap(x + c + sx, fW)];
+        } else if (stride == 4) {
           float fg[4];
           fold_gather4_s4(G, y, x, fH, fW, sy, sx, ny, nx, row_begin, row_end, fg);
 #pragma unroll

@@ -150,38 +150,51 @@ def test_unsupported_geometries_are_refused():
 
 
 @pytest.mark.parametrize("with_prior", [True, False])
-def test_joint_update_kernels_match_fold_plus_adam(with_prior):
+@pytest.mark.parametrize("fH,fW,stride,shift_yx,rows", [
+    (72, 88, 4, (1, -2), None),        # per-pixel gather (four pixels per thread, stride-4 shifts)
+    (40, 1024, 4, (1, -2), None),      # one image row per CTA pass: the rolled row folded through shared memory
+    (40, 1024, 4, (-2, 3), (2, 7)),    # ... on a patch-row block (multi-GPU shard), another shift
+    (40, 1024, 4, (0, 0), None),
+    (48, 64, 2, (2, 1), None),         # other strides: the general gather
+])
+def test_joint_update_kernels_match_fold_plus_adam(with_prior, fH, fW, stride, shift_yx, rows):
     """jd_adam_joint_step_dev == sum of parts + jd_patch_fold + jd_adam_step_dev; jd_grad_reduce_local == the gradient."""
     rng = np.random.default_rng(9)
-    fH, fW, D, stride = 72, 88, 3, 4
+    D = 3
     n = fH * fW
     ny, nx = ops.patch_grid(fH, fW, stride)
+    r0, r1 = (0, ny) if rows is None else rows
     theta = t(rng.normal(size=(fH, fW)))
     flux = ops.flux_forward(theta)
     parts = t(rng.normal(size=(D, fH, fW)))
-    G = t(rng.normal(size=(ny * nx, 64))) if with_prior else None
-    shift = torch.tensor([1, -2], dtype=torch.int32, device=DEV)
+    G = t(rng.normal(size=((r1 - r0) * nx, 64))) if with_prior else None
+    shift = torch.tensor(list(shift_yx), dtype=torch.int32, device=DEV)
     scalars = t(np.array([0.1 / (1 - 0.9), np.sqrt(1 - 0.999)], dtype=np.float32))
     s = torch.cuda.current_stream().cuda_stream
     p = lambda x: None if x is None else x.data_ptr()  # noqa: E731
     # reference: explicit sum, fold, Adam
     g = parts.sum(dim=0)
     if with_prior:
-        g = g + 0.7 * ops.patch_fold(G, fH, fW, shift, stride)
+        g = g + 0.7 * ops.patch_fold(G, fH, fW, shift, stride, rows=(r0, r1))
     th_ref, m_ref, v_ref = theta.clone(), torch.zeros_like(theta), torch.zeros_like(theta)
     _lib.call("jd_adam_step_dev", p(th_ref), p(m_ref), p(v_ref), p(flux), None, p(g.contiguous()), None, 0.0, 1, n,
               p(scalars), 0.9, 0.999, 1e-8, s)
     th, m, v = theta.clone(), torch.zeros_like(theta), torch.zeros_like(theta)
     _lib.call("jd_adam_joint_step_dev", p(th), p(m), p(v), p(flux), None, p(parts), D, n, p(G), 0.7, 1, fH, fW, p(shift),
-              stride, 0, ny, p(scalars), 0.9, 0.999, 1e-8, s)
+              stride, r0, r1, p(scalars), 0.9, 0.999, 1e-8, s)
     assert_allclose(th.cpu().numpy(), th_ref.cpu().numpy(), rtol=1e-5, atol=1e-6)
     assert_allclose(m.cpu().numpy(), m_ref.cpu().numpy(), rtol=1e-5, atol=1e-7)
     out = torch.empty_like(theta)
-    _lib.call("jd_grad_reduce_local", p(parts), D, n, p(G), 0.7, fH, fW, p(shift), stride, 0, ny, p(out), s)
+    _lib.call("jd_grad_reduce_local", p(parts), D, n, p(G), 0.7, fH, fW, p(shift), stride, r0, r1, p(out), s)
     assert_allclose(out.cpu().numpy(), g.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    if with_prior:  # the fold itself: same summation order in every variant of the gather -> bit-identical
+        only = torch.empty_like(theta)
+        _lib.call("jd_grad_reduce_local", p(torch.zeros_like(parts)), 1, n, p(G), 1.0, fH, fW, p(shift), stride, r0, r1,
+                  p(only), s)
+        assert torch.equal(only, ops.patch_fold(G, fH, fW, shift, stride, rows=(r0, r1)))
     # in place on parts[0] (the NCCL path reduces into the first part)
     parts2 = parts.clone()
-    _lib.call("jd_grad_reduce_local", p(parts2), D, n, p(G), 0.7, fH, fW, p(shift), stride, 0, ny, p(parts2), s)
+    _lib.call("jd_grad_reduce_local", p(parts2), D, n, p(G), 0.7, fH, fW, p(shift), stride, r0, r1, p(parts2), s)
     assert torch.equal(parts2[0], out)
 
 
