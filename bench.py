@@ -467,7 +467,7 @@ def parity_check(J, E, workload, args, device, rank, world, pg):
     g_full = (full.dflux_l * full.flux).double()  # d total / d theta = d total / d flux * flux  (use_log_flux)
     acc = full.acc.cpu().numpy()
     npix = full.counts_shape[0] * full.counts_shape[1]
-    ours_total = acc[0] / npix - full.beta * acc[1] * full.c
+    ours_total = full.poisson_sum(acc) / npix - full.beta * acc[1] * full.c
     scale = float(g_full.abs().max())
     if world > 1:
         part = build_engine(J, E, workload, args, device, rank, world, pg, n_draws=8, shift_table=[shift] * 8,

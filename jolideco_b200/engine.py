@@ -166,9 +166,14 @@ class MapEngine:
         self.counters = torch.zeros(2, dtype=torch.int32, device=self.dev)
         self.cur_shift = torch.zeros(2, dtype=torch.int32, device=self.dev)
         self.adam_scalars = torch.zeros(2, **f32)
-        # acc[0] = Poisson loss sum of the last step, acc[1] = sum_p v_p of the last prior evaluation, then three slots
-        # per local dataset j: acc[2+3j] = d loss / d log(background norm), acc[3+3j : 5+3j] = d loss / d (shift_x, shift_y)
-        self.acc = torch.zeros(2 + 3 * max(self.D, 1), dtype=torch.float64, device=self.dev)
+        # acc[0] = Poisson loss sum of the last reference step, acc[1] = sum_p v_p of the last prior evaluation, then three
+        # slots per local dataset j: acc[2+3j] = d loss / d log(background norm), acc[3+3j : 5+3j] = d loss / d (shift_x,
+        # shift_y), then one slot per local dataset: its Poisson loss sum in the last JOINT step (kept apart so that the
+        # per-epoch trace can reuse them, `_trace_body`)
+        Dm = max(self.D, 1)
+        self._loss0 = 2 + 3 * Dm
+        self.acc = torch.zeros(self._loss0 + Dm, dtype=torch.float64, device=self.dev)
+        self._last_joint = False
         for d in self.datasets + self.datasets_validation:
             if d.shift_xy is not None and d.flux_s is None:
                 d.flux_s = torch.empty_like(theta)   # this dataset's shifted flux
@@ -177,6 +182,7 @@ class MapEngine:
             if d.dpool is None:
                 d.dpool = torch.empty((d.H, d.W), **f32)
         self._tables = {}
+        self._trace_dst = None
         self.n_trace = self.Dg + 1 + self.Vg
         self.acc_trace = torch.zeros(self.n_trace, dtype=torch.float64, device=self.dev)
         self.shift_table = None
@@ -315,6 +321,14 @@ class MapEngine:
     def _slot(self, j):
         """device address of the calibration-gradient accumulators (dlogb, dshift_x, dshift_y) of local dataset j"""
         return self.acc.data_ptr() + 8 * (2 + 3 * j)
+
+    def _loss_slot(self, j):
+        """device address of local dataset j's loss accumulator of a joint step"""
+        return self.acc.data_ptr() + 8 * (self._loss0 + j)
+
+    def poisson_sum(self, vals):
+        """Poisson loss sum of the last step from a host copy of `acc` (reference step: acc[0]; joint step: the slots)"""
+        return float(vals[0] + vals[self._loss0:].sum())
 
     def _table(self, entries, want_grad, fft=False):
         """Device table of jd_lik_dataset (fft: jd_fftlik_dataset) records for one batched launch pair (cached: every
@@ -527,7 +541,7 @@ class MapEngine:
         """Joint step up to the local gradient: d L_d / d flux of the local datasets in parts[j], the gradient rows G
         of the local patch rows scaled by beta c (loss.py:257-261)."""
         self._begin_flux(advance_adam=1, zero_acc=self.acc)
-        entries = [(d, self.acc.data_ptr(), j) for j, d in enumerate(self.datasets)]
+        entries = [(d, self._loss_slot(j), j) for j, d in enumerate(self.datasets)]
         return self._gradients(entries, self.c * self.beta if self.prior else 0.0)
 
     def _joint_body(self):
@@ -621,9 +635,11 @@ class MapEngine:
             torch.distributed.barrier(group=self.pg)
 
     def step(self, i):
+        self._last_joint = False
         self._run(("step", i), lambda: self._step_body(i))
 
     def joint_step(self):
+        self._last_joint = True
         if self.world == 1 or self.collective == "peer":
             self._run(("joint",), self._joint_body)  # one graph: the peer kernel carries its own cross-rank barriers
             return
@@ -635,7 +651,8 @@ class MapEngine:
     def trace_enqueue(self, out_row, refresh_flux=False):
         """Same evaluation as `trace_losses` but asynchronous: the raw accumulators are copied on the
         stream into `out_row` (a device double tensor of n_trace entries); decode with `trace_decode`."""
-        self._run(("trace", bool(refresh_flux)), lambda: self._trace_body(refresh_flux))
+        reuse = self._trace_reuse(refresh_flux)
+        self._run(("trace", bool(refresh_flux), reuse), lambda: self._trace_body(refresh_flux, reuse))
         out_row.copy_(self.acc_trace, non_blocking=True)
 
     def trace_decode(self, vals):
@@ -646,12 +663,26 @@ class MapEngine:
         lv = [float(vals[self.Dg + 1 + j] / npix) for j in range(self.Vg)]
         return ld, lp, lv
 
-    def _trace_body(self, refresh_flux):
+    def _trace_reuse(self, refresh_flux):
+        """After a joint step the training datasets' losses of the trace are the ones that step just accumulated: same
+        flux (the trace is evaluated at the flux of the step's start), same data - unless a calibration parameter is
+        trained (the reference evaluates the trace with the parameters AFTER the step, core.py:229/245)."""
+        return bool(self._last_joint and not refresh_flux and self.D > 0
+                    and not any(d.train_bkg_norm or d.train_shift for d in self.datasets))
+
+    def _trace_body(self, refresh_flux, reuse=False):
         self._begin(advance_adam=0, zero_acc=self.acc_trace, with_shift=True)
         if refresh_flux:
             self._flux()
         base = self.acc_trace.data_ptr()
-        entries = [(d, base + 8 * j, None) for j, d in zip(self.dataset_index, self.datasets)]
+        entries = []
+        if reuse:
+            if self._trace_dst is None:
+                self._trace_dst = torch.tensor(self.dataset_index, dtype=torch.int64, device=self.dev)
+            if not _STATS["dry"]:
+                self.acc_trace.index_copy_(0, self._trace_dst, self.acc[self._loss0:self._loss0 + self.D])
+        else:
+            entries = [(d, base + 8 * j, None) for j, d in zip(self.dataset_index, self.datasets)]
         entries += [(d, base + 8 * (self.Dg + 1 + j), None) for j, d in zip(self.validation_index, self.datasets_validation)]
         has_prior = self.prior is not None and self.P > 0
         if self.overlap and has_prior and len(entries) > 1:
@@ -670,7 +701,8 @@ class MapEngine:
         evaluated at the flux of the LAST step's start (the reference hands the stale `fluxes` tuple
         to append_trace, core.py:217/245).  One host sync.  Returns (datasets, prior, validation)."""
 
-        self._run(("trace", bool(refresh_flux)), lambda: self._trace_body(refresh_flux))
+        reuse = self._trace_reuse(refresh_flux)
+        self._run(("trace", bool(refresh_flux), reuse), lambda: self._trace_body(refresh_flux, reuse))
         if self.world > 1:  # every slot is written by exactly one rank (prior: partial sums): one all-reduce
             torch.distributed.all_reduce(self.acc_trace, group=self.pg)
         return self.trace_decode(self.acc_trace.cpu().numpy())
@@ -682,7 +714,7 @@ class MapEngine:
             torch.distributed.all_reduce(vals, group=self.pg)
         vals = vals.cpu().numpy()
         npix = self.counts_shape[0] * self.counts_shape[1]
-        return float(vals[0] / npix), float(vals[1] * self.c) if self.prior is not None else 0.0
+        return self.poisson_sum(vals) / npix, float(vals[1] * self.c) if self.prior is not None else 0.0
 
     def flux_numpy(self):
         self._flux()

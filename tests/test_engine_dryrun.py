@@ -139,7 +139,7 @@ def test_calibration_accumulators_and_shift_sequence(recorder):
     ds = [dataset(bkg_log_norm=logb, train_bkg_norm=True, shift_xy=shift, train_shift=True),
           dataset(bkg_log_norm=torch.zeros(1), train_bkg_norm=True)]
     eng = E.MapEngine(torch.zeros(32, 32), ds, prior=None, use_graph=False)
-    assert ds[0].flux_s is not None and ds[1].flux_s is None and eng.acc.numel() == 2 + 3 * 2
+    assert ds[0].flux_s is not None and ds[1].flux_s is None and eng.acc.numel() == 2 + 3 * 2 + 2
     eng.step(0)
     seq = names(recorder)
     assert seq == ["jd_step_begin_flux", "jd_shift_forward", "jd_likelihood_forward", "jd_adam_scalar_step_dev",
@@ -320,8 +320,16 @@ def test_overlap_forks_the_likelihood_chain_and_joins_before_the_update(recorder
     assert seq[seq.index("main.wait(side)") + 1:] == ["jd_adam_joint_step_dev"]  # parts + fold + Adam in one launch
     assert seq.count("jd_likelihood_backward") == 1
     del events[:]
+    # trace after a joint step: the datasets' losses are the ones the step accumulated (copied on the device), only the
+    # prior is evaluated again (with the trace's own cycle-spin draw)
+    eng.trace_enqueue(torch.zeros(eng.n_trace, dtype=torch.float64))
+    assert names(events) == ["jd_step_begin", "jd_gmm_prior_forward_tc"]
+    del events[:]
+    eng.step(0)  # ... after a reference step every dataset is evaluated: likelihood chain beside the prior
+    del events[:]
     eng.trace_enqueue(torch.zeros(eng.n_trace, dtype=torch.float64))
     seq = names(events)
     assert seq[0] == "jd_step_begin" and seq[-2:] == ["jd_gmm_prior_forward_tc", "main.wait(side)"]
+    assert "jd_likelihood_forward" in seq
     # JD_OVERLAP=0 (the fixture's setting): no side stream at all
     assert E.MapEngine(torch.zeros(32, 32), [dataset()], prior=prior, use_graph=False)._side is None

@@ -108,7 +108,7 @@ def engine_gradient(eng):
     g = (eng.dflux_l * eng.flux).double().cpu().numpy()  # d total / d theta (log-flux parameterisation)
     acc = eng.acc.cpu().numpy()
     npix = eng.counts_shape[0] * eng.counts_shape[1]
-    return g, acc[0] / npix, acc[1] * eng.c
+    return g, eng.poisson_sum(acc) / npix, acc[1] * eng.c
 
 
 class _Args:

@@ -6,20 +6,21 @@ import bench
 import jolideco_b200 as J
 from jolideco_b200 import synthetic
 
-class A: marginalize = False; backend = None; no_graph = False; collective = "nccl"
+class A: marginalize = False; backend = None; no_graph = False; collective = "nccl"; datasets = None
 wl = synthetic.make_workload(sys.argv[1] if len(sys.argv) > 1 else "cfg2", seed=0)
 epochs = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-deco, comps = bench.build_run(J, wl, A, "cuda:0", n_epochs=2)
+mode = "joint" if wl["name"] in bench.JOINT_WORKLOADS else "sequential"
+deco, comps = bench.build_run(J, wl, A, "cuda:0", n_epochs=2, mode=mode)
 deco.run(datasets=wl["datasets"], components=comps)
 for rep in range(2):
-    deco, comps = bench.build_run(J, wl, A, "cuda:0", n_epochs=epochs)
+    deco, comps = bench.build_run(J, wl, A, "cuda:0", n_epochs=epochs, mode=mode)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     res = deco.run(datasets=wl["datasets"], components=comps)
     flux = res.flux_upsampled_total
     torch.cuda.synchronize()
     print(f"run {rep}: {1e3 * (time.perf_counter() - t0):.2f} ms for {epochs} epochs")
-deco, comps = bench.build_run(J, wl, A, "cuda:0", n_epochs=epochs)
+deco, comps = bench.build_run(J, wl, A, "cuda:0", n_epochs=epochs, mode=mode)
 pr = cProfile.Profile()
 pr.enable()
 res = deco.run(datasets=wl["datasets"], components=comps)
