@@ -12,7 +12,7 @@ epochs = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 mode = "joint" if wl["name"] in bench.JOINT_WORKLOADS else "sequential"
 deco, comps = bench.build_run(J, wl, A, "cuda:0", n_epochs=2, mode=mode)
 deco.run(datasets=wl["datasets"], components=comps)
-for rep in range(2):
+for rep in range(int(os.environ.get('REPS', 2))):
     deco, comps = bench.build_run(J, wl, A, "cuda:0", n_epochs=epochs, mode=mode)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
