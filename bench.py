@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--datasets", type=int, default=None,
                     help="experiments only: override the workload's number of datasets (the line's config says so)")
+    ap.add_argument("--gmm-mean-scale", type=float, default=0.0,
+                    help="std of the synthetic mixture's component means (0 = zero-mean mixture, SURVEY 8d; > 0 times the "
+                         "kernels' general path, the line's config says so)")
     ap.add_argument("--collective", default="peer", choices=["nccl", "peer"],
                     help="joint multi-GPU step: NCCL all-reduce + Adam, or the fused peer-memory reduce+Adam kernel")
     return ap.parse_args()
@@ -234,7 +237,10 @@ def main():
     if args.workload == "cfg5":
         return bench_batched(args, rank, local_rank, world)
     joint = args.workload in JOINT_WORKLOADS
-    workload = synthetic.make_workload(args.workload, seed=0 if joint else rank, n_datasets=args.datasets)
+    workload = synthetic.make_workload(args.workload, seed=0 if joint else rank, n_datasets=args.datasets,
+                                       gmm_mean_scale=args.gmm_mean_scale)
+    if args.gmm_mean_scale:
+        workload["variant"] = f"mixture component means ~ N(0, {args.gmm_mean_scale}^2) instead of zero"
     if args.datasets is not None:
         workload["variant"] = f"{args.datasets} datasets instead of the workload's own number (experiment)"
 

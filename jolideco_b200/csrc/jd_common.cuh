@@ -63,6 +63,16 @@ __device__ __forceinline__ int wrap(int a, int n) {  // a mod n for a in [-n, 2n
   return a >= n ? a - n : a;
 }
 
+// true the first time it is called for (this call site's flag array, current device): function attributes
+// (cudaFuncSetAttribute) are per device / context, so the opt-in is repeated on every device that is used
+inline bool first_use_on_device(bool (&seen)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (seen[dev & 63]) return false;
+  seen[dev & 63] = true;
+  return true;
+}
+
 inline cudaStream_t to_stream(jd_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int num_sms();

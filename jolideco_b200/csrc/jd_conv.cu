@@ -171,10 +171,9 @@ static int launch_conv_t(const float* in, const float* scale, const float* psf, 
   size_t sm = smem_for(kchunk);
   JD_CHECK_ARG(sm <= 200 * 1024, "%s: PSF too wide for the direct kernel (kw=%d)", name, kw);
   auto kern = conv_kernel<MODE, TY, TX, R>;
-  static bool attr_set = false;  // once per process and instantiation: opt in to the 200 KB limit checked above
-  if (!attr_set) {
+  static bool attr_set[64] = {};  // once per process and instantiation: opt in to the 200 KB limit checked above
+  if (first_use_on_device(attr_set)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
   }
   dim3 grid((fW + C * TX - 1) / (C * TX), (fH + R * TY - 1) / (R * TY));
   kern<<<grid, TY * TX, sm, st>>>(in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, kchunk);
@@ -504,14 +503,13 @@ static int launch_conv3_t(const Conv3Plan& p, const float* in, const float* scal
                           const char* name) {
   constexpr int TY = TY3;
   auto kern = conv3_kernel<MODE, TY, TX, CG, KT>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV3_SMEM_MAX);
     if (e != cudaSuccess) {
       set_error("%s: cannot reserve shared memory: %s", name, cudaGetErrorString(e));
       return JD_ERR_CUDA;
     }
-    attr_set = true;
   }
   dim3 grid((fW + C * TX * CG - 1) / (C * TX * CG), (fH + R3 * TY - 1) / (R3 * TY));
   kern<<<grid, TY * TX * p.S, p.smem, st>>>(in, scale, psf, out, fH, fW, kh, kw, oy, ox, f, H, W, accumulate, p.dx, p.vec,

@@ -634,10 +634,9 @@ int gmm_prior_forward_simt(const float* flux, int fH, int fW, const int32_t* shi
   int rc = make_geom("jd_gmm_prior_forward", fH, fW, stride, row_begin, row_end, &g);
   if (rc) return rc;
   auto kern = gmm_tile_kernel<0>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM);
-    attr_set = true;
   }
   int grid = (g.P + TM - 1) / TM;
   kern<<<grid, NT, TILE_SMEM, st>>>(flux, g, shift_yx, Lw, mw, ck, K, marginalize, value, argmax, logp, sum, 0.f,
@@ -694,10 +693,9 @@ int jd_gmm_prior_backward(const float* flux, int fH, int fW, const int32_t* shif
   if (marginalize) {
     JD_CHECK_ARG(logp && value, "jd_gmm_prior_backward: marginalize=1 needs logp and value from the forward");
     auto kern = gmm_tile_kernel<1>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};
+    if (first_use_on_device(attr_set)) {
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM);
-      attr_set = true;
     }
     int grid = (g.P + TM - 1) / TM;
     kern<<<grid, NT, TILE_SMEM, st>>>(flux, g, shift_yx, Lam, bk, nullptr, K, 1, const_cast<float*>(value), nullptr,

@@ -1027,8 +1027,8 @@ int jd_gmm_prior_forward_tc(const float* flux, int fH, int fW, const int32_t* sh
   JD_CHECK_ARG((reinterpret_cast<uintptr_t>(Bt) & 15) == 0 && (reinterpret_cast<uintptr_t>(mw) & 15) == 0,
                "jd_gmm_prior_forward_tc: Bt and mw must be 16-byte aligned");
   tc::Geom g{fH, fW, 0, 0, stride, nx, row_begin, (row_end - row_begin) * nx};
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     cudaError_t e = cudaSuccess;
     const void* kerns[4] = {(const void*)tc::gmm_fwd_tc_kernel<false, false>, (const void*)tc::gmm_fwd_tc_kernel<false, true>,
                             (const void*)tc::gmm_fwd_tc_kernel<true, false>, (const void*)tc::gmm_fwd_tc_kernel<true, true>};
@@ -1039,7 +1039,6 @@ int jd_gmm_prior_forward_tc(const float* flux, int fH, int fW, const int32_t* sh
                 cudaGetErrorString(e));
       return JD_ERR_CUDA;
     }
-    attr_set = true;
   }
   int grid = (g.P + tc::TM - 1) / tc::TM;
   grid = (grid + tc::CLUSTER - 1) / tc::CLUSTER * tc::CLUSTER;  // whole clusters; surplus CTAs own no patch
@@ -1141,8 +1140,8 @@ int jd_gmm_prior_forward_tc_sk(const float* flux, int fH, int fW, const int32_t*
                    (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
                "jd_gmm_prior_forward_tc_sk: Bt and mw must be 16-byte aligned, the workspace 256-byte aligned");
   tc::Geom g{fH, fW, 0, 0, stride, nx, row_begin, (row_end - row_begin) * nx};
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     cudaError_t e = cudaSuccess;
     const void* kerns[4] = {(const void*)tc::gmm_fwd_tc_sk_kernel<false, false>, (const void*)tc::gmm_fwd_tc_sk_kernel<false, true>,
                             (const void*)tc::gmm_fwd_tc_sk_kernel<true, false>, (const void*)tc::gmm_fwd_tc_sk_kernel<true, true>};
@@ -1153,7 +1152,6 @@ int jd_gmm_prior_forward_tc_sk(const float* flux, int fH, int fW, const int32_t*
                 cudaGetErrorString(e));
       return JD_ERR_CUDA;
     }
-    attr_set = true;
   }
   const tc::SkPlan p = tc::sk_plan(g.P, K);
   static int rot_env = -1;
@@ -1205,8 +1203,8 @@ int jd_gmm_prior_backward_lse_tc(const float* flux, int fH, int fW, const int32_
                    (reinterpret_cast<uintptr_t>(G) & 15) == 0,
                "jd_gmm_prior_backward_lse_tc: Bt_lam, bk and G must be 16-byte aligned");
   tcx::Geom g{fH, fW, 0, 0, stride, nx, row_begin, (row_end - row_begin) * nx};
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     cudaError_t e = cudaFuncSetAttribute(tc::gmm_bwd_lse_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)tc::SMEM_BYTES_BWD);
     if (e != cudaSuccess) {
@@ -1214,7 +1212,6 @@ int jd_gmm_prior_backward_lse_tc(const float* flux, int fH, int fW, const int32_
                 cudaGetErrorString(e));
       return JD_ERR_CUDA;
     }
-    attr_set = true;
   }
   int grid = (g.P + tc::TM - 1) / tc::TM;
   grid = (grid + tc::CLUSTER - 1) / tc::CLUSTER * tc::CLUSTER;

@@ -423,8 +423,8 @@ int jd_gmm_prior_forward_tc16(const float* flux, int fH, int fW, const int32_t* 
   JD_CHECK_ARG((reinterpret_cast<uintptr_t>(Bt) & 15) == 0 && (reinterpret_cast<uintptr_t>(mw) & 15) == 0,
                "jd_gmm_prior_forward_tc16: Bt and mw must be 16-byte aligned");
   tcx::Geom g{fH, fW, 0, 0, stride, nx, row_begin, (row_end - row_begin) * nx};
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     cudaError_t e = cudaSuccess;
     const void* kerns[4] = {(const void*)tc16::gmm_fwd_tc16_kernel<false, false>,
                             (const void*)tc16::gmm_fwd_tc16_kernel<false, true>,
@@ -437,7 +437,6 @@ int jd_gmm_prior_forward_tc16(const float* flux, int fH, int fW, const int32_t* 
                 cudaGetErrorString(e));
       return JD_ERR_CUDA;
     }
-    attr_set = true;
   }
   int grid = (g.P + tc16::TM - 1) / tc16::TM;
   grid = (grid + tc16::CLUSTER - 1) / tc16::CLUSTER * tc16::CLUSTER;

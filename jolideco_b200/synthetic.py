@@ -71,8 +71,9 @@ def synthetic_datasets(H, W, psf_size, D, seed=0, background=0.5):
     return datasets, sky
 
 
-def make_workload(name, seed=0, n_datasets=None, K=None):
-    """Returns dict(datasets, flux_init, f, gmm_arrays or None, cfg)."""
+def make_workload(name, seed=0, n_datasets=None, K=None, gmm_mean_scale=0.0):
+    """Returns dict(datasets, flux_init, f, gmm_arrays or None, cfg).  gmm_mean_scale > 0: mixture components with
+    non-zero means (the kernels' general path; SURVEY 8d's synthetic mixture is zero-mean)."""
     cfg = dict(WORKLOADS[name])
     if n_datasets is not None:
         cfg["D"] = n_datasets
@@ -82,5 +83,5 @@ def make_workload(name, seed=0, n_datasets=None, K=None):
     datasets, _ = synthetic_datasets(H, H, cfg["psf"], cfg["D"], seed=seed)
     rng = np.random.default_rng(seed + 1000)
     flux_init = rng.gamma(20.0, size=(H, H)) / 20.0
-    gmm_arrays = synthetic_gmm(cfg["K"], seed=seed + 7) if cfg["K"] else None
+    gmm_arrays = synthetic_gmm(cfg["K"], seed=seed + 7, mean_scale=gmm_mean_scale) if cfg["K"] else None
     return dict(datasets=datasets, flux_init=flux_init, f=cfg["f"], gmm_arrays=gmm_arrays, cfg=cfg, name=name)
