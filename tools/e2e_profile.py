@@ -9,6 +9,10 @@ from jolideco_b200 import synthetic
 class A: marginalize = False; backend = None; no_graph = False; collective = "nccl"; datasets = None
 wl = synthetic.make_workload(sys.argv[1] if len(sys.argv) > 1 else "cfg2", seed=0)
 epochs = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+if os.environ.get("PINNED", "0") == "1":  # host arrays in page-locked memory, as bench.py's e2e leg hands them over
+    import numpy as np
+    wl["datasets"] = {n: {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() if isinstance(v, np.ndarray) else v
+                          for k, v in d.items()} for n, d in wl["datasets"].items()}
 mode = "joint" if wl["name"] in bench.JOINT_WORKLOADS else "sequential"
 deco, comps = bench.build_run(J, wl, A, "cuda:0", n_epochs=2, mode=mode)
 deco.run(datasets=wl["datasets"], components=comps)
