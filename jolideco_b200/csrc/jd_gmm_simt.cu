@@ -403,7 +403,8 @@ bwd_hist_kernel(const int32_t* __restrict__ argmax, int P, int K, int32_t* __res
 // one warp: exclusive scans of the K counts (patch offsets) and of the per-component item counts.  The counts of eight
 // 32-component chunks are loaded together (one L2 round trip per 256 components instead of one per 32).
 __global__ void bwd_scan_kernel(int K, int32_t* __restrict__ counts, int32_t* __restrict__ cursor0,
-                                int32_t* __restrict__ cursor, int32_t* __restrict__ item_base) {
+                                int32_t* __restrict__ cursor, int32_t* __restrict__ item_base,
+                                int32_t* __restrict__ next_item) {
   const int lane = threadIdx.x;
   int off = 0, ioff = 0;
   for (int kb = 0; kb < K; kb += 256) {
@@ -434,7 +435,10 @@ __global__ void bwd_scan_kernel(int K, int32_t* __restrict__ counts, int32_t* __
       ioff += __shfl_sync(0xffffffffu, si, 31);
     }
   }
-  if (lane == 0) item_base[K] = ioff;
+  if (lane == 0) {
+    item_base[K] = ioff;
+    *next_item = 0;  // the bucket kernel's work counter
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -569,6 +573,142 @@ gmm_bwd_bucket_kernel(const float* __restrict__ flux, PatchGeom g, const int32_t
   }
 }
 
+// Second generation of the bucket kernel.  The first one (above) is bound by its load/store wavefronts (ncu: 68 % of
+// the L1 data pipe, `short_scoreboard` + `barrier` stalls): a 4 x 4 register tile needs one LDS.128 per 8 FMAs and its
+// gather issues 32 scattered 4-byte loads per instruction; 1.4 waves of CTAs leave half the machine idle in the second.
+// Here 128 threads own 8 patches x 4 outputs each (one LDS.128 per 10.7 FMAs, the patch operand a one-wavefront
+// broadcast), a gather instruction covers 4 rows x 8 columns of ONE patch (4-8 sectors instead of 32) as 4-byte
+// cp.async straight into shared memory (ptxas serialises plain loads + shuffles patch by patch: one L2 round trip
+// each), Lam_k arrives through cp.async while the gather runs, and a resident grid takes items from a device counter.
+constexpr int BNT2 = 128;
+
+__device__ __forceinline__ void bwd_cp_async16(float* dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void bwd_cp_async4(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(BNT2, 5)
+gmm_bwd_bucket8_kernel(const float* __restrict__ flux, PatchGeom g, const int32_t* __restrict__ shift_yx,
+                       const float* __restrict__ Lam, const float* __restrict__ bk, int K,
+                       const int32_t* __restrict__ perm, const int32_t* __restrict__ cursor0,
+                       const int32_t* __restrict__ cursor_end, const int32_t* __restrict__ item_base,
+                       int32_t* __restrict__ next_item, float scale, float* __restrict__ G) {
+  __shared__ __align__(16) float Ls[PD * PD];    // Lam_k, row i = input feature
+  __shared__ __align__(16) float Xs[BCH * BXS];  // centred patches of the item, row = patch
+  __shared__ __align__(16) float bs[PD];
+  __shared__ int s_p[BCH], s_y[BCH], s_x[BCH];
+  __shared__ int s_item, s_k, s_start, s_cnt;
+  if (shift_yx) {
+    g.sy = shift_yx[0];
+    g.sx = shift_yx[1];
+  }
+  const int n_items = item_base[K];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (;;) {
+    if (threadIdx.x == 0) s_item = atomicAdd(next_item, 1);
+    __syncthreads();  // also: every thread is done with the previous item's shared memory
+    const int item = s_item;
+    if (item >= n_items) break;
+    // component of this item: the one k with item_base[k] <= item < item_base[k + 1] (independent loads, one round
+    // trip instead of the dependent ones of a binary search)
+    for (int kk = threadIdx.x; kk < K; kk += BNT2) {
+      const int b0 = item_base[kk], b1 = item_base[kk + 1];
+      if (b0 <= item && item < b1) {
+        const int first = cursor0[kk] + BCH * (item - b0);
+        s_k = kk;
+        s_start = first;
+        s_cnt = min(BCH, cursor_end[kk] - first);  // after the scatter the running cursor of k is the end of its bucket
+      }
+    }
+    __syncthreads();
+    const int k = s_k, start = s_start, cnt = s_cnt;
+    {
+      const float* Lsrc = Lam + (int64_t)k * PD * PD;
+#pragma unroll
+      for (int i = 0; i < PD * PD / (4 * BNT2); ++i)
+        bwd_cp_async16(Ls + 4 * (threadIdx.x + i * BNT2), Lsrc + 4 * (threadIdx.x + i * BNT2));
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    if (threadIdx.x < BCH) {
+      const int t = threadIdx.x;
+      const int p = t < cnt ? perm[start + t] : -1;
+      s_p[t] = p;
+      const int iy = p >= 0 ? p / g.nx + g.row_begin : 0, ix = p >= 0 ? p % g.nx : 0;
+      s_y[t] = iy * g.stride - g.sy;  // same arithmetic as patch_src_row / patch_src_col, the element offset added below
+      s_x[t] = ix * g.stride - g.sx;
+      bs[t] = bk[(int64_t)k * PD + t];
+    }
+    __syncthreads();
+    {  // gather: a warp takes 16 patches; lane = (row r of a half patch, column c): two copies cover the 8 x 8 patch
+      const int r = lane >> 3, c = lane & 7;
+      constexpr int PW = BCH / (BNT2 / 32);
+#pragma unroll 8
+      for (int j = 0; j < PW; ++j) {
+        const int pi = PW * w + j;
+        float* dst = Xs + pi * BXS + 8 * r + c;
+        if (s_p[pi] >= 0) {
+          const int y0 = s_y[pi], col = wrap(s_x[pi] + c, g.fW);
+          bwd_cp_async4(dst, flux + (int64_t)wrap(y0 + r, g.fH) * g.fW + col);
+          bwd_cp_async4(dst + 32, flux + (int64_t)wrap(y0 + r + 4, g.fH) * g.fW + col);
+        } else {
+          dst[0] = 0.f;
+          dst[32] = 0.f;
+        }
+      }
+      asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");  // also Lam_k
+#pragma unroll 8
+      for (int j = 0; j < PW; ++j) {  // every lane centres the two elements it copied itself
+        float* dst = Xs + (PW * w + j) * BXS + 8 * r + c;
+        const float a = dst[0], b = dst[32];
+        const float mean = warp_sum(a + b) * (1.f / 64.f);
+        dst[0] = a - mean;
+        dst[32] = b - mean;
+      }
+    }
+    __syncthreads();
+    // product: thread (ty, tx) = 8 patches (ty + 8 r) x 4 outputs (4 tx + c)
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    float acc[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+#pragma unroll 2
+    for (int i = 0; i < PD; i += 4) {
+      float4 xr[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) xr[r] = *reinterpret_cast<const float4*>(Xs + (ty + 8 * r) * BXS + i);
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii) {
+        const float4 l = *reinterpret_cast<const float4*>(Ls + (i + ii) * PD + 4 * tx);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const float x = ii == 0 ? xr[r].x : ii == 1 ? xr[r].y : ii == 2 ? xr[r].z : xr[r].w;
+          acc[r][0] = fmaf(x, l.x, acc[r][0]);
+          acc[r][1] = fmaf(x, l.y, acc[r][1]);
+          acc[r][2] = fmaf(x, l.z, acc[r][2]);
+          acc[r][3] = fmaf(x, l.w, acc[r][3]);
+        }
+      }
+    }
+    const float4 b4 = *reinterpret_cast<const float4*>(bs + 4 * tx);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      acc[r][0] -= b4.x, acc[r][1] -= b4.y, acc[r][2] -= b4.z, acc[r][3] -= b4.w;
+      float sg = (acc[r][0] + acc[r][1]) + (acc[r][2] + acc[r][3]);
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) sg += __shfl_xor_sync(0xffffffffu, sg, o);  // the 16 threads tx of a patch row
+      const float gm = sg * (1.f / 64.f);
+      const int p = s_p[ty + 8 * r];
+      if (p >= 0)
+        *reinterpret_cast<float4*>(G + (int64_t)p * PD + 4 * tx) =
+            make_float4(scale * (acc[r][0] - gm), scale * (acc[r][1] - gm), scale * (acc[r][2] - gm), scale * (acc[r][3] - gm));
+    }
+  }
+}
+
 // Raw patch extraction (cycle_spin roll + view_as_overlapping_patches_torch): X[p', 8u+v].
 __global__ void extract_patches_kernel(const float* __restrict__ flux, PatchGeom g,
                                        const int32_t* __restrict__ shift_yx, float* __restrict__ X) {
@@ -677,8 +817,8 @@ int jd_extract_patches(const float* flux, int fH, int fW, const int32_t* shift_y
 }
 
 int64_t jd_gmm_backward_workspace_elems(int64_t P, int K) {
-  // counts[K] (zero at entry, left at zero) cursor0[K] cursor[K] item_base[K + 1] perm[P]
-  return 4 * (int64_t)K + 1 + P;
+  // counts[K] (zero at entry, left at zero) cursor0[K] cursor[K] item_base[K + 1] next_item[1] perm[P]
+  return 4 * (int64_t)K + 2 + P;
 }
 
 int jd_gmm_prior_backward(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
@@ -708,14 +848,20 @@ int jd_gmm_prior_backward(const float* flux, int fH, int fW, const int32_t* shif
       int32_t* cursor0 = counts + K;
       int32_t* cursor = cursor0 + K;
       int32_t* item_base = cursor + K;
-      int32_t* perm = item_base + K + 1;
+      int32_t* next_item = item_base + K + 1;
+      int32_t* perm = next_item + 1;
       const int max_items = K + g.P / BCH + 1;
       const int hb = (int)std::min<int64_t>(((int64_t)g.P + 1023) / 1024, (int64_t)num_sms() * 4);
       bwd_hist_kernel<<<hb, 256, sizeof(int32_t) * K, st>>>(argmax, g.P, K, counts, G);
-      bwd_scan_kernel<<<1, 32, 0, st>>>(K, counts, cursor0, cursor, item_base);
+      bwd_scan_kernel<<<1, 32, 0, st>>>(K, counts, cursor0, cursor, item_base, next_item);
       bwd_scatter_kernel<<<(g.P + 1023) / 1024, 256, 2 * sizeof(int32_t) * K, st>>>(argmax, g.P, K, cursor, perm);
-      gmm_bwd_bucket_kernel<<<max_items, 256, 0, st>>>(flux, g, shift_yx, Lam, bk, K, perm, cursor0, cursor, item_base,
-                                                       scale, G);
+      static const bool v1 = getenv("JD_BWD_BUCKET_V1") && atoi(getenv("JD_BWD_BUCKET_V1")) != 0;  // A/B knob
+      if (v1)
+        gmm_bwd_bucket_kernel<<<max_items, 256, 0, st>>>(flux, g, shift_yx, Lam, bk, K, perm, cursor0, cursor, item_base,
+                                                         scale, G);
+      else
+        gmm_bwd_bucket8_kernel<<<std::min(max_items, num_sms() * 5), BNT2, 0, st>>>(
+            flux, g, shift_yx, Lam, bk, K, perm, cursor0, cursor, item_base, next_item, scale, G);
     } else {
       int64_t blocks = ((int64_t)g.P + 7) / 8;
       int64_t cap = (int64_t)num_sms() * 16;

@@ -252,7 +252,7 @@ def test_two_tile_prior_kernels_and_bucketed_backward_are_wired(recorder, monkey
     lib = types.SimpleNamespace(
         jd_gmm_tcm_workspace_bytes=lambda P, K: sizes.append(("tcm", P, K)) or 512,
         jd_gmm_tcm2_workspace_bytes=lambda P, K: sizes.append(("tcm2", P, K)) or 1024,
-        jd_gmm_backward_workspace_elems=lambda P, K: sizes.append(("bwd", P, K)) or 4 * K + 1 + P,
+        jd_gmm_backward_workspace_elems=lambda P, K: sizes.append(("bwd", P, K)) or 4 * K + 2 + P,
         jd_likelihood_supported=lambda kh, kw, f: 1)
     monkeypatch.setattr(E._lib, "load", lambda: lib)
     monkeypatch.setattr(ops._lib, "load", lambda: lib)
@@ -263,7 +263,7 @@ def test_two_tile_prior_kernels_and_bucketed_backward_are_wired(recorder, monkey
     prior = dict(packed=packed, stride=4, marginalize=False, backend=backend)
     monkeypatch.setattr(ops, "BWD_BUCKETED_MIN_PATCHES", 10)
     eng = E.MapEngine(torch.zeros(32, 32), [dataset()], prior=prior, use_graph=False)
-    assert eng.P == 49 and eng.bwd_ws is not None and eng.bwd_ws.numel() == 4 * 4 + 1 + 49 and not eng.bwd_ws.any()
+    assert eng.P == 49 and eng.bwd_ws is not None and eng.bwd_ws.numel() == 4 * 4 + 2 + 49 and not eng.bwd_ws.any()
     assert sizes[0] == (("tcm2" if backend in (4, 5) else "tcm"), 49, 4)
     assert eng.sk_ws.numel() == (1024 if backend in (4, 5) else 512) and not eng.sk_ws.any()
     eng.step(0)
