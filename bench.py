@@ -391,6 +391,8 @@ def main():
                 "config": config_of(workload, args, {"parallelism": parallelism_of(joint, world, eng.collective),
                                                      "prior_backend": eng.backend if eng.prior else None,
                                                      "overlap_streams": bool(eng.overlap),
+                                                     "prior_forward_sm_pairs": eng.split_clusters or "all",
+                                                     "split_tuning_ms": getattr(eng, "split_timings_ms", None),
                                                      "cuda_graph": eng.use_graph,
                                                      "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps}),
                 "roofline": roofline, "roofline_kernels": kernels, "cpu_baseline": cpu, "gpu_baseline": gpu_base,

@@ -261,6 +261,17 @@ int jd_gmm_prior_forward_tc16x2(const float* flux, int fH, int fW, const int32_t
                                 int K, int upper_tri, int zero_mean, int marginalize, void* workspace, float* value,
                                 int32_t* argmax, float* logp, double* sum, jd_stream_t stream);
 
+/* The two-tile forward (recipe 0 = jd_gmm_prior_forward_tcm2, 1 = jd_gmm_prior_forward_tc16x2, same arguments) on at most
+ * `clusters` CTA pairs (0 = every SM pair): the kernel owns the SMs it runs on, so a step whose likelihood chain is
+ * short (one dataset) runs that chain on the remaining SMs from a second stream.  Max / argmax results do not depend on
+ * `clusters`; logsumexp values can differ in the last bits (the partial sums of a split tile are merged per chunk).  The
+ * workspace of jd_gmm_tcm2_workspace_bytes is large enough for every cluster count. */
+int jd_gmm_prior_forward_tcx2_on(int recipe, int clusters, const float* flux, int fH, int fW, const int32_t* shift_yx,
+                                 int stride, int row_begin, int row_end, const void* Bt, const float* binv,
+                                 const float* mw, const float* ck, int K, int upper_tri, int zero_mean, int marginalize,
+                                 void* workspace, float* value, int32_t* argmax, float* logp, double* sum,
+                                 jd_stream_t stream);
+
 /* Per-patch gradient  G[p',:] = scale * sum_k R[p',k] (xc_p Lam_k - bk_k),  minus its row mean,
  * R = one-hot(argmax) or softmax_k(logp) (marginalize=1; needs logp and value from the forward);
  * Lam_k = Lw_k Lw_k^T, bk_k = mw_k Lw_k^T.  (Autograd mirror of gmm.py:270-272 + norms.py:97-103.)

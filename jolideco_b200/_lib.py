@@ -85,6 +85,9 @@ PROTOTYPES = {
     "jd_gmm_prior_forward_tc16x2": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, ctypes.c_void_p, c_f32p, c_f32p,
                                  c_f32p, c_int, c_int, c_int, c_int, ctypes.c_void_p, c_f32p, c_i32p, c_f32p, c_f64p,
                                  c_stream],
+    "jd_gmm_prior_forward_tcx2_on": [c_int, c_int, c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, ctypes.c_void_p, c_f32p,
+                                     c_f32p, c_f32p, c_int, c_int, c_int, c_int, ctypes.c_void_p, c_f32p, c_i32p, c_f32p,
+                                     c_f64p, c_stream],
     "jd_gmm_backward_workspace_elems": [c_i64, c_int],
     "jd_gmm_prior_backward": [c_f32p, c_int, c_int, c_i32p, c_int, c_int, c_int, c_f32p, c_f32p, c_int, c_int,
                               c_i32p, c_f32p, c_f32p, c_float, c_f32p, c_i32p, c_stream],

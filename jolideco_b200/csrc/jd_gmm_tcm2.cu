@@ -622,12 +622,13 @@ struct Plan {
   int n_clusters, chunk, smax, n_tiles2;
   size_t off_m, off_s, off_k, bytes;
 };
-static Plan plan(int64_t P, int K) {
+static Plan plan(int64_t P, int K, int clusters = 0) {
   Plan p;
   const int64_t n_tiles = (P + TM - 1) / TM, n_groups = (n_tiles + CLUSTER * TPC - 1) / (CLUSTER * TPC);
   const int64_t w_tot = n_groups * K;
   int C = num_sms() / CLUSTER;  // one CTA per SM, two SMs per pair
   if (const char* e = getenv("JD_TCM_CLUSTERS")) C = atoi(e) > 0 ? atoi(e) : C;
+  if (clusters > 0 && clusters < C) C = clusters;  // fewer pairs: longer chunks, never a larger workspace
   int64_t chunk = (w_tot + C - 1) / C;
   if (K % 8 == 0) chunk = (chunk + 7) / 8 * 8;  // no segment shorter than 8 components
   if (chunk < 1) chunk = 1;
@@ -648,7 +649,7 @@ template <int R>
 static int launch(const char* who, const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,
                   int row_end, const void* Bt, const float* binv, const float* mw, const float* ck, int K, int upper_tri,
                   int zero_mean, int marginalize, void* workspace, float* value, int32_t* argmax, float* logp,
-                  double* sum, jd_stream_t stream) {
+                  double* sum, jd_stream_t stream, int clusters = 0) {
   JD_CHECK_ARG(flux && Bt && binv && mw && ck && workspace && K > 0, "%s: null pointer", who);
   JD_CHECK_ARG(fH >= PATCH && fW >= PATCH && stride >= 1 && stride <= PATCH, "%s: bad geometry", who);
   int ny = (fH - PATCH) / stride + 1, nx = (fW - PATCH) / stride + 1;
@@ -673,7 +674,7 @@ static int launch(const char* who, const float* flux, int fH, int fW, const int3
     }
     attr_set[dev & 63] = true;
   }
-  const Plan p = plan(g.P, K);
+  const Plan p = plan(g.P, K, clusters);
   static int rot_env = -1, dbg = -1;
   if (rot_env < 0) {
     const char* e = getenv("JD_TC_SK_ROT");  // 0: visit the components of a segment in ascending order
@@ -750,6 +751,20 @@ int jd_gmm_prior_forward_tcm2(const float* flux, int fH, int fW, const int32_t* 
                               int32_t* argmax, float* logp, double* sum, jd_stream_t stream) {
   return tcx2::launch<0>("jd_gmm_prior_forward_tcm2", flux, fH, fW, shift_yx, stride, row_begin, row_end, Bt, binv, mw,
                          ck, K, upper_tri, zero_mean, marginalize, workspace, value, argmax, logp, sum, stream);
+}
+
+int jd_gmm_prior_forward_tcx2_on(int recipe, int clusters, const float* flux, int fH, int fW, const int32_t* shift_yx,
+                                 int stride, int row_begin, int row_end, const void* Bt, const float* binv,
+                                 const float* mw, const float* ck, int K, int upper_tri, int zero_mean, int marginalize,
+                                 void* workspace, float* value, int32_t* argmax, float* logp, double* sum,
+                                 jd_stream_t stream) {
+  JD_CHECK_ARG((recipe == 0 || recipe == 1) && clusters >= 0, "jd_gmm_prior_forward_tcx2_on: recipe 0 / 1, clusters >= 0");
+  if (recipe == 0)
+    return tcx2::launch<0>("jd_gmm_prior_forward_tcx2_on", flux, fH, fW, shift_yx, stride, row_begin, row_end, Bt, binv,
+                           mw, ck, K, upper_tri, zero_mean, marginalize, workspace, value, argmax, logp, sum, stream,
+                           clusters);
+  return tcx2::launch<1>("jd_gmm_prior_forward_tcx2_on", flux, fH, fW, shift_yx, stride, row_begin, row_end, Bt, binv, mw,
+                         ck, K, upper_tri, zero_mean, marginalize, workspace, value, argmax, logp, sum, stream, clusters);
 }
 
 int jd_gmm_prior_forward_tc16x2(const float* flux, int fH, int fW, const int32_t* shift_yx, int stride, int row_begin,

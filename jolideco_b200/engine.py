@@ -37,6 +37,9 @@ _KERNELS_PER_CALL = {"jd_conv_forward_fft": 3, "jd_conv_backward_fft": 3, "jd_li
                      "jd_likelihood_backward_fft": 3}
 
 
+_SPLIT_CACHE = {}  # tuned `split_clusters` per engine shape (see MapEngine._tune_split)
+
+
 def _call(name, *args):
     if _STATS["dry"]:  # argument-building pass before a graph capture (lazy device tables are created here)
         return
@@ -244,6 +247,12 @@ class MapEngine:
         self._graph_nodes = {}
         self._capture_stream = None
         self.overlap = (os.environ.get("JD_OVERLAP", "1") == "1") if overlap is None else bool(overlap)
+        # steps with ONE dataset: the two-tile prior forward on `split_clusters` CTA pairs, enqueued first, and the
+        # likelihood chain on the remaining SMs from the side stream (0: in order on one stream).  "auto": chosen by
+        # `warmup` from timings of this engine's own gradient pass (JD_SPLIT_CLUSTERS = auto | n)
+        split = os.environ.get("JD_SPLIT_CLUSTERS", "auto")
+        self.split_auto = split == "auto"
+        self.split_clusters = 0 if self.split_auto else int(split)
         # created outside any capture
         self._side = torch.cuda.Stream(device=self.dev) if (self.overlap and self.dev.type == "cuda") else None
 
@@ -449,8 +458,16 @@ class MapEngine:
         if d.shift_xy is not None:
             self._shift_backward(d, j)
 
-    def _prior_forward(self, sum_acc):
+    def _prior_forward(self, sum_acc, clusters=0):
         if self.P <= 0:
+            return
+        if clusters and self.backend in (4, 5):  # on part of the SMs (see _gradients)
+            bt, binv = ops._bt16(self.packed) if self.backend == 5 else ops._btm(self.packed)
+            _call("jd_gmm_prior_forward_tcx2_on", self.backend - 4, int(clusters), _p(self.flux), self.fH, self.fW,
+                  _p(self.cur_shift), self.stride, self.rows[0], self.rows[1], _p(bt), _p(binv), _p(self.packed.mw),
+                  _p(self.packed.ck), self.packed.K, int(self.packed.upper_tri), int(self.packed.zero_mean),
+                  int(self.marginalize), _p(self.sk_ws), _p(self.value), _p(self.argmax), _p(self.logp), sum_acc,
+                  self._s())
             return
         if self.backend in (3, 4, 5):
             bt, binv = ops._bt16(self.packed) if self.backend == 5 else ops._btm(self.packed)
@@ -516,12 +533,21 @@ class MapEngine:
         G, acc[1]): with `overlap` the likelihood chain runs on a side stream beside the tensor-core prior kernels
         (which leave shared memory and registers for co-resident FP32 CTAs) and joins before the update."""
         has_prior = self.prior is not None and self.P > 0
-        # (one dataset: a handful of launches beside a prior kernel that owns every SM - measured slower than in order)
+        # (one dataset: a handful of launches beside a prior kernel that owns every SM is slower than in order; beside
+        # a prior kernel on part of the SMs it can be faster - `split_clusters`)
         if self.overlap and has_prior and len(entries) > 1:
             side = self._fork()
             with torch.cuda.stream(side):
                 self._likelihoods(entries, want_grad=True)
             self._prior_forward(self.acc.data_ptr() + 8)
+            self._prior_gradient(prior_scale)
+            self._join(side)
+            return has_prior
+        if self.overlap and has_prior and self.split_clusters and self.backend in (4, 5):
+            side = self._fork()
+            self._prior_forward(self.acc.data_ptr() + 8, self.split_clusters)  # first: its CTA pairs claim their SMs
+            with torch.cuda.stream(side):
+                self._likelihoods(entries, want_grad=True)
             self._prior_gradient(prior_scale)
             self._join(side)
             return has_prior
@@ -626,6 +652,7 @@ class MapEngine:
                 self._step_body(i)
         self.use_graph = graph
         torch.cuda.synchronize(self.dev)
+        self._tune_split(joint)
         if joint and self.world > 1:
             torch.distributed.barrier(group=self.pg)  # no peer is still writing theta slices into this replica
         for t, s in zip(tensors, state):
@@ -633,6 +660,57 @@ class MapEngine:
         torch.cuda.synchronize(self.dev)
         if joint and self.world > 1:
             torch.distributed.barrier(group=self.pg)
+
+    def _tune_split(self, joint):
+        """One-dataset steps: time this engine's gradient pass (local kernels only, scratch outputs, state restored by
+        `warmup`) in order and with the prior forward on a fraction of the SM pairs beside the likelihood chain; keep
+        the split only if it is clearly faster.  Which split wins depends on the balance of the two chains (P, K, PSF
+        size, direct or FFT path), so it is measured rather than modelled: ~2 ms once per run.  Ranks of a joint run
+        decide together (MAX of the timings over ranks): one rank left in order would be the step time of all."""
+        pairs = (torch.cuda.get_device_properties(self.dev).multi_processor_count // 2) if self.dev.type == "cuda" else 0
+        cands = [0] + sorted({max(1, int(round(pairs * f))) for f in (0.25, 0.35, 0.5, 0.65, 0.8)})
+        collective = bool(joint and self.world > 1 and self.split_auto and self.dev.type == "cuda")
+        single = (joint and self.D == 1) or (not joint and self.D >= 1)
+        eligible = bool(self.split_auto and self.overlap and single and self.prior is not None and self.P > 0
+                        and self.backend in (4, 5) and self.dev.type == "cuda")
+        if not eligible and not collective:
+            return
+        key = None
+        if eligible:
+            d0 = self.datasets[0]
+            key = (self.dev.index, self.fH, self.fW, self.P, self.packed.K, self.backend, bool(self.marginalize),
+                   self.stride, d0.geom, d0.shift_xy is not None, bool(joint), self.world)
+            if not collective and key in _SPLIT_CACHE:  # batched independent runs build many engines of one shape
+                self.split_clusters = _SPLIT_CACHE[key]
+                return
+        timings = {c: 0.0 for c in cands}
+        if eligible:
+            entries = [(d0, self.acc.data_ptr() if not joint else self._loss_slot(0), 0)]
+            start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            graph, self.use_graph = self.use_graph, False
+            try:
+                for c in cands:
+                    self.split_clusters = c
+                    self._gradients(entries, self.c)
+                    start.record()
+                    for _ in range(3):
+                        self._gradients(entries, self.c)
+                    end.record()
+                    end.synchronize()
+                    timings[c] = start.elapsed_time(end)
+            finally:
+                self.use_graph = graph
+                self.split_clusters = 0
+        if collective:  # every rank of the group takes part, eligible or not (ineligible ranks contribute zeros)
+            t = torch.tensor([timings[c] for c in cands], dtype=torch.float64, device=self.dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX, group=self.pg)
+            timings = dict(zip(cands, t.tolist()))
+        if not eligible:
+            return
+        best = min(timings, key=timings.get)
+        self.split_clusters = best if timings[best] < 0.95 * timings[0] else 0
+        self.split_timings_ms = {c: t / 3 for c, t in timings.items()}
+        _SPLIT_CACHE[key] = self.split_clusters
 
     def step(self, i):
         self._last_joint = False
