@@ -371,8 +371,9 @@ def extract_patches(flux, shift_yx=(0, 0), stride=4, rows=None):
 
 
 def gmm_prior_forward(flux, shift_yx, packed, stride=4, marginalize=False, rows=None, want_logp=None, sum_out=None,
-                      backend=0):
-    """Returns (value[P'], argmax[P'], logp[P',K] or None, sum double[1])."""
+                      backend=0, clusters=0):
+    """Returns (value[P'], argmax[P'], logp[P',K] or None, sum double[1]).  clusters > 0 (backends 4 / 5): on at most
+    that many CTA pairs (jd_gmm_prior_forward_tcx2_on)."""
     _check(flux, "flux")
     if packed.D != PD:
         raise _lib.JolidecoB200Error("gmm_prior_forward: only 8x8 patches (D=64) are supported")
@@ -392,7 +393,14 @@ def gmm_prior_forward(flux, shift_yx, packed, stride=4, marginalize=False, rows=
         logp = torch.empty((packed.K, P) if tc else (P, packed.K), dtype=torch.float32, device=flux.device)
     if sum_out is None:
         sum_out = torch.zeros(1, dtype=torch.float64, device=flux.device)
-    if int(backend) in (3, 4, 5):
+    if int(backend) in (4, 5) and clusters:
+        bt, binv = _bt16(packed) if int(backend) == 5 else _btm(packed)
+        ws = tcm_workspace(P, packed.K, flux.device, backend)
+        _lib.call("jd_gmm_prior_forward_tcx2_on", int(backend) - 4, int(clusters), _ptr(flux), fH, fW, _ptr(shift),
+                  int(stride), r0, r1, _ptr(bt), _ptr(binv), _ptr(packed.mw), _ptr(packed.ck), packed.K,
+                  int(packed.upper_tri), int(packed.zero_mean), int(bool(marginalize)), _ptr(ws), _ptr(value),
+                  _ptr(argmax), _ptr(logp), _ptr(sum_out), _stream())
+    elif int(backend) in (3, 4, 5):
         bt, binv = _bt16(packed) if int(backend) == 5 else _btm(packed)
         ws = tcm_workspace(P, packed.K, flux.device, backend)
         _lib.call(TCM_ENTRY[int(backend)], _ptr(flux), fH, fW, _ptr(shift), int(stride), r0, r1, _ptr(bt), _ptr(binv),

@@ -333,3 +333,69 @@ def test_overlap_forks_the_likelihood_chain_and_joins_before_the_update(recorder
     assert "jd_likelihood_forward" in seq
     # JD_OVERLAP=0 (the fixture's setting): no side stream at all
     assert E.MapEngine(torch.zeros(32, 32), [dataset()], prior=prior, use_graph=False)._side is None
+
+
+def test_one_dataset_step_puts_the_prior_forward_first_on_part_of_the_sm_pairs(recorder, monkeypatch):
+    """JD_SPLIT_CLUSTERS=n (or the value tuned at warm-up): the two-tile prior forward is enqueued first through
+    jd_gmm_prior_forward_tcx2_on(recipe, n, ...), then the likelihood chain on the side stream (forked BEFORE the prior
+    forward, so it does not wait for it), the prior backward on the main stream, join, update.  0 / other backends /
+    several datasets per step: unchanged."""
+    events = recorder
+
+    class FakeStream:
+        def __init__(self, name="side", **kw):
+            self.name = name
+
+        def wait_stream(self, other):
+            events.append((f"{self.name}.wait({other.name})", ()))
+
+    main = FakeStream("main")
+
+    @contextlib.contextmanager
+    def fake_stream_ctx(stream):
+        events.append((f"enter({stream.name})", ()))
+        yield
+        events.append((f"exit({stream.name})", ()))
+
+    monkeypatch.setattr(torch.cuda, "Stream", FakeStream)
+    monkeypatch.setattr(torch.cuda, "stream", fake_stream_ctx)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: main)
+    lib = types.SimpleNamespace(jd_gmm_tcm_workspace_bytes=lambda P, K: 512, jd_gmm_tcm2_workspace_bytes=lambda P, K: 1024,
+                                jd_gmm_backward_workspace_elems=lambda P, K: 4 * K + 2 + P,
+                                jd_likelihood_supported=lambda kh, kw, f: 1)
+    monkeypatch.setattr(E._lib, "load", lambda: lib)
+    monkeypatch.setattr(ops._lib, "load", lambda: lib)
+    images = (torch.zeros(8, dtype=torch.uint8), torch.zeros(4))
+    monkeypatch.setattr(ops, "_btm", lambda p: images)
+    monkeypatch.setattr(ops, "_bt16", lambda p: images)
+    monkeypatch.setenv("JD_SPLIT_CLUSTERS", "20")
+    for backend in (4, 5):
+        prior = dict(packed=fake_packed(), stride=4, marginalize=False, backend=backend)
+        eng = E.MapEngine(torch.zeros(32, 32), [dataset(), dataset()], prior=prior, use_graph=False, overlap=True)
+        assert eng.split_clusters == 20 and not eng.split_auto
+        del events[:]
+        eng.step(1)
+        seq = names(events)
+        assert seq == ["jd_step_begin_flux", "side.wait(main)", "jd_gmm_prior_forward_tcx2_on", "enter(side)",
+                       "jd_likelihood_forward", "jd_likelihood_backward", "exit(side)", "jd_gmm_prior_backward_max_tri",
+                       "main.wait(side)", "jd_adam_joint_step_dev"]
+        call = [a for n, a in events if n == "jd_gmm_prior_forward_tcx2_on"][0]
+        assert call[0] == backend - 4 and call[1] == 20
+        del events[:]
+        eng.joint_step()  # two datasets per step: the multi-dataset overlap, prior forward on every SM pair
+        assert "jd_gmm_prior_forward_tcx2_on" not in names(events)
+        assert ops.TCM_ENTRY[backend] in names(events)
+    # the one-tile kernels have no such entry: in order
+    prior = dict(packed=fake_packed(), stride=4, marginalize=False, backend=3)
+    eng = E.MapEngine(torch.zeros(32, 32), [dataset()], prior=prior, use_graph=False, overlap=True)
+    del events[:]
+    eng.step(0)
+    assert names(events)[:4] == ["jd_step_begin_flux", "jd_likelihood_forward", "jd_likelihood_backward",
+                                 "jd_gmm_prior_forward_tcm"]
+    # default: "auto" = in order until warmup() has timed the candidates (CUDA only; nothing to tune on the host)
+    monkeypatch.delenv("JD_SPLIT_CLUSTERS")
+    prior = dict(packed=fake_packed(), stride=4, marginalize=False, backend=4)
+    eng = E.MapEngine(torch.zeros(32, 32), [dataset()], prior=prior, use_graph=False, overlap=True)
+    assert eng.split_auto and eng.split_clusters == 0
+    eng._tune_split(joint=False)
+    assert eng.split_clusters == 0

@@ -388,6 +388,25 @@ def test_goldens_through_the_batched_likelihood_kernels(monkeypatch, name, f, n,
     assert "jd_poisson_forward_backward" not in seen and "jd_conv_backward_direct" not in seen
 
 
+@pytest.mark.parametrize("name,f,n,seed", [("run_gmm_max.npz", 1, 8, 4), ("run_gmm_lse.npz", 1, 8, 4),
+                                           ("run_gmm_up2.npz", 2, 6, 5)])
+@pytest.mark.parametrize("graph", [True, False])
+def test_goldens_with_the_prior_forward_beside_the_likelihood_chain(monkeypatch, name, f, n, seed, graph):
+    """One-dataset steps with the prior forward on part of the SM pairs (here forced to one pair; normally tuned at
+    warm-up) and the likelihood chain on the side stream reproduce the reference run: the two chains only share the
+    flux."""
+    from jolideco_b200 import engine as E
+
+    monkeypatch.setenv("JD_SPLIT_CLUSTERS", "1")
+    seen = []
+    real = E._lib.call
+    monkeypatch.setattr(E._lib, "call", lambda name_, *a: (seen.append(name_), real(name_, *a))[1])
+    g = load_golden(name)
+    res = run(g, f, n, make_prior(g, seed), fused=True, graph=graph)
+    check(res, g, n)
+    assert "jd_gmm_prior_forward_tcx2_on" in seen
+
+
 def test_calibration_goldens_through_the_batched_likelihood_kernels(monkeypatch):
     from jolideco_b200 import engine as E
 

@@ -425,6 +425,40 @@ def test_gmm_prior_two_tiles_per_cta_equals_one_tile(shape, rows, K, mean_scale,
     assert int(ws[:4 * n_tiles4].view(torch.int32).abs().sum()) == 0
 
 
+@pytest.mark.parametrize("backend", [4, 5])
+@pytest.mark.parametrize("marginalize", [False, True])
+@pytest.mark.parametrize("shape,rows,K,clusters", [((1024, 1024), None, 256, 37), ((1024, 1024), (0, 32), 256, 18),
+                                                   ((512, 512), None, 256, 48), ((200, 328), None, 40, 5),
+                                                   ((64, 80), None, 3, 1), ((512, 512), None, 256, 1000)])
+def test_gmm_prior_forward_on_part_of_the_sm_pairs(shape, rows, K, clusters, marginalize, backend):
+    """jd_gmm_prior_forward_tcx2_on: the two-tile forward on at most `clusters` CTA pairs (the split of one-dataset
+    steps).  Only the chunking of the (tile group, component) space changes: per-component log-probabilities, max and
+    argmax are bit-identical to the launch on every SM pair, logsumexp values agree to FP32 rounding of the merged
+    partial sums; the workspace of the full launch is large enough and is left clean."""
+    rng = np.random.default_rng(21)
+    flux = t(rng.gamma(2.0, size=shape) * np.exp(rng.normal(0, 0.7, size=shape)))
+    packed = pack(O.GMM(*synthetic_gmm(K, seed=9, mean_scale=0.0)))
+    v0, k0, lp0, s0 = ops.gmm_prior_forward(flux, (1, -2), packed, 4, marginalize, rows=rows, want_logp=True,
+                                            backend=backend)
+    ws = ops.tcm_workspace(v0.numel(), packed.K, flux.device, backend)
+    orig = ops.tcm_workspace
+    ops.tcm_workspace = lambda *a: ws
+    try:
+        v1, k1, lp1, s1 = ops.gmm_prior_forward(flux, (1, -2), packed, 4, marginalize, rows=rows, want_logp=True,
+                                                backend=backend, clusters=clusters)
+    finally:
+        ops.tcm_workspace = orig
+    assert torch.equal(lp0, lp1) and torch.equal(k0, k1)
+    if marginalize:
+        assert_allclose(v1.cpu().numpy(), v0.cpu().numpy(), rtol=2e-6)
+    else:
+        assert torch.equal(v0, v1)
+    assert_allclose(s1.item(), s0.item(), rtol=1e-9 if not marginalize else 1e-6)
+    P = v0.numel()
+    n_tiles4 = ((P + 127) // 128 + 3) // 4 * 4
+    assert int(ws[:4 * n_tiles4].view(torch.int32).abs().sum()) == 0
+
+
 def test_gmm_prior_tensor_core_dense_precision_factors():
     """Non-triangular component matrices take the untrimmed MMA schedule (upper_tri = 0)."""
     rng = np.random.default_rng(10)
