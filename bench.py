@@ -798,11 +798,22 @@ def measure_e2e(J, workload, args, device, rank, joint=False):
     deco.run(datasets=datasets, components=comps)
     deco, comps = build_run(J, workload, args, device, n_epochs=epochs, seed=seed, mode=mode)
     torch.cuda.synchronize()
+    prof = None
+    if os.environ.get("JD_E2E_PROFILE") == "1" and rank == 0:  # where does the fixed per-run cost go? (stderr)
+        import cProfile
+
+        prof = cProfile.Profile()
+        prof.enable()
     t0 = time.perf_counter()
     res = deco.run(datasets=datasets, components=comps)
     flux = res.flux_upsampled_total
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    if prof is not None:
+        import pstats
+
+        prof.disable()
+        pstats.Stats(prof, stream=sys.stderr).sort_stats("cumulative").print_stats(35)
     iters = epochs if joint else epochs * D
     h2d = sum(a.nbytes for d in workload["datasets"].values() for a in d.values()) + comps["flux"]._flux_upsampled.numel() * 4
     if workload["gmm_arrays"] is not None:

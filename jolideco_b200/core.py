@@ -338,6 +338,7 @@ class MAPDeconvolver:
                 total_loss.append_trace_values(ld, [lp] * len(prior_names), filename, lv if lv else None)
         engine.sync_theta()
         torch.cuda.synchronize(self.device)
+        engine.release_peer()  # the next run on this process group takes over the symmetric buffers
 
     def _run_autograd(self, total_loss, components, calibrations):
         """The reference loop verbatim (core.py:197-267) on the autograd bindings of the kernels."""

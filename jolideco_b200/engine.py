@@ -38,6 +38,7 @@ _KERNELS_PER_CALL = {"jd_conv_forward_fft": 3, "jd_conv_backward_fft": 3, "jd_li
 
 
 _SPLIT_CACHE = {}  # tuned `split_clusters` per engine shape (see MapEngine._tune_split)
+_PEER_POOL = {}  # free symmetric-memory buffer sets per (device, process group, pixels) (see MapEngine._enable_peer)
 
 
 def _call(name, *args):
@@ -259,20 +260,30 @@ class MapEngine:
     # ------------------------------------------------------------------------------------------
     def _enable_peer(self):
         """Move theta and the partial-gradient buffer into symmetric memory (peer-addressable over NVLink), plus the
-        flag block of the in-kernel cross-rank barriers (jd_adam_allreduce_peer_sync)."""
+        flag block of the in-kernel cross-rank barriers (jd_adam_allreduce_peer_sync).  Allocation + rendezvous of
+        the three buffers costs several hundred ms (handle exchange, mapping every peer): a finished run hands its
+        set back (`release_peer`) and the next engine of the same size on the same group takes it over.  Acquire and
+        release happen in program order on every rank, so the ranks always pair up the same set."""
         import torch.distributed._symmetric_memory as symm
 
         if self.n % 4:
             raise _lib.JolidecoB200Error("collective='peer' needs a flux pixel count divisible by 4")
         if self.world > 32:
             raise _lib.JolidecoB200Error("collective='peer' supports up to 32 ranks")
+        key = (self.dev.index, getattr(self.pg, "group_name", None) or id(self.pg), self.n)
+        free = _PEER_POOL.setdefault(key, [])
         with torch.cuda.device(self.dev):
-            self.sym_grad = symm.empty(self.n, dtype=torch.float32, device=self.dev)
-            self.sym_theta = symm.empty(self.n, dtype=torch.float32, device=self.dev)
-            self.sym_sig = symm.empty(64, dtype=torch.int32, device=self.dev)
-            self.h_grad = symm.rendezvous(self.sym_grad, self.pg)
-            self.h_theta = symm.rendezvous(self.sym_theta, self.pg)
-            self.h_sig = symm.rendezvous(self.sym_sig, self.pg)
+            if free:
+                bufs = free.pop()
+            else:
+                bufs = {"grad": symm.empty(self.n, dtype=torch.float32, device=self.dev),
+                        "theta": symm.empty(self.n, dtype=torch.float32, device=self.dev),
+                        "sig": symm.empty(64, dtype=torch.int32, device=self.dev)}
+                for name in ("grad", "theta", "sig"):
+                    bufs["h_" + name] = symm.rendezvous(bufs[name], self.pg)
+            self._peer_key, self._peer_bufs = key, bufs
+            self.sym_grad, self.sym_theta, self.sym_sig = bufs["grad"], bufs["theta"], bufs["sig"]
+            self.h_grad, self.h_theta, self.h_sig = bufs["h_grad"], bufs["h_theta"], bufs["h_sig"]
             self.sym_grad.zero_()
             self.sym_sig.zero_()
             self.sym_theta.copy_(self.theta.reshape(-1))
@@ -283,6 +294,21 @@ class MapEngine:
         self._theta_param = self.theta  # the component's parameter storage: refreshed by sync_theta()
         self.theta = self.sym_theta.view(self.fH, self.fW)
         self.dflux_l = self.sym_grad.view(self.fH, self.fW)  # output of the local gradient reduce, read by the peers
+
+    def release_peer(self):
+        """End of a run (every rank, same program point): theta goes back to the component's parameter storage, the
+        symmetric buffers to the pool.  The engine cannot step afterwards."""
+        if getattr(self, "_peer_bufs", None) is None:
+            return
+        self.sync_theta()
+        torch.cuda.synchronize(self.dev)
+        self.theta = self._theta_param
+        self._theta_param = None
+        self.dflux_l = None
+        self._graphs, self._graph_nodes = {}, {}  # they hold the symmetric addresses
+        _PEER_POOL[self._peer_key].append(self._peer_bufs)
+        self._peer_bufs = None
+        self.sym_grad = self.sym_theta = self.sym_sig = self.h_grad = self.h_theta = self.h_sig = None
 
     def sync_theta(self):
         """Copy the working theta back into the component's parameter storage (peer mode only)."""
@@ -586,6 +612,8 @@ class MapEngine:
             self._joint_post()
 
     def _peer_update(self):
+        if self.h_grad is None:
+            raise _lib.JolidecoB200Error("this engine's peer buffers were released at the end of its run")
         _call("jd_adam_allreduce_peer_sync", self.h_grad.buffer_ptrs_dev, self.h_theta.buffer_ptrs_dev,
               self.h_sig.buffer_ptrs_dev, _p(self.sync_state), self.rank, self.world, _p(self.m), _p(self.v),
               _p(self.flux), _p(self.mask), int(self.use_log_flux), self.n, _p(self.adam_scalars), self.b1, self.b2,
