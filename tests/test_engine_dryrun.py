@@ -399,3 +399,172 @@ def test_one_dataset_step_puts_the_prior_forward_first_on_part_of_the_sm_pairs(r
     assert eng.split_auto and eng.split_clusters == 0
     eng._tune_split(joint=False)
     assert eng.split_clusters == 0
+
+
+def test_peer_buffers_are_pooled_across_engines(monkeypatch):
+    """collective='peer': allocation + rendezvous of the symmetric-memory buffers happens once per (device, group,
+    pixel count); `release_peer` (end of MAPDeconvolver's joint run, same program point on every rank) syncs theta back
+    into the component's storage and returns the set, the next engine takes it over with zeroed flags / gradient and
+    its own theta; an engine that starts while another still holds the set allocates a second one."""
+    import torch.distributed._symmetric_memory as symm
+
+    made = []
+
+    class Handle:
+        buffer_ptrs_dev = 0
+
+        def __init__(self):
+            self.barriers = 0
+
+        def barrier(self, channel=0):
+            self.barriers += 1
+
+    def empty(n, dtype=None, device=None):
+        made.append(("empty", n))
+        return torch.full((n,), 7, dtype=dtype)
+
+    def rendezvous(tensor, group):
+        made.append(("rendezvous", tensor.numel()))
+        return Handle()
+
+    monkeypatch.setattr(symm, "empty", empty)
+    monkeypatch.setattr(symm, "rendezvous", rendezvous)
+    monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(E, "_PEER_POOL", {})
+    group = types.SimpleNamespace(group_name="g0")
+
+    def engine(value):
+        eng = object.__new__(E.MapEngine)
+        eng.fH, eng.fW, eng.n, eng.world, eng.pg, eng.dev = 4, 8, 32, 2, group, torch.device("cpu")
+        eng.theta = torch.full((4, 8), float(value))
+        eng._theta_param, eng._graphs, eng._graph_nodes = None, {"joint": object()}, {"joint": 3}
+        eng._enable_peer()
+        return eng
+
+    a = engine(1.0)
+    assert [m[0] for m in made] == ["empty"] * 3 + ["rendezvous"] * 3
+    assert a.theta.data_ptr() == a.sym_theta.data_ptr() and float(a.theta[0, 0]) == 1.0
+    assert not a.sym_grad.any() and not a.sym_sig.any() and a.h_sig.barriers == 1
+    param = a._theta_param
+    a.theta += 2.0  # training moves the symmetric copy only
+    a.sym_sig += 5  # barrier epochs of the run
+    assert float(param[0, 0]) == 1.0
+    first = a.sym_theta
+    a.release_peer()
+    assert a.theta is param and float(param[0, 0]) == 3.0 and a._graphs == {} and a.h_grad is None
+    with pytest.raises(E._lib.JolidecoB200Error, match="released"):
+        a._peer_update()
+    a.release_peer()  # idempotent
+    b = engine(10.0)
+    assert len(made) == 6 and b.sym_theta is first  # taken over: no allocation, no rendezvous
+    assert float(b.theta[0, 0]) == 10.0 and not b.sym_sig.any() and not b.sym_grad.any() and b.h_sig.barriers == 2
+    c = engine(20.0)  # b still holds the set
+    assert len(made) == 12 and c.sym_theta is not first
+    b.release_peer()
+    c.release_peer()
+    assert len(E._PEER_POOL[(None, "g0", 32)]) == 2
+    # another pixel count never takes a set of the wrong size
+    d = object.__new__(E.MapEngine)
+    d.fH, d.fW, d.n, d.world, d.pg, d.dev = 4, 4, 16, 2, group, torch.device("cpu")
+    d.theta, d._theta_param, d._graphs, d._graph_nodes = torch.zeros(4, 4), None, {}, {}
+    d._enable_peer()
+    assert len(made) == 18 and d.sym_grad.numel() == 16
+
+
+def test_split_tuner_decision_rules(recorder, monkeypatch):
+    """MapEngine._tune_split: candidates 0 / 25 / 35 / 50 / 65 / 80 % of the SM pairs, each timed over three gradient
+    passes after one untimed pass; the fastest split is kept only if it beats the in-order pass by more than 5 %; the
+    decision is cached per engine shape; ranks of a joint run use the MAX of the timings over ranks and every rank takes
+    part in that all-reduce, eligible or not."""
+    lib = types.SimpleNamespace(jd_gmm_tcm_workspace_bytes=lambda P, K: 512, jd_gmm_tcm2_workspace_bytes=lambda P, K: 1024,
+                                jd_gmm_backward_workspace_elems=lambda P, K: 4 * K + 2 + P,
+                                jd_likelihood_supported=lambda kh, kw, f: 1)
+    monkeypatch.setattr(E._lib, "load", lambda: lib)
+    monkeypatch.setattr(ops._lib, "load", lambda: lib)
+    images = (torch.zeros(8, dtype=torch.uint8), torch.zeros(4))
+    monkeypatch.setattr(ops, "_btm", lambda p: images)
+    monkeypatch.setattr(E, "_SPLIT_CACHE", {})
+    passes = []
+
+    class FakeDev:
+        type, index = "cuda", 0
+
+    class FakeEvent:
+        table = {}
+        current = [0]
+
+        def __init__(self, enable_timing=True):
+            pass
+
+        def record(self):
+            pass
+
+        def synchronize(self):
+            pass
+
+        def elapsed_time(self, other):
+            return FakeEvent.table[FakeEvent.current[0]]
+
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda dev: types.SimpleNamespace(multi_processor_count=148))
+
+    def build(n_datasets=1):
+        prior = dict(packed=fake_packed(), stride=4, marginalize=False, backend=4)
+        eng = E.MapEngine(torch.zeros(32, 32), [dataset() for _ in range(n_datasets)], prior=prior, use_graph=False,
+                          overlap=False)
+        eng.overlap, eng.dev = True, FakeDev()
+        real = eng._gradients
+
+        def gradients(entries, scale):
+            FakeEvent.current[0] = eng.split_clusters
+            passes.append(eng.split_clusters)
+
+        eng._gradients = gradients
+        return eng
+
+    cands = [0, 18, 26, 37, 48, 59]
+    # clearly faster split
+    FakeEvent.table = {0: 3.0, 18: 4.0, 26: 3.3, 37: 2.4, 48: 2.7, 59: 2.9}
+    eng = build()
+    eng._tune_split(joint=False)
+    assert passes == [c for c in cands for _ in range(4)]  # one untimed + three timed passes per candidate
+    assert eng.split_clusters == 37 and eng.split_timings_ms[37] == pytest.approx(0.8)
+    # same shape again: cached, nothing is timed
+    del passes[:]
+    eng = build()
+    eng._tune_split(joint=False)
+    assert passes == [] and eng.split_clusters == 37
+    # less than 5 % faster: stay in order
+    monkeypatch.setattr(E, "_SPLIT_CACHE", {})
+    FakeEvent.table = {0: 3.0, 18: 4.0, 26: 3.3, 37: 2.9, 48: 2.95, 59: 3.1}
+    eng = build()
+    eng._tune_split(joint=False)
+    assert eng.split_clusters == 0
+    # several datasets per joint step: not a one-dataset step, nothing to tune
+    del passes[:]
+    eng = build(2)
+    eng._tune_split(joint=True)
+    assert passes == [] and eng.split_clusters == 0
+    # joint run on several ranks: MAX over ranks decides (here another rank is slow at 37 pairs), and an ineligible rank
+    # (two datasets) still takes part in the all-reduce
+    monkeypatch.setattr(E, "_SPLIT_CACHE", {})
+    FakeEvent.table = {0: 3.0, 18: 4.0, 26: 3.3, 37: 2.4, 48: 2.7, 59: 2.9}
+    other = torch.tensor([3.0, 4.0, 3.3, 3.5, 2.6, 2.9], dtype=torch.float64)
+    reduced = []
+
+    def all_reduce(t, op=None, group=None):
+        reduced.append(t.clone())
+        t.copy_(torch.maximum(t, other))
+
+    monkeypatch.setattr(torch.distributed, "all_reduce", all_reduce)
+    real_tensor = torch.tensor
+    monkeypatch.setattr(torch, "tensor", lambda data, **kw: real_tensor(data, **{k: v for k, v in kw.items() if k != "device"}))
+    eng = build()
+    eng.world, eng.pg = 2, object()
+    eng._tune_split(joint=True)
+    assert eng.split_clusters == 48 and reduced[0].tolist() == [3.0, 4.0, 3.3, 2.4, 2.7, 2.9]
+    eng = build(2)
+    eng.world, eng.pg = 2, object()
+    eng._tune_split(joint=True)
+    assert len(reduced) == 2 and not reduced[1].any() and eng.split_clusters == 0
