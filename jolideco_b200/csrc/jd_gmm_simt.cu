@@ -844,6 +844,8 @@ int jd_gmm_prior_backward(const float* flux, int fH, int fW, const int32_t* shif
     JD_CHECK_ARG(argmax, "jd_gmm_prior_backward: marginalize=0 needs argmax from the forward");
     if (workspace) {
       JD_CHECK_ARG(K <= 4096, "jd_gmm_prior_backward: the bucketed backward supports up to 4096 components");
+      JD_CHECK_ARG((reinterpret_cast<uintptr_t>(Lam) & 15) == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0,
+                   "jd_gmm_prior_backward: Lam and G must be 16-byte aligned for the bucketed backward");
       int32_t* counts = workspace;
       int32_t* cursor0 = counts + K;
       int32_t* cursor = cursor0 + K;
