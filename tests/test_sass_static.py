@@ -74,3 +74,20 @@ def test_slot_release_arrive_follows_the_consumers_of_the_loads(functions):
         assert releases >= 1, name
         checked += releases
     assert checked >= 25
+
+
+def test_bucket_kernel_gathers_with_asynchronous_copies(functions):
+    """gmm_bwd_bucket8_kernel: Lam_k (16-byte) and the patch elements (4-byte) enter shared memory as cp.async (LDGSTS),
+    all of them issued before the wait.  With plain loads ptxas interleaved each patch's two loads with that patch's
+    shuffle reduction - one L2 round trip per patch, 63 us instead of 33 us (profiles/r02_summary.md)."""
+    kernels = {n: b for n, b in functions.items() if "gmm_bwd_bucket8_kernel" in n}
+    assert len(kernels) == 1
+    body = next(iter(kernels.values()))
+    copies = [i for i, line in enumerate(body) if "LDGSTS" in line]
+    wide = [i for i in copies if ".128" in body[i]]
+    assert len(wide) >= 8 and len(copies) - len(wide) >= 16  # 8 x 16 B per thread of Lam_k, 2 copies x 8 unrolled patches
+    waits = [i for i, line in enumerate(body) if "DEPBAR" in line and "LDGDEPBAR" not in line]
+    assert waits and waits[0] > copies[-1]  # one wait, after the last copy
+    # no warp shuffle (the centring) between the first copy and the wait
+    assert not any("SHFL" in line for line in body[copies[0]:waits[0]])
+    assert sum("FFMA" in line for line in body) >= 256
